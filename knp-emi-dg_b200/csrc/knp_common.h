@@ -1,0 +1,173 @@
+// knp_common.h - launch / memory layer shared by all translation units.
+//
+// Two builds exist from the same sources:
+//   * nvcc -gencode arch=compute_100a,code=sm_100a  -> libknpemi.so, the product;
+//   * g++ -DKNP_EMU                                  -> tests/emu/libknpemi_emu.so, a
+//     host emulation that runs the per-thread kernel bodies in a loop.  It exists
+//     only so that the CPU test-suite (`pytest -m "not gpu"`) can check the host
+//     logic and the kernel arithmetic against the oracle without a GPU.  The Python
+//     package never loads it (knpemidg/_lib.py only looks for libknpemi.so and
+//     raises if it is missing).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <stdexcept>
+
+#ifdef KNP_EMU
+#define KNP_HD inline
+#define KNP_D inline
+typedef int knp_stream_t;
+#else
+#include <cuda_runtime.h>
+#define KNP_HD __host__ __device__ __forceinline__
+#define KNP_D __device__ __forceinline__
+typedef cudaStream_t knp_stream_t;
+#endif
+
+namespace knp {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] inline void fail(const std::string& msg) { throw Error(msg); }
+
+#ifndef KNP_EMU
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+  if (e != cudaSuccess) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %s at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+    throw Error(buf);
+  }
+}
+#define KNP_CUDA(x) ::knp::cuda_check((x), #x, __FILE__, __LINE__)
+#endif
+
+// ---- memory ---------------------------------------------------------------
+inline void* dev_alloc_bytes(size_t bytes) {
+  if (bytes == 0) bytes = 8;
+#ifdef KNP_EMU
+  void* p = calloc(1, bytes);
+  if (!p) fail("host emulation: out of memory");
+  return p;
+#else
+  void* p = nullptr;
+  KNP_CUDA(cudaMalloc(&p, bytes));
+  KNP_CUDA(cudaMemset(p, 0, bytes));
+  return p;
+#endif
+}
+inline void dev_free(void* p) {
+  if (!p) return;
+#ifdef KNP_EMU
+  free(p);
+#else
+  cudaFree(p);
+#endif
+}
+inline void h2d(void* dst, const void* src, size_t bytes, knp_stream_t s) {
+  if (!bytes) return;
+#ifdef KNP_EMU
+  (void)s;
+  memcpy(dst, src, bytes);
+#else
+  KNP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+  KNP_CUDA(cudaStreamSynchronize(s));
+#endif
+}
+inline void d2h(void* dst, const void* src, size_t bytes, knp_stream_t s) {
+  if (!bytes) return;
+#ifdef KNP_EMU
+  (void)s;
+  memcpy(dst, src, bytes);
+#else
+  KNP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+  KNP_CUDA(cudaStreamSynchronize(s));
+#endif
+}
+inline void d2d(void* dst, const void* src, size_t bytes, knp_stream_t s) {
+  if (!bytes) return;
+#ifdef KNP_EMU
+  (void)s;
+  memmove(dst, src, bytes);
+#else
+  KNP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+#endif
+}
+inline void dev_zero(void* dst, size_t bytes, knp_stream_t s) {
+  if (!bytes) return;
+#ifdef KNP_EMU
+  (void)s;
+  memset(dst, 0, bytes);
+#else
+  KNP_CUDA(cudaMemsetAsync(dst, 0, bytes, s));
+#endif
+}
+inline void stream_sync(knp_stream_t s) {
+#ifdef KNP_EMU
+  (void)s;
+#else
+  KNP_CUDA(cudaStreamSynchronize(s));
+#endif
+}
+
+// Owning device array.
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { dev_free(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { dev_free(p); }
+  void alloc(size_t count) {
+    dev_free(p);
+    p = static_cast<T*>(dev_alloc_bytes(count * sizeof(T)));
+    n = count;
+  }
+  void upload(const T* src, size_t count, knp_stream_t s) {
+    if (count != n) alloc(count);
+    h2d(p, src, count * sizeof(T), s);
+  }
+  void upload(const std::vector<T>& v, knp_stream_t s) { upload(v.data(), v.size(), s); }
+  std::vector<T> download(knp_stream_t s) const {
+    std::vector<T> v(n);
+    d2h(v.data(), p, n * sizeof(T), s);
+    return v;
+  }
+};
+
+// ---- launch ---------------------------------------------------------------
+// One-thread-per-index kernels are functor structs with `void operator()(int64_t) const`;
+// the functor type names the kernel in profiles (knp::pf_kernel<knp::EmiCellKernel<3>>).
+#ifdef KNP_EMU
+template <class F>
+inline void parallel_for(knp_stream_t, int64_t n, const F& f, int = 256) {
+  for (int64_t i = 0; i < n; ++i) f(i);
+}
+#else
+template <class F>
+__global__ void pf_kernel(int64_t n, const F f) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) f(i);
+}
+template <class F>
+inline void parallel_for(knp_stream_t s, int64_t n, const F& f, int block = 256) {
+  if (n <= 0) return;
+  int64_t grid = (n + block - 1) / block;
+  pf_kernel<F><<<(unsigned)grid, block, 0, s>>>(n, f);
+  KNP_CUDA(cudaGetLastError());
+}
+#endif
+
+}  // namespace knp

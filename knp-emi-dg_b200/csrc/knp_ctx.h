@@ -1,0 +1,80 @@
+// knp_ctx.h - the context object behind the C ABI (include/knpemi.h).
+#pragma once
+#include <chrono>
+#include <memory>
+#include "knp_common.h"
+#include "knp_dg.h"
+#include "knp_linalg.h"
+#include "knp_amg.h"
+#include "knp_ode.h"
+
+namespace knp {
+
+struct LinkSpec { int col, kind, which, idx, side; };
+
+struct MembraneSet {
+  int model_id = -1, ns = 0, np = 0;
+  int64_t nrows = 0;
+  DevBuf<int32_t> rows;
+  DevBuf<double> states, params;
+  DevBuf<uint8_t> mask;
+  bool has_mask = false;
+  std::vector<LinkSpec> links;
+  int v_col = -1, n_ion = 0;
+  int ich_cols[MAX_IONS] = {0};
+  int nstim = 0; int stim_cols[MAX_STIM] = {0}; double stim_vals[MAX_STIM] = {0};
+};
+
+struct SolverOptions {
+  int pc = 1;           // 0 block-Jacobi, 1 AMG
+  int nu_pre = 1, nu_post = 1, gamma = 1;
+  double omega = 0.7;   // level-0 block-Jacobi damping
+  int restart = 30, knp_min_it = 5;
+};
+
+enum { T_EMI_ASM = 0, T_EMI_SOLVE, T_KNP_ASM, T_KNP_SOLVE, T_ODE, T_POST, T_COUNT };
+
+}  // namespace knp
+
+struct knp_ctx {
+  int device = 0;
+  knp_stream_t stream = 0;
+  // mesh
+  int d = 0, nd = 0;
+  int64_t nc = 0, n = 0, nm = 0, nnz_export = 0, nsip = 0;
+  std::vector<int32_t> h_nbr, h_finfo, h_fmem;                 // [nd][nc]
+  std::vector<int32_t> h_mem_facet, h_mem_ci, h_mem_ce, h_mem_tag, h_mem_fi;
+  knp::DevBuf<double> grad, vol, h;
+  knp::DevBuf<int32_t> region, nbr, finfo, fmem, mem_ci, mem_fi;
+  // parameters
+  knp::Params P{};
+  bool params_set = false;
+  // fields
+  knp::DevBuf<double> c[knp::MAX_IONS], cn_own[knp::MAX_IONS], phi, phiM;
+  bool cn_separate[knp::MAX_IONS] = {false};
+  knp::DevBuf<double> Ich[knp::MAX_IONS], E[knp::MAX_IONS];
+  knp::DevBuf<double> rhs_emi, rhs_knp[knp::MAX_IONS], load_emi, load_knp[knp::MAX_IONS];
+  bool has_load_emi = false, has_load_knp[knp::MAX_IONS] = {false};
+  knp::DevBuf<double> kappa, q, gphi;
+  // matrices: A_emi = (nd+1) slots (slot 0 holds the diagonal blocks of B_emi, so the AMG
+  // Galerkin plan addresses EMI and KNP matrices alike) followed by A_emi's own diagonal blocks
+  knp::DevBuf<double> A_emi, A_knp[knp::MAX_IONS];
+  bool emi_assembled = false, knp_assembled = false;
+  // solver
+  knp::SolverOptions opt;
+  knp::DevBuf<double> kr_r, kr_z, kr_p, kr_q, kr_V, kr_w, kr_scal, kr_partial;
+  knp::AmgPlan amg;
+  knp::AmgValues amg_emi, amg_knp[knp::MAX_IONS];
+  knp::DevBuf<double> bj_emi, bj_knp[knp::MAX_IONS];   // block-Jacobi inverses
+  // membranes
+  std::vector<std::unique_ptr<knp::MembraneSet>> membranes;
+  knp::DevBuf<int64_t> ode_stats;
+  knp::DevBuf<double> trace_tmp;
+  double timers[knp::T_COUNT] = {0};
+
+  const double* cn(int k) const { return cn_separate[k] ? cn_own[k].p : c[k].p; }
+  int64_t bs() const { return (int64_t)nd * nd; }
+  int64_t slot_stride() const { return nc * bs(); }
+  double* Bdiag() { return A_emi.p; }
+  double* Adiag_emi() { return A_emi.p + (int64_t)(nd + 1) * slot_stride(); }
+};

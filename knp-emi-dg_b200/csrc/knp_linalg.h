@@ -1,0 +1,351 @@
+// knp_linalg.h - SpMV (block-ELL and CSR), smoothers, transfer operators, vector
+// kernels and deterministic reductions.
+//
+// Replaces what the reference gets from PETSc (MatMult on AIJ, VecAXPY/VecDot inside
+// KSPSolve, src/knpemidg/solver.py:509, 771) and from hypre BoomerAMG's cycle.
+#pragma once
+#include "knp_common.h"
+
+namespace knp {
+
+// A scalar matrix in block-ELL form; `diag` may point somewhere else than slot 0 of
+// `off` (the EMI preconditioner matrix B shares A's off-diagonal blocks, solver.py:393-395).
+struct BellMat {
+  int64_t nc = 0;
+  const double* off = nullptr;   // (ND+1) slot arrays, slot 0 unused when diag != off
+  const double* diag = nullptr;  // [nc][ND][ND]
+  const int32_t* nbr = nullptr;  // [ND][nc], -1 = no coupling
+};
+
+// y = A x (mode 0), y = b - A x (mode 1).  One thread per row; consecutive threads read
+// consecutive ND-double row segments of every slot array (fully coalesced), x is
+// gathered per neighbour cell (ND contiguous doubles, shared by the ND rows of a cell).
+template <int ND>
+struct BellSpmvKernel {
+  BellMat A;
+  const double* x; const double* b; double* y; int mode;
+  KNP_HD void operator()(int64_t row) const {
+    const int64_t cell = row / ND;
+    const int i = (int)(row - cell * ND);
+    const int64_t bs = ND * ND;
+    double acc = 0.0;
+    {
+      const double* a = A.diag + cell * bs + i * ND;
+      const double* xc = x + cell * ND;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) acc += a[j] * xc[j];
+    }
+#pragma unroll
+    for (int f = 0; f < ND; ++f) {
+      const int64_t c2 = A.nbr[f * A.nc + cell];
+      if (c2 < 0) continue;
+      const double* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND;
+      const double* xc = x + c2 * ND;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) acc += a[j] * xc[j];
+    }
+    y[row] = mode ? b[row] - acc : acc;
+  }
+};
+
+// z = w * Dinv r (mode 0)   or   x += w * Dinv r (mode 1); Dinv = inverse diagonal blocks
+template <int ND>
+struct BlockDiagApplyKernel {
+  const double* dinv; const double* r; double* out; double w; int mode;
+  KNP_HD void operator()(int64_t row) const {
+    const int64_t cell = row / ND;
+    const int i = (int)(row - cell * ND);
+    const double* a = dinv + cell * ND * ND + i * ND;
+    const double* rc = r + cell * ND;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) acc += a[j] * rc[j];
+    if (mode) out[row] += w * acc; else out[row] = w * acc;
+  }
+};
+
+// fused block-Jacobi sweep on level 0: xout = xin + w Dinv (b - A xin) needs the whole
+// cell residual, so it runs one thread per cell.
+template <int ND>
+struct BellJacobiKernel {
+  BellMat A; const double* dinv; const double* b; const double* xin; double* xout; double w;
+  KNP_HD void operator()(int64_t cell) const {
+    const int64_t bs = ND * ND;
+    double r[ND];
+    for (int i = 0; i < ND; ++i) r[i] = b[cell * ND + i];
+    {
+      const double* a = A.diag + cell * bs;
+      const double* xc = xin + cell * ND;
+      for (int i = 0; i < ND; ++i)
+        for (int j = 0; j < ND; ++j) r[i] -= a[i * ND + j] * xc[j];
+    }
+    for (int f = 0; f < ND; ++f) {
+      const int64_t c2 = A.nbr[f * A.nc + cell];
+      if (c2 < 0) continue;
+      const double* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs;
+      const double* xc = xin + c2 * ND;
+      for (int i = 0; i < ND; ++i)
+        for (int j = 0; j < ND; ++j) r[i] -= a[i * ND + j] * xc[j];
+    }
+    const double* di = dinv + cell * bs;
+    for (int i = 0; i < ND; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < ND; ++j) acc += di[i * ND + j] * r[j];
+      xout[cell * ND + i] = xin[cell * ND + i] + w * acc;
+    }
+  }
+};
+
+// ---- CSR (coarse levels, transfer operators) -------------------------------------
+struct CsrMat {
+  int64_t n = 0;
+  const int32_t* ptr = nullptr; const int32_t* col = nullptr; const double* val = nullptr;
+};
+
+struct CsrSpmvKernel {  // y = A x | y = b - A x
+  CsrMat A; const double* x; const double* b; double* y; int mode;
+  KNP_HD void operator()(int64_t row) const {
+    double acc = 0.0;
+    for (int32_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) acc += A.val[k] * x[A.col[k]];
+    y[row] = mode ? b[row] - acc : acc;
+  }
+};
+
+struct CsrJacobiKernel {  // xout = xin + w dinv (b - A xin)
+  CsrMat A; const double* dinv; const double* b; const double* xin; double* xout; double w;
+  KNP_HD void operator()(int64_t row) const {
+    double acc = b[row];
+    for (int32_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) acc -= A.val[k] * xin[A.col[k]];
+    xout[row] = xin[row] + w * dinv[row] * acc;
+  }
+};
+
+struct DiagScaleKernel {  // out = w dinv b
+  const double* dinv; const double* b; double* out; double w;
+  KNP_HD void operator()(int64_t row) const { out[row] = w * dinv[row] * b[row]; }
+};
+
+// l1-Jacobi diagonal: dinv_i = 1 / sum_j |a_ij|  (always convergent for SPD, no
+// eigenvalue estimate needed)
+struct CsrL1DiagKernel {
+  CsrMat A; double* dinv;
+  KNP_HD void operator()(int64_t row) const {
+    double s = 0.0;
+    for (int32_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) s += fabs(A.val[k]);
+    dinv[row] = s > 0.0 ? 1.0 / s : 0.0;
+  }
+};
+
+// y (=|+=) T x for a sparse transfer operator in CSR with optional weights (nullptr = 1)
+struct TransferKernel {
+  int64_t n; const int32_t* ptr; const int32_t* idx; const double* w;
+  const double* x; double* y; int add;
+  KNP_HD void operator()(int64_t row) const {
+    double acc = 0.0;
+    if (w) for (int32_t k = ptr[row]; k < ptr[row + 1]; ++k) acc += w[k] * x[idx[k]];
+    else   for (int32_t k = ptr[row]; k < ptr[row + 1]; ++k) acc += x[idx[k]];
+    if (add) y[row] += acc; else y[row] = acc;
+  }
+};
+
+// Galerkin refresh with a frozen plan: coarse value k = sum_t w_t * fine[gidx_t]
+struct GalerkinKernel {
+  const int32_t* gptr; const int32_t* gidx; const double* gw; const double* fine; double* coarse;
+  KNP_HD void operator()(int64_t k) const {
+    double acc = 0.0;
+    if (gw) for (int32_t t = gptr[k]; t < gptr[k + 1]; ++t) acc += gw[t] * fine[gidx[t]];
+    else    for (int32_t t = gptr[k]; t < gptr[k + 1]; ++t) acc += fine[gidx[t]];
+    coarse[k] = acc;
+  }
+};
+
+struct CsrToDenseKernel {  // dense[m*m] (zeroed before) <- CSR
+  CsrMat A; double* dense;
+  KNP_HD void operator()(int64_t row) const {
+    for (int32_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) dense[row * A.n + A.col[k]] = A.val[k];
+  }
+};
+
+struct DenseMatvecKernel {
+  int64_t m; const double* M; const double* x; double* y;
+  KNP_HD void operator()(int64_t row) const {
+    double acc = 0.0;
+    for (int64_t j = 0; j < m; ++j) acc += M[row * m + j] * x[j];
+    y[row] = acc;
+  }
+};
+
+// ---- vector kernels ---------------------------------------------------------------
+struct AxpbyKernel {  // y = a x + b y
+  double a; const double* x; double b; double* y;
+  KNP_HD void operator()(int64_t i) const { y[i] = a * x[i] + b * y[i]; }
+};
+struct Axpy2Kernel {  // x += a p ; r -= a q     (CG update)
+  double a; const double* p; const double* q; double* x; double* r;
+  KNP_HD void operator()(int64_t i) const { x[i] += a * p[i]; r[i] -= a * q[i]; }
+};
+struct ScaleKernel {  // y = a x
+  double a; const double* x; double* y;
+  KNP_HD void operator()(int64_t i) const { y[i] = a * x[i]; }
+};
+struct AddConstKernel {  // x += a
+  double a; double* x;
+  KNP_HD void operator()(int64_t i) const { x[i] += a; }
+};
+// w -= sum_i h_i V_i  (Gram-Schmidt update), V = k vectors of length n, contiguous
+struct GsUpdateKernel {
+  int64_t n; int k; const double* V; const double* h /*device, k entries*/; double* w;
+  KNP_HD void operator()(int64_t e) const {
+    double acc = w[e];
+    for (int i = 0; i < k; ++i) acc -= h[i] * V[(int64_t)i * n + e];
+    w[e] = acc;
+  }
+};
+// x += sum_i y_i V_i
+struct CombineKernel {
+  int64_t n; int k; const double* V; const double* yv /*device*/; double* x;
+  KNP_HD void operator()(int64_t e) const {
+    double acc = x[e];
+    for (int i = 0; i < k; ++i) acc += yv[i] * V[(int64_t)i * n + e];
+    x[e] = acc;
+  }
+};
+
+// ---- deterministic reductions -------------------------------------------------------
+// out[i] = sum_e V[i*n + e] * w[e], i < k <= DOT_MAX per call.  Two passes with a fixed
+// grid: per-block partials, then one block sums them in a fixed order (bit-reproducible
+// for a given n; no atomics).
+constexpr int DOT_MAX = 8;
+constexpr int RED_BLOCKS = 592;   // 4 x 148 SMs
+constexpr int RED_THREADS = 256;
+
+#ifndef KNP_EMU
+template <int K>
+__global__ void __launch_bounds__(RED_THREADS) multi_dot_partial(int64_t n, const double* __restrict__ V,
+                                                                 const double* __restrict__ w,
+                                                                 double* __restrict__ partial) {
+  double acc[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) acc[i] = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const double we = w[e];
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc[i] += V[(int64_t)i * n + e] * we;
+  }
+  __shared__ double sm[K][RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double v = 0.0;
+    for (int wv = 0; wv < RED_THREADS / 32; ++wv) v += sm[threadIdx.x][wv];
+    partial[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
+  }
+}
+
+static __global__ void __launch_bounds__(RED_THREADS) multi_dot_final(int k, int nblocks,
+                                                               const double* __restrict__ partial,
+                                                               double* __restrict__ out) {
+  __shared__ double sm[RED_THREADS / 32];
+  for (int i = 0; i < k; ++i) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partial[(int64_t)i * nblocks + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int wv = 0; wv < RED_THREADS / 32; ++wv) s += sm[wv];
+      out[i] = s;
+    }
+    __syncthreads();
+  }
+}
+#endif
+
+// device-side dots; `out` (device, >= k doubles) receives the results, `partial` is a
+// scratch buffer of DOT_MAX*RED_BLOCKS doubles.
+inline void multi_dot_device(knp_stream_t s, int64_t n, int k, const double* V, const double* w,
+                             double* partial, double* out) {
+  for (int base = 0; base < k; base += DOT_MAX) {
+    const int kk = (k - base < DOT_MAX) ? k - base : DOT_MAX;
+    const double* Vb = V + (int64_t)base * n;
+#ifdef KNP_EMU
+    (void)s; (void)partial;
+    for (int i = 0; i < kk; ++i) {
+      double acc = 0.0;
+      for (int64_t e = 0; e < n; ++e) acc += Vb[(int64_t)i * n + e] * w[e];
+      out[base + i] = acc;
+    }
+#else
+    switch (kk) {
+#define KNP_CASE(K) case K: multi_dot_partial<K><<<RED_BLOCKS, RED_THREADS, 0, s>>>(n, Vb, w, partial); break;
+      KNP_CASE(1) KNP_CASE(2) KNP_CASE(3) KNP_CASE(4) KNP_CASE(5) KNP_CASE(6) KNP_CASE(7) KNP_CASE(8)
+#undef KNP_CASE
+    }
+    KNP_CUDA(cudaGetLastError());
+    multi_dot_final<<<1, RED_THREADS, 0, s>>>(kk, RED_BLOCKS, partial, out + base);
+    KNP_CUDA(cudaGetLastError());
+#endif
+  }
+}
+
+// in-place inverse of a dense m x m matrix (row major) by Gauss-Jordan without pivoting
+// (coarsest AMG level: SPD for EMI, diagonally dominant for KNP).
+#ifndef KNP_EMU
+static __global__ void __launch_bounds__(1024) dense_inverse_kernel(int m, double* __restrict__ A,
+                                                             double* __restrict__ colbuf) {
+  // single block; A is overwritten by its inverse (in-place Gauss-Jordan)
+  for (int p = 0; p < m; ++p) {
+    const double piv = A[(int64_t)p * m + p];
+    const double ip = 1.0 / piv;
+    __syncthreads();
+    // save column p, scale pivot row
+    for (int i = threadIdx.x; i < m; i += blockDim.x) colbuf[i] = A[(int64_t)i * m + p];
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x)
+      A[(int64_t)p * m + j] = (j == p) ? ip : A[(int64_t)p * m + j] * ip;
+    __syncthreads();
+    for (int64_t idx = threadIdx.x; idx < (int64_t)m * m; idx += blockDim.x) {
+      const int i = (int)(idx / m), j = (int)(idx - (int64_t)i * m);
+      if (i == p) continue;
+      const double f = colbuf[i];
+      const double prow = A[(int64_t)p * m + j];
+      A[idx] = (j == p) ? -f * prow : A[idx] - f * prow;
+    }
+    __syncthreads();
+  }
+}
+#endif
+
+inline void dense_inverse_device(knp_stream_t s, int m, double* A, double* colbuf) {
+#ifdef KNP_EMU
+  (void)s;
+  for (int p = 0; p < m; ++p) {
+    const double ip = 1.0 / A[(int64_t)p * m + p];
+    for (int i = 0; i < m; ++i) colbuf[i] = A[(int64_t)i * m + p];
+    for (int j = 0; j < m; ++j) A[(int64_t)p * m + j] = (j == p) ? ip : A[(int64_t)p * m + j] * ip;
+    for (int i = 0; i < m; ++i) {
+      if (i == p) continue;
+      const double f = colbuf[i];
+      for (int j = 0; j < m; ++j) {
+        const double prow = A[(int64_t)p * m + j];
+        A[(int64_t)i * m + j] = (j == p) ? -f * prow : A[(int64_t)i * m + j] - f * prow;
+      }
+    }
+  }
+#else
+  dense_inverse_kernel<<<1, 1024, 0, s>>>(m, A, colbuf);
+  KNP_CUDA(cudaGetLastError());
+#endif
+}
+
+}  // namespace knp

@@ -19,7 +19,8 @@ import ast
 import inspect
 import textwrap
 
-__all__ = ["TranslationError", "python_rhs_source", "translate_rhs", "model_cuda_source"]
+__all__ = ["TranslationError", "python_rhs_source", "translate_rhs", "model_cuda_source",
+           "model_struct_source", "models_header"]
 
 
 class TranslationError(Exception):
@@ -175,8 +176,9 @@ class _Emitter(ast.NodeVisitor):
         raise TranslationError("unsupported statement " + type(s).__name__)
 
 
-def translate_rhs(source, name):
-    """Translate the Python RHS source text to a CUDA __device__ function."""
+def translate_rhs(source, name, qualifier=""):
+    """Translate the Python RHS source text to a CUDA function (`KNP_HD` expands
+    to `__host__ __device__ __forceinline__`, csrc/knp_common.h)."""
     tree = ast.parse(textwrap.dedent(source))
     fn = next((n for n in tree.body if isinstance(n, ast.FunctionDef)), None)
     if fn is None:
@@ -189,7 +191,7 @@ def translate_rhs(source, name):
         em.stmt(s)
     decl = "".join(f"    double v_{v};\n" for v in em.locals)
     body = "".join(f"    {ln}\n" for ln in em.lines)
-    return (f"__device__ __forceinline__ void {name}(double t, const double* __restrict__ y, "
+    return (f"KNP_HD {qualifier}void {name}(double t, const double* __restrict__ y, "
             f"double* __restrict__ dy, double* __restrict__ p)\n{{\n{decl}{body}}}\n")
 
 
@@ -198,3 +200,32 @@ def model_cuda_source(module, name=None):
     ns = len(module.init_state_values())
     npar = len(module.init_parameter_values())
     return translate_rhs(python_rhs_source(module), name), name, ns, npar
+
+
+def model_struct_source(module, struct_name):
+    """`struct NAME { NS, NP, static rhs }` as consumed by knp::OdeStepKernel."""
+    ns = len(module.init_state_values())
+    npar = len(module.init_parameter_values())
+    fn = translate_rhs(python_rhs_source(module), "rhs", qualifier="static ")
+    fn = "".join("  " + ln + "\n" for ln in fn.splitlines())
+    return (f"struct {struct_name} {{\n  static constexpr int NS = {ns};\n"
+            f"  static constexpr int NP = {npar};\n{fn}}};\n")
+
+
+def models_header(modules):
+    """csrc/generated/models_gen.h for an ordered list of (name, module)."""
+    out = ["// generated by knpemidg.odegen.models_header - do not edit\n#pragma once\n"
+           '#include "../knp_ode.h"\nnamespace knp {\n']
+    for name, mod in modules:
+        out.append(model_struct_source(mod, "Model_" + name))
+    out.append("}  // namespace knp\n")
+    out.append(f"#define KNP_NUM_MODELS {len(modules)}\n")
+    out.append("#define KNP_MODEL_LIST(X) \\\n" + " \\\n".join(
+        f'  X({i}, knp::Model_{name}, "{name}")' for i, (name, _) in enumerate(modules)) + "\n")
+    names = ", ".join(f'"{name}"' for name, _ in modules)
+    ns = ", ".join(str(len(m.init_state_values())) for _, m in modules)
+    npar = ", ".join(str(len(m.init_parameter_values())) for _, m in modules)
+    out.append(f"static const char* const knp_model_names[] = {{{names}}};\n")
+    out.append(f"static const int knp_model_ns[] = {{{ns}}};\n")
+    out.append(f"static const int knp_model_np[] = {{{npar}}};\n")
+    return "".join(out)

@@ -1,0 +1,121 @@
+"""Shared fixtures of the parity tests: a synthetic case is built once as an
+oracle `Problem` (CPU restatement, oracle/) and once as a library context
+(knpemidg._lib.Context) holding the same mesh, parameters and fields.
+
+`lib_for(kind)`: "gpu" -> the product libknpemi.so (CUDA, sm_100a);
+                 "emu" -> the host-emulation build of the same sources
+                          (tests/emu/libknpemi_emu.so), CPU test-suite only.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "knp-emi-dg_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from knpemidg import _lib  # noqa: E402
+from knpemidg import mesh as kmesh  # noqa: E402
+from oracle import forms  # noqa: E402
+
+_LIBS = {}
+
+
+def lib_for(kind):
+    if kind in _LIBS:
+        return _LIBS[kind]
+    if kind == "gpu":
+        lib = _lib.get()
+    else:
+        path = os.path.join(ROOT, "tests", "emu", "libknpemi_emu.so")
+        subprocess.run([sys.executable, os.path.join(PKG, "build.py"), "--emu"], check=True,
+                       stdout=subprocess.DEVNULL)
+        lib = _lib.Lib(path)
+        assert not lib.is_cuda()
+    _LIBS[kind] = lib
+    return lib
+
+
+PHYS = dict(F=96485.0, R=8.314, T=300.0, C_M=0.02, dt=1.0e-4)
+D_PHYS = [1.96e-9, 2.03e-9, 1.33e-9]      # K, Cl, Na (run_2D.py:117-139)
+Z_PHYS = [1.0, -1.0, 1.0]
+C_ICS = [125.0, 137.0, 12.0]
+C_ECS = [4.0, 104.0, 100.0]
+
+
+def make_mesh(name):
+    if name == "2d":
+        return kmesh.neuron_2d_mesh(0) + ((1,),)
+    if name == "2d_r1":
+        return kmesh.neuron_2d_mesh(1) + ((1,),)
+    if name == "3d":
+        return kmesh.bundle_3d_mesh(dims=(16, 9, 9)) + ((1, 2),)
+    if name == "3d_small":
+        return kmesh.bundle_3d_mesh(dims=(8, 9, 9)) + ((1, 2),)
+    if name == "3d_r0":
+        return kmesh.bundle_3d_mesh(0) + ((1, 2),)
+    if name == "emix":
+        return kmesh.emix_like_mesh(10, n_cells=6) + ((1, 2),)
+    raise ValueError(name)
+
+
+class Case:
+    """physiological KNP-EMI case with seeded, perturbed fields"""
+
+    def __init__(self, name, lib, seed=0, splitting=True, D_scale=(1.0, 1.0)):
+        mesh, sub, surf, mtags = make_mesh(name)
+        self.mesh, self.sub, self.surf, self.mtags = mesh, sub, surf, mtags
+        tags = np.unique(sub.array())
+        region = np.searchsorted(tags, sub.array()).astype(np.int32)
+        self.tags = tags
+        dt, C_M = PHYS["dt"], PHYS["C_M"]
+        # per-region diffusion (second entry scales ICS regions to exercise jump(D u))
+        D_sub = [{int(t): D_PHYS[k] * (D_scale[0] if t == 0 else D_scale[1]) for t in tags}
+                 for k in range(3)]
+        rho_sub = {int(t): 0.0 for t in tags}
+        self.P = forms.Problem(mesh, sub.array(), surf.array(), F=PHYS["F"], R=PHYS["R"], T=PHYS["T"],
+                               C_M=C_M, C_phi=C_M / dt, dt=dt, z=Z_PHYS, D_sub=D_sub, rho_sub=rho_sub,
+                               membrane_tags=mtags)
+        P = self.P
+        rng = np.random.default_rng(seed)
+        ics = (sub.array() != 0)[:, None]
+        c_all = np.stack([np.where(ics, C_ICS[k], C_ECS[k]) * (1.0 + 0.01 * rng.uniform(-1, 1, (P.nc, P.nd)))
+                          for k in range(3)])
+        self.c_all = c_all
+        self.c_n = c_all[:2] * (1.0 + 0.001 * rng.uniform(-1, 1, (2, P.nc, P.nd)))
+        self.phi = np.where(ics, -0.07, 0.0) * (1.0 + 0.01 * rng.uniform(-1, 1, (P.nc, P.nd)))
+        self.phi_M = -0.07 * (1.0 + 0.01 * rng.uniform(-1, 1, P.nm))
+        self.I_ch = 1e-3 * rng.uniform(-1, 1, (3, P.nm))
+        self.splitting = splitting
+        # library side
+        ctx = _lib.Context(0, lib)
+        ctx.set_mesh(mesh.coords, mesh.cells, region, mesh.facet_cells, surf.array(), mtags)
+        Dtab = np.array([[D_sub[k][int(t)] for t in tags] for k in range(3)])
+        ctx.set_params(F=P.F, R=P.R, T=P.T, C_M=P.C_M, C_phi=P.C_phi, dt=P.dt, tau_emi=P.tau, tau_knp=P.tau,
+                       Lp=P.Lp, z=Z_PHYS, D=Dtab, rho=[0.0] * len(tags), splitting=splitting)
+        for k in range(3):
+            ctx.set_field(_lib.F_C, k, c_all[k])
+            ctx.set_field(_lib.F_ICH, k, self.I_ch[k])
+        for k in range(2):
+            ctx.set_field(_lib.F_CN, k, self.c_n[k])
+        ctx.set_field(_lib.F_PHI, 0, self.phi)
+        ctx.set_field(_lib.F_PHIM, 0, self.phi_M)
+        self.ctx = ctx
+
+
+def rel_err(a, b):
+    """max |a-b| relative to max |b| (entrywise parity measure for matrices/vectors)"""
+    import scipy.sparse as sp
+    if sp.issparse(a):
+        d = (a - b).tocoo()
+        num = np.abs(d.data).max() if d.nnz else 0.0
+        den = np.abs(b.tocoo().data).max()
+        return num / den
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    den = np.abs(b).max()
+    return np.abs(a - b).max() / (den if den > 0 else 1.0)
