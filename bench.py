@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py - KNP-EMI time-steps/s on the 3D axon-bundle workload (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one full time step of the reference's loop (solver.py:1072-1127): membrane
+ODE step -> EMI assembly + CG/AMG solve -> KNP assembly + GMRES/AMG solves -> post-step.
+Workload: 32 x 0.9 x 0.9 um box with four axons (make_mesh_3D.py:81-111) at 96 x 27 x 27 x 6
+tetrahedra = 419,904 cells, 5.04 M DOFs (3 fields x 4 dofs x cells), Hodgkin-Huxley membranes
+with the synaptic stimulus of run_3D.py, dt = 0.1 ms, CG rtol 1e-5, GMRES(30) rtol 1e-7.
+
+Prints ONE JSON line (rank 0).  `value` = steps/s with everything resident in HBM;
+`e2e` = the same loop driven with HOST buffers through the C ABI (state uploaded from
+pinned memory before and downloaded after every step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "knp-emi-dg_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD_DIMS = (96, 27, 27)
+SAMPLE_DIMS = (32, 9, 9)          # CPU arms: bundle r=0 (make_mesh_3D.py resolution 0)
+DT, C_M = 1.0e-4, 0.02
+PHYS = dict(F=96485.0, R=8.314, T=300.0, C_M=C_M, C_phi=C_M / DT, dt=DT, z=[1.0, -1.0, 1.0],
+            D_sub=[{0: 1.96e-9, 1: 1.96e-9}, {0: 2.03e-9, 1: 2.03e-9}, {0: 1.33e-9, 1: 1.33e-9}],
+            rho_sub={0: 0.0, 1: 0.0})
+NA_I, NA_E, K_I, K_E = 12.838513108648856, 100.71925900027354, 124.15397583491901, 3.3236967382705265
+C_INIT = [{1: K_I, 0: K_E}, {1: NA_I + K_I, 0: NA_E + K_E}, {1: NA_I, 0: NA_E}]   # K, Cl, Na (run_3D.py)
+ION_NAMES = ["K", "Cl", "Na"]
+STIMULUS = {"stim_amplitude": 10.0}
+
+
+def stim_locator(x):
+    return x[0] < 20.0e-6
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_engine(dims, device):
+    from knpemidg import mesh as kmesh
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_hh, mm_hh_no_stim
+    mesh, sub, surf = kmesh.bundle_3d_mesh(dims=dims)
+    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), device=device, **PHYS)
+    eng.set_concentrations_by_tag(C_INIT)
+    eng.add_membrane_model(1, mm_hh, ION_NAMES, stimulus=STIMULUS, stimulus_locator=stim_locator)
+    eng.add_membrane_model(2, mm_hh_no_stim, ION_NAMES, stimulus=STIMULUS, stimulus_locator=stim_locator)
+    eng.initialize(pc=1)
+    return eng
+
+
+def cpu_reference_steps(nsteps, dims=SAMPLE_DIMS):
+    """The CPU restatement (oracle/) stepping the same kind of workload on a bounded
+    sample; returns (seconds per step, dofs of the sample, timers)."""
+    from knpemidg import mesh as kmesh
+    from knpemidg.models import mm_hh, mm_hh_no_stim
+    from oracle import forms, stepper
+    mesh, sub, surf = kmesh.bundle_3d_mesh(dims=dims)
+    P = forms.Problem(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), **PHYS)
+    c0 = np.stack([np.where((sub.array() == 1)[:, None], ci[1], ci[0]) * np.ones((P.nc, P.nd)) for ci in C_INIT])
+    O = stepper.OracleSolver(P, c0, models={1: mm_hh, 2: mm_hh_no_stim}, stimulus=STIMULUS,
+                             stimulus_locator=stim_locator, ion_names=ION_NAMES, direct=False)
+    O.step()                                   # warm-up (numpy/scipy first-call costs, AMG plan)
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        O.step()
+    dt = (time.perf_counter() - t0) / nsteps
+    return dt, 3 * P.ndof, {"emi_niter": O.niter["emi"][-1:], "knp_niter": O.niter["knp"][-2:]}
+
+
+def workload_dofs(dims):
+    return 3 * 4 * 6 * dims[0] * dims[1] * dims[2]
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    sec, dofs, info = cpu_reference_steps(steps)
+    full = workload_dofs(WORKLOAD_DIMS)
+    value = (dofs / full) / sec                # steps/s on the full workload at equal DOF-steps/s
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count()
+    sample = (f"bundle {SAMPLE_DIMS[0]}x{SAMPLE_DIMS[1]}x{SAMPLE_DIMS[2]}x6 tets ({dofs} DOFs), {steps} steps of "
+              f"{sec:.2f} s; scaled to the {full}-DOF workload at equal DOF-steps/s")
+    line = {"impl": "reference", "metric": "time_steps_per_s", "value": value, "unit": "steps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "3D axon bundle 96x27x27x6 tets, 5.04M DOFs, HH membranes (BASELINE configs[2])",
+                       "note": "dolfin+PETSc cannot be installed here; CPU restatement (oracle/) on numpy/scipy"},
+            "dof_steps_per_s": dofs / sec,
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample,
+                             "host_cores_available": cores},
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "detail": info}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--dims", default=None, help="nx,ny,nz override (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    dims = tuple(int(v) for v in args.dims.split(",")) if args.dims else WORKLOAD_DIMS
+    warmup = max(args.warmup, 3)
+
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng = build_engine(dims, local_rank)
+    ctx = eng.ctx
+    for _ in range(warmup):
+        eng.step()
+    # ---- timed region: K steps, state resident in HBM -----------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.timers(reset=True)
+    barrier()
+    ctx.sync()
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        eng.step()
+    ms = ctx.timer_stop()
+    ctx.sync()
+    barrier()
+    launches = ctx.launch_count() - l0
+    phase = ctx.timers()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms)
+    value = world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the same loop with host buffers through the C ABI -------------------
+    from knpemidg import _lib
+    n, nm, N = eng.n, eng.nm, eng.N
+    host = {("c", k): torch.empty(n, dtype=torch.float64).pin_memory().numpy() for k in range(N)}
+    host["phi"] = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    host["phiM"] = torch.empty(nm, dtype=torch.float64).pin_memory().numpy()
+
+    def download():
+        for k in range(N):
+            host[("c", k)][:] = ctx.get_field(_lib.F_C, k)
+        host["phi"][:] = ctx.get_field(_lib.F_PHI)
+        host["phiM"][:] = ctx.get_field(_lib.F_PHIM)
+
+    def upload():
+        for k in range(N):
+            ctx.set_field(_lib.F_C, k, host[("c", k)])
+        ctx.set_field(_lib.F_PHI, 0, host["phi"])
+        ctx.set_field(_lib.F_PHIM, 0, host["phiM"])
+
+    download()
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        upload()
+        eng.step()
+        download()
+    ms_e2e = ctx.timer_stop()
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e * 1e3))
+    e2e_value = world * e2e_steps / (ms_e2e * 1e-3)
+    bytes_dir = 8 * ((N + 1) * n + nm)
+
+    # ---- roofline of the hot kernels (CUDA events on the library's stream) ----------
+    peak, peak_src = read_peaks()
+    kern = {}
+    for kid, name in ((0, "bell_spmv"), (3, "bell_block_jacobi_sweep"), (1, "emi_assembly"), (2, "knp_assembly")):
+        kms, kbytes = ctx.bench_kernel(kid, reps=20)
+        kern[name] = {"ms": kms, "algorithmic_bytes": kbytes, "gbs": kbytes / (kms * 1e-3) / 1e9,
+                      "frac": kbytes / (kms * 1e-3) / 1e9 / peak}
+    dom = kern["bell_spmv"]
+    roofline = {"bound": "hbm", "kernel": "knp::BellSpmvKernel<4> (block-ELL fp64 SpMV)",
+                "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
+                "ms_per_launch": dom["ms"], "other_kernels": kern}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        sec, dofs, info = cpu_reference_steps(2)
+        full = workload_dofs(dims)
+        cpu = {"value": (dofs / full) / sec, "unit": "steps/s", "cores": 1, "kind": "port",
+               "sample": f"oracle/ restatement, bundle {SAMPLE_DIMS} x6 tets ({dofs} DOFs), 2 steps of {sec:.2f} s, "
+                         f"scaled to the {full}-DOF workload at equal DOF-steps/s",
+               "dof_steps_per_s": dofs / sec}
+    dofs = eng.dofs()
+    line = {"metric": "time_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D axon bundle {dims[0]}x{dims[1]}x{dims[2]}x6 tets (BASELINE configs[2]), "
+                                   f"{eng.nc} cells, {dofs} DOFs, {eng.nm} HH membrane facets, dt=1e-4 s",
+                       "parallelism": "replicas" if world > 1 else "single",
+                       "l2_policy": "inputs larger than L2 (matrices 3 x %.0f MB)" % (ctx.nnz * 8 / 1e6),
+                       "solver": "CG rtol 1e-5 / GMRES(30) rtol 1e-7, aggregation AMG (plan reused, Galerkin refreshed per step)"},
+            "dof_steps_per_s": value * dofs,
+            "seconds_per_step": {k: v / args.steps for k, v in phase.items()},
+            "iterations": {"emi": eng.stats["emi_niter"][-args.steps:], "knp": eng.stats["knp_niter"][-args.steps:]},
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": bytes_dir,
+                    "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

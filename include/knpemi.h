@@ -110,7 +110,8 @@ int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, int* niter,
 /* ---- post-step updates: replaces solver.py:809-842 (c_prev <- c, phi_M
  * facet mean of phi_i - phi_e, Nernst potentials, eliminated ion) and the
  * pcws_constant_project calls (utils.py:100-124). */
-int knp_post_step(knp_ctx* ctx);
+enum { KNP_POST_ELIMINATED = 1, KNP_POST_PHIM = 2, KNP_POST_NERNST = 4, KNP_POST_ALL = 7 };
+int knp_post_step(knp_ctx* ctx, int what);
 /* facet mean of the one-sided trace of a field on the membrane rows;
  * side 0 = plus (ECS, utils.py:87), 1 = minus (ICS, utils.py:94). out[nm]. */
 int knp_facet_trace(knp_ctx* ctx, int which, int idx, int side, double* out);
@@ -149,6 +150,21 @@ int knp_ode_step(knp_ctx* ctx, int handle, double t0, double dt, double rtol, do
 /* ---- timers (solver.py:77-81): seconds accumulated since the last reset in
  * out[0..5] = emi assembly, emi solve, knp assembly, knp solve, ode, post. */
 int knp_timers_get(knp_ctx* ctx, double* out, int reset);
+
+/* ---- measurement hooks (bench.py) ----------------------------------------
+ * knp_launch_count: kernels launched by this library since it was loaded.
+ * knp_timer_start/stop: CUDA events recorded on the context's stream (the
+ *   library does not launch on torch's current stream, so torch.cuda.Event
+ *   cannot see its kernels); stop returns the elapsed milliseconds.
+ * knp_bench_kernel: `reps` back-to-back launches of one hot kernel on the
+ *   current state, timed with CUDA events; *ms = average per launch and
+ *   *bytes = algorithmic bytes one launch moves.
+ *   kernel ids: 0 block-ELL SpMV (A_emi), 1 EMI assembly (pre-pass + cells),
+ *   2 KNP assembly (all solved ions), 3 block-Jacobi sweep (B_emi). */
+long long knp_launch_count(void);
+int knp_timer_start(knp_ctx* ctx);
+int knp_timer_stop(knp_ctx* ctx, double* ms);
+int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* bytes);
 
 #ifdef __cplusplus
 }

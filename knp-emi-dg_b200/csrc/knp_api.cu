@@ -446,28 +446,32 @@ int knp_spmv(knp_ctx* ctx, int which, const double* x, double* y) {
 // post-step
 // ---------------------------------------------------------------------------------
 template <int D>
-static void post_step_t(knp_ctx* c) {
+static void post_step_t(knp_ctx* c, int what) {
   knp_stream_t s = c->stream;
+  if (what & KNP_POST_ELIMINATED) {
   EliminatedIonKernel<D> ek;
   ek.P = c->P; ek.region = c->region.p;
   for (int k = 0; k < MAX_IONS; ++k) ek.c[k] = c->c[k].p;
   ek.celim = c->c[c->P.N - 1].p;
   parallel_for(s, c->n, ek);
-  if (c->nm > 0) {
+  }
+  if (c->nm > 0 && (what & (KNP_POST_PHIM | KNP_POST_NERNST))) {
     MembranePostKernel<D> mk;
     mk.P = c->P; mk.nc = c->nc; mk.mem_ci = c->mem_ci.p; mk.mem_fi = c->mem_fi.p;
     mk.nbr = c->nbr.p; mk.finfo = c->finfo.p; mk.phi = c->phi.p;
     for (int k = 0; k < MAX_IONS; ++k) { mk.c[k] = c->c[k].p; mk.E[k] = c->E[k].p; }
-    mk.phiM = c->phiM.p; mk.do_nernst = c->P.mms ? 0 : 1;
+    mk.phiM = c->phiM.p;
+    mk.do_phim = (what & KNP_POST_PHIM) ? 1 : 0;
+    mk.do_nernst = (!c->P.mms && (what & KNP_POST_NERNST)) ? 1 : 0;
     parallel_for(s, c->nm, mk, 128);
   }
 }
 
-int knp_post_step(knp_ctx* ctx) {
+int knp_post_step(knp_ctx* ctx, int what) {
   KNP_TRY
   if (!ctx->params_set) fail("knp_post_step: parameters not set");
   PhaseTimer t(ctx, T_POST);
-  if (ctx->d == 2) post_step_t<2>(ctx); else post_step_t<3>(ctx);
+  if (ctx->d == 2) post_step_t<2>(ctx, what); else post_step_t<3>(ctx, what);
   KNP_CATCH
 }
 
@@ -642,3 +646,81 @@ int knp_timers_get(knp_ctx* ctx, double* out, int reset) {
   KNP_CATCH
 }
 
+
+// ---------------------------------------------------------------------------------
+// measurement hooks
+// ---------------------------------------------------------------------------------
+long long knp_launch_count(void) { return launch_counter(); }
+
+int knp_timer_start(knp_ctx* ctx) {
+  KNP_TRY
+#ifdef KNP_EMU
+  ctx->host_t0 = now_s();
+#else
+  if (!ctx->ev0) { KNP_CUDA(cudaEventCreate(&ctx->ev0)); KNP_CUDA(cudaEventCreate(&ctx->ev1)); }
+  KNP_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+#endif
+  KNP_CATCH
+}
+
+int knp_timer_stop(knp_ctx* ctx, double* ms) {
+  KNP_TRY
+#ifdef KNP_EMU
+  *ms = (now_s() - ctx->host_t0) * 1e3;
+#else
+  if (!ctx->ev0) fail("knp_timer_stop without knp_timer_start");
+  KNP_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  KNP_CUDA(cudaEventSynchronize(ctx->ev1));
+  float f = 0.f;
+  KNP_CUDA(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+  *ms = f;
+#endif
+  KNP_CATCH
+}
+
+int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* bytes) {
+  KNP_TRY
+  if (!ctx->params_set) fail("knp_bench_kernel: context not set up");
+  if (reps < 1) reps = 1;
+  const double nc = (double)ctx->nc, n = (double)ctx->n, nd = ctx->nd, d = ctx->d, bs = (double)ctx->bs();
+  const double N = ctx->P.N;
+  const double geom = 8.0 * nc * nd * d + 16.0 * nc + 4.0 * nc + 8.0 * nd * nc;  // grad, vol+h, region, nbr+finfo
+  DevBuf<double> x, y;
+  if (kernel == 0 || kernel == 3) { x.alloc(ctx->n); y.alloc(ctx->n); }
+  stream_sync(ctx->stream);
+  double t_ms = 0.0;
+  knp_timer_start(ctx);
+  for (int r = 0; r < reps; ++r) {
+    switch (kernel) {
+      case 0: {
+        BellMat M = bell_of(ctx, 0);
+        if (ctx->d == 2) { BellSpmvKernel<3> k{M, x.p, nullptr, y.p, 0}; parallel_for(ctx->stream, ctx->n, k); }
+        else { BellSpmvKernel<4> k{M, x.p, nullptr, y.p, 0}; parallel_for(ctx->stream, ctx->n, k); }
+        break;
+      }
+      case 1: if (ctx->d == 2) assemble_emi_t<2>(ctx); else assemble_emi_t<3>(ctx); break;
+      case 2: if (ctx->d == 2) assemble_knp_t<2>(ctx); else assemble_knp_t<3>(ctx); break;
+      case 3: {
+        BellMat M = bell_of(ctx, 1);
+        if (ctx->d == 2) { BellJacobiKernel<3> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->nc, k, 128); }
+        else { BellJacobiKernel<4> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->nc, k, 128); }
+        break;
+      }
+      default: fail("unknown kernel id");
+    }
+  }
+  if (knp_timer_stop(ctx, &t_ms)) fail(g_last_error);
+  *ms = t_ms / reps;
+  double b = 0.0;
+  const double mat = 8.0 * (double)ctx->nnz_export;
+  switch (kernel) {
+    case 0: b = mat + 4.0 * nd * nc + 16.0 * n; break;
+    case 1: b = /*prepass*/ 8.0 * n * N + 8.0 * nc * nd * d + 4.0 * nc + 8.0 * n + 8.0 * nc * d
+              /*cells*/ + geom + 8.0 * n + 8.0 * nc * d + mat + 8.0 * nc * bs + 8.0 * n; break;
+    case 2: b = /*grad*/ 8.0 * n + 8.0 * nc * nd * d + 8.0 * nc * d
+              + (N - 1) * (geom + 8.0 * nc * d + 8.0 * n + mat + 8.0 * n); break;
+    case 3: b = mat + 8.0 * nc * bs + 4.0 * nd * nc + 24.0 * n; break;
+  }
+  *bytes = b;
+  KNP_CATCH
+}

@@ -147,6 +147,12 @@ struct DevBuf {
   }
 };
 
+// number of kernel launches issued by this library (bench.py reports it as gpu_launches)
+inline long long& launch_counter() {
+  static long long n = 0;
+  return n;
+}
+
 // ---- launch ---------------------------------------------------------------
 // One-thread-per-index kernels are functor structs with `void operator()(int64_t) const`;
 // the functor type names the kernel in profiles (knp::pf_kernel<knp::EmiCellKernel<3>>).
@@ -165,6 +171,7 @@ template <class F>
 inline void parallel_for(knp_stream_t s, int64_t n, const F& f, int block = 256) {
   if (n <= 0) return;
   int64_t grid = (n + block - 1) / block;
+  ++launch_counter();
   pf_kernel<F><<<(unsigned)grid, block, 0, s>>>(n, f);
   KNP_CUDA(cudaGetLastError());
 }

@@ -71,6 +71,10 @@ struct knp_ctx {
   knp::DevBuf<int64_t> ode_stats;
   knp::DevBuf<double> trace_tmp;
   double timers[knp::T_COUNT] = {0};
+#ifndef KNP_EMU
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+#endif
+  double host_t0 = 0.0;
 
   const double* cn(int k) const { return cn_separate[k] ? cn_own[k].p : c[k].p; }
   int64_t bs() const { return (int64_t)nd * nd; }

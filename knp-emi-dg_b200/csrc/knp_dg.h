@@ -520,14 +520,15 @@ struct MembranePostKernel {
   const double* c[MAX_IONS];
   double* phiM;
   double* E[MAX_IONS];
-  int do_nernst;
+  int do_phim, do_nernst;
   KNP_HD void operator()(int64_t m) const {
     const int64_t ci = mem_ci[m];
     const int fi = mem_fi[m];
     const int w = finfo[fi * nc + ci];
     const int64_t ce = nbr[fi * nc + ci];
     // phi_M = facet mean of phi_i - phi_e (solver.py:813-814)
-    phiM[m] = facet_mean_trace<D>(phi, 1, ci, fi, w, ce) - facet_mean_trace<D>(phi, 0, ci, fi, w, ce);
+    if (do_phim)
+      phiM[m] = facet_mean_trace<D>(phi, 1, ci, fi, w, ce) - facet_mean_trace<D>(phi, 0, ci, fi, w, ce);
     if (!do_nernst) return;
     // E_k = RT/(F z_k) mean_F ln(c_e/c_i)  (solver.py:299, 823-828, 841-842)
     for (int k = 0; k < P.N; ++k) {

@@ -292,6 +292,7 @@ inline void multi_dot_device(knp_stream_t s, int64_t n, int k, const double* V, 
 #undef KNP_CASE
     }
     KNP_CUDA(cudaGetLastError());
+    launch_counter() += 2;
     multi_dot_final<<<1, RED_THREADS, 0, s>>>(kk, RED_BLOCKS, partial, out + base);
     KNP_CUDA(cudaGetLastError());
 #endif
@@ -343,6 +344,7 @@ inline void dense_inverse_device(knp_stream_t s, int m, double* A, double* colbu
     }
   }
 #else
+  ++launch_counter();
   dense_inverse_kernel<<<1, 1024, 0, s>>>(m, A, colbuf);
   KNP_CUDA(cudaGetLastError());
 #endif

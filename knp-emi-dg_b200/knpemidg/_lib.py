@@ -19,6 +19,8 @@ LIB_PATH = os.path.join(_HERE, "libknpemi.so")
 # field ids (include/knpemi.h)
 F_C, F_CN, F_PHI, F_PHIM, F_ICH, F_NERNST, F_RHS_EMI, F_RHS_KNP, F_LOAD_EMI, F_LOAD_KNP = range(10)
 
+POST_ELIMINATED, POST_PHIM, POST_NERNST, POST_ALL = 1, 2, 4, 7
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _lp = C.POINTER(C.c_int64)
@@ -49,7 +51,7 @@ _PROTOS = {
     "knp_solver_options": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]),
     "knp_solve_emi": (C.c_int, [_ctx, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), _dp]),
     "knp_solve_knp": (C.c_int, [_ctx, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), _dp]),
-    "knp_post_step": (C.c_int, [_ctx]),
+    "knp_post_step": (C.c_int, [_ctx, C.c_int]),
     "knp_facet_trace": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _dp]),
     "knp_model_count": (C.c_int, []),
     "knp_model_name": (C.c_char_p, [C.c_int]),
@@ -64,6 +66,10 @@ _PROTOS = {
     "knp_membrane_stimulus": (C.c_int, [_ctx, C.c_int, _bp, C.c_int, _ip, _dp]),
     "knp_ode_step": (C.c_int, [_ctx, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _lp]),
     "knp_timers_get": (C.c_int, [_ctx, _dp, C.c_int]),
+    "knp_launch_count": (C.c_longlong, []),
+    "knp_timer_start": (C.c_int, [_ctx]),
+    "knp_timer_stop": (C.c_int, [_ctx, _dp]),
+    "knp_bench_kernel": (C.c_int, [_ctx, C.c_int, C.c_int, _dp, _dp]),
 }
 
 SYMBOLS = tuple(_PROTOS)
@@ -247,8 +253,8 @@ class Context:
         self._call("knp_solve_knp", rtol, atol, maxit, C.byref(it), C.byref(res))
         return it.value, res.value
 
-    def post_step(self):
-        self._call("knp_post_step")
+    def post_step(self, what=POST_ALL):
+        self._call("knp_post_step", int(what))
 
     def facet_trace(self, which, idx, side):
         out = np.empty(self.nm)
@@ -300,3 +306,20 @@ class Context:
 
     def sync(self):
         self._call("knp_sync")
+
+    # -- measurement hooks ---------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.dll.knp_launch_count())
+
+    def timer_start(self):
+        self._call("knp_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._call("knp_timer_stop", C.byref(ms))
+        return ms.value
+
+    def bench_kernel(self, kernel, reps=20):
+        ms, nbytes = C.c_double(), C.c_double()
+        self._call("knp_bench_kernel", int(kernel), int(reps), C.byref(ms), C.byref(nbytes))
+        return ms.value, nbytes.value

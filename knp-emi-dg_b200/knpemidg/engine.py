@@ -1,0 +1,182 @@
+"""Engine: the per-time-step loop of the reference's Solver on one device context.
+
+It owns the order of operations of `Solver.solve_system_active` /
+`solve_for_time_step` (src/knpemidg/solver.py:1072-1127, 794-847):
+
+    ODE phase   per membrane model: phi_M, Nernst potentials and update_ode links
+                -> parameter columns, step, V and I_ch back         (:1077-1113)
+    EMI         assemble A, B, L; CG + AMG(B)                        (:470-529)
+    KNP         assemble A_k, L_k; GMRES + AMG(A_k)                  (:723-789)
+    updates     phi_M, Nernst, eliminated ion                        (:809-842)
+
+All arithmetic happens in libknpemi.so; this class only sequences C-ABI calls
+and keeps the small amount of host state (step counter, times, statistics).
+`knpemidg.Solver` (the reference-facing API) is a thin layer over it.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from ._lib import F_C, F_CN, F_ICH, F_NERNST, F_PHI, F_PHIM  # noqa: F401
+
+
+class MembraneHandle:
+    """One membrane tag = one ODE model instance on the device."""
+
+    def __init__(self, engine, tag, module, rows, model_id, ns, npar):
+        self.engine, self.tag, self.module = engine, tag, module
+        self.rows = rows
+        self.model_id, self.ns, self.np = model_id, ns, npar
+        self.time = 0.0
+        self.handle = None
+
+
+class Engine:
+    def __init__(self, mesh, cell_tags, facet_tags, *, F, R, T, C_M, C_phi, dt, z, D_sub, rho_sub=None,
+                 membrane_tags=(), degree=1, splitting=True, mms=False, C_sub=None, device=0, lib=None):
+        mesh.init_topology()
+        self.mesh = mesh
+        self.ctx = _lib.Context(device, lib)
+        ctx = self.ctx
+        cell_tags = np.asarray(cell_tags)
+        self.tags = np.unique(cell_tags)
+        region = np.searchsorted(self.tags, cell_tags).astype(np.int32)
+        ctx.set_mesh(mesh.coords, mesh.cells, region, mesh.facet_cells, np.asarray(facet_tags),
+                     tuple(int(t) for t in membrane_tags))
+        self.d, self.nd, self.nc, self.n, self.nm = ctx.d, ctx.nd, ctx.nc, ctx.n, ctx.nm
+        self.N = len(z)
+        self.dt = float(dt)
+        tau = 20.0 * self.d * degree                                   # solver.py:110-111
+        ext = mesh.coords.max(axis=0) - mesh.coords.min(axis=0)
+        Lp = float(ext.max())                                          # solver.py:383-391
+
+        def table(sub):
+            return [float(sub[int(t)]) if int(t) in sub else 0.0 for t in self.tags]
+
+        D = np.array([table(Dk) for Dk in D_sub])
+        rho = np.zeros(len(self.tags)) if rho_sub is None else np.array(table(rho_sub))
+        Cs = None if C_sub is None else np.array([table(Ck) for Ck in C_sub])
+        ctx.set_params(F=F, R=R, T=T, C_M=C_M, C_phi=C_phi, dt=dt, tau_emi=tau, tau_knp=tau, Lp=Lp, z=z,
+                       D=D, rho=rho, C_sub=Cs, splitting=splitting, mms=mms)
+        self.C_M = float(C_M)
+        self.cell_tags = cell_tags
+        self.mem = ctx.membrane_table()
+        self.members = []
+        self.k = 0
+        self.t = 0.0
+        self.amg_ready = False
+        self.stats = {"emi_niter": [], "knp_niter": []}
+        self.rtol_emi, self.atol_emi = 1e-5, 1e-40
+        self.rtol_knp, self.atol_knp = 1e-7, 1e-40
+        self.ode_rtol, self.ode_atol = 1e-8, 0.0                       # membrane.py:112
+        self.phi_M_init_type = "constant"
+
+    # -- initial data --------------------------------------------------------
+    def set_concentrations_by_tag(self, c_init_sub):
+        """c_init_sub[k]: {cell tag: value} for all N ions (solver.py:179-206, 'constant')."""
+        for k, sub in enumerate(c_init_sub):
+            vals = np.zeros(self.nc)
+            for t in self.tags:
+                vals[self.cell_tags == t] = float(sub[int(t)])
+            self.ctx.set_field(F_C, k, np.repeat(vals, self.nd))
+
+    def set_concentration(self, k, nodal):
+        self.ctx.set_field(F_C, k, nodal)
+
+    def membrane_midpoints(self):
+        return self.mesh.facet_midpoints()[self.mem["facet"]]
+
+    # -- membrane models -----------------------------------------------------
+    def add_membrane_model(self, tag, module, ion_names, stimulus=None, stimulus_locator=None,
+                           links=(("K_e", 0, "plus"), ("Na_i", -1, "minus"))):
+        """setup_membrane_model for one tag (solver.py:228-267).  `links`: the
+        update_ode hook as data: (parameter name, ion index, side)."""
+        lib = self.ctx.lib
+        name = module.__name__.split(".")[-1]
+        models = lib.models()
+        if name not in models:
+            raise _lib.KnpError(f"membrane model '{name}' is not compiled into libknpemi.so "
+                                f"(available: {sorted(models)})")
+        mid, ns, npar = models[name]
+        rows = np.flatnonzero(self.mem["tag"] == tag).astype(np.int32)   # ascending facet index
+        m = MembraneHandle(self, tag, module, rows, mid, ns, npar)
+        states = np.tile(np.asarray(module.init_state_values(), dtype=float), (len(rows), 1))
+        params = np.tile(np.asarray(module.init_parameter_values(), dtype=float), (len(rows), 1))
+        params[:, module.parameter_indices("Cm")] = self.C_M              # solver.py:248
+        m.handle = self.ctx.membrane_register(mid, rows, states, params)
+        ich = [module.parameter_indices("I_ch_" + nme) for nme in ion_names]
+        self.ctx.membrane_outputs(m.handle, module.state_indices("V"), ich)
+        for k, nme in enumerate(ion_names):                               # solver.py:1097-1098
+            self.ctx.membrane_link(m.handle, module.parameter_indices("E_" + nme), 0, F_NERNST, k)
+        for pname, ion, side in links:                                    # update_ode hook
+            self.ctx.membrane_link(m.handle, module.parameter_indices(pname), 1, F_C, ion % self.N,
+                                   0 if side == "plus" else 1)
+        if stimulus:
+            mid_pts = self.membrane_midpoints()[rows]
+            if stimulus_locator is None:
+                mask = np.ones(len(rows), dtype=np.uint8)
+            else:
+                mask = np.fromiter((bool(stimulus_locator(x)) for x in mid_pts), dtype=np.uint8,
+                                   count=len(rows))                       # membrane.py:92
+            cols = [module.parameter_indices(key) for key in stimulus]
+            self.ctx.membrane_stimulus(m.handle, mask, cols, [float(v) for v in stimulus.values()])
+        # I_ch_k functions start from the ODE parameter table (solver.py:251-259)
+        for k in range(len(ion_names)):
+            cur = self.ctx.get_field(F_ICH, k)
+            cur[rows] = params[:, ich[k]]
+            self.ctx.set_field(F_ICH, k, cur)
+        self.members.append(m)
+        return m
+
+    # -- one step --------------------------------------------------------------
+    def initialize(self, pc=1, amg_theta=0.08):
+        """What the reference does before the loop: initial Nernst potentials
+        (setup_varform_emi, solver.py:299) and the first assembly (setup_solver_*,
+        :452-453, 710); here the first assembly also fixes the AMG plan."""
+        self.ctx.post_step(_lib.POST_NERNST)
+        self.ctx.assemble_emi()
+        if pc == 1:
+            self.ctx.amg_setup(theta=amg_theta)
+            self.amg_ready = True
+        self.ctx.solver_options(pc=pc)
+        self._initialized = True
+
+    def ode_phase(self):
+        for m in self.members:
+            set_v = not (self.phi_M_init_type == "constant" and self.k == 0)   # solver.py:1086-1094
+            self.ctx.ode_step(m.handle, m.time, self.dt, self.ode_rtol, self.ode_atol, set_v)
+            m.time += self.dt                                                  # membrane.py:115
+
+    def pde_phase(self):
+        ctx = self.ctx
+        ctx.assemble_emi()
+        it, _ = ctx.solve_emi(self.rtol_emi, self.atol_emi, 1000)
+        self.stats["emi_niter"].append(it)
+        ctx.assemble_knp()
+        it, _ = ctx.solve_knp(self.rtol_knp, self.atol_knp, 1000)
+        self.stats["knp_niter"].append(it)
+        ctx.post_step(_lib.POST_ALL)
+        self.t += self.dt
+
+    def step(self):
+        if not getattr(self, "_initialized", False):
+            self.initialize()
+        if self.members:
+            self.ode_phase()
+        self.pde_phase()
+        self.k += 1
+
+    # -- observables ---------------------------------------------------------
+    def phi(self):
+        return self.ctx.get_field(F_PHI).reshape(self.nc, self.nd)
+
+    def concentration(self, k):
+        return self.ctx.get_field(F_C, k).reshape(self.nc, self.nd)
+
+    def phi_M(self):
+        return self.ctx.get_field(F_PHIM)
+
+    def dofs(self):
+        """V_emi.dim() + V_knp.dim() (solver.py:1163-1164)."""
+        return self.N * self.n

@@ -15,7 +15,7 @@ import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from . import forms, ode
+from . import forms, ode, amg
 
 
 def solve_singular_direct(A, b):
@@ -53,6 +53,8 @@ class OracleSolver:
         self.t = 0.0
         self.k = 0
         self.niter = {"emi": [], "knp": []}
+        self._plan = None
+        self.timers = {"emi_assemble": 0.0, "emi_solve": 0.0, "knp_assemble": 0.0, "knp_solve": 0.0, "ode": 0.0}
         # default update_ode hook of the idealized examples (run_2D.py:38-50)
         self.ode_links = ode_links if ode_links is not None else \
             [("K_e", 0, "plus"), ("Na_i", P.N - 1, "minus")]
@@ -124,8 +126,10 @@ class OracleSolver:
         if self.direct:
             x = solve_singular_direct(A, b)
         else:
-            Binv = spla.splu(B.tocsc())
-            M = spla.LinearOperator(A.shape, matvec=Binv.solve)
+            if self._plan is None:                      # aggregates are kept across steps
+                self._plan = amg.Plan(self.P, B)
+            H = amg.Hierarchy(self._plan, B)
+            M = spla.LinearOperator(A.shape, matvec=H.apply)
             it = [0]
             x, info = spla.cg(A, b, x0=self.phi.ravel().copy(), rtol=self.rtol_emi, atol=0.0,
                               maxiter=1000, M=M, callback=lambda _: it.__setitem__(0, it[0] + 1))
@@ -140,8 +144,10 @@ class OracleSolver:
             if self.direct:
                 x = spla.spsolve(A.tocsc(), b)
             else:
-                ilu = spla.spilu(A.tocsc(), drop_tol=1e-6, fill_factor=20)
-                M = spla.LinearOperator(A.shape, matvec=ilu.solve)
+                if self._plan is None:
+                    self._plan = amg.Plan(self.P, A)
+                H = amg.Hierarchy(self._plan, A)
+                M = spla.LinearOperator(A.shape, matvec=H.apply)
                 it = [0]
                 x, info = spla.gmres(A, b, x0=self.c[k].ravel().copy(), rtol=self.rtol_knp, atol=0.0,
                                      restart=30, maxiter=1000, M=M, callback_type="pr_norm",
