@@ -163,7 +163,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--dims", default=None, help="nx,ny,nz override (debug)")
@@ -241,7 +241,7 @@ def main():
         ctx.set_field(_lib.F_PHIM, 0, host["phiM"])
 
     download()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 10))
     barrier()
     t0 = time.perf_counter()
     ctx.timer_start()

@@ -1,6 +1,7 @@
 // knp_api.cu - C ABI: context, mesh tables, parameters, fields, assembly, post-step,
 // membrane ODE step.  The linear solvers live in knp_solve.cu.
 #include "../../include/knpemi.h"
+#include <algorithm>
 #include "knp_ctx.h"
 #include "generated/models_gen.h"
 
@@ -198,6 +199,14 @@ static void build_mesh(knp_ctx* c, int64_t nc, int64_t nv, const double* coords,
   c->region.upload(region, nc, s);
   c->nbr.upload(c->h_nbr, s); c->finfo.upload(c->h_finfo, s); c->fmem.upload(c->h_fmem, s);
   c->mem_ci.upload(c->h_mem_ci, s); c->mem_fi.upload(c->h_mem_fi, s);
+  {
+    std::vector<int32_t> mc(c->h_mem_ci);
+    mc.insert(mc.end(), c->h_mem_ce.begin(), c->h_mem_ce.end());
+    std::sort(mc.begin(), mc.end());
+    mc.erase(std::unique(mc.begin(), mc.end()), mc.end());
+    c->nmc = (int64_t)mc.size();
+    c->memcell.upload(mc, s);
+  }
   // fields and matrices
   const int64_t n = c->n, nm = c->nm;
   c->phi.alloc(n); c->phiM.alloc(nm); c->rhs_emi.alloc(n);
@@ -336,7 +345,7 @@ static void assemble_emi_t(knp_ctx* c) {
   for (int k = 0; k < MAX_IONS; ++k) pre.c[k] = c->c[k].p;
   pre.grad = c->grad.p; pre.region = c->region.p; pre.kappa = c->kappa.p; pre.q = c->q.p;
   parallel_for(s, c->nc, pre, 128);
-  EmiCellKernel<D> k;
+  EmiArgs<D> k;
   k.P = c->P; k.nc = c->nc;
   k.grad = c->grad.p; k.vol = c->vol.p; k.h = c->h.p;
   k.nbr = c->nbr.p; k.finfo = c->finfo.p; k.fmem = c->fmem.p;
@@ -344,7 +353,13 @@ static void assemble_emi_t(knp_ctx* c) {
   for (int i = 0; i < MAX_IONS; ++i) k.Ich[i] = c->Ich[i].p;
   k.load = c->has_load_emi ? c->load_emi.p : nullptr;
   k.A = c->A_emi.p; k.Adiag = c->Adiag_emi(); k.rhs = c->rhs_emi.p;
-  parallel_for(s, c->nc, k, 128);
+#ifdef KNP_EMU
+  parallel_for(s, c->nc, EmiCellKernel<D>{k}, 128);
+#else
+  ++launch_counter();
+  emi_assemble_kernel<D><<<(unsigned)((c->nc + ASM_CPB - 1) / ASM_CPB), ASM_CPB*(D + 1), 0, s>>>(k);
+  KNP_CUDA(cudaGetLastError());
+#endif
 }
 
 template <int D>
@@ -354,7 +369,7 @@ static void assemble_knp_t(knp_ctx* c) {
   gk.phi = c->phi.p; gk.grad = c->grad.p; gk.gphi = c->gphi.p;
   parallel_for(s, c->nc, gk, 128);
   for (int ion = 0; ion < c->P.N - 1; ++ion) {
-    KnpCellKernel<D> k;
+    KnpArgs<D> k;
     k.P = c->P; k.nc = c->nc; k.ion = ion;
     k.grad = c->grad.p; k.vol = c->vol.p; k.h = c->h.p; k.region = c->region.p;
     k.nbr = c->nbr.p; k.finfo = c->finfo.p; k.fmem = c->fmem.p;
@@ -363,7 +378,21 @@ static void assemble_knp_t(knp_ctx* c) {
     k.cn = c->cn(ion); k.phiM = c->phiM.p;
     k.load = c->has_load_knp[ion] ? c->load_knp[ion].p : nullptr;
     k.A = c->A_knp[ion].p; k.rhs = c->rhs_knp[ion].p;
-    parallel_for(s, c->nc, k, 128);
+#ifdef KNP_EMU
+    parallel_for(s, c->nc, KnpCellKernel<D>{k}, 128);
+#else
+    ++launch_counter();
+    knp_assemble_kernel<D><<<(unsigned)((c->nc + ASM_CPB - 1) / ASM_CPB), ASM_CPB*(D + 1), 0, s>>>(k);
+    KNP_CUDA(cudaGetLastError());
+#endif
+  }
+  if (c->nmc > 0) {
+    KnpMembraneRhsKernel<D> m;
+    m.P = c->P; m.nc = c->nc; m.memcell = c->memcell.p; m.vol = c->vol.p; m.grad = c->grad.p;
+    m.region = c->region.p; m.nbr = c->nbr.p; m.finfo = c->finfo.p; m.fmem = c->fmem.p;
+    m.phi = c->phi.p; m.phiM = c->phiM.p;
+    for (int i = 0; i < MAX_IONS; ++i) { m.c[i] = c->c[i].p; m.Ich[i] = c->Ich[i].p; m.rhs[i] = c->rhs_knp[i].p; }
+    parallel_for(s, c->nmc, m, 64);
   }
 }
 
@@ -702,8 +731,8 @@ int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* byt
       case 2: if (ctx->d == 2) assemble_knp_t<2>(ctx); else assemble_knp_t<3>(ctx); break;
       case 3: {
         BellMat M = bell_of(ctx, 1);
-        if (ctx->d == 2) { BellJacobiKernel<3> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->nc, k, 128); }
-        else { BellJacobiKernel<4> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->nc, k, 128); }
+        if (ctx->d == 2) { BellJacobiKernel<3> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->n, k, 192); }
+        else { BellJacobiKernel<4> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->n, k, 256); }
         break;
       }
       default: fail("unknown kernel id");

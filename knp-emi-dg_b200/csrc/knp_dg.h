@@ -69,8 +69,8 @@ template <> struct FacetRule5<3> {
     const double s = first ? (6.0 - s15) / 21.0 : (6.0 + s15) / 21.0;
     w = first ? (155.0 - s15) / 1200.0 : (155.0 + s15) / 1200.0;
     const int k = (q - 1) % 3;
-    b[0] = b[1] = b[2] = s;
-    b[k] = 1.0 - 2.0 * s;
+    const double t = 1.0 - 2.0 * s;
+    b[0] = (k == 0) ? t : s; b[1] = (k == 1) ? t : s; b[2] = (k == 2) ? t : s;
   }
 };
 template <> struct FacetRule4<3> {
@@ -80,8 +80,8 @@ template <> struct FacetRule4<3> {
     const double s = first ? 0.445948490915965 : 0.091576213509771;
     w = first ? 0.223381589678011 : 0.109951743655322;
     const int k = q % 3;
-    b[0] = b[1] = b[2] = s;
-    b[k] = 1.0 - 2.0 * s;
+    const double t = 1.0 - 2.0 * s;
+    b[0] = (k == 0) ? t : s; b[1] = (k == 1) ? t : s; b[2] = (k == 2) ? t : s;
   }
 };
 
@@ -147,10 +147,16 @@ struct GradKernel {  // gphi = grad(phi) per cell (solver.py:583, 593)
 };
 
 // ---------------------------------------------------------------------------
-// EMI assembly, one cell-row block per index.
+// EMI assembly.  The arithmetic of one cell-row block is split into
+//   emi_cell_row : cell integrals for test function i
+//   emi_facet    : everything one facet contributes (its off-diagonal block, its
+//                  share of the diagonal block and of the right-hand side)
+// and is used by two drivers: EmiCellKernel (one index per cell: host emulation and
+// small meshes) and emi_assemble_kernel (CUDA: one thread per (cell, facet), blocks staged
+// through shared memory so that every global store is a full coalesced line).
 // ---------------------------------------------------------------------------
 template <int D>
-struct EmiCellKernel {
+struct EmiArgs {
   static constexpr int ND = D + 1;
   Params P;
   int64_t nc;
@@ -163,148 +169,327 @@ struct EmiCellKernel {
   double* A;                     // (ND+1) slots; slot 0 receives the diagonal blocks of B
   double* Adiag;                 // [nc][ND][ND] diagonal blocks of A
   double* rhs;                   // [n]
+};
 
-  KNP_HD void operator()(int64_t cell) const {
-    constexpr double c_m2 = 1.0 / (D * (D + 1));              // facet mass
-    constexpr double c_m3 = (D == 3) ? 1.0 / 60.0 : 1.0 / 24.0;   // facet cubic moment
-    constexpr double c_k3 = (D == 3) ? 1.0 / 120.0 : 1.0 / 60.0;  // cell cubic moment
-    const int64_t bs = ND * ND;
-    double g[ND][D];
+// cell integrals for test function i: kappa grad u . grad v (solver.py:325), rhs
+// -q.grad v (:309) and the mass shift of the preconditioner form (:393)
+template <int D, int I>
+KNP_HD void emi_cell_row(const EmiArgs<D>& a, const double (&g)[D + 1][D], double K,
+                         const double (&kap)[D + 1], double kbar, const double (&qc)[D],
+                         double* dgrow, double* bdrow, double& ri) {
+  constexpr int ND = D + 1;
+  constexpr double c_k3 = (D == 3) ? 1.0 / 120.0 : 1.0 / 60.0;  // cell cubic moment
+  constexpr int i = I;
+  double qi = 0.0;
+  #pragma unroll
+  for (int x = 0; x < D; ++x) qi += qc[x] * g[i][x];
+  ri = -K * qi;
+  #pragma unroll
+  for (int j = 0; j < ND; ++j) {
+    double gg = 0.0;
+    #pragma unroll
+    for (int x = 0; x < D; ++x) gg += g[i][x] * g[j][x];
+    dgrow[j] = K * kbar * gg;
+    double mk = 0.0;
+    #pragma unroll
+    for (int m = 0; m < ND; ++m) mk += kap[m] * mult3(m, i, j);
+    bdrow[j] = K * c_k3 * mk * a.P.inv_Lp2;
+  }
+}
+
+// facet f of `cell`: O = coupling block to the neighbour (zero when the facet carries no
+// terms), dg += share of the diagonal block, r += share of the rhs.
+template <int D, int F>
+KNP_HD void emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1][D], double K,
+                      double hK, const double (&kap)[D + 1], const double (&qc)[D],
+                      double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1], double (&r)[D + 1]) {
+  constexpr int ND = D + 1;
+  constexpr double c_m2 = 1.0 / (D * (D + 1));                  // facet mass
+  constexpr double c_m3 = (D == 3) ? 1.0 / 60.0 : 1.0 / 24.0;   // facet cubic moment
+  constexpr int f = F;
+  const int64_t nc = a.nc;
+  const int w = a.finfo[f * nc + cell];
+  const int kind = fi_kind(w);
+  #pragma unroll
+  for (int i = 0; i < ND; ++i)
+    #pragma unroll
+    for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
+  if (kind == FK_NONE) return;
+  const int64_t c2 = a.nbr[f * nc + cell];
+  double gn2 = 0.0;
+  #pragma unroll
+  for (int x = 0; x < D; ++x) gn2 += g[f][x] * g[f][x];
+  const double gnorm = sqrt(gn2);
+  const double area = gnorm * D * K;
+  double n[D];
+  #pragma unroll
+  for (int x = 0; x < D; ++x) n[x] = -g[f][x] / gnorm;
+  int perm[ND];
+  #pragma unroll
+  for (int v = 0; v < ND; ++v) perm[v] = fi_perm(w, v);
+  if (kind == FK_SIP) {
+    double g2[ND][D], kap2[ND];
+    #pragma unroll
     for (int i = 0; i < ND; ++i)
-      for (int x = 0; x < D; ++x) g[i][x] = grad[cell * (ND * D) + i * D + x];
-    const double K = vol[cell], hK = h[cell];
-    double kap[ND], qc[D];
-    double kbar = 0.0;
-    for (int m = 0; m < ND; ++m) { kap[m] = kappa[cell * ND + m]; kbar += kap[m]; }
-    kbar /= ND;
-    for (int x = 0; x < D; ++x) qc[x] = q[cell * D + x];
-
-    double dg[ND][ND], bd[ND][ND], r[ND];
-    // cell integrals: kappa grad u . grad v (solver.py:325), rhs -q.grad v (:309),
-    // and the mass shift of the preconditioner form (:393)
-    for (int i = 0; i < ND; ++i) {
-      double qi = 0.0;
-      for (int x = 0; x < D; ++x) qi += qc[x] * g[i][x];
-      r[i] = -K * qi;
-      for (int j = 0; j < ND; ++j) {
-        double gg = 0.0;
-        for (int x = 0; x < D; ++x) gg += g[i][x] * g[j][x];
-        dg[i][j] = K * kbar * gg;
-        double mk = 0.0;
-        for (int m = 0; m < ND; ++m) mk += kap[m] * mult3(m, i, j);
-        bd[i][j] = K * c_k3 * mk * P.inv_Lp2;
-      }
+      #pragma unroll
+      for (int x = 0; x < D; ++x) g2[i][x] = a.grad[c2 * (ND * D) + i * D + x];
+    #pragma unroll
+    for (int m = 0; m < ND; ++m) kap2[m] = a.kappa[c2 * ND + m];
+    const double beta = a.P.tau_emi / (0.5 * (hK + a.h[c2]));
+    double gn_me[ND], gn_nb[ND];
+    #pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      double a1 = 0.0, a2 = 0.0;
+      #pragma unroll
+      for (int x = 0; x < D; ++x) { a1 += g[j][x] * n[x]; a2 += g2[j][x] * n[x]; }
+      gn_me[j] = a1; gn_nb[j] = a2;
     }
-
-    for (int f = 0; f < ND; ++f) {
-      const int w = finfo[f * nc + cell];
-      const int kind = fi_kind(w);
-      double O[ND][ND];
-      for (int i = 0; i < ND; ++i)
-        for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
-      if (kind != FK_NONE) {
-        const int64_t c2 = nbr[f * nc + cell];
-        double gn2 = 0.0;
-        for (int x = 0; x < D; ++x) gn2 += g[f][x] * g[f][x];
-        const double gnorm = sqrt(gn2);
-        const double area = gnorm * D * K;
-        double n[D];
-        for (int x = 0; x < D; ++x) n[x] = -g[f][x] / gnorm;
-        int perm[ND];
-        for (int a = 0; a < ND; ++a) perm[a] = fi_perm(w, a);
-        if (kind == FK_SIP) {
-          double g2[ND][D], kap2[ND];
-          for (int i = 0; i < ND; ++i)
-            for (int x = 0; x < D; ++x) g2[i][x] = grad[c2 * (ND * D) + i * D + x];
-          for (int m = 0; m < ND; ++m) kap2[m] = kappa[c2 * ND + m];
-          const double beta = P.tau_emi / (0.5 * (hK + h[c2]));
-          double gn_me[ND], gn_nb[ND];
-          for (int j = 0; j < ND; ++j) {
-            double a1 = 0.0, a2 = 0.0;
-            for (int x = 0; x < D; ++x) { a1 += g[j][x] * n[x]; a2 += g2[j][x] * n[x]; }
-            gn_me[j] = a1; gn_nb[j] = a2;
-          }
-          double S_me[ND], S_nb[ND], knb[ND];
-          for (int a = 0; a < ND; ++a) knb[a] = (a == f) ? 0.0 : kap2[perm[a]];
-          for (int i = 0; i < ND; ++i) {
-            double s1 = 0.0, s2 = 0.0;
-            if (i != f) {
-              for (int a = 0; a < ND; ++a) {
-                if (a == f) continue;
-                const double m2 = (a == i) ? 2.0 : 1.0;
-                s1 += kap[a] * m2; s2 += knb[a] * m2;
-              }
-            }
-            S_me[i] = s1 * c_m2 * area; S_nb[i] = s2 * c_m2 * area;
-          }
-          for (int i = 0; i < ND; ++i) {
-            for (int j = 0; j < ND; ++j) {
-              double pen = 0.0;
-              if (i != f && j != f) {
-                for (int a = 0; a < ND; ++a) {
-                  if (a == f) continue;
-                  pen += 0.5 * (kap[a] + knb[a]) * mult3(a, i, j);
-                }
-                pen *= c_m3 * area * beta;
-              }
-              dg[i][j] += -0.5 * gn_me[j] * S_me[i] - 0.5 * gn_me[i] * S_me[j] + pen;
-              if (j != f) O[i][perm[j]] += 0.5 * gn_me[i] * S_me[j] - pen;
-            }
-            for (int jp = 0; jp < ND; ++jp) O[i][jp] += -0.5 * gn_nb[jp] * S_nb[i];
-          }
-          // rhs: avg(q).n+ jump(v)  (solver.py:310)
-          double fl = 0.0;
-          for (int x = 0; x < D; ++x) fl += 0.5 * (qc[x] + q[c2 * D + x]) * n[x];
-          fl *= area / D;
-          for (int i = 0; i < ND; ++i)
-            if (i != f) r[i] += fl;
-        } else {  // membrane: C_phi jump(u) jump(v), robin data (solver.py:334-346)
-          const double cm = P.C_phi * c_m2 * area;
-          for (int i = 0; i < ND; ++i) {
-            if (i == f) continue;
-            for (int j = 0; j < ND; ++j) {
-              if (j == f) continue;
-              const double v = cm * ((i == j) ? 2.0 : 1.0);
-              dg[i][j] += v;
-              O[i][perm[j]] -= v;
-            }
-          }
-          if (!P.mms) {
-            const int64_t m = fmem[f * nc + cell];
-            double gr = phiM[m];
-            if (!P.splitting) {
-              double It = 0.0;
-              for (int k = 0; k < P.N; ++k) It += Ich[k][m];
-              gr -= It / P.C_phi;
-            }
-            const double st = fi_ics(w) ? 1.0 : -1.0;
-            const double v = P.C_phi * gr * st * area / D;
-            for (int i = 0; i < ND; ++i)
-              if (i != f) r[i] += v;
-          }
+    double S_me[ND], S_nb[ND], knb[ND];
+    #pragma unroll
+    for (int v = 0; v < ND; ++v) {
+      double t = 0.0;                                   // kap2[perm[v]] without dynamic indexing
+      #pragma unroll
+      for (int m = 0; m < ND; ++m) t = (perm[v] == m) ? kap2[m] : t;
+      knb[v] = (v == f) ? 0.0 : t;
+    }
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      double s1 = 0.0, s2 = 0.0;
+      if (i != f) {
+        #pragma unroll
+        for (int v = 0; v < ND; ++v) {
+          if (v == f) continue;
+          const double m2 = (v == i) ? 2.0 : 1.0;
+          s1 += kap[v] * m2; s2 += knb[v] * m2;
         }
       }
-      double* Of = A + (int64_t)(1 + f) * nc * bs + cell * bs;
+      S_me[i] = s1 * c_m2 * area; S_nb[i] = s2 * c_m2 * area;
+    }
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      #pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        double pen = 0.0;
+        if (i != f && j != f) {
+          #pragma unroll
+          for (int v = 0; v < ND; ++v) {
+            if (v == f) continue;
+            pen += 0.5 * (kap[v] + knb[v]) * mult3(v, i, j);
+          }
+          pen *= c_m3 * area * beta;
+        }
+        dg[i][j] += -0.5 * gn_me[j] * S_me[i] - 0.5 * gn_me[i] * S_me[j] + pen;
+        if (j != f) {
+          const double t = 0.5 * gn_me[i] * S_me[j] - pen;
+          #pragma unroll
+          for (int jp = 0; jp < ND; ++jp)
+            if (perm[j] == jp) O[i][jp] += t;
+        }
+      }
+      #pragma unroll
+      for (int jp = 0; jp < ND; ++jp) O[i][jp] += -0.5 * gn_nb[jp] * S_nb[i];
+    }
+    // rhs: avg(q).n+ jump(v)  (solver.py:310)
+    double fl = 0.0;
+    #pragma unroll
+    for (int x = 0; x < D; ++x) fl += 0.5 * (qc[x] + a.q[c2 * D + x]) * n[x];
+    fl *= area / D;
+    #pragma unroll
+    for (int i = 0; i < ND; ++i)
+      if (i != f) r[i] += fl;
+  } else {  // membrane: C_phi jump(u) jump(v), robin data (solver.py:334-346)
+    const double cm = a.P.C_phi * c_m2 * area;
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      if (i == f) continue;
+      #pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        if (j == f) continue;
+        const double v = cm * ((i == j) ? 2.0 : 1.0);
+        dg[i][j] += v;
+        #pragma unroll
+        for (int jp = 0; jp < ND; ++jp)
+          if (perm[j] == jp) O[i][jp] -= v;
+      }
+    }
+    if (!a.P.mms) {
+      const int64_t m = a.fmem[f * nc + cell];
+      double gr = a.phiM[m];
+      if (!a.P.splitting) {
+        double It = 0.0;
+        #pragma unroll
+        for (int k = 0; k < MAX_IONS; ++k) if (k < a.P.N) It += a.Ich[k][m];
+        gr -= It / a.P.C_phi;
+      }
+      const double st = fi_ics(w) ? 1.0 : -1.0;
+      const double v = a.P.C_phi * gr * st * area / D;
+      #pragma unroll
       for (int i = 0; i < ND; ++i)
+        if (i != f) r[i] += v;
+    }
+  }
+}
+
+template <int D>
+struct EmiCellKernel {
+  static constexpr int ND = D + 1;
+  EmiArgs<D> a;
+  KNP_HD void operator()(int64_t cell) const {
+    const int64_t bs = ND * ND;
+    double g[ND][D];
+    #pragma unroll
+    for (int i = 0; i < ND; ++i)
+      #pragma unroll
+      for (int x = 0; x < D; ++x) g[i][x] = a.grad[cell * (ND * D) + i * D + x];
+    const double K = a.vol[cell], hK = a.h[cell];
+    double kap[ND], qc[D];
+    double kbar = 0.0;
+    #pragma unroll
+    for (int m = 0; m < ND; ++m) { kap[m] = a.kappa[cell * ND + m]; kbar += kap[m]; }
+    kbar /= ND;
+    #pragma unroll
+    for (int x = 0; x < D; ++x) qc[x] = a.q[cell * D + x];
+    double dg[ND][ND], bd[ND][ND], r[ND];
+    emi_cell_row<D, 0>(a, g, K, kap, kbar, qc, dg[0], bd[0], r[0]);
+    emi_cell_row<D, 1>(a, g, K, kap, kbar, qc, dg[1], bd[1], r[1]);
+    emi_cell_row<D, 2>(a, g, K, kap, kbar, qc, dg[2], bd[2], r[2]);
+    if constexpr (D == 3) emi_cell_row<D, D>(a, g, K, kap, kbar, qc, dg[D], bd[D], r[D]);
+    #pragma unroll
+    for (int f = 0; f < ND; ++f) {
+      double O[ND][ND];
+      if (f == 0) emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      else if (f == 1) emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      else if (f == 2) emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      else emi_facet<D, D>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      double* Of = a.A + (int64_t)(1 + f) * a.nc * bs + cell * bs;
+      #pragma unroll
+      for (int i = 0; i < ND; ++i)
+        #pragma unroll
         for (int j = 0; j < ND; ++j) Of[i * ND + j] = O[i][j];
     }
-    double* Ad = Adiag + cell * bs;
-    double* Bd = A + cell * bs;
+    double* Ad = a.Adiag + cell * bs;
+    double* Bd = a.A + cell * bs;
+    #pragma unroll
     for (int i = 0; i < ND; ++i) {
+      #pragma unroll
       for (int j = 0; j < ND; ++j) {
         Ad[i * ND + j] = dg[i][j];
         Bd[i * ND + j] = dg[i][j] + bd[i][j];
       }
-      rhs[cell * ND + i] = r[i] + (load ? load[cell * ND + i] : 0.0);
+      a.rhs[cell * ND + i] = r[i] + (a.load ? a.load[cell * ND + i] : 0.0);
     }
   }
 };
 
+#ifndef KNP_EMU
+constexpr int ASM_CPB = 32;  // cells per thread block
+
+// One thread per (cell, facet), warp w of a block = facet w of 32 consecutive cells (the
+// facet index is warp uniform, so the templated facet code runs without divergence):
+// thread (f, cl) computes facet f's blocks and row f of the cell integrals; the block's
+// results are staged in shared memory (pitch 17/10 doubles per ND x ND block: conflict
+// free) and written out slot by slot as contiguous runs of ASM_CPB * ND * ND doubles.
+template <int D>
+__global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) emi_assemble_kernel(const EmiArgs<D> a) {
+  constexpr int ND = D + 1, BS = ND * ND, PITCH = BS + 1, NT = ASM_CPB * ND;
+  __shared__ double sO[ND][ASM_CPB][PITCH];   // off-diagonal blocks per facet
+  __shared__ double sD[ND][ASM_CPB][PITCH];   // diagonal-block contributions per facet thread
+  __shared__ double sB[ASM_CPB][PITCH];       // mass shift of B
+  __shared__ double sR[ND][ASM_CPB][ND];      // rhs contributions
+  const int t = threadIdx.x;
+  const int f = t / ASM_CPB, cl = t - f * ASM_CPB;
+  const int64_t cell0 = (int64_t)blockIdx.x * ASM_CPB;
+  const int64_t cell = cell0 + cl;
+  const int64_t nc = a.nc;
+  if (cell < nc) {
+    double g[ND][D];
+    #pragma unroll
+    for (int i = 0; i < ND; ++i)
+      #pragma unroll
+      for (int x = 0; x < D; ++x) g[i][x] = a.grad[cell * (ND * D) + i * D + x];
+    const double K = a.vol[cell], hK = a.h[cell];
+    double kap[ND], qc[D];
+    double kbar = 0.0;
+    #pragma unroll
+    for (int m = 0; m < ND; ++m) { kap[m] = a.kappa[cell * ND + m]; kbar += kap[m]; }
+    kbar /= ND;
+    #pragma unroll
+    for (int x = 0; x < D; ++x) qc[x] = a.q[cell * D + x];
+    double dg[ND][ND], r[ND], O[ND][ND];
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) { r[i] = 0.0; for (int j = 0; j < ND; ++j) dg[i][j] = 0.0; }
+    // facet f and row f of the cell integrals (f is warp uniform)
+    double bdrow[ND];
+    switch (f) {
+      case 0: emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, O, dg, r);
+              { double row[ND], ri; emi_cell_row<D, 0>(a, g, K, kap, kbar, qc, row, bdrow, ri);
+                #pragma unroll
+                for (int j = 0; j < ND; ++j) dg[0][j] += row[j]; r[0] += ri; } break;
+      case 1: emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, O, dg, r);
+              { double row[ND], ri; emi_cell_row<D, 1>(a, g, K, kap, kbar, qc, row, bdrow, ri);
+                #pragma unroll
+                for (int j = 0; j < ND; ++j) dg[1][j] += row[j]; r[1] += ri; } break;
+      case 2: emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, O, dg, r);
+              { double row[ND], ri; emi_cell_row<D, 2>(a, g, K, kap, kbar, qc, row, bdrow, ri);
+                #pragma unroll
+                for (int j = 0; j < ND; ++j) dg[2][j] += row[j]; r[2] += ri; } break;
+      default: emi_facet<D, D>(a, cell, g, K, hK, kap, qc, O, dg, r);
+              { double row[ND], ri; emi_cell_row<D, D>(a, g, K, kap, kbar, qc, row, bdrow, ri);
+                #pragma unroll
+                for (int j = 0; j < ND; ++j) dg[D][j] += row[j]; r[D] += ri; } break;
+    }
+    #pragma unroll
+    for (int j = 0; j < ND; ++j) sB[cl][f * ND + j] = bdrow[j];
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      #pragma unroll
+      for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + j] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
+      sR[f][cl][i] = r[i];
+    }
+  }
+  __syncthreads();
+  const int64_t ncell_blk = (nc - cell0 < ASM_CPB) ? (nc - cell0) : ASM_CPB;
+  const int nval = (int)ncell_blk * BS;
+  // off-diagonal slots
+  #pragma unroll
+  for (int s = 0; s < ND; ++s) {
+    double* dst = a.A + (int64_t)(1 + s) * nc * BS + cell0 * BS;
+    for (int e = t; e < nval; e += NT) dst[e] = sO[s][e / BS][e % BS];
+  }
+  // diagonal blocks of A and of B
+  {
+    double* dA = a.Adiag + cell0 * BS;
+    double* dB = a.A + cell0 * BS;
+    for (int e = t; e < nval; e += NT) {
+      const int c = e / BS, k = e % BS;
+      double v = 0.0;
+      #pragma unroll
+      for (int s = 0; s < ND; ++s) v += sD[s][c][k];
+      dA[e] = v;
+      dB[e] = v + sB[c][k];
+    }
+  }
+  // rhs
+  {
+    const int nrow = (int)ncell_blk * ND;
+    double* dr = a.rhs + cell0 * ND;
+    const double* ld = a.load ? a.load + cell0 * ND : nullptr;
+    for (int e = t; e < nrow; e += NT) {
+      const int c = e / ND, i = e % ND;
+      double v = 0.0;
+      #pragma unroll
+      for (int s = 0; s < ND; ++s) v += sR[s][c][i];
+      dr[e] = v + (ld ? ld[e] : 0.0);
+    }
+  }
+}
+#endif
+
 // ---------------------------------------------------------------------------
-// KNP assembly for one solved ion, one cell-row block per index.
+// KNP assembly for one solved ion (same structure as EMI).
 // ---------------------------------------------------------------------------
 template <int D>
-struct KnpCellKernel {
+struct KnpArgs {
   static constexpr int ND = D + 1;
   Params P;
   int64_t nc;
@@ -319,161 +504,329 @@ struct KnpCellKernel {
   const double* load;            // extra load vector or nullptr
   double* A;                     // (ND+1) slots
   double* rhs;
+};
 
-  KNP_HD void operator()(int64_t cell) const {
-    constexpr double c_m2 = 1.0 / (D * (D + 1));
-    constexpr double c_mass = 1.0 / ((D + 1) * (D + 2));
-    const int64_t bs = ND * ND;
-    const int reg = region[cell];
-    const double Dme = P.D[ion][reg], z = P.z[ion];
-    const double zpsi = z * P.psi;
-    double g[ND][D];
-    for (int i = 0; i < ND; ++i)
-      for (int x = 0; x < D; ++x) g[i][x] = grad[cell * (ND * D) + i * D + x];
-    const double K = vol[cell], hK = h[cell];
-    double gp[D];
-    for (int x = 0; x < D; ++x) gp[x] = gphi[cell * D + x];
+// cell integrals for test function i (solver.py:586-587, 593, 597)
+template <int D, int I>
+KNP_HD void knp_cell_row(const KnpArgs<D>& a, const double (&g)[D + 1][D], double K, double Dme,
+                         const double (&gp)[D], const double (&cnl)[D + 1], double* dgrow, double& ri) {
+  constexpr int ND = D + 1;
+  constexpr double c_mass = 1.0 / ((D + 1) * (D + 2));
+  constexpr int i = I;
+  const double zpsi = a.P.z[a.ion] * a.P.psi;
+  double dr = 0.0;
+  #pragma unroll
+  for (int x = 0; x < D; ++x) dr += gp[x] * g[i][x];
+  const double drift = zpsi * Dme * dr * K / (D + 1);
+  double acc = 0.0;
+  #pragma unroll
+  for (int j = 0; j < ND; ++j) {
+    double gg = 0.0;
+    #pragma unroll
+    for (int x = 0; x < D; ++x) gg += g[i][x] * g[j][x];
+    const double mij = K * c_mass * ((i == j) ? 2.0 : 1.0);
+    dgrow[j] = mij / a.P.dt + Dme * K * gg + drift;
+    acc += mij * cnl[j];
+  }
+  ri = acc / a.P.dt;
+}
 
-    double dg[ND][ND], r[ND];
-    double cnl[ND];
-    for (int m = 0; m < ND; ++m) cnl[m] = cn[cell * ND + m];
-    for (int i = 0; i < ND; ++i) {
-      double dr = 0.0;
-      for (int x = 0; x < D; ++x) dr += gp[x] * g[i][x];
-      const double drift = zpsi * Dme * dr * K / (D + 1);   // solver.py:593
-      double ri = 0.0;
-      for (int j = 0; j < ND; ++j) {
-        double gg = 0.0;
-        for (int x = 0; x < D; ++x) gg += g[i][x] * g[j][x];
-        const double mij = K * c_mass * ((i == j) ? 2.0 : 1.0);
-        dg[i][j] = mij / P.dt + Dme * K * gg + drift;         // solver.py:586-587
-        ri += mij * cnl[j];
+template <int D, int F>
+KNP_HD void knp_facet(const KnpArgs<D>& a, int64_t cell, int reg, const double (&g)[D + 1][D],
+                      double K, double hK, double Dme, const double (&gp)[D],
+                      double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1], double (&r)[D + 1]) {
+  constexpr int ND = D + 1;
+  constexpr double c_m2 = 1.0 / (D * (D + 1));
+  constexpr int f = F;
+  const int64_t nc = a.nc;
+  const int ion = a.ion;
+  const double z = a.P.z[ion], zpsi = z * a.P.psi;
+  const int w = a.finfo[f * nc + cell];
+  const int kind = fi_kind(w);
+  #pragma unroll
+  for (int i = 0; i < ND; ++i)
+    #pragma unroll
+    for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
+  if (kind == FK_NONE) return;
+  const int64_t c2 = a.nbr[f * nc + cell];
+  double gn2 = 0.0;
+  #pragma unroll
+  for (int x = 0; x < D; ++x) gn2 += g[f][x] * g[f][x];
+  const double gnorm = sqrt(gn2);
+  const double area = gnorm * D * K;
+  double n[D];
+  #pragma unroll
+  for (int x = 0; x < D; ++x) n[x] = -g[f][x] / gnorm;
+  int perm[ND];
+  #pragma unroll
+  for (int v = 0; v < ND; ++v) perm[v] = fi_perm(w, v);
+  if (kind == FK_SIP) {
+    const int nf = fi_nfacet(w);
+    const double Dnb = a.P.D[ion][a.region[c2]];
+    const double beta = a.P.tau_knp / (0.5 * (hK + a.h[c2]));
+    double gn_me[ND], gn_nb[ND];
+    double un_me = 0.0, un_nb = 0.0;
+    #pragma unroll
+    for (int x = 0; x < D; ++x) { un_me += gp[x] * n[x]; un_nb -= a.gphi[c2 * D + x] * n[x]; }
+    un_me = fmax(Dme * un_me, 0.0);                      // solver.py:583
+    un_nb = fmax(Dnb * un_nb, 0.0);
+    #pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      double a1 = 0.0, a2 = 0.0;
+      #pragma unroll
+      for (int x = 0; x < D; ++x) {
+        a1 += g[j][x] * n[x];
+        a2 += a.grad[c2 * (ND * D) + j * D + x] * n[x];
       }
-      r[i] = ri / P.dt;                                       // solver.py:597
+      gn_me[j] = a1; gn_nb[j] = a2;
     }
+    const double af = area / D;       // int_F lambda_a
+    const double pm = (beta * Dme - zpsi * un_me) * c_m2 * area;
+    const double pn = (-beta * Dnb + zpsi * un_nb) * c_m2 * area;
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      #pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        double v = 0.0;
+        if (i != f) v += -0.5 * Dme * gn_me[j] * af;
+        if (j != f) v += -0.5 * Dme * gn_me[i] * af;
+        if (i != f && j != f) {
+          const double m2 = (i == j) ? 2.0 : 1.0;
+          v += pm * m2;
+          #pragma unroll
+          for (int jp = 0; jp < ND; ++jp)
+            if (perm[j] == jp) O[i][jp] += pn * m2;
+        }
+        dg[i][j] += v;
+      }
+      #pragma unroll
+      for (int jp = 0; jp < ND; ++jp) {
+        double v = 0.0;
+        if (i != f) v += -0.5 * Dnb * gn_nb[jp] * af;
+        if (jp != nf) v += 0.5 * Dme * gn_me[i] * af;
+        O[i][jp] += v;
+      }
+    }
+  }
+  // membrane facets: nothing in the matrix; their right-hand side is KnpMembraneRhsKernel
+}
 
+// membrane right-hand side of KNP (solver.py:603-629) for ALL solved ions, one index per
+// cell that owns at least one membrane facet (facets visited in local order: deterministic,
+// atomic free).  Runs after the cell/facet kernel and adds to its right-hand sides.
+template <int D>
+struct KnpMembraneRhsKernel {
+  static constexpr int ND = D + 1;
+  Params P;
+  int64_t nc;
+  const int32_t* memcell;        // cells with >= 1 membrane facet
+  const double* vol; const double* grad;
+  const int32_t* region; const int32_t* nbr; const int32_t* finfo; const int32_t* fmem;
+  const double* phi;
+  const double* c[MAX_IONS];
+  const double* phiM; const double* Ich[MAX_IONS];
+  double* rhs[MAX_IONS];
+  KNP_HD void operator()(int64_t idx) const {
+    const int64_t cell = memcell[idx];
+    const int reg = region[cell];
+    const double K = vol[cell];
+    double r[MAX_IONS][ND];
+    for (int k = 0; k < MAX_IONS; ++k)
+      for (int v = 0; v < ND; ++v) r[k][v] = 0.0;
+    double pme[ND], cme[MAX_IONS][ND], wk[MAX_IONS];
+    for (int v = 0; v < ND; ++v) pme[v] = phi[cell * ND + v];
+    if (!P.mms)
+      for (int k = 0; k < P.N; ++k) {
+        wk[k] = P.D[k][reg] * P.z[k] * P.z[k];
+        for (int v = 0; v < ND; ++v) cme[k][v] = c[k][cell * ND + v];
+      }
     for (int f = 0; f < ND; ++f) {
       const int w = finfo[f * nc + cell];
-      const int kind = fi_kind(w);
-      double O[ND][ND];
-      for (int i = 0; i < ND; ++i)
-        for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
-      if (kind != FK_NONE) {
-        const int64_t c2 = nbr[f * nc + cell];
-        double gn2 = 0.0;
-        for (int x = 0; x < D; ++x) gn2 += g[f][x] * g[f][x];
-        const double gnorm = sqrt(gn2);
-        const double area = gnorm * D * K;
-        double n[D];
-        for (int x = 0; x < D; ++x) n[x] = -g[f][x] / gnorm;
-        int perm[ND];
-        for (int a = 0; a < ND; ++a) perm[a] = fi_perm(w, a);
-        if (kind == FK_SIP) {
-          const int nf = fi_nfacet(w);
-          const double Dnb = P.D[ion][region[c2]];
-          const double beta = P.tau_knp / (0.5 * (hK + h[c2]));
-          double gn_me[ND], gn_nb[ND];
-          double un_me = 0.0, un_nb = 0.0;
-          for (int x = 0; x < D; ++x) { un_me += gp[x] * n[x]; un_nb -= gphi[c2 * D + x] * n[x]; }
-          un_me = fmax(Dme * un_me, 0.0);                      // solver.py:583
-          un_nb = fmax(Dnb * un_nb, 0.0);
-          for (int j = 0; j < ND; ++j) {
-            double a1 = 0.0, a2 = 0.0;
-            for (int x = 0; x < D; ++x) {
-              a1 += g[j][x] * n[x];
-              a2 += grad[c2 * (ND * D) + j * D + x] * n[x];
-            }
-            gn_me[j] = a1; gn_nb[j] = a2;
+      if (fi_kind(w) != FK_MEMBRANE) continue;
+      const int64_t c2 = nbr[f * nc + cell];
+      const int64_t m = fmem[f * nc + cell];
+      double gn2 = 0.0;
+      for (int x = 0; x < D; ++x) { const double gx = grad[cell * (ND * D) + f * D + x]; gn2 += gx * gx; }
+      const double area = sqrt(gn2) * D * K;
+      const double st = fi_ics(w) ? 1.0 : -1.0;
+      double pnb[ND];
+      for (int v = 0; v < ND; ++v) pnb[v] = (v == f) ? 0.0 : phi[c2 * ND + fi_perm(w, v)];
+      double It = 0.0, pM = 0.0;
+      if (!P.mms) {
+        pM = phiM[m];
+        if (P.splitting)
+          for (int k = 0; k < P.N; ++k) It += Ich[k][m];
+      }
+      for (int qd = 0; qd < FacetRule5<D>::NQ; ++qd) {
+        double b[D], wq;
+        FacetRule5<D>::point(qd, b, wq);
+        double lam[ND];   // facet barycentric coordinate of local vertex v (v != f)
+        for (int v = 0; v < ND; ++v) lam[v] = (v == f) ? 0.0 : b[v < f ? v : v - 1];
+        double dphi = 0.0;
+        for (int v = 0; v < ND; ++v) dphi += lam[v] * (pme[v] - pnb[v]);
+        dphi *= st;                                       // phi_i - phi_e
+        double tk[MAX_IONS], tot = 0.0;
+        if (!P.mms)
+          for (int k = 0; k < P.N; ++k) {
+            double ck = 0.0;
+            for (int v = 0; v < ND; ++v) ck += lam[v] * cme[k][v];
+            tk[k] = wk[k] * ck;
+            tot += tk[k];
           }
-          const double af = area / D;       // int_F lambda_a
-          const double pm = (beta * Dme - zpsi * un_me) * c_m2 * area;
-          const double pn = (-beta * Dnb + zpsi * un_nb) * c_m2 * area;
-          for (int i = 0; i < ND; ++i) {
-            for (int j = 0; j < ND; ++j) {
-              double v = 0.0;
-              if (i != f) v += -0.5 * Dme * gn_me[j] * af;
-              if (j != f) v += -0.5 * Dme * gn_me[i] * af;
-              if (i != f && j != f) {
-                const double m2 = (i == j) ? 2.0 : 1.0;
-                v += pm * m2;
-                O[i][perm[j]] += pn * m2;
-              }
-              dg[i][j] += v;
-            }
-            for (int jp = 0; jp < ND; ++jp) {
-              double v = 0.0;
-              if (i != f) v += -0.5 * Dnb * gn_nb[jp] * af;
-              if (jp != nf) v += 0.5 * Dme * gn_me[i] * af;
-              O[i][jp] += v;
-            }
-          }
-        } else {
-          // membrane right-hand side (solver.py:603-629); matrix gets nothing.
-          const int64_t m = fmem[f * nc + cell];
-          const double st = fi_ics(w) ? 1.0 : -1.0;
-          double pme[ND], pnb[ND];
-          for (int a = 0; a < ND; ++a) {
-            pme[a] = phi[cell * ND + a];
-            pnb[a] = (a == f) ? 0.0 : phi[c2 * ND + perm[a]];
-          }
-          double cme[MAX_IONS][ND];
-          double wk[MAX_IONS];
+        for (int ion = 0; ion < P.N - 1; ++ion) {
+          double val;
           if (!P.mms) {
-            for (int k = 0; k < P.N; ++k) {
-              wk[k] = P.D[k][reg] * P.z[k] * P.z[k];
-              for (int a = 0; a < ND; ++a) cme[k][a] = c[k][cell * ND + a];
-            }
+            const double Fz = P.F * P.z[ion];
+            const double alpha = tk[ion] / tot;               // solver.py:603
+            const double C = alpha * P.C_M / (Fz * P.dt);     // solver.py:606
+            // C*g_robin (solver.py:616-622) minus the jump(phi) coupling (:628-629)
+            val = C * pM - Ich[ion][m] / Fz + alpha * It / Fz - C * dphi;
+          } else {
+            val = -P.Csub[ion][reg] * dphi;
           }
-          double Ik = 0.0, It = 0.0, pM = 0.0;
-          if (!P.mms) {
-            pM = phiM[m];
-            Ik = Ich[ion][m];
-            if (P.splitting)
-              for (int k = 0; k < P.N; ++k) It += Ich[k][m];
-          }
-          const double Fz = P.F * z;
-          for (int qd = 0; qd < FacetRule5<D>::NQ; ++qd) {
-            double b[D], wq;
-            FacetRule5<D>::point(qd, b, wq);
-            // facet barycentric coordinate of local vertex a (a != f)
-            double lam[ND];
-            { int t = 0; for (int a = 0; a < ND; ++a) lam[a] = (a == f) ? 0.0 : b[t++]; }
-            double dphi = 0.0;
-            for (int a = 0; a < ND; ++a) dphi += lam[a] * (pme[a] - pnb[a]);
-            dphi *= st;                                       // phi_i - phi_e
-            double val;
-            if (!P.mms) {
-              double num = 0.0, tot = 0.0;
-              for (int k = 0; k < P.N; ++k) {
-                double ck = 0.0;
-                for (int a = 0; a < ND; ++a) ck += lam[a] * cme[k][a];
-                const double t = wk[k] * ck;
-                tot += t;
-                if (k == ion) num = t;
-              }
-              const double alpha = num / tot;                  // solver.py:603
-              const double C = alpha * P.C_M / (Fz * P.dt);    // solver.py:606
-              // C*g_robin (solver.py:616-622) minus the jump(phi) coupling (:628-629)
-              val = C * pM - Ik / Fz + alpha * It / Fz - C * dphi;
-            } else {
-              val = -P.Csub[ion][reg] * dphi;
-            }
-            val *= st * wq * area;
-            for (int a = 0; a < ND; ++a) r[a] += val * lam[a];
-          }
+          val *= st * wq * area;
+          for (int v = 0; v < ND; ++v) r[ion][v] += val * lam[v];
         }
       }
-      double* Of = A + (int64_t)(1 + f) * nc * bs + cell * bs;
+    }
+    for (int ion = 0; ion < P.N - 1; ++ion)
+      for (int v = 0; v < ND; ++v) rhs[ion][cell * ND + v] += r[ion][v];
+  }
+};
+
+template <int D>
+struct KnpCellKernel {
+  static constexpr int ND = D + 1;
+  KnpArgs<D> a;
+  KNP_HD void operator()(int64_t cell) const {
+    const int64_t bs = ND * ND;
+    const int reg = a.region[cell];
+    const double Dme = a.P.D[a.ion][reg];
+    double g[ND][D];
+    #pragma unroll
+    for (int i = 0; i < ND; ++i)
+      #pragma unroll
+      for (int x = 0; x < D; ++x) g[i][x] = a.grad[cell * (ND * D) + i * D + x];
+    const double K = a.vol[cell], hK = a.h[cell];
+    double gp[D], cnl[ND];
+    #pragma unroll
+    for (int x = 0; x < D; ++x) gp[x] = a.gphi[cell * D + x];
+    #pragma unroll
+    for (int m = 0; m < ND; ++m) cnl[m] = a.cn[cell * ND + m];
+    double dg[ND][ND], r[ND];
+    knp_cell_row<D, 0>(a, g, K, Dme, gp, cnl, dg[0], r[0]);
+    knp_cell_row<D, 1>(a, g, K, Dme, gp, cnl, dg[1], r[1]);
+    knp_cell_row<D, 2>(a, g, K, Dme, gp, cnl, dg[2], r[2]);
+    if constexpr (D == 3) knp_cell_row<D, D>(a, g, K, Dme, gp, cnl, dg[D], r[D]);
+    #pragma unroll
+    for (int f = 0; f < ND; ++f) {
+      double O[ND][ND];
+      if (f == 0) knp_facet<D, 0>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      else if (f == 1) knp_facet<D, 1>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      else if (f == 2) knp_facet<D, 2>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      else knp_facet<D, D>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      double* Of = a.A + (int64_t)(1 + f) * a.nc * bs + cell * bs;
+      #pragma unroll
       for (int i = 0; i < ND; ++i)
+        #pragma unroll
         for (int j = 0; j < ND; ++j) Of[i * ND + j] = O[i][j];
     }
-    double* Ad = A + cell * bs;
+    double* Ad = a.A + cell * bs;
+    #pragma unroll
     for (int i = 0; i < ND; ++i) {
+      #pragma unroll
       for (int j = 0; j < ND; ++j) Ad[i * ND + j] = dg[i][j];
-      rhs[cell * ND + i] = r[i] + (load ? load[cell * ND + i] : 0.0);
+      a.rhs[cell * ND + i] = r[i] + (a.load ? a.load[cell * ND + i] : 0.0);
     }
   }
 };
+
+#ifndef KNP_EMU
+template <int D>
+__global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) knp_assemble_kernel(const KnpArgs<D> a) {
+  constexpr int ND = D + 1, BS = ND * ND, PITCH = BS + 1, NT = ASM_CPB * ND;
+  __shared__ double sO[ND][ASM_CPB][PITCH];
+  __shared__ double sD[ND][ASM_CPB][PITCH];
+  __shared__ double sR[ND][ASM_CPB][ND];
+  const int t = threadIdx.x;
+  const int f = t / ASM_CPB, cl = t - f * ASM_CPB;
+  const int64_t cell0 = (int64_t)blockIdx.x * ASM_CPB;
+  const int64_t cell = cell0 + cl;
+  const int64_t nc = a.nc;
+  if (cell < nc) {
+    const int reg = a.region[cell];
+    const double Dme = a.P.D[a.ion][reg];
+    double g[ND][D];
+    #pragma unroll
+    for (int i = 0; i < ND; ++i)
+      #pragma unroll
+      for (int x = 0; x < D; ++x) g[i][x] = a.grad[cell * (ND * D) + i * D + x];
+    const double K = a.vol[cell], hK = a.h[cell];
+    double gp[D], cnl[ND];
+    #pragma unroll
+    for (int x = 0; x < D; ++x) gp[x] = a.gphi[cell * D + x];
+    #pragma unroll
+    for (int m = 0; m < ND; ++m) cnl[m] = a.cn[cell * ND + m];
+    double dg[ND][ND], r[ND], O[ND][ND];
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) { r[i] = 0.0; for (int j = 0; j < ND; ++j) dg[i][j] = 0.0; }
+    switch (f) {
+      case 0: knp_facet<D, 0>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+              { double row[ND], ri; knp_cell_row<D, 0>(a, g, K, Dme, gp, cnl, row, ri);
+                #pragma unroll
+                for (int j = 0; j < ND; ++j) dg[0][j] += row[j]; r[0] += ri; } break;
+      case 1: knp_facet<D, 1>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+              { double row[ND], ri; knp_cell_row<D, 1>(a, g, K, Dme, gp, cnl, row, ri);
+                #pragma unroll
+                for (int j = 0; j < ND; ++j) dg[1][j] += row[j]; r[1] += ri; } break;
+      case 2: knp_facet<D, 2>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+              { double row[ND], ri; knp_cell_row<D, 2>(a, g, K, Dme, gp, cnl, row, ri);
+                #pragma unroll
+                for (int j = 0; j < ND; ++j) dg[2][j] += row[j]; r[2] += ri; } break;
+      default: knp_facet<D, D>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+              { double row[ND], ri; knp_cell_row<D, D>(a, g, K, Dme, gp, cnl, row, ri);
+                #pragma unroll
+                for (int j = 0; j < ND; ++j) dg[D][j] += row[j]; r[D] += ri; } break;
+    }
+    #pragma unroll
+    for (int i = 0; i < ND; ++i) {
+      #pragma unroll
+      for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + j] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
+      sR[f][cl][i] = r[i];
+    }
+  }
+  __syncthreads();
+  const int64_t ncell_blk = (nc - cell0 < ASM_CPB) ? (nc - cell0) : ASM_CPB;
+  const int nval = (int)ncell_blk * BS;
+  #pragma unroll
+  for (int s = 0; s < ND; ++s) {
+    double* dst = a.A + (int64_t)(1 + s) * nc * BS + cell0 * BS;
+    for (int e = t; e < nval; e += NT) dst[e] = sO[s][e / BS][e % BS];
+  }
+  {
+    double* dA = a.A + cell0 * BS;
+    for (int e = t; e < nval; e += NT) {
+      const int c = e / BS, k = e % BS;
+      double v = 0.0;
+      #pragma unroll
+      for (int s = 0; s < ND; ++s) v += sD[s][c][k];
+      dA[e] = v;
+    }
+  }
+  {
+    const int nrow = (int)ncell_blk * ND;
+    double* dr = a.rhs + cell0 * ND;
+    const double* ld = a.load ? a.load + cell0 * ND : nullptr;
+    for (int e = t; e < nrow; e += NT) {
+      const int c = e / ND, i = e % ND;
+      double v = 0.0;
+      #pragma unroll
+      for (int s = 0; s < ND; ++s) v += sR[s][c][i];
+      dr[e] = v + (ld ? ld[e] : 0.0);
+    }
+  }
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // post-step (solver.py:809-842)

@@ -64,35 +64,55 @@ struct BlockDiagApplyKernel {
   }
 };
 
-// fused block-Jacobi sweep on level 0: xout = xin + w Dinv (b - A xin) needs the whole
-// cell residual, so it runs one thread per cell.
+// fused block-Jacobi sweep on level 0: xout = xin + w Dinv (b - A xin).  One thread per
+// row like the SpMV (coalesced slot reads); the ND residuals of a cell are exchanged
+// between the ND lanes that own its rows with warp shuffles (ND = 4: groups of 4 lanes
+// never straddle a warp; ND = 3: each lane recomputes the cell's other rows, the loads
+// are warp broadcasts).
 template <int ND>
 struct BellJacobiKernel {
   BellMat A; const double* dinv; const double* b; const double* xin; double* xout; double w;
-  KNP_HD void operator()(int64_t cell) const {
+  KNP_HD double row_residual(int64_t cell, int i) const {
     const int64_t bs = ND * ND;
-    double r[ND];
-    for (int i = 0; i < ND; ++i) r[i] = b[cell * ND + i];
+    double acc = b[cell * ND + i];
     {
-      const double* a = A.diag + cell * bs;
+      const double* a = A.diag + cell * bs + i * ND;
       const double* xc = xin + cell * ND;
-      for (int i = 0; i < ND; ++i)
-        for (int j = 0; j < ND; ++j) r[i] -= a[i * ND + j] * xc[j];
+#pragma unroll
+      for (int j = 0; j < ND; ++j) acc -= a[j] * xc[j];
     }
+#pragma unroll
     for (int f = 0; f < ND; ++f) {
       const int64_t c2 = A.nbr[f * A.nc + cell];
       if (c2 < 0) continue;
-      const double* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs;
+      const double* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND;
       const double* xc = xin + c2 * ND;
-      for (int i = 0; i < ND; ++i)
-        for (int j = 0; j < ND; ++j) r[i] -= a[i * ND + j] * xc[j];
+#pragma unroll
+      for (int j = 0; j < ND; ++j) acc -= a[j] * xc[j];
     }
-    const double* di = dinv + cell * bs;
-    for (int i = 0; i < ND; ++i) {
-      double acc = 0.0;
-      for (int j = 0; j < ND; ++j) acc += di[i * ND + j] * r[j];
-      xout[cell * ND + i] = xin[cell * ND + i] + w * acc;
+    return acc;
+  }
+  KNP_HD void operator()(int64_t row) const {
+    const int64_t cell = row / ND;
+    const int i = (int)(row - cell * ND);
+    double r[ND];
+#if defined(__CUDA_ARCH__)
+    if (ND == 4) {
+      const double mine = row_residual(cell, i);
+      const unsigned mask = __activemask();
+      const int base = (threadIdx.x & 31) & ~3;
+#pragma unroll
+      for (int j = 0; j < ND; ++j) r[j] = __shfl_sync(mask, mine, base + j);
+    } else
+#endif
+    {
+      for (int j = 0; j < ND; ++j) r[j] = row_residual(cell, j);
     }
+    const double* di = dinv + cell * ND * ND + i * ND;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j) acc += di[j] * r[j];
+    xout[row] = xin[row] + w * acc;
   }
 };
 
@@ -166,11 +186,11 @@ struct CsrToDenseKernel {  // dense[m*m] (zeroed before) <- CSR
   }
 };
 
-struct DenseMatvecKernel {
-  int64_t m; const double* M; const double* x; double* y;
+struct DenseMatvecKernel {  // y = M x with M stored TRANSPOSED (MT[j*m + i] = M[i][j])
+  int64_t m; const double* MT; const double* x; double* y;
   KNP_HD void operator()(int64_t row) const {
     double acc = 0.0;
-    for (int64_t j = 0; j < m; ++j) acc += M[row * m + j] * x[j];
+    for (int64_t j = 0; j < m; ++j) acc += MT[j * m + row] * x[j];
     y[row] = acc;
   }
 };
@@ -299,17 +319,49 @@ inline void multi_dot_device(knp_stream_t s, int64_t n, int k, const double* V, 
   }
 }
 
-// in-place inverse of a dense m x m matrix (row major) by Gauss-Jordan without pivoting
-// (coarsest AMG level: SPD for EMI, diagonally dominant for KNP).
+// inverse of the dense m x m coarsest-level matrix by Gauss-Jordan without pivoting (SPD
+// for EMI, diagonally dominant for KNP); the result is stored TRANSPOSED for
+// DenseMatvecKernel.  One thread block; the matrix lives in shared memory (odd pitch, no
+// bank conflicts on column access) when it fits (m <= 168), else in global memory.
+constexpr int DENSE_SMEM_MAX = 168;
 #ifndef KNP_EMU
+static __global__ void __launch_bounds__(1024) dense_inverse_smem_kernel(int m, double* __restrict__ A) {
+  extern __shared__ double sm[];
+  const int pitch = m | 1;
+  double* a = sm;
+  double* colbuf = sm + (size_t)m * pitch;
+  for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+    const int i = idx / m, j = idx - i * m;
+    a[i * pitch + j] = A[idx];
+  }
+  __syncthreads();
+  for (int p = 0; p < m; ++p) {
+    const double ip = 1.0 / a[p * pitch + p];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) colbuf[i] = a[i * pitch + p];
+    __syncthreads();
+    for (int j = threadIdx.x; j < m; j += blockDim.x)
+      a[p * pitch + j] = (j == p) ? ip : a[p * pitch + j] * ip;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+      const int i = idx / m, j = idx - i * m;
+      if (i == p) continue;
+      const double f = colbuf[i];
+      const double prow = a[p * pitch + j];
+      a[i * pitch + j] = (j == p) ? -f * prow : a[i * pitch + j] - f * prow;
+    }
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < m * m; idx += blockDim.x) {
+    const int i = idx / m, j = idx - i * m;
+    A[(size_t)j * m + i] = a[i * pitch + j];
+  }
+}
+
 static __global__ void __launch_bounds__(1024) dense_inverse_kernel(int m, double* __restrict__ A,
                                                              double* __restrict__ colbuf) {
-  // single block; A is overwritten by its inverse (in-place Gauss-Jordan)
   for (int p = 0; p < m; ++p) {
-    const double piv = A[(int64_t)p * m + p];
-    const double ip = 1.0 / piv;
+    const double ip = 1.0 / A[(int64_t)p * m + p];
     __syncthreads();
-    // save column p, scale pivot row
     for (int i = threadIdx.x; i < m; i += blockDim.x) colbuf[i] = A[(int64_t)i * m + p];
     __syncthreads();
     for (int j = threadIdx.x; j < m; j += blockDim.x)
@@ -323,6 +375,11 @@ static __global__ void __launch_bounds__(1024) dense_inverse_kernel(int m, doubl
       A[idx] = (j == p) ? -f * prow : A[idx] - f * prow;
     }
     __syncthreads();
+  }
+  // transpose in place
+  for (int64_t idx = threadIdx.x; idx < (int64_t)m * m; idx += blockDim.x) {
+    const int i = (int)(idx / m), j = (int)(idx - (int64_t)i * m);
+    if (i < j) { const double t = A[idx]; A[idx] = A[(int64_t)j * m + i]; A[(int64_t)j * m + i] = t; }
   }
 }
 #endif
@@ -343,9 +400,26 @@ inline void dense_inverse_device(knp_stream_t s, int m, double* A, double* colbu
       }
     }
   }
+  for (int i = 0; i < m; ++i)
+    for (int j = i + 1; j < m; ++j) {
+      const double t = A[(int64_t)i * m + j];
+      A[(int64_t)i * m + j] = A[(int64_t)j * m + i];
+      A[(int64_t)j * m + i] = t;
+    }
 #else
   ++launch_counter();
-  dense_inverse_kernel<<<1, 1024, 0, s>>>(m, A, colbuf);
+  if (m <= DENSE_SMEM_MAX) {
+    const size_t bytes = ((size_t)m * (m | 1) + m) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+      KNP_CUDA(cudaFuncSetAttribute(dense_inverse_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(((size_t)DENSE_SMEM_MAX * (DENSE_SMEM_MAX | 1) + DENSE_SMEM_MAX) * sizeof(double))));
+      configured = true;
+    }
+    dense_inverse_smem_kernel<<<1, 1024, bytes, s>>>(m, A);
+  } else {
+    dense_inverse_kernel<<<1, 1024, 0, s>>>(m, A, colbuf);
+  }
   KNP_CUDA(cudaGetLastError());
 #endif
 }

@@ -42,8 +42,8 @@ static void block_apply(knp_ctx* c, const double* dinv, const double* r, double*
 }
 static void bell_jacobi(knp_ctx* c, const BellMat& A, const double* dinv, const double* b,
                         const double* xin, double* xout, double w) {
-  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->nc, k, 128); }
-  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->nc, k, 128); }
+  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n, k, 192); }
+  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n, k, 256); }
 }
 static void block_inverse(knp_ctx* c, const double* blocks, double* inv) {
   if (c->nd == 3) { BlockInverseKernel<3> k{blocks, inv}; parallel_for(c->stream, c->nc, k, 128); }

@@ -229,7 +229,7 @@ class Context:
         return y
 
     # -- solvers ----------------------------------------------------------
-    def amg_setup(self, theta=0.08, max_levels=12, coarse_size=200):
+    def amg_setup(self, theta=0.08, max_levels=12, coarse_size=64):
         self._call("knp_amg_setup", float(theta), int(max_levels), int(coarse_size))
 
     def amg_info(self):
