@@ -125,11 +125,13 @@ static void build_mesh(knp_ctx* c, int64_t nc, int64_t nv, const double* coords,
     }
     if (det == 0.0) fail("degenerate cell");
     vol[k] = fabs(det) / (D == 2 ? 2.0 : 6.0);
-    // rows of T^-1 are grad lambda_1..D
-    double* g = &grad[(size_t)k * ND * D];
-    for (int x = 0; x < D; ++x) g[x] = 0.0;
+    // rows of T^-1 are grad lambda_1..D; stored component major [ND*D][nc] so that
+    // consecutive cells (= consecutive lanes) read consecutive addresses
+    double g0[D];
+    for (int x = 0; x < D; ++x) g0[x] = 0.0;
     for (int e = 0; e < D; ++e)
-      for (int x = 0; x < D; ++x) { g[(e + 1) * D + x] = Ti[e][x]; g[x] -= Ti[e][x]; }
+      for (int x = 0; x < D; ++x) { grad[(size_t)((e + 1) * D + x) * nc + k] = Ti[e][x]; g0[x] -= Ti[e][x]; }
+    for (int x = 0; x < D; ++x) grad[(size_t)x * nc + k] = g0[x];
     double hm = 0.0;
     for (int a = 0; a < ND; ++a)
       for (int b = a + 1; b < ND; ++b) {
@@ -341,7 +343,7 @@ template <int D>
 static void assemble_emi_t(knp_ctx* c) {
   knp_stream_t s = c->stream;
   EmiPrepassKernel<D> pre;
-  pre.P = c->P;
+  pre.P = c->P; pre.nc = c->nc;
   for (int k = 0; k < MAX_IONS; ++k) pre.c[k] = c->c[k].p;
   pre.grad = c->grad.p; pre.region = c->region.p; pre.kappa = c->kappa.p; pre.q = c->q.p;
   parallel_for(s, c->nc, pre, 128);
@@ -366,7 +368,7 @@ template <int D>
 static void assemble_knp_t(knp_ctx* c) {
   knp_stream_t s = c->stream;
   GradKernel<D> gk;
-  gk.phi = c->phi.p; gk.grad = c->grad.p; gk.gphi = c->gphi.p;
+  gk.nc = c->nc; gk.phi = c->phi.p; gk.grad = c->grad.p; gk.gphi = c->gphi.p;
   parallel_for(s, c->nc, gk, 128);
   for (int ion = 0; ion < c->P.N - 1; ++ion) {
     KnpArgs<D> k;

@@ -85,6 +85,22 @@ template <> struct FacetRule4<3> {
   }
 };
 
+// the ND nodal values of one cell of a DG field (dof = ND*cell + i); 16-byte vector loads
+// for ND = 4 (cudaMalloc'ed fields are 256-byte aligned, a cell is 32 bytes)
+template <int ND>
+KNP_HD void load_cell(const double* field, int64_t cell, double (&out)[ND]) {
+#if defined(__CUDA_ARCH__)
+  if (ND == 4) {
+    const double2* p = reinterpret_cast<const double2*>(field + cell * 4);
+    const double2 a = p[0], b = p[1];
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[ND - 1] = b.y;
+    return;
+  }
+#endif
+#pragma unroll
+  for (int i = 0; i < ND; ++i) out[i] = field[cell * ND + i];
+}
+
 // multiplicity factor alpha! of lambda_a lambda_b lambda_c
 KNP_HD double mult3(int a, int b, int c) {
   if (a == b && b == c) return 6.0;
@@ -101,16 +117,17 @@ template <int D>
 struct EmiPrepassKernel {
   static constexpr int ND = D + 1;
   Params P;
+  int64_t nc;
   const double* c[MAX_IONS];
   const double* grad;
   const int32_t* region;
-  double* kappa;  // [nc][ND]
-  double* q;      // [nc][D]
+  double* kappa;  // [ND][nc]  (component major: consecutive cells are consecutive addresses)
+  double* q;      // [D][nc]
   KNP_HD void operator()(int64_t cell) const {
     const int r = region[cell];
     double g[ND][D];
     for (int i = 0; i < ND; ++i)
-      for (int x = 0; x < D; ++x) g[i][x] = grad[cell * (ND * D) + i * D + x];
+      for (int x = 0; x < D; ++x) g[i][x] = grad[(i * D + x) * nc + cell];
     double kap[ND], qq[D];
     for (int m = 0; m < ND; ++m) kap[m] = 0.0;
     for (int x = 0; x < D; ++x) qq[x] = 0.0;
@@ -118,31 +135,36 @@ struct EmiPrepassKernel {
       const double Dk = P.D[k][r], zk = P.z[k];
       const double wk = P.F * zk * zk * Dk * P.psi;
       const double wq = P.F * zk * Dk;
+      double cl[ND];
+      load_cell<ND>(c[k], cell, cl);
       for (int m = 0; m < ND; ++m) {
-        const double cm = c[k][cell * ND + m];
+        const double cm = cl[m];
         kap[m] += wk * cm;
         for (int x = 0; x < D; ++x) qq[x] += wq * cm * g[m][x];
       }
     }
-    for (int m = 0; m < ND; ++m) kappa[cell * ND + m] = kap[m];
-    for (int x = 0; x < D; ++x) q[cell * D + x] = qq[x];
+    for (int m = 0; m < ND; ++m) kappa[m * nc + cell] = kap[m];
+    for (int x = 0; x < D; ++x) q[x * nc + cell] = qq[x];
   }
 };
 
 template <int D>
 struct GradKernel {  // gphi = grad(phi) per cell (solver.py:583, 593)
   static constexpr int ND = D + 1;
+  int64_t nc;
   const double* phi;
   const double* grad;
   double* gphi;
   KNP_HD void operator()(int64_t cell) const {
     double out[D];
     for (int x = 0; x < D; ++x) out[x] = 0.0;
+    double pl[ND];
+    load_cell<ND>(phi, cell, pl);
     for (int m = 0; m < ND; ++m) {
-      const double pm = phi[cell * ND + m];
-      for (int x = 0; x < D; ++x) out[x] += pm * grad[cell * (ND * D) + m * D + x];
+      const double pm = pl[m];
+      for (int x = 0; x < D; ++x) out[x] += pm * grad[(m * D + x) * nc + cell];
     }
-    for (int x = 0; x < D; ++x) gphi[cell * D + x] = out[x];
+    for (int x = 0; x < D; ++x) gphi[x * nc + cell] = out[x];
   }
 };
 
@@ -232,9 +254,9 @@ KNP_HD void emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1
     #pragma unroll
     for (int i = 0; i < ND; ++i)
       #pragma unroll
-      for (int x = 0; x < D; ++x) g2[i][x] = a.grad[c2 * (ND * D) + i * D + x];
+      for (int x = 0; x < D; ++x) g2[i][x] = a.grad[(i * D + x) * a.nc + c2];
     #pragma unroll
-    for (int m = 0; m < ND; ++m) kap2[m] = a.kappa[c2 * ND + m];
+    for (int m = 0; m < ND; ++m) kap2[m] = a.kappa[m * a.nc + c2];
     const double beta = a.P.tau_emi / (0.5 * (hK + a.h[c2]));
     double gn_me[ND], gn_nb[ND];
     #pragma unroll
@@ -292,7 +314,7 @@ KNP_HD void emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1
     // rhs: avg(q).n+ jump(v)  (solver.py:310)
     double fl = 0.0;
     #pragma unroll
-    for (int x = 0; x < D; ++x) fl += 0.5 * (qc[x] + a.q[c2 * D + x]) * n[x];
+    for (int x = 0; x < D; ++x) fl += 0.5 * (qc[x] + a.q[x * a.nc + c2]) * n[x];
     fl *= area / D;
     #pragma unroll
     for (int i = 0; i < ND; ++i)
@@ -340,15 +362,15 @@ struct EmiCellKernel {
     #pragma unroll
     for (int i = 0; i < ND; ++i)
       #pragma unroll
-      for (int x = 0; x < D; ++x) g[i][x] = a.grad[cell * (ND * D) + i * D + x];
+      for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * a.nc + cell];
     const double K = a.vol[cell], hK = a.h[cell];
     double kap[ND], qc[D];
     double kbar = 0.0;
     #pragma unroll
-    for (int m = 0; m < ND; ++m) { kap[m] = a.kappa[cell * ND + m]; kbar += kap[m]; }
+    for (int m = 0; m < ND; ++m) { kap[m] = a.kappa[m * a.nc + cell]; kbar += kap[m]; }
     kbar /= ND;
     #pragma unroll
-    for (int x = 0; x < D; ++x) qc[x] = a.q[cell * D + x];
+    for (int x = 0; x < D; ++x) qc[x] = a.q[x * a.nc + cell];
     double dg[ND][ND], bd[ND][ND], r[ND];
     emi_cell_row<D, 0>(a, g, K, kap, kbar, qc, dg[0], bd[0], r[0]);
     emi_cell_row<D, 1>(a, g, K, kap, kbar, qc, dg[1], bd[1], r[1]);
@@ -406,15 +428,15 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) emi_assemble_kernel(const 
     #pragma unroll
     for (int i = 0; i < ND; ++i)
       #pragma unroll
-      for (int x = 0; x < D; ++x) g[i][x] = a.grad[cell * (ND * D) + i * D + x];
+      for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * a.nc + cell];
     const double K = a.vol[cell], hK = a.h[cell];
     double kap[ND], qc[D];
     double kbar = 0.0;
     #pragma unroll
-    for (int m = 0; m < ND; ++m) { kap[m] = a.kappa[cell * ND + m]; kbar += kap[m]; }
+    for (int m = 0; m < ND; ++m) { kap[m] = a.kappa[m * a.nc + cell]; kbar += kap[m]; }
     kbar /= ND;
     #pragma unroll
-    for (int x = 0; x < D; ++x) qc[x] = a.q[cell * D + x];
+    for (int x = 0; x < D; ++x) qc[x] = a.q[x * a.nc + cell];
     double dg[ND][ND], r[ND], O[ND][ND];
     #pragma unroll
     for (int i = 0; i < ND; ++i) { r[i] = 0.0; for (int j = 0; j < ND; ++j) dg[i][j] = 0.0; }
@@ -567,7 +589,7 @@ KNP_HD void knp_facet(const KnpArgs<D>& a, int64_t cell, int reg, const double (
     double gn_me[ND], gn_nb[ND];
     double un_me = 0.0, un_nb = 0.0;
     #pragma unroll
-    for (int x = 0; x < D; ++x) { un_me += gp[x] * n[x]; un_nb -= a.gphi[c2 * D + x] * n[x]; }
+    for (int x = 0; x < D; ++x) { un_me += gp[x] * n[x]; un_nb -= a.gphi[x * a.nc + c2] * n[x]; }
     un_me = fmax(Dme * un_me, 0.0);                      // solver.py:583
     un_nb = fmax(Dnb * un_nb, 0.0);
     #pragma unroll
@@ -576,7 +598,7 @@ KNP_HD void knp_facet(const KnpArgs<D>& a, int64_t cell, int reg, const double (
       #pragma unroll
       for (int x = 0; x < D; ++x) {
         a1 += g[j][x] * n[x];
-        a2 += a.grad[c2 * (ND * D) + j * D + x] * n[x];
+        a2 += a.grad[(j * D + x) * a.nc + c2] * n[x];
       }
       gn_me[j] = a1; gn_nb[j] = a2;
     }
@@ -646,7 +668,7 @@ struct KnpMembraneRhsKernel {
       const int64_t c2 = nbr[f * nc + cell];
       const int64_t m = fmem[f * nc + cell];
       double gn2 = 0.0;
-      for (int x = 0; x < D; ++x) { const double gx = grad[cell * (ND * D) + f * D + x]; gn2 += gx * gx; }
+      for (int x = 0; x < D; ++x) { const double gx = grad[(f * D + x) * nc + cell]; gn2 += gx * gx; }
       const double area = sqrt(gn2) * D * K;
       const double st = fi_ics(w) ? 1.0 : -1.0;
       double pnb[ND];
@@ -706,13 +728,13 @@ struct KnpCellKernel {
     #pragma unroll
     for (int i = 0; i < ND; ++i)
       #pragma unroll
-      for (int x = 0; x < D; ++x) g[i][x] = a.grad[cell * (ND * D) + i * D + x];
+      for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * a.nc + cell];
     const double K = a.vol[cell], hK = a.h[cell];
     double gp[D], cnl[ND];
     #pragma unroll
-    for (int x = 0; x < D; ++x) gp[x] = a.gphi[cell * D + x];
+    for (int x = 0; x < D; ++x) gp[x] = a.gphi[x * a.nc + cell];
     #pragma unroll
-    for (int m = 0; m < ND; ++m) cnl[m] = a.cn[cell * ND + m];
+    load_cell<ND>(a.cn, cell, cnl);
     double dg[ND][ND], r[ND];
     knp_cell_row<D, 0>(a, g, K, Dme, gp, cnl, dg[0], r[0]);
     knp_cell_row<D, 1>(a, g, K, Dme, gp, cnl, dg[1], r[1]);
@@ -760,13 +782,13 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) knp_assemble_kernel(const 
     #pragma unroll
     for (int i = 0; i < ND; ++i)
       #pragma unroll
-      for (int x = 0; x < D; ++x) g[i][x] = a.grad[cell * (ND * D) + i * D + x];
+      for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * a.nc + cell];
     const double K = a.vol[cell], hK = a.h[cell];
     double gp[D], cnl[ND];
     #pragma unroll
-    for (int x = 0; x < D; ++x) gp[x] = a.gphi[cell * D + x];
+    for (int x = 0; x < D; ++x) gp[x] = a.gphi[x * a.nc + cell];
     #pragma unroll
-    for (int m = 0; m < ND; ++m) cnl[m] = a.cn[cell * ND + m];
+    load_cell<ND>(a.cn, cell, cnl);
     double dg[ND][ND], r[ND], O[ND][ND];
     #pragma unroll
     for (int i = 0; i < ND; ++i) { r[i] = 0.0; for (int j = 0; j < ND; ++j) dg[i][j] = 0.0; }
