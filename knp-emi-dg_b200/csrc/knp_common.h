@@ -58,7 +58,10 @@ inline void* dev_alloc_bytes(size_t bytes) {
 #else
   void* p = nullptr;
   KNP_CUDA(cudaMalloc(&p, bytes));
+  // the memset runs on the legacy default stream, the library's streams are non-blocking:
+  // wait for it, or it may land after the first kernel that writes the buffer
   KNP_CUDA(cudaMemset(p, 0, bytes));
+  KNP_CUDA(cudaStreamSynchronize(0));
   return p;
 #endif
 }
