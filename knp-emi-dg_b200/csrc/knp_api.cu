@@ -143,7 +143,9 @@ static void build_mesh(knp_ctx* c, int64_t nc, int64_t nv, const double* coords,
   }
   // facet tables
   c->h_nbr.assign((size_t)ND * nc, -1);
-  c->h_finfo.assign((size_t)ND * nc, FK_NONE);
+  int none_word = FK_NONE;                       // identity column map for facets without terms
+  for (int a = 0; a < ND; ++a) none_word |= a << (4 + 2 * a);
+  c->h_finfo.assign((size_t)ND * nc, none_word);
   c->h_fmem.assign((size_t)ND * nc, -1);
   c->h_mem_facet.clear(); c->h_mem_ci.clear(); c->h_mem_ce.clear(); c->h_mem_tag.clear();
   c->h_mem_fi.clear();
@@ -171,9 +173,10 @@ static void build_mesh(knp_ctx* c, int64_t nc, int64_t nv, const double* coords,
     if (shared != D || f0 < 0 || f1 < 0) fail("facet_cells: the two cells do not share a facet");
     const bool c0_ics = region[c0] >= region[c1];  // n_g: lower -> higher tag (utils.py:80)
     int w0 = kind | (f1 << 2), w1 = kind | (f0 << 2);
+    // column map: my vertex a -> neighbour's local index; my opposite vertex -> its opposite vertex
     for (int a = 0; a < ND; ++a) {
-      if (a != f0) w0 |= p0[a] << (4 + 2 * a);
-      if (a != f1) w1 |= p1[a] << (4 + 2 * a);
+      w0 |= ((a != f0) ? p0[a] : f1) << (4 + 2 * a);
+      w1 |= ((a != f1) ? p1[a] : f0) << (4 + 2 * a);
     }
     if (kind == FK_MEMBRANE) {
       if (c0_ics) w0 |= 1 << 12; else w1 |= 1 << 12;

@@ -219,137 +219,123 @@ KNP_HD void emi_cell_row(const EmiArgs<D>& a, const double (&g)[D + 1][D], doubl
   }
 }
 
-// facet f of `cell`: O = coupling block to the neighbour (zero when the facet carries no
-// terms), dg += share of the diagonal block, r += share of the rhs.
+// facet F of `cell`.  Outputs are in the cell's OWN vertex numbering: O[i][j] couples my
+// dof i with the neighbour dof that sits at my vertex j (neighbour local index
+// fi_perm(w, j)); column F, which has no counterpart on my side, holds the coupling with
+// the neighbour's vertex opposite the facet (fi_perm(w, F) = its local facet index).  The
+// writer applies that column map in the store address, so no register array is ever
+// indexed dynamically.  dg += share of the diagonal block, r += share of the rhs.
+// Returns the facet info word (column map).
 template <int D, int F>
-KNP_HD void emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1][D], double K,
-                      double hK, const double (&kap)[D + 1], const double (&qc)[D],
-                      double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1], double (&r)[D + 1]) {
+KNP_HD int emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1][D], double K,
+                     double hK, const double (&kap)[D + 1], const double (&qc)[D],
+                     double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1], double (&r)[D + 1]) {
   constexpr int ND = D + 1;
   constexpr double c_m2 = 1.0 / (D * (D + 1));                  // facet mass
   constexpr double c_m3 = (D == 3) ? 1.0 / 60.0 : 1.0 / 24.0;   // facet cubic moment
-  constexpr int f = F;
   const int64_t nc = a.nc;
-  const int w = a.finfo[f * nc + cell];
+  const int w = a.finfo[F * nc + cell];
   const int kind = fi_kind(w);
-  #pragma unroll
+#pragma unroll
   for (int i = 0; i < ND; ++i)
-    #pragma unroll
+#pragma unroll
     for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
-  if (kind == FK_NONE) return;
-  const int64_t c2 = a.nbr[f * nc + cell];
+  if (kind == FK_NONE) return w;
+  const int64_t c2 = a.nbr[F * nc + cell];
   double gn2 = 0.0;
-  #pragma unroll
-  for (int x = 0; x < D; ++x) gn2 += g[f][x] * g[f][x];
+#pragma unroll
+  for (int x = 0; x < D; ++x) gn2 += g[F][x] * g[F][x];
   const double gnorm = sqrt(gn2);
   const double area = gnorm * D * K;
+  const double inv_gnorm = 1.0 / gnorm;
   double n[D];
-  #pragma unroll
-  for (int x = 0; x < D; ++x) n[x] = -g[f][x] / gnorm;
-  int perm[ND];
-  #pragma unroll
-  for (int v = 0; v < ND; ++v) perm[v] = fi_perm(w, v);
+#pragma unroll
+  for (int x = 0; x < D; ++x) n[x] = -g[F][x] * inv_gnorm;
   if (kind == FK_SIP) {
-    double g2[ND][D], kap2[ND];
-    #pragma unroll
-    for (int i = 0; i < ND; ++i)
-      #pragma unroll
-      for (int x = 0; x < D; ++x) g2[i][x] = a.grad[(i * D + x) * a.nc + c2];
-    #pragma unroll
-    for (int m = 0; m < ND; ++m) kap2[m] = a.kappa[m * a.nc + c2];
-    const double beta = a.P.tau_emi / (0.5 * (hK + a.h[c2]));
-    double gn_me[ND], gn_nb[ND];
-    #pragma unroll
+    // neighbour data gathered directly in my vertex order
+    double gn_me[ND], gn_nb[ND], knb[ND];
+#pragma unroll
     for (int j = 0; j < ND; ++j) {
+      const int64_t pj = fi_perm(w, j);
       double a1 = 0.0, a2 = 0.0;
-      #pragma unroll
-      for (int x = 0; x < D; ++x) { a1 += g[j][x] * n[x]; a2 += g2[j][x] * n[x]; }
+#pragma unroll
+      for (int x = 0; x < D; ++x) {
+        a1 += g[j][x] * n[x];
+        a2 += a.grad[(pj * D + x) * nc + c2] * n[x];
+      }
       gn_me[j] = a1; gn_nb[j] = a2;
+      knb[j] = (j == F) ? 0.0 : a.kappa[pj * nc + c2];
     }
-    double S_me[ND], S_nb[ND], knb[ND];
-    #pragma unroll
-    for (int v = 0; v < ND; ++v) {
-      double t = 0.0;                                   // kap2[perm[v]] without dynamic indexing
-      #pragma unroll
-      for (int m = 0; m < ND; ++m) t = (perm[v] == m) ? kap2[m] : t;
-      knb[v] = (v == f) ? 0.0 : t;
-    }
-    #pragma unroll
+    const double beta = a.P.tau_emi / (0.5 * (hK + a.h[c2]));
+    double S_me[ND], S_nb[ND];
+#pragma unroll
     for (int i = 0; i < ND; ++i) {
       double s1 = 0.0, s2 = 0.0;
-      if (i != f) {
-        #pragma unroll
+      if (i != F) {
+#pragma unroll
         for (int v = 0; v < ND; ++v) {
-          if (v == f) continue;
+          if (v == F) continue;
           const double m2 = (v == i) ? 2.0 : 1.0;
           s1 += kap[v] * m2; s2 += knb[v] * m2;
         }
       }
       S_me[i] = s1 * c_m2 * area; S_nb[i] = s2 * c_m2 * area;
     }
-    #pragma unroll
+    const double pscale = c_m3 * area * beta;
+#pragma unroll
     for (int i = 0; i < ND; ++i) {
-      #pragma unroll
+#pragma unroll
       for (int j = 0; j < ND; ++j) {
         double pen = 0.0;
-        if (i != f && j != f) {
-          #pragma unroll
+        if (i != F && j != F) {
+#pragma unroll
           for (int v = 0; v < ND; ++v) {
-            if (v == f) continue;
+            if (v == F) continue;
             pen += 0.5 * (kap[v] + knb[v]) * mult3(v, i, j);
           }
-          pen *= c_m3 * area * beta;
+          pen *= pscale;
         }
         dg[i][j] += -0.5 * gn_me[j] * S_me[i] - 0.5 * gn_me[i] * S_me[j] + pen;
-        if (j != f) {
-          const double t = 0.5 * gn_me[i] * S_me[j] - pen;
-          #pragma unroll
-          for (int jp = 0; jp < ND; ++jp)
-            if (perm[j] == jp) O[i][jp] += t;
-        }
+        O[i][j] = -0.5 * gn_nb[j] * S_nb[i] + ((j != F) ? 0.5 * gn_me[i] * S_me[j] - pen : 0.0);
       }
-      #pragma unroll
-      for (int jp = 0; jp < ND; ++jp) O[i][jp] += -0.5 * gn_nb[jp] * S_nb[i];
     }
     // rhs: avg(q).n+ jump(v)  (solver.py:310)
     double fl = 0.0;
-    #pragma unroll
-    for (int x = 0; x < D; ++x) fl += 0.5 * (qc[x] + a.q[x * a.nc + c2]) * n[x];
+#pragma unroll
+    for (int x = 0; x < D; ++x) fl += 0.5 * (qc[x] + a.q[x * nc + c2]) * n[x];
     fl *= area / D;
-    #pragma unroll
+#pragma unroll
     for (int i = 0; i < ND; ++i)
-      if (i != f) r[i] += fl;
+      if (i != F) r[i] += fl;
   } else {  // membrane: C_phi jump(u) jump(v), robin data (solver.py:334-346)
     const double cm = a.P.C_phi * c_m2 * area;
-    #pragma unroll
+#pragma unroll
     for (int i = 0; i < ND; ++i) {
-      if (i == f) continue;
-      #pragma unroll
+      if (i == F) continue;
+#pragma unroll
       for (int j = 0; j < ND; ++j) {
-        if (j == f) continue;
+        if (j == F) continue;
         const double v = cm * ((i == j) ? 2.0 : 1.0);
         dg[i][j] += v;
-        #pragma unroll
-        for (int jp = 0; jp < ND; ++jp)
-          if (perm[j] == jp) O[i][jp] -= v;
+        O[i][j] = -v;
       }
     }
     if (!a.P.mms) {
-      const int64_t m = a.fmem[f * nc + cell];
+      const int64_t m = a.fmem[F * nc + cell];
       double gr = a.phiM[m];
       if (!a.P.splitting) {
         double It = 0.0;
-        #pragma unroll
-        for (int k = 0; k < MAX_IONS; ++k) if (k < a.P.N) It += a.Ich[k][m];
+        for (int k = 0; k < a.P.N; ++k) It += a.Ich[k][m];
         gr -= It / a.P.C_phi;
       }
       const double st = fi_ics(w) ? 1.0 : -1.0;
       const double v = a.P.C_phi * gr * st * area / D;
-      #pragma unroll
+#pragma unroll
       for (int i = 0; i < ND; ++i)
-        if (i != f) r[i] += v;
+        if (i != F) r[i] += v;
     }
   }
+  return w;
 }
 
 template <int D>
@@ -379,15 +365,16 @@ struct EmiCellKernel {
     #pragma unroll
     for (int f = 0; f < ND; ++f) {
       double O[ND][ND];
-      if (f == 0) emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, O, dg, r);
-      else if (f == 1) emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, O, dg, r);
-      else if (f == 2) emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, O, dg, r);
-      else emi_facet<D, D>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      int w;
+      if (f == 0) w = emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      else if (f == 1) w = emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      else if (f == 2) w = emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      else w = emi_facet<D, D>(a, cell, g, K, hK, kap, qc, O, dg, r);
       double* Of = a.A + (int64_t)(1 + f) * a.nc * bs + cell * bs;
       #pragma unroll
       for (int i = 0; i < ND; ++i)
         #pragma unroll
-        for (int j = 0; j < ND; ++j) Of[i * ND + j] = O[i][j];
+        for (int j = 0; j < ND; ++j) Of[i * ND + fi_perm(w, j)] = O[i][j];
     }
     double* Ad = a.Adiag + cell * bs;
     double* Bd = a.A + cell * bs;
@@ -442,20 +429,21 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) emi_assemble_kernel(const 
     for (int i = 0; i < ND; ++i) { r[i] = 0.0; for (int j = 0; j < ND; ++j) dg[i][j] = 0.0; }
     // facet f and row f of the cell integrals (f is warp uniform)
     double bdrow[ND];
+    int w;
     switch (f) {
-      case 0: emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      case 0: w = emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, O, dg, r);
               { double row[ND], ri; emi_cell_row<D, 0>(a, g, K, kap, kbar, qc, row, bdrow, ri);
                 #pragma unroll
                 for (int j = 0; j < ND; ++j) dg[0][j] += row[j]; r[0] += ri; } break;
-      case 1: emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      case 1: w = emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, O, dg, r);
               { double row[ND], ri; emi_cell_row<D, 1>(a, g, K, kap, kbar, qc, row, bdrow, ri);
                 #pragma unroll
                 for (int j = 0; j < ND; ++j) dg[1][j] += row[j]; r[1] += ri; } break;
-      case 2: emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      case 2: w = emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, O, dg, r);
               { double row[ND], ri; emi_cell_row<D, 2>(a, g, K, kap, kbar, qc, row, bdrow, ri);
                 #pragma unroll
                 for (int j = 0; j < ND; ++j) dg[2][j] += row[j]; r[2] += ri; } break;
-      default: emi_facet<D, D>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      default: w = emi_facet<D, D>(a, cell, g, K, hK, kap, qc, O, dg, r);
               { double row[ND], ri; emi_cell_row<D, D>(a, g, K, kap, kbar, qc, row, bdrow, ri);
                 #pragma unroll
                 for (int j = 0; j < ND; ++j) dg[D][j] += row[j]; r[D] += ri; } break;
@@ -465,7 +453,7 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) emi_assemble_kernel(const 
     #pragma unroll
     for (int i = 0; i < ND; ++i) {
       #pragma unroll
-      for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + j] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
+      for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + fi_perm(w, j)] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
       sR[f][cl][i] = r[i];
     }
   }
@@ -553,84 +541,73 @@ KNP_HD void knp_cell_row(const KnpArgs<D>& a, const double (&g)[D + 1][D], doubl
   ri = acc / a.P.dt;
 }
 
+// facet F of `cell` for ion a.ion; same output convention as emi_facet.
 template <int D, int F>
-KNP_HD void knp_facet(const KnpArgs<D>& a, int64_t cell, int reg, const double (&g)[D + 1][D],
-                      double K, double hK, double Dme, const double (&gp)[D],
-                      double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1], double (&r)[D + 1]) {
+KNP_HD int knp_facet(const KnpArgs<D>& a, int64_t cell, int reg, const double (&g)[D + 1][D],
+                     double K, double hK, double Dme, const double (&gp)[D],
+                     double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1], double (&r)[D + 1]) {
   constexpr int ND = D + 1;
   constexpr double c_m2 = 1.0 / (D * (D + 1));
-  constexpr int f = F;
   const int64_t nc = a.nc;
   const int ion = a.ion;
-  const double z = a.P.z[ion], zpsi = z * a.P.psi;
-  const int w = a.finfo[f * nc + cell];
+  const double zpsi = a.P.z[ion] * a.P.psi;
+  const int w = a.finfo[F * nc + cell];
   const int kind = fi_kind(w);
-  #pragma unroll
+  (void)reg; (void)r;
+#pragma unroll
   for (int i = 0; i < ND; ++i)
-    #pragma unroll
+#pragma unroll
     for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
-  if (kind == FK_NONE) return;
-  const int64_t c2 = a.nbr[f * nc + cell];
+  if (kind != FK_SIP) return w;   // membrane facets: nothing in the matrix (rhs: KnpMembraneRhsKernel)
+  const int64_t c2 = a.nbr[F * nc + cell];
   double gn2 = 0.0;
-  #pragma unroll
-  for (int x = 0; x < D; ++x) gn2 += g[f][x] * g[f][x];
+#pragma unroll
+  for (int x = 0; x < D; ++x) gn2 += g[F][x] * g[F][x];
   const double gnorm = sqrt(gn2);
   const double area = gnorm * D * K;
+  const double inv_gnorm = 1.0 / gnorm;
   double n[D];
-  #pragma unroll
-  for (int x = 0; x < D; ++x) n[x] = -g[f][x] / gnorm;
-  int perm[ND];
-  #pragma unroll
-  for (int v = 0; v < ND; ++v) perm[v] = fi_perm(w, v);
-  if (kind == FK_SIP) {
-    const int nf = fi_nfacet(w);
-    const double Dnb = a.P.D[ion][a.region[c2]];
-    const double beta = a.P.tau_knp / (0.5 * (hK + a.h[c2]));
-    double gn_me[ND], gn_nb[ND];
-    double un_me = 0.0, un_nb = 0.0;
-    #pragma unroll
-    for (int x = 0; x < D; ++x) { un_me += gp[x] * n[x]; un_nb -= a.gphi[x * a.nc + c2] * n[x]; }
-    un_me = fmax(Dme * un_me, 0.0);                      // solver.py:583
-    un_nb = fmax(Dnb * un_nb, 0.0);
-    #pragma unroll
-    for (int j = 0; j < ND; ++j) {
-      double a1 = 0.0, a2 = 0.0;
-      #pragma unroll
-      for (int x = 0; x < D; ++x) {
-        a1 += g[j][x] * n[x];
-        a2 += a.grad[(j * D + x) * a.nc + c2] * n[x];
-      }
-      gn_me[j] = a1; gn_nb[j] = a2;
+#pragma unroll
+  for (int x = 0; x < D; ++x) n[x] = -g[F][x] * inv_gnorm;
+  const double Dnb = a.P.D[ion][a.region[c2]];
+  const double beta = a.P.tau_knp / (0.5 * (hK + a.h[c2]));
+  double gn_me[ND], gn_nb[ND];
+  double un_me = 0.0, un_nb = 0.0;
+#pragma unroll
+  for (int x = 0; x < D; ++x) { un_me += gp[x] * n[x]; un_nb -= a.gphi[x * nc + c2] * n[x]; }
+  un_me = fmax(Dme * un_me, 0.0);                      // solver.py:583
+  un_nb = fmax(Dnb * un_nb, 0.0);
+#pragma unroll
+  for (int j = 0; j < ND; ++j) {
+    const int64_t pj = fi_perm(w, j);
+    double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int x = 0; x < D; ++x) {
+      a1 += g[j][x] * n[x];
+      a2 += a.grad[(pj * D + x) * nc + c2] * n[x];
     }
-    const double af = area / D;       // int_F lambda_a
-    const double pm = (beta * Dme - zpsi * un_me) * c_m2 * area;
-    const double pn = (-beta * Dnb + zpsi * un_nb) * c_m2 * area;
-    #pragma unroll
-    for (int i = 0; i < ND; ++i) {
-      #pragma unroll
-      for (int j = 0; j < ND; ++j) {
-        double v = 0.0;
-        if (i != f) v += -0.5 * Dme * gn_me[j] * af;
-        if (j != f) v += -0.5 * Dme * gn_me[i] * af;
-        if (i != f && j != f) {
-          const double m2 = (i == j) ? 2.0 : 1.0;
-          v += pm * m2;
-          #pragma unroll
-          for (int jp = 0; jp < ND; ++jp)
-            if (perm[j] == jp) O[i][jp] += pn * m2;
-        }
-        dg[i][j] += v;
+    gn_me[j] = a1; gn_nb[j] = a2;
+  }
+  const double af = area / D;       // int_F lambda_a
+  const double pm = (beta * Dme - zpsi * un_me) * c_m2 * area;
+  const double pn = (-beta * Dnb + zpsi * un_nb) * c_m2 * area;
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      double v = 0.0, o = 0.0;
+      if (i != F) { v += -0.5 * Dme * gn_me[j] * af; o += -0.5 * Dnb * gn_nb[j] * af; }
+      if (j != F) { v += -0.5 * Dme * gn_me[i] * af; o += 0.5 * Dme * gn_me[i] * af; }
+      if (i != F && j != F) {
+        const double m2 = (i == j) ? 2.0 : 1.0;
+        v += pm * m2;
+        o += pn * m2;
       }
-      #pragma unroll
-      for (int jp = 0; jp < ND; ++jp) {
-        double v = 0.0;
-        if (i != f) v += -0.5 * Dnb * gn_nb[jp] * af;
-        if (jp != nf) v += 0.5 * Dme * gn_me[i] * af;
-        O[i][jp] += v;
-      }
+      dg[i][j] += v;
+      O[i][j] = o;
     }
   }
-  // membrane facets: nothing in the matrix; their right-hand side is KnpMembraneRhsKernel
+  return w;
 }
 
 // membrane right-hand side of KNP (solver.py:603-629) for ALL solved ions, one index per
@@ -733,7 +710,6 @@ struct KnpCellKernel {
     double gp[D], cnl[ND];
     #pragma unroll
     for (int x = 0; x < D; ++x) gp[x] = a.gphi[x * a.nc + cell];
-    #pragma unroll
     load_cell<ND>(a.cn, cell, cnl);
     double dg[ND][ND], r[ND];
     knp_cell_row<D, 0>(a, g, K, Dme, gp, cnl, dg[0], r[0]);
@@ -743,15 +719,16 @@ struct KnpCellKernel {
     #pragma unroll
     for (int f = 0; f < ND; ++f) {
       double O[ND][ND];
-      if (f == 0) knp_facet<D, 0>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-      else if (f == 1) knp_facet<D, 1>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-      else if (f == 2) knp_facet<D, 2>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-      else knp_facet<D, D>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      int w;
+      if (f == 0) w = knp_facet<D, 0>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      else if (f == 1) w = knp_facet<D, 1>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      else if (f == 2) w = knp_facet<D, 2>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      else w = knp_facet<D, D>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
       double* Of = a.A + (int64_t)(1 + f) * a.nc * bs + cell * bs;
       #pragma unroll
       for (int i = 0; i < ND; ++i)
         #pragma unroll
-        for (int j = 0; j < ND; ++j) Of[i * ND + j] = O[i][j];
+        for (int j = 0; j < ND; ++j) Of[i * ND + fi_perm(w, j)] = O[i][j];
     }
     double* Ad = a.A + cell * bs;
     #pragma unroll
@@ -787,25 +764,25 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) knp_assemble_kernel(const 
     double gp[D], cnl[ND];
     #pragma unroll
     for (int x = 0; x < D; ++x) gp[x] = a.gphi[x * a.nc + cell];
-    #pragma unroll
     load_cell<ND>(a.cn, cell, cnl);
     double dg[ND][ND], r[ND], O[ND][ND];
     #pragma unroll
     for (int i = 0; i < ND; ++i) { r[i] = 0.0; for (int j = 0; j < ND; ++j) dg[i][j] = 0.0; }
+    int w;
     switch (f) {
-      case 0: knp_facet<D, 0>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      case 0: w = knp_facet<D, 0>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
               { double row[ND], ri; knp_cell_row<D, 0>(a, g, K, Dme, gp, cnl, row, ri);
                 #pragma unroll
                 for (int j = 0; j < ND; ++j) dg[0][j] += row[j]; r[0] += ri; } break;
-      case 1: knp_facet<D, 1>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      case 1: w = knp_facet<D, 1>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
               { double row[ND], ri; knp_cell_row<D, 1>(a, g, K, Dme, gp, cnl, row, ri);
                 #pragma unroll
                 for (int j = 0; j < ND; ++j) dg[1][j] += row[j]; r[1] += ri; } break;
-      case 2: knp_facet<D, 2>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      case 2: w = knp_facet<D, 2>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
               { double row[ND], ri; knp_cell_row<D, 2>(a, g, K, Dme, gp, cnl, row, ri);
                 #pragma unroll
                 for (int j = 0; j < ND; ++j) dg[2][j] += row[j]; r[2] += ri; } break;
-      default: knp_facet<D, D>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
+      default: w = knp_facet<D, D>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
               { double row[ND], ri; knp_cell_row<D, D>(a, g, K, Dme, gp, cnl, row, ri);
                 #pragma unroll
                 for (int j = 0; j < ND; ++j) dg[D][j] += row[j]; r[D] += ri; } break;
@@ -813,7 +790,7 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) knp_assemble_kernel(const 
     #pragma unroll
     for (int i = 0; i < ND; ++i) {
       #pragma unroll
-      for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + j] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
+      for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + fi_perm(w, j)] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
       sR[f][cl][i] = r[i];
     }
   }
