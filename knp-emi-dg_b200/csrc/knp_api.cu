@@ -373,16 +373,17 @@ static void assemble_knp_t(knp_ctx* c) {
   GradKernel<D> gk;
   gk.nc = c->nc; gk.phi = c->phi.p; gk.grad = c->grad.p; gk.gphi = c->gphi.p;
   parallel_for(s, c->nc, gk, 128);
-  for (int ion = 0; ion < c->P.N - 1; ++ion) {
+  {
     KnpArgs<D> k;
-    k.P = c->P; k.nc = c->nc; k.ion = ion;
+    k.P = c->P; k.nc = c->nc; k.nion = c->P.N - 1;
     k.grad = c->grad.p; k.vol = c->vol.p; k.h = c->h.p; k.region = c->region.p;
-    k.nbr = c->nbr.p; k.finfo = c->finfo.p; k.fmem = c->fmem.p;
-    k.gphi = c->gphi.p; k.phi = c->phi.p;
-    for (int i = 0; i < MAX_IONS; ++i) { k.c[i] = c->c[i].p; k.Ich[i] = c->Ich[i].p; }
-    k.cn = c->cn(ion); k.phiM = c->phiM.p;
-    k.load = c->has_load_knp[ion] ? c->load_knp[ion].p : nullptr;
-    k.A = c->A_knp[ion].p; k.rhs = c->rhs_knp[ion].p;
+    k.nbr = c->nbr.p; k.finfo = c->finfo.p; k.gphi = c->gphi.p;
+    for (int i = 0; i < MAX_IONS; ++i) { k.cn[i] = nullptr; k.load[i] = nullptr; k.A[i] = nullptr; k.rhs[i] = nullptr; }
+    for (int ion = 0; ion < k.nion; ++ion) {
+      k.cn[ion] = c->cn(ion);
+      k.load[ion] = c->has_load_knp[ion] ? c->load_knp[ion].p : nullptr;
+      k.A[ion] = c->A_knp[ion].p; k.rhs[ion] = c->rhs_knp[ion].p;
+    }
 #ifdef KNP_EMU
     parallel_for(s, c->nc, KnpCellKernel<D>{k}, 128);
 #else
@@ -752,7 +753,7 @@ int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* byt
     case 1: b = /*prepass*/ 8.0 * n * N + 8.0 * nc * nd * d + 4.0 * nc + 8.0 * n + 8.0 * nc * d
               /*cells*/ + geom + 8.0 * n + 8.0 * nc * d + mat + 8.0 * nc * bs + 8.0 * n; break;
     case 2: b = /*grad*/ 8.0 * n + 8.0 * nc * nd * d + 8.0 * nc * d
-              + (N - 1) * (geom + 8.0 * nc * d + 8.0 * n + mat + 8.0 * n); break;
+              + geom + 8.0 * nc * d + (N - 1) * (8.0 * n + mat + 8.0 * n); break;
     case 3: b = mat + 8.0 * nc * bs + 4.0 * nd * nc + 24.0 * n; break;
   }
   *bytes = b;

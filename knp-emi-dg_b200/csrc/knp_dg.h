@@ -496,108 +496,122 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) emi_assemble_kernel(const 
 #endif
 
 // ---------------------------------------------------------------------------
-// KNP assembly for one solved ion (same structure as EMI).
+// KNP assembly (same structure as EMI).  The facet work is split into an ion-independent
+// part (geometry, normal fluxes of the basis gradients, upwind direction) and a cheap
+// per-ion part, so the CUDA kernel assembles ALL solved ions in one launch while loading
+// the cell and neighbour data once.
 // ---------------------------------------------------------------------------
 template <int D>
 struct KnpArgs {
   static constexpr int ND = D + 1;
   Params P;
   int64_t nc;
-  int ion;
+  int nion;                      // number of solved ions (N-1)
   const double* grad; const double* vol; const double* h;
-  const int32_t* region; const int32_t* nbr; const int32_t* finfo; const int32_t* fmem;
-  const double* gphi;            // [nc][D]
-  const double* phi;             // [n]
-  const double* c[MAX_IONS];     // c_prev_k of all ions (alpha, solver.py:603)
-  const double* cn;              // c_prev_n of this ion
-  const double* phiM; const double* Ich[MAX_IONS];
-  const double* load;            // extra load vector or nullptr
-  double* A;                     // (ND+1) slots
-  double* rhs;
+  const int32_t* region; const int32_t* nbr; const int32_t* finfo;
+  const double* gphi;            // [D][nc]
+  const double* cn[MAX_IONS];    // c_prev_n per solved ion
+  const double* load[MAX_IONS];  // extra load vector or nullptr
+  double* A[MAX_IONS];           // (ND+1) slots per solved ion
+  double* rhs[MAX_IONS];
 };
 
-// cell integrals for test function i (solver.py:586-587, 593, 597)
+template <int D>
+struct KnpFacetGeom {
+  int w, kind, regnb;
+  double area, beta, dphin_me, dphin_nb;   // grad(phi).n on both sides (own outward normals)
+  double gn_me[D + 1], gn_nb[D + 1];
+};
+
+// cell integrals for test function I of ion `ion` (solver.py:586-587, 593, 597)
 template <int D, int I>
-KNP_HD void knp_cell_row(const KnpArgs<D>& a, const double (&g)[D + 1][D], double K, double Dme,
+KNP_HD void knp_cell_row(const Params& P, int ion, const double (&g)[D + 1][D], double K, double Dme,
                          const double (&gp)[D], const double (&cnl)[D + 1], double* dgrow, double& ri) {
   constexpr int ND = D + 1;
   constexpr double c_mass = 1.0 / ((D + 1) * (D + 2));
   constexpr int i = I;
-  const double zpsi = a.P.z[a.ion] * a.P.psi;
+  const double zpsi = P.z[ion] * P.psi;
   double dr = 0.0;
-  #pragma unroll
+#pragma unroll
   for (int x = 0; x < D; ++x) dr += gp[x] * g[i][x];
   const double drift = zpsi * Dme * dr * K / (D + 1);
   double acc = 0.0;
-  #pragma unroll
+#pragma unroll
   for (int j = 0; j < ND; ++j) {
     double gg = 0.0;
-    #pragma unroll
+#pragma unroll
     for (int x = 0; x < D; ++x) gg += g[i][x] * g[j][x];
     const double mij = K * c_mass * ((i == j) ? 2.0 : 1.0);
-    dgrow[j] = mij / a.P.dt + Dme * K * gg + drift;
+    dgrow[j] = mij / P.dt + Dme * K * gg + drift;
     acc += mij * cnl[j];
   }
-  ri = acc / a.P.dt;
+  ri = acc / P.dt;
 }
 
-// facet F of `cell` for ion a.ion; same output convention as emi_facet.
+// ion-independent part of facet F (neighbour data gathered in my vertex order, see emi_facet)
 template <int D, int F>
-KNP_HD int knp_facet(const KnpArgs<D>& a, int64_t cell, int reg, const double (&g)[D + 1][D],
-                     double K, double hK, double Dme, const double (&gp)[D],
-                     double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1], double (&r)[D + 1]) {
+KNP_HD void knp_facet_geom(const KnpArgs<D>& a, int64_t cell, const double (&g)[D + 1][D], double K,
+                           double hK, const double (&gp)[D], KnpFacetGeom<D>& G) {
   constexpr int ND = D + 1;
-  constexpr double c_m2 = 1.0 / (D * (D + 1));
   const int64_t nc = a.nc;
-  const int ion = a.ion;
-  const double zpsi = a.P.z[ion] * a.P.psi;
-  const int w = a.finfo[F * nc + cell];
-  const int kind = fi_kind(w);
-  (void)reg; (void)r;
-#pragma unroll
-  for (int i = 0; i < ND; ++i)
-#pragma unroll
-    for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
-  if (kind != FK_SIP) return w;   // membrane facets: nothing in the matrix (rhs: KnpMembraneRhsKernel)
+  G.w = a.finfo[F * nc + cell];
+  G.kind = fi_kind(G.w);
+  if (G.kind != FK_SIP) return;   // membrane / untagged facets: nothing in the KNP matrix
   const int64_t c2 = a.nbr[F * nc + cell];
   double gn2 = 0.0;
 #pragma unroll
   for (int x = 0; x < D; ++x) gn2 += g[F][x] * g[F][x];
   const double gnorm = sqrt(gn2);
-  const double area = gnorm * D * K;
+  G.area = gnorm * D * K;
   const double inv_gnorm = 1.0 / gnorm;
   double n[D];
 #pragma unroll
   for (int x = 0; x < D; ++x) n[x] = -g[F][x] * inv_gnorm;
-  const double Dnb = a.P.D[ion][a.region[c2]];
-  const double beta = a.P.tau_knp / (0.5 * (hK + a.h[c2]));
-  double gn_me[ND], gn_nb[ND];
-  double un_me = 0.0, un_nb = 0.0;
+  G.regnb = a.region[c2];
+  G.beta = a.P.tau_knp / (0.5 * (hK + a.h[c2]));
+  double d1 = 0.0, d2 = 0.0;
 #pragma unroll
-  for (int x = 0; x < D; ++x) { un_me += gp[x] * n[x]; un_nb -= a.gphi[x * nc + c2] * n[x]; }
-  un_me = fmax(Dme * un_me, 0.0);                      // solver.py:583
-  un_nb = fmax(Dnb * un_nb, 0.0);
+  for (int x = 0; x < D; ++x) { d1 += gp[x] * n[x]; d2 -= a.gphi[x * nc + c2] * n[x]; }
+  G.dphin_me = d1; G.dphin_nb = d2;
 #pragma unroll
   for (int j = 0; j < ND; ++j) {
-    const int64_t pj = fi_perm(w, j);
+    const int64_t pj = fi_perm(G.w, j);
     double a1 = 0.0, a2 = 0.0;
 #pragma unroll
     for (int x = 0; x < D; ++x) {
       a1 += g[j][x] * n[x];
       a2 += a.grad[(pj * D + x) * nc + c2] * n[x];
     }
-    gn_me[j] = a1; gn_nb[j] = a2;
+    G.gn_me[j] = a1; G.gn_nb[j] = a2;
   }
-  const double af = area / D;       // int_F lambda_a
-  const double pm = (beta * Dme - zpsi * un_me) * c_m2 * area;
-  const double pn = (-beta * Dnb + zpsi * un_nb) * c_m2 * area;
+}
+
+// per-ion part of facet F: O (own vertex order, column F = neighbour's opposite vertex),
+// dg += share of the diagonal block (solver.py:583-594)
+template <int D, int F>
+KNP_HD void knp_facet_ion(const Params& P, int ion, const KnpFacetGeom<D>& G, double Dme,
+                          double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1]) {
+  constexpr int ND = D + 1;
+  constexpr double c_m2 = 1.0 / (D * (D + 1));
+#pragma unroll
+  for (int i = 0; i < ND; ++i)
+#pragma unroll
+    for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
+  if (G.kind != FK_SIP) return;
+  const double zpsi = P.z[ion] * P.psi;
+  const double Dnb = P.D[ion][G.regnb];
+  const double un_me = fmax(Dme * G.dphin_me, 0.0);     // upwinding, solver.py:583
+  const double un_nb = fmax(Dnb * G.dphin_nb, 0.0);
+  const double af = G.area / D;                          // int_F lambda_a
+  const double pm = (G.beta * Dme - zpsi * un_me) * c_m2 * G.area;
+  const double pn = (-G.beta * Dnb + zpsi * un_nb) * c_m2 * G.area;
 #pragma unroll
   for (int i = 0; i < ND; ++i) {
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
       double v = 0.0, o = 0.0;
-      if (i != F) { v += -0.5 * Dme * gn_me[j] * af; o += -0.5 * Dnb * gn_nb[j] * af; }
-      if (j != F) { v += -0.5 * Dme * gn_me[i] * af; o += 0.5 * Dme * gn_me[i] * af; }
+      if (i != F) { v += -0.5 * Dme * G.gn_me[j] * af; o += -0.5 * Dnb * G.gn_nb[j] * af; }
+      if (j != F) { v += -0.5 * Dme * G.gn_me[i] * af; o += 0.5 * Dme * G.gn_me[i] * af; }
       if (i != F && j != F) {
         const double m2 = (i == j) ? 2.0 : 1.0;
         v += pm * m2;
@@ -607,7 +621,6 @@ KNP_HD int knp_facet(const KnpArgs<D>& a, int64_t cell, int reg, const double (&
       O[i][j] = o;
     }
   }
-  return w;
 }
 
 // membrane right-hand side of KNP (solver.py:603-629) for ALL solved ions, one index per
@@ -694,48 +707,47 @@ struct KnpMembraneRhsKernel {
 };
 
 template <int D>
-struct KnpCellKernel {
+struct KnpCellKernel {   // one index per cell, all solved ions (host emulation / reference driver)
   static constexpr int ND = D + 1;
   KnpArgs<D> a;
   KNP_HD void operator()(int64_t cell) const {
     const int64_t bs = ND * ND;
     const int reg = a.region[cell];
-    const double Dme = a.P.D[a.ion][reg];
     double g[ND][D];
-    #pragma unroll
     for (int i = 0; i < ND; ++i)
-      #pragma unroll
       for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * a.nc + cell];
     const double K = a.vol[cell], hK = a.h[cell];
-    double gp[D], cnl[ND];
-    #pragma unroll
+    double gp[D];
     for (int x = 0; x < D; ++x) gp[x] = a.gphi[x * a.nc + cell];
-    load_cell<ND>(a.cn, cell, cnl);
-    double dg[ND][ND], r[ND];
-    knp_cell_row<D, 0>(a, g, K, Dme, gp, cnl, dg[0], r[0]);
-    knp_cell_row<D, 1>(a, g, K, Dme, gp, cnl, dg[1], r[1]);
-    knp_cell_row<D, 2>(a, g, K, Dme, gp, cnl, dg[2], r[2]);
-    if constexpr (D == 3) knp_cell_row<D, D>(a, g, K, Dme, gp, cnl, dg[D], r[D]);
-    #pragma unroll
-    for (int f = 0; f < ND; ++f) {
-      double O[ND][ND];
-      int w;
-      if (f == 0) w = knp_facet<D, 0>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-      else if (f == 1) w = knp_facet<D, 1>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-      else if (f == 2) w = knp_facet<D, 2>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-      else w = knp_facet<D, D>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-      double* Of = a.A + (int64_t)(1 + f) * a.nc * bs + cell * bs;
-      #pragma unroll
-      for (int i = 0; i < ND; ++i)
-        #pragma unroll
-        for (int j = 0; j < ND; ++j) Of[i * ND + fi_perm(w, j)] = O[i][j];
-    }
-    double* Ad = a.A + cell * bs;
-    #pragma unroll
-    for (int i = 0; i < ND; ++i) {
-      #pragma unroll
-      for (int j = 0; j < ND; ++j) Ad[i * ND + j] = dg[i][j];
-      a.rhs[cell * ND + i] = r[i] + (a.load ? a.load[cell * ND + i] : 0.0);
+    KnpFacetGeom<D> G[ND];
+    knp_facet_geom<D, 0>(a, cell, g, K, hK, gp, G[0]);
+    knp_facet_geom<D, 1>(a, cell, g, K, hK, gp, G[1]);
+    knp_facet_geom<D, 2>(a, cell, g, K, hK, gp, G[2]);
+    if constexpr (D == 3) knp_facet_geom<D, D>(a, cell, g, K, hK, gp, G[D]);
+    for (int ion = 0; ion < a.nion; ++ion) {
+      const double Dme = a.P.D[ion][reg];
+      double cnl[ND];
+      load_cell<ND>(a.cn[ion], cell, cnl);
+      double dg[ND][ND], r[ND];
+      knp_cell_row<D, 0>(a.P, ion, g, K, Dme, gp, cnl, dg[0], r[0]);
+      knp_cell_row<D, 1>(a.P, ion, g, K, Dme, gp, cnl, dg[1], r[1]);
+      knp_cell_row<D, 2>(a.P, ion, g, K, Dme, gp, cnl, dg[2], r[2]);
+      if constexpr (D == 3) knp_cell_row<D, D>(a.P, ion, g, K, Dme, gp, cnl, dg[D], r[D]);
+      for (int f = 0; f < ND; ++f) {
+        double O[ND][ND];
+        if (f == 0) knp_facet_ion<D, 0>(a.P, ion, G[0], Dme, O, dg);
+        else if (f == 1) knp_facet_ion<D, 1>(a.P, ion, G[1], Dme, O, dg);
+        else if (f == 2) knp_facet_ion<D, 2>(a.P, ion, G[2], Dme, O, dg);
+        else knp_facet_ion<D, D>(a.P, ion, G[D], Dme, O, dg);
+        double* Of = a.A[ion] + (int64_t)(1 + f) * a.nc * bs + cell * bs;
+        for (int i = 0; i < ND; ++i)
+          for (int j = 0; j < ND; ++j) Of[i * ND + fi_perm(G[f].w, j)] = O[i][j];
+      }
+      double* Ad = a.A[ion] + cell * bs;
+      for (int i = 0; i < ND; ++i) {
+        for (int j = 0; j < ND; ++j) Ad[i * ND + j] = dg[i][j];
+        a.rhs[ion][cell * ND + i] = r[i] + (a.load[ion] ? a.load[ion][cell * ND + i] : 0.0);
+      }
     }
   }
 };
@@ -746,83 +758,89 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) knp_assemble_kernel(const 
   constexpr int ND = D + 1, BS = ND * ND, PITCH = BS + 1, NT = ASM_CPB * ND;
   __shared__ double sO[ND][ASM_CPB][PITCH];
   __shared__ double sD[ND][ASM_CPB][PITCH];
-  __shared__ double sR[ND][ASM_CPB][ND];
+  __shared__ double sR[ASM_CPB][ND];
   const int t = threadIdx.x;
   const int f = t / ASM_CPB, cl = t - f * ASM_CPB;
   const int64_t cell0 = (int64_t)blockIdx.x * ASM_CPB;
   const int64_t cell = cell0 + cl;
   const int64_t nc = a.nc;
-  if (cell < nc) {
-    const int reg = a.region[cell];
-    const double Dme = a.P.D[a.ion][reg];
-    double g[ND][D];
-    #pragma unroll
+  const bool active = cell < nc;
+  double g[ND][D], gp[D];
+  double K = 0.0, hK = 0.0;
+  int reg = 0;
+  KnpFacetGeom<D> G;
+  G.w = 0; G.kind = FK_NONE;
+  if (active) {
+    reg = a.region[cell];
+#pragma unroll
     for (int i = 0; i < ND; ++i)
-      #pragma unroll
-      for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * a.nc + cell];
-    const double K = a.vol[cell], hK = a.h[cell];
-    double gp[D], cnl[ND];
-    #pragma unroll
-    for (int x = 0; x < D; ++x) gp[x] = a.gphi[x * a.nc + cell];
-    load_cell<ND>(a.cn, cell, cnl);
-    double dg[ND][ND], r[ND], O[ND][ND];
-    #pragma unroll
-    for (int i = 0; i < ND; ++i) { r[i] = 0.0; for (int j = 0; j < ND; ++j) dg[i][j] = 0.0; }
-    int w;
-    switch (f) {
-      case 0: w = knp_facet<D, 0>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-              { double row[ND], ri; knp_cell_row<D, 0>(a, g, K, Dme, gp, cnl, row, ri);
-                #pragma unroll
-                for (int j = 0; j < ND; ++j) dg[0][j] += row[j]; r[0] += ri; } break;
-      case 1: w = knp_facet<D, 1>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-              { double row[ND], ri; knp_cell_row<D, 1>(a, g, K, Dme, gp, cnl, row, ri);
-                #pragma unroll
-                for (int j = 0; j < ND; ++j) dg[1][j] += row[j]; r[1] += ri; } break;
-      case 2: w = knp_facet<D, 2>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-              { double row[ND], ri; knp_cell_row<D, 2>(a, g, K, Dme, gp, cnl, row, ri);
-                #pragma unroll
-                for (int j = 0; j < ND; ++j) dg[2][j] += row[j]; r[2] += ri; } break;
-      default: w = knp_facet<D, D>(a, cell, reg, g, K, hK, Dme, gp, O, dg, r);
-              { double row[ND], ri; knp_cell_row<D, D>(a, g, K, Dme, gp, cnl, row, ri);
-                #pragma unroll
-                for (int j = 0; j < ND; ++j) dg[D][j] += row[j]; r[D] += ri; } break;
-    }
-    #pragma unroll
-    for (int i = 0; i < ND; ++i) {
-      #pragma unroll
-      for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + fi_perm(w, j)] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
-      sR[f][cl][i] = r[i];
+#pragma unroll
+      for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * nc + cell];
+    K = a.vol[cell]; hK = a.h[cell];
+#pragma unroll
+    for (int x = 0; x < D; ++x) gp[x] = a.gphi[x * nc + cell];
+    switch (f) {   // warp uniform
+      case 0: knp_facet_geom<D, 0>(a, cell, g, K, hK, gp, G); break;
+      case 1: knp_facet_geom<D, 1>(a, cell, g, K, hK, gp, G); break;
+      case 2: knp_facet_geom<D, 2>(a, cell, g, K, hK, gp, G); break;
+      default: knp_facet_geom<D, D>(a, cell, g, K, hK, gp, G); break;
     }
   }
-  __syncthreads();
   const int64_t ncell_blk = (nc - cell0 < ASM_CPB) ? (nc - cell0) : ASM_CPB;
   const int nval = (int)ncell_blk * BS;
-  #pragma unroll
-  for (int s = 0; s < ND; ++s) {
-    double* dst = a.A + (int64_t)(1 + s) * nc * BS + cell0 * BS;
-    for (int e = t; e < nval; e += NT) dst[e] = sO[s][e / BS][e % BS];
-  }
-  {
-    double* dA = a.A + cell0 * BS;
-    for (int e = t; e < nval; e += NT) {
-      const int c = e / BS, k = e % BS;
-      double v = 0.0;
-      #pragma unroll
-      for (int s = 0; s < ND; ++s) v += sD[s][c][k];
-      dA[e] = v;
+  const int nrow = (int)ncell_blk * ND;
+  for (int ion = 0; ion < a.nion; ++ion) {
+    if (active) {
+      const double Dme = a.P.D[ion][reg];
+      double cnl[ND];
+      load_cell<ND>(a.cn[ion], cell, cnl);
+      double dg[ND][ND], O[ND][ND], row[ND], ri;
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+#pragma unroll
+        for (int j = 0; j < ND; ++j) dg[i][j] = 0.0;
+      switch (f) {
+        case 0: knp_facet_ion<D, 0>(a.P, ion, G, Dme, O, dg);
+                knp_cell_row<D, 0>(a.P, ion, g, K, Dme, gp, cnl, row, ri);
+                for (int j = 0; j < ND; ++j) dg[0][j] += row[j]; break;
+        case 1: knp_facet_ion<D, 1>(a.P, ion, G, Dme, O, dg);
+                knp_cell_row<D, 1>(a.P, ion, g, K, Dme, gp, cnl, row, ri);
+                for (int j = 0; j < ND; ++j) dg[1][j] += row[j]; break;
+        case 2: knp_facet_ion<D, 2>(a.P, ion, G, Dme, O, dg);
+                knp_cell_row<D, 2>(a.P, ion, g, K, Dme, gp, cnl, row, ri);
+                for (int j = 0; j < ND; ++j) dg[2][j] += row[j]; break;
+        default: knp_facet_ion<D, D>(a.P, ion, G, Dme, O, dg);
+                knp_cell_row<D, D>(a.P, ion, g, K, Dme, gp, cnl, row, ri);
+                for (int j = 0; j < ND; ++j) dg[D][j] += row[j]; break;
+      }
+#pragma unroll
+      for (int i = 0; i < ND; ++i)
+#pragma unroll
+        for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + fi_perm(G.w, j)] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
+      sR[cl][f] = ri;   // the facets add nothing to the KNP rhs (membrane part: KnpMembraneRhsKernel)
     }
-  }
-  {
-    const int nrow = (int)ncell_blk * ND;
-    double* dr = a.rhs + cell0 * ND;
-    const double* ld = a.load ? a.load + cell0 * ND : nullptr;
-    for (int e = t; e < nrow; e += NT) {
-      const int c = e / ND, i = e % ND;
-      double v = 0.0;
-      #pragma unroll
-      for (int s = 0; s < ND; ++s) v += sR[s][c][i];
-      dr[e] = v + (ld ? ld[e] : 0.0);
+    __syncthreads();
+    double* Aion = a.A[ion];
+    for (int s = 0; s < ND; ++s) {
+      double* dst = Aion + (int64_t)(1 + s) * nc * BS + cell0 * BS;
+      for (int e = t; e < nval; e += NT) dst[e] = sO[s][e / BS][e % BS];
     }
+    {
+      double* dA = Aion + cell0 * BS;
+      for (int e = t; e < nval; e += NT) {
+        const int c = e / BS, k = e % BS;
+        double v = 0.0;
+#pragma unroll
+        for (int s = 0; s < ND; ++s) v += sD[s][c][k];
+        dA[e] = v;
+      }
+    }
+    {
+      double* dr = a.rhs[ion] + cell0 * ND;
+      const double* ld = a.load[ion] ? a.load[ion] + cell0 * ND : nullptr;
+      for (int e = t; e < nrow; e += NT) dr[e] = sR[e / ND][e % ND] + (ld ? ld[e] : 0.0);
+    }
+    __syncthreads();
   }
 }
 #endif

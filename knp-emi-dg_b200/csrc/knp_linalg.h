@@ -179,6 +179,46 @@ struct GalerkinKernel {
   }
 };
 
+// ---- fused coarse-level sweeps (unit aggregation transfer, V-cycle, one pre-smoothing
+// sweep from a zero guess) ---------------------------------------------------------------
+// down: x = dinv b (pre-smoothing from zero), r = b - A x, bc = R r in ONE pass:
+//   bc[I] = sum_{i in aggregate I} ( b_i - sum_k a_ik dinv_k b_k ),  x_i = dinv_i b_i
+// one thread per coarse row I (its members are rptr/ridx of the next level).
+struct CoarseDownKernel {
+  CsrMat A; const double* dinv; const double* b; double* x;
+  const int32_t* rptr; const int32_t* ridx; double* bc;
+  KNP_HD void operator()(int64_t I) const {
+    double acc = 0.0;
+    for (int32_t t = rptr[I]; t < rptr[I + 1]; ++t) {
+      const int32_t i = ridx[t];
+      const double bi = b[i];
+      double ri = bi;
+      for (int32_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+        const int32_t j = A.col[k];
+        ri -= A.val[k] * dinv[j] * b[j];
+      }
+      x[i] = dinv[i] * bi;
+      acc += ri;
+    }
+    bc[I] = acc;
+  }
+};
+
+// up: x' = x + P xc (prolongation), xout = x' + dinv (b - A x') (post-smoothing) in ONE pass;
+// P has exactly one unit entry per row: (P xc)_j = xc[agg_j].
+struct CoarseUpKernel {
+  CsrMat A; const double* dinv; const double* b; const double* x; const int32_t* agg;
+  const double* xc; double* xout;
+  KNP_HD void operator()(int64_t i) const {
+    double acc = b[i];
+    for (int32_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+      const int32_t j = A.col[k];
+      acc -= A.val[k] * (x[j] + xc[agg[j]]);
+    }
+    xout[i] = x[i] + xc[agg[i]] + dinv[i] * acc;
+  }
+};
+
 struct CsrToDenseKernel {  // dense[m*m] (zeroed before) <- CSR
   CsrMat A; double* dense;
   KNP_HD void operator()(int64_t row) const {

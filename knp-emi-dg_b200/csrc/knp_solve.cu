@@ -255,6 +255,14 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li) {
   }
   CsrMat A = csr_of(L, V, li);
   AmgLevelPlan& C = c->amg.lev[li + 1];
+  if (c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1 && C.t_unit) {
+    // fused V(1,1) path: one kernel down, one kernel up per level
+    { CoarseDownKernel k{A, V.dinv[li].p, L.b.p, L.x.p, C.rptr.p, C.ridx.p, C.b.p}; parallel_for(s, C.n, k, 128); }
+    coarse_cycle(c, V, li + 1);
+    { CoarseUpKernel k{A, V.dinv[li].p, L.b.p, L.x.p, C.pidx.p, C.x.p, L.t.p}; parallel_for(s, L.n, k, 128); }
+    std::swap(L.x.p, L.t.p);
+    return;
+  }
   // pre-smoothing from a zero guess
   { DiagScaleKernel k{V.dinv[li].p, L.b.p, L.x.p, 1.0}; parallel_for(s, L.n, k); }
   for (int it = 1; it < c->opt.nu_pre; ++it) {
@@ -306,7 +314,7 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
 // ---------------------------------------------------------------------------------
 static void ensure_krylov(knp_ctx* c) {
   const size_t n = c->n;
-  if (c->kr_r.n != n) { c->kr_r.alloc(n); c->kr_z.alloc(n); c->kr_p.alloc(n); c->kr_q.alloc(n); c->kr_w.alloc(n); }
+  if (c->kr_r.n != 2 * n) { c->kr_r.alloc(2 * n); c->kr_p.alloc(n); c->kr_q.alloc(n); c->kr_w.alloc(n); }
   const size_t need = (size_t)(c->opt.restart + 1) * n;
   if (c->kr_V.n < need) c->kr_V.alloc(need);
 }
@@ -324,7 +332,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   // preconditioner refresh (the reference rebuilds BoomerAMG at every setOperators)
   if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_emi, c->A_emi.p, c->Bdiag());
   else { if (c->bj_emi.n != (size_t)c->slot_stride()) c->bj_emi.alloc(c->slot_stride()); block_inverse(c, c->Bdiag(), c->bj_emi.p); }
-  double* x = c->phi.p; double* r = c->kr_r.p; double* z = c->kr_z.p; double* p = c->kr_p.p; double* q = c->kr_q.p;
+  double* x = c->phi.p; double* r = c->kr_r.p; double* z = c->kr_r.p + n; double* p = c->kr_p.p; double* q = c->kr_q.p;
   const double* b = c->rhs_emi.p;
   // reference norm ||M^-1 b||
   precondition(c, c->amg_emi, B, c->bj_emi.p, b, z);
@@ -348,12 +356,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
       { Axpy2Kernel k{alpha, p, q, x, r}; parallel_for(s, n, k); }
       precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
       double d2[2];
-      // r.z and z.z in one pass: V = {r, z}, w = z
-      {
-        // r and z are separate buffers; two single dots keep the code simple
-        d2[0] = dot_host(c, r, z);
-        d2[1] = dot_host(c, z, z);
-      }
+      dots_host(c, 2, r, z, d2);     // {r, z} are contiguous: r.z and z.z in one pass
       zn = sqrt(d2[1]);
       if (zn <= tol) break;
       const double beta = d2[0] / rz;
@@ -408,10 +411,13 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
       double* vn = V + (int64_t)(j + 1) * n;
       bell_spmv(c, A, vj, nullptr, r, 0);
       precondition(c, Vv, A, bj, r, w);            // w = M^-1 A v_j
-      dots_host(c, j + 1, V, w, hcol.data());      // classical Gram-Schmidt, one pass
-      h2d(hdev, hcol.data(), (j + 1) * sizeof(double), s);
+      // classical Gram-Schmidt, one pass: h = V^T w stays on the device for the update,
+      // ||w||^2 lands right behind it; one host read per iteration
+      multi_dot_device(s, n, j + 1, V, w, c->kr_partial.p, hdev);
       { GsUpdateKernel k{n, j + 1, V, hdev, w}; parallel_for(s, n, k); }
-      const double hn = sqrt(dot_host(c, w, w));
+      multi_dot_device(s, n, 1, w, w, c->kr_partial.p, hdev + j + 1);
+      d2h(hcol.data(), hdev, (j + 2) * sizeof(double), s);
+      const double hn = sqrt(hcol[j + 1]);
       for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
       H[(size_t)(j + 1) * m + j] = hn;
       if (hn > 0.0) { ScaleKernel k{1.0 / hn, w, vn}; parallel_for(s, n, k); }
