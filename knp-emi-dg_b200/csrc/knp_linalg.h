@@ -179,29 +179,67 @@ struct GalerkinKernel {
   }
 };
 
-// ---- fused coarse-level sweeps (unit aggregation transfer, V-cycle, one pre-smoothing
-// sweep from a zero guess) ---------------------------------------------------------------
-// down: x = dinv b (pre-smoothing from zero), r = b - A x, bc = R r in ONE pass:
-//   bc[I] = sum_{i in aggregate I} ( b_i - sum_k a_ik dinv_k b_k ),  x_i = dinv_i b_i
-// one thread per coarse row I (its members are rptr/ridx of the next level).
-struct CoarseDownKernel {
-  CsrMat A; const double* dinv; const double* b; double* x;
-  const int32_t* rptr; const int32_t* ridx; double* bc;
-  KNP_HD void operator()(int64_t I) const {
+// ---- sub-warp-per-row launcher --------------------------------------------------------
+// Coarse AMG levels have 10^2..10^5 rows of ~25 entries: too few rows to hide the latency of
+// a serial per-row loop, so LANES lanes share a row (strided partial sums, shuffle tree) and
+// lane 0 finishes it.  Functors provide  double partial(row, lane, nlanes)  and
+// void finish(row, sum).
+#ifndef KNP_EMU
+template <int LANES, class F>
+__global__ void __launch_bounds__(256) subwarp_kernel(int64_t nrows, const F f) {
+  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = gt / LANES;
+  const int lane = (int)(gt % LANES);
+  const bool ok = row < nrows;
+  double acc = ok ? f.partial(row, lane, LANES) : 0.0;
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LANES);
+  if (ok && lane == 0) f.finish(row, acc);
+}
+#endif
+template <int LANES, class F>
+inline void parallel_rows(knp_stream_t s, int64_t nrows, const F& f) {
+  if (nrows <= 0) return;
+#ifdef KNP_EMU
+  (void)s;
+  for (int64_t r = 0; r < nrows; ++r) f.finish(r, f.partial(r, 0, 1));
+#else
+  const int64_t threads = nrows * LANES;
+  ++launch_counter();
+  subwarp_kernel<LANES, F><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(nrows, f);
+  KNP_CUDA(cudaGetLastError());
+#endif
+}
+
+// ---- fused coarse-level sweeps (unit aggregation transfer, V(1,1) cycle) ----------------
+// down, pass 1: x = dinv b (pre-smoothing from a zero guess) and r = b - A x in one pass
+struct CoarseResidualKernel {
+  CsrMat A; const double* dinv; const double* b; double* x; double* r;
+  KNP_HD double partial(int64_t i, int lane, int nl) const {
     double acc = 0.0;
-    for (int32_t t = rptr[I]; t < rptr[I + 1]; ++t) {
-      const int32_t i = ridx[t];
-      const double bi = b[i];
-      double ri = bi;
-      for (int32_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
-        const int32_t j = A.col[k];
-        ri -= A.val[k] * dinv[j] * b[j];
-      }
-      x[i] = dinv[i] * bi;
-      acc += ri;
+    for (int32_t k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += nl) {
+      const int32_t j = A.col[k];
+      acc += A.val[k] * dinv[j] * b[j];
     }
-    bc[I] = acc;
+    return acc;
   }
+  KNP_HD void finish(int64_t i, double sum) const {
+    const double bi = b[i];
+    x[i] = dinv[i] * bi;
+    r[i] = bi - sum;
+  }
+};
+
+// restriction / any CSR transfer with optional weights: y (=|+=) T x
+struct TransferRowsKernel {
+  const int32_t* ptr; const int32_t* idx; const double* w; const double* x; double* y; int add;
+  KNP_HD double partial(int64_t row, int lane, int nl) const {
+    double acc = 0.0;
+    if (w) for (int32_t k = ptr[row] + lane; k < ptr[row + 1]; k += nl) acc += w[k] * x[idx[k]];
+    else   for (int32_t k = ptr[row] + lane; k < ptr[row + 1]; k += nl) acc += x[idx[k]];
+    return acc;
+  }
+  KNP_HD void finish(int64_t row, double sum) const { if (add) y[row] += sum; else y[row] = sum; }
 };
 
 // up: x' = x + P xc (prolongation), xout = x' + dinv (b - A x') (post-smoothing) in ONE pass;
@@ -209,13 +247,16 @@ struct CoarseDownKernel {
 struct CoarseUpKernel {
   CsrMat A; const double* dinv; const double* b; const double* x; const int32_t* agg;
   const double* xc; double* xout;
-  KNP_HD void operator()(int64_t i) const {
-    double acc = b[i];
-    for (int32_t k = A.ptr[i]; k < A.ptr[i + 1]; ++k) {
+  KNP_HD double partial(int64_t i, int lane, int nl) const {
+    double acc = 0.0;
+    for (int32_t k = A.ptr[i] + lane; k < A.ptr[i + 1]; k += nl) {
       const int32_t j = A.col[k];
-      acc -= A.val[k] * (x[j] + xc[agg[j]]);
+      acc += A.val[k] * (x[j] + xc[agg[j]]);
     }
-    xout[i] = x[i] + xc[agg[i]] + dinv[i] * acc;
+    return acc;
+  }
+  KNP_HD void finish(int64_t i, double sum) const {
+    xout[i] = x[i] + xc[agg[i]] + dinv[i] * (b[i] - sum);
   }
 };
 

@@ -256,10 +256,11 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li) {
   CsrMat A = csr_of(L, V, li);
   AmgLevelPlan& C = c->amg.lev[li + 1];
   if (c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1 && C.t_unit) {
-    // fused V(1,1) path: one kernel down, one kernel up per level
-    { CoarseDownKernel k{A, V.dinv[li].p, L.b.p, L.x.p, C.rptr.p, C.ridx.p, C.b.p}; parallel_for(s, C.n, k, 128); }
+    // fused V(1,1) path: two kernels down (smooth+residual, restrict), one up (prolong+smooth)
+    { CoarseResidualKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.r.p}; parallel_rows<8>(s, L.n, k); }
+    { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, L.r.p, C.b.p, 0}; parallel_rows<8>(s, C.n, k); }
     coarse_cycle(c, V, li + 1);
-    { CoarseUpKernel k{A, V.dinv[li].p, L.b.p, L.x.p, C.pidx.p, C.x.p, L.t.p}; parallel_for(s, L.n, k, 128); }
+    { CoarseUpKernel k{A, V.dinv[li].p, L.b.p, L.x.p, C.pidx.p, C.x.p, L.t.p}; parallel_rows<8>(s, L.n, k); }
     std::swap(L.x.p, L.t.p);
     return;
   }
@@ -296,7 +297,7 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
   block_apply(c, V.binv.p, r, x, w, 0);
   for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, V.binv.p, r, x, t, w); std::swap(x, t); }
   bell_spmv(c, A0, x, r, amg.r0.p, 1);
-  transfer(c, C.n, C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, amg.r0.p, C.b.p, 0);
+  { TransferRowsKernel k{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, amg.r0.p, C.b.p, 0}; parallel_rows<8>(c->stream, C.n, k); }
   coarse_cycle(c, V, 0);
   transfer(c, c->n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, C.x.p, x, 1);
   if (c->opt.nu_post == 0) { d2d(z, x, c->n * sizeof(double), c->stream); return; }
