@@ -187,6 +187,8 @@ struct AmgValues {                 // numeric part, one per linear system
   std::vector<DevBuf<double>> dinv;  // l1-Jacobi diagonals
   DevBuf<double> dense;              // inverse of the last level
   DevBuf<double> binv;               // level-0 inverse diagonal blocks [nc][ND][ND]
+  double omega = 0.0;                // level-0 damping 4/(3 lambda_max(Dinv A)), estimated
+  int age = 0;                       // refreshes since the last estimate
 };
 
 }  // namespace knp

@@ -28,7 +28,7 @@ struct MembraneSet {
 struct SolverOptions {
   int pc = 1;           // 0 block-Jacobi, 1 AMG
   int nu_pre = 1, nu_post = 1, gamma = 1;
-  double omega = 0.7;   // level-0 block-Jacobi damping
+  double omega = 0.0;   // level-0 block-Jacobi damping; <= 0: estimate 4/(3 lambda_max)
   int restart = 30, knp_min_it = 5;
 };
 
@@ -63,7 +63,7 @@ struct knp_ctx {
   bool emi_assembled = false, knp_assembled = false;
   // solver
   knp::SolverOptions opt;
-  knp::DevBuf<double> kr_r, kr_z, kr_p, kr_q, kr_V, kr_w, kr_scal, kr_partial;
+  knp::DevBuf<double> kr_r, kr_z, kr_p, kr_q, kr_V, kr_w, kr_scal, kr_partial, kr_ones;
   knp::AmgPlan amg;
   knp::AmgValues amg_emi, amg_knp[knp::MAX_IONS];
   knp::DevBuf<double> bj_emi, bj_knp[knp::MAX_IONS];   // block-Jacobi inverses

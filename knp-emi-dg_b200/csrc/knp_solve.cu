@@ -201,6 +201,8 @@ extern "C" int knp_solver_options(knp_ctx* ctx, int pc, int nu_pre, int nu_post,
   KNP_TRY
   if (pc < 0 || pc > 1) fail("pc must be 0 (block-Jacobi) or 1 (AMG)");
   if (nu_pre < 1 || nu_post < 0 || gamma < 1 || gamma > 2) fail("bad cycle parameters");
+  ctx->amg_emi.omega = 0.0;
+  for (int k = 0; k < MAX_IONS; ++k) ctx->amg_knp[k].omega = 0.0;
   if (gmres_restart < 1 || gmres_restart > 200) fail("bad GMRES restart");
   ctx->opt.pc = pc; ctx->opt.nu_pre = nu_pre; ctx->opt.nu_post = nu_post; ctx->opt.gamma = gamma;
   ctx->opt.omega = omega; ctx->opt.restart = gmres_restart; ctx->opt.knp_min_it = knp_min_it;
@@ -215,9 +217,37 @@ static CsrMat csr_of(const AmgLevelPlan& L, const AmgValues& V, size_t l) {
   return M;
 }
 
-static void amg_refresh(knp_ctx* c, AmgValues& V, const double* fine_values, const double* diag_blocks) {
+// lambda_max(Dinv A) by power iteration (the block-Jacobi smoother converges iff
+// omega * lambda_max < 2; the matrices change slowly in time, so the estimate is redone
+// only every OMEGA_PERIOD refreshes)
+constexpr int OMEGA_PERIOD = 200;
+static double estimate_lambda_max(knp_ctx* c, const BellMat& A, const double* dinv) {
+  const int64_t n = c->n;
+  double* v = c->amg.x0.p; double* w = c->amg.t0.p; double* u = c->amg.r0.p;
+  std::vector<double> h(n);
+  for (int64_t i = 0; i < n; ++i) h[i] = 1.0 + 0.5 * sin(1.7 * (double)i) + ((i * 2654435761u) % 1024) / 1024.0;
+  h2d(v, h.data(), n * sizeof(double), c->stream);
+  double lam = 1.0;
+  for (int it = 0; it < 12; ++it) {
+    bell_spmv(c, A, v, nullptr, u, 0);
+    block_apply(c, dinv, u, w, 1.0, 0);
+    const double nv = sqrt(dot_host(c, v, v)), nw = sqrt(dot_host(c, w, w));
+    if (!(nv > 0.0) || !(nw > 0.0)) break;
+    lam = nw / nv;
+    ScaleKernel k{1.0 / nw, w, v};
+    parallel_for(c->stream, n, k);
+  }
+  return lam;
+}
+
+static void amg_refresh(knp_ctx* c, AmgValues& V, const BellMat& A0, const double* fine_values, const double* diag_blocks) {
   knp_stream_t s = c->stream;
   block_inverse(c, diag_blocks, V.binv.p);
+  if (c->opt.omega > 0.0) V.omega = c->opt.omega;
+  else if (V.omega <= 0.0 || ++V.age >= OMEGA_PERIOD) {
+    V.omega = 4.0 / (3.0 * 1.05 * estimate_lambda_max(c, A0, V.binv.p));
+    V.age = 0;
+  }
   const double* fine = fine_values;
   for (size_t l = 0; l < c->amg.lev.size(); ++l) {
     AmgLevelPlan& L = c->amg.lev[l];
@@ -292,7 +322,7 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
   }
   AmgPlan& amg = c->amg;
   AmgLevelPlan& C = amg.lev[0];
-  const double w = c->opt.omega;
+  const double w = V.omega;
   double* x = amg.x0.p; double* t = amg.t0.p;
   block_apply(c, V.binv.p, r, x, w, 0);
   for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, V.binv.p, r, x, t, w); std::swap(x, t); }
@@ -313,9 +343,23 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
 // ---------------------------------------------------------------------------------
 // CG (EMI)
 // ---------------------------------------------------------------------------------
+// A_emi is singular (pure Neumann: constants, solver.py:465-466).  The preconditioned
+// residual is kept orthogonal to the constants, otherwise the round-off component of r
+// along them, amplified by the mass-shifted preconditioner, puts a floor under ||M^-1 r||.
+static void remove_mean(knp_ctx* c, double* v) {
+  const double s = dot_host(c, v, c->kr_ones.p);
+  AddConstKernel k{-s / (double)c->n, v};
+  parallel_for(c->stream, c->n, k);
+}
+
 static void ensure_krylov(knp_ctx* c) {
   const size_t n = c->n;
   if (c->kr_r.n != 2 * n) { c->kr_r.alloc(2 * n); c->kr_p.alloc(n); c->kr_q.alloc(n); c->kr_w.alloc(n); }
+  if (c->kr_ones.n != n) {
+    c->kr_ones.alloc(n);
+    std::vector<double> one(n, 1.0);
+    h2d(c->kr_ones.p, one.data(), n * sizeof(double), c->stream);
+  }
   const size_t need = (size_t)(c->opt.restart + 1) * n;
   if (c->kr_V.n < need) c->kr_V.alloc(need);
 }
@@ -331,18 +375,21 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   const int64_t n = c->n;
   BellMat A = bell_of(c, 0), B = bell_of(c, 1);
   // preconditioner refresh (the reference rebuilds BoomerAMG at every setOperators)
-  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_emi, c->A_emi.p, c->Bdiag());
+  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_emi, B, c->A_emi.p, c->Bdiag());
   else { if (c->bj_emi.n != (size_t)c->slot_stride()) c->bj_emi.alloc(c->slot_stride()); block_inverse(c, c->Bdiag(), c->bj_emi.p); }
   double* x = c->phi.p; double* r = c->kr_r.p; double* z = c->kr_r.p + n; double* p = c->kr_p.p; double* q = c->kr_q.p;
   const double* b = c->rhs_emi.p;
   // reference norm ||M^-1 b||
   precondition(c, c->amg_emi, B, c->bj_emi.p, b, z);
+  remove_mean(c, z);
   const double bnorm = sqrt(dot_host(c, z, z));
   const double tol = fmax(rtol * bnorm, atol);
   bell_spmv(c, A, x, b, r, 1);
   precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
+  remove_mean(c, z);
   double zn = sqrt(dot_host(c, z, z));
-  int it = 0;
+  int it = 0, best_it = 0;
+  double best = zn;
   if (zn > tol) {
     d2d(p, z, n * sizeof(double), s);
     double rz = dot_host(c, r, z);
@@ -350,16 +397,24 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
       bell_spmv(c, A, p, nullptr, q, 0);
       const double pq = dot_host(c, p, q);
       if (!(pq > 0.0)) {
+        // at round-off level p can fall into the (constant) null space of A: the iteration
+        // has converged as far as fp64 allows
+        if (pq == pq && zn <= 1e-8 * bnorm) { --it; break; }
         if (pq == 0.0 || pq != pq) fail("knp_solve_emi: CG breakdown (p.Ap = " + std::to_string(pq) + ")");
         fail("knp_solve_emi: operator or preconditioner is indefinite");
       }
       const double alpha = rz / pq;
       { Axpy2Kernel k{alpha, p, q, x, r}; parallel_for(s, n, k); }
       precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
+      remove_mean(c, z);
       double d2[2];
       dots_host(c, 2, r, z, d2);     // {r, z} are contiguous: r.z and z.z in one pass
       zn = sqrt(d2[1]);
       if (zn <= tol) break;
+      // attainable accuracy: a tolerance below the fp64 floor of this system is treated as
+      // reached once the preconditioned residual has stagnated at round-off level
+      if (zn < best) { best = zn; best_it = it; }
+      else if (it - best_it >= 25 && best <= 1e-8 * bnorm) break;
       const double beta = d2[0] / rz;
       rz = d2[0];
       { AxpbyKernel k{1.0, z, beta, p}; parallel_for(s, n, k); }
@@ -383,7 +438,7 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
   const int m = c->opt.restart;
   BellMat A = bell_of(c, 2 + ion);
   AmgValues& Vv = c->amg_knp[ion];
-  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, Vv, c->A_knp[ion].p, c->A_knp[ion].p);
+  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, Vv, A, c->A_knp[ion].p, c->A_knp[ion].p);
   else { if (c->bj_knp[ion].n != (size_t)c->slot_stride()) c->bj_knp[ion].alloc(c->slot_stride()); block_inverse(c, c->A_knp[ion].p, c->bj_knp[ion].p); }
   const double* bj = c->bj_knp[ion].p;
   double* x = c->c[ion].p;

@@ -240,7 +240,7 @@ class Context:
         k = int(nl.value)
         return list(map(int, rows[:k])), list(map(int, nnz[:k]))
 
-    def solver_options(self, pc=1, nu_pre=1, nu_post=1, gamma=1, omega=0.7, restart=30, knp_min_it=5):
+    def solver_options(self, pc=1, nu_pre=1, nu_post=1, gamma=1, omega=0.0, restart=30, knp_min_it=5):
         self._call("knp_solver_options", pc, nu_pre, nu_post, gamma, float(omega), restart, knp_min_it)
 
     def solve_emi(self, rtol=1e-5, atol=1e-40, maxit=1000):

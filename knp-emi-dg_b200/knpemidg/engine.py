@@ -32,6 +32,23 @@ class MembraneHandle:
         self.handle = None
 
 
+def _simplex_rule(dim, n):
+    """collapsed tensor Gauss rule on the reference simplex (barycentric points, weights
+    summing to 1), exact to degree 2n-1-(dim-1)"""
+    x, w = np.polynomial.legendre.leggauss(n)
+    x, w = 0.5 * (x + 1.0), 0.5 * w
+    if dim == 2:
+        U, V = np.meshgrid(x, x, indexing="ij")
+        WU, WV = np.meshgrid(w, w, indexing="ij")
+        l1, l2 = U.ravel(), (V * (1 - U)).ravel()
+        return np.column_stack([1 - l1 - l2, l1, l2]), (WU * WV * (1 - U)).ravel() * 2.0
+    U, V, W = np.meshgrid(x, x, x, indexing="ij")
+    WU, WV, WW = np.meshgrid(w, w, w, indexing="ij")
+    l1, l2, l3 = U.ravel(), (V * (1 - U)).ravel(), (W * (1 - U) * (1 - V)).ravel()
+    return (np.column_stack([1 - l1 - l2 - l3, l1, l2, l3]),
+            (WU * WV * WW * (1 - U) ** 2 * (1 - V)).ravel() * 6.0)
+
+
 class Engine:
     def __init__(self, mesh, cell_tags, facet_tags, *, F, R, T, C_M, C_phi, dt, z, D_sub, rho_sub=None,
                  membrane_tags=(), degree=1, splitting=True, mms=False, C_sub=None, device=0, lib=None):
@@ -57,8 +74,10 @@ class Engine:
         D = np.array([table(Dk) for Dk in D_sub])
         rho = np.zeros(len(self.tags)) if rho_sub is None else np.array(table(rho_sub))
         Cs = None if C_sub is None else np.array([table(Ck) for Ck in C_sub])
-        ctx.set_params(F=F, R=R, T=T, C_M=C_M, C_phi=C_phi, dt=dt, tau_emi=tau, tau_knp=tau, Lp=Lp, z=z,
-                       D=D, rho=rho, C_sub=Cs, splitting=splitting, mms=mms)
+        self._params = dict(F=F, R=R, T=T, C_M=C_M, C_phi=C_phi, dt=dt, tau_emi=tau, tau_knp=tau, Lp=Lp, z=z,
+                            D=D, rho=rho, C_sub=Cs, mms=mms)
+        self.splitting = bool(splitting)
+        ctx.set_params(splitting=splitting, **self._params)
         self.C_M = float(C_M)
         self.cell_tags = cell_tags
         self.mem = ctx.membrane_table()
@@ -86,6 +105,68 @@ class Engine:
 
     def membrane_midpoints(self):
         return self.mesh.facet_midpoints()[self.mem["facet"]]
+
+    def set_splitting(self, splitting):
+        """splitting scheme on/off (solver.py:958, 1042) without touching the fields"""
+        self.splitting = bool(splitting)
+        self.ctx.set_params(splitting=splitting, **self._params)
+
+    def set_source(self, k, f):
+        """f_source of solved ion k as a load vector: int_{Omega_0} f lambda_i dx over the
+        ECS cells (cell tag 0) only (solver.py:599).  f: number or callable(x)."""
+        d, nd = self.d, self.nd
+        ecs = np.flatnonzero(self.cell_tags == 0)
+        X = self.mesh.coords[self.mesh.cells[ecs]]                       # [ne, nd, d]
+        vol = self.mesh.cell_volume()[ecs]
+        load = np.zeros((self.nc, nd))
+        if callable(f):
+            bq, wq = _simplex_rule(d, 3)                                   # degree-5 collapsed Gauss rule
+            xq = np.einsum("qa,cak->cqk", bq, X)
+            fv = np.array([[float(f(x)) for x in cell] for cell in xq])
+            load[ecs] = np.einsum("q,c,cq,qi->ci", wq, vol, fv, bq)
+        else:
+            load[ecs] = (float(f) * vol / (d + 1))[:, None]
+        self.ctx.set_field(_lib.F_LOAD_KNP, k, load)
+
+    def resolve_model(self, ode):
+        """name of the compiled model that implements the user's ODE module: same table
+        sizes, same defaults and the same right-hand side on probe inputs (two different
+        example directories of the reference ship different modules called mm_hh)."""
+        import importlib
+        from .models import BUNDLED
+        s0 = np.asarray(ode.init_state_values(), dtype=float)
+        p0 = np.asarray(ode.init_parameter_values(), dtype=float)
+        f = getattr(ode, "rhs_numba", None)
+        user_rhs = None
+        for attr in ("py_func", "_pyfunc"):
+            if f is not None and hasattr(f, attr):
+                user_rhs = getattr(f, attr)
+        rng = np.random.default_rng(7)
+        probes = [(0.01 * i, s0 * (1 + 0.1 * rng.uniform(-1, 1, s0.size)), p0 + 0.1 * rng.uniform(0.5, 1, p0.size))
+                  for i in range(3)]
+        compiled = self.ctx.lib.models()
+        for name in BUNDLED:
+            if name not in compiled:
+                continue
+            mod = importlib.import_module("knpemidg.models." + name)
+            if mod is ode:
+                return name
+            if len(mod.init_state_values()) != s0.size or len(mod.init_parameter_values()) != p0.size:
+                continue
+            if not (np.array_equal(mod.init_state_values(), s0) and np.array_equal(mod.init_parameter_values(), p0)):
+                continue
+            if user_rhs is None:
+                return name
+            ok = True
+            for t, y, p in probes:
+                d1, d2, p1, p2 = np.zeros_like(y), np.zeros_like(y), p.copy(), p.copy()
+                user_rhs(t, y, d1, p1)
+                mod.rhs_numba.py_func(t, y, d2, p2)
+                ok &= np.allclose(d1, d2, rtol=1e-12, atol=0) and np.allclose(p1, p2, rtol=1e-12, atol=0)
+            if ok:
+                return name
+        raise _lib.KnpError(f"membrane model '{ode.__name__}' has no compiled counterpart in libknpemi.so "
+                            f"(available: {sorted(compiled)}); add it to knpemidg/models and rebuild")
 
     # -- membrane models -----------------------------------------------------
     def add_membrane_model(self, tag, module, ion_names, stimulus=None, stimulus_locator=None,

@@ -1,0 +1,112 @@
+"""Checks of the reference-facing Python API (knpemidg.Solver / MembraneModel / utils),
+written the way the reference's run scripts use it (examples/idealized-geometries/run_2D.py,
+tests/run_MMS_space.py), shared by the CPU (emulation) and GPU test modules."""
+from collections import namedtuple
+
+import numpy as np
+
+from common import kmesh, rel_err
+from knpemidg import Solver, plus, minus, pcws_constant_project
+from knpemidg.frontend import Constant
+from knpemidg.models import mm_hh
+from oracle import forms, mms as omms, stepper
+
+DT, C_M, F, R, T = 1e-4, 0.02, 96485, 8.314, 300
+NA_I, NA_E, K_I, K_E = 12.838513108648856, 100.71925900027354, 124.15397583491901, 3.3236967382705265
+
+SolverParams = namedtuple("solver_params", "direct_emi direct_knp resolution rtol_emi rtol_knp atol_emi atol_knp "
+                                           "threshold_emi threshold_knp")
+
+
+class Solver2D(Solver):
+    """as examples/idealized-geometries/run_2D.py:30-50"""
+
+    def __init__(self, params, ion_list, **kw):
+        Solver.__init__(self, params, ion_list, degree_emi=1, degree_knp=1, mms=None, sf=1, **kw)
+
+    def update_ode(self, ode_model):
+        K_e = plus(self.c_prev_k.split()[0], self.n_g)
+        ode_model.set_parameter("K_e", pcws_constant_project(K_e, self.Q))
+        Na_i = minus(self.ion_list[-1]["c"], self.n_g)
+        ode_model.set_parameter("Na_i", pcws_constant_project(Na_i, self.Q))
+
+
+def _ion(name, z, D, ci, ce):
+    return {"c_init_sub": {1: Constant(ci), 0: Constant(ce)}, "c_init_sub_type": "constant",
+            "bdry": Constant((0, 0)), "z": z, "name": name, "D_sub": {1: Constant(D), 0: Constant(D)},
+            "f_source": Constant(0)}
+
+
+def run_2d_neuron(lib, nsteps, rtol_emi=1e-5, rtol_knp=1e-7, outdir=None, g_syn=10.0):
+    params = namedtuple("params", "dt n_steps_ODE F psi phi_M_init C_phi C_M R temperature phi_M_init_type "
+                                  "rho_sub")(DT, 25, F, F / (R * T), Constant(-0.0743), C_M / DT, C_M, R, T,
+                                             "constant", {0: Constant(0), 1: Constant(0)})
+    ion_list = [_ion("K", 1.0, 1.96e-9, K_I, K_E), _ion("Cl", -1.0, 2.03e-9, NA_I + K_I, NA_E + K_E),
+                _ion("Na", 1.0, 1.33e-9, NA_I, NA_E)]
+    stim = namedtuple("membrane_params", "g_syn_bar stimulus stimulus_locator")(
+        g_syn, {"stim_amplitude": g_syn}, lambda x: x[0] < 20e-6)
+    sp = SolverParams(False, False, 0, rtol_emi, rtol_knp, 1e-40, 1e-40, None, None)
+    mesh, sub, surf = kmesh.neuron_2d_mesh(0)
+    S = Solver2D(params, ion_list, lib=lib)
+    S.setup_domain(mesh, sub, surf)
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    S.setup_membrane_model(stim, {1: mm_hh})
+    t = Constant(0.0)
+    S.solve_system_active(nsteps * DT, t, sp, filename=outdir, save_fields=outdir is not None,
+                          save_solver_stats=outdir is not None)
+    assert abs(float(t) - nsteps * DT) < 1e-15
+    # oracle run of the same problem
+    kw = dict(F=F, R=R, T=T, C_M=C_M, C_phi=C_M / DT, dt=DT, z=[1.0, -1.0, 1.0],
+              D_sub=[{0: 1.96e-9, 1: 1.96e-9}, {0: 2.03e-9, 1: 2.03e-9}, {0: 1.33e-9, 1: 1.33e-9}],
+              rho_sub={0: 0.0, 1: 0.0})
+    P = forms.Problem(mesh, sub.array(), surf.array(), membrane_tags=(1,), **kw)
+    cinit = [{1: K_I, 0: K_E}, {1: NA_I + K_I, 0: NA_E + K_E}, {1: NA_I, 0: NA_E}]
+    c0 = np.stack([np.where((sub.array() == 1)[:, None], ci[1], ci[0]) * np.ones((P.nc, P.nd)) for ci in cinit])
+    O = stepper.OracleSolver(P, c0, models={1: mm_hh}, stimulus={"stim_amplitude": g_syn},
+                             stimulus_locator=lambda x: x[0] < 20e-6, ion_names=["K", "Cl", "Na"])
+    O.run(nsteps)
+    return S, O
+
+
+class MMSLoads:
+    """manufactured-solution data for Solver(mms=...): load vectors of the MMS-only terms
+    (solver.py:365-374, 645-657) computed by the oracle's sympy restatement of
+    tests/mms_space.py, plus the exact fields for the error norms."""
+
+    def __init__(self, mesh, sub, surf, dt):
+        self.mm = omms.MMS("space", dt=dt)
+        self.P = forms.Problem(mesh, sub.array(), surf.array(), **self.mm.problem_kwargs())
+
+    def load_emi(self, t):
+        self.mm.t = t
+        return self.mm.emi_rhs(self.P)
+
+    def load_knp(self, k, t):
+        self.mm.t = t
+        return self.mm.knp_rhs(self.P, k)
+
+
+def run_mms(lib, r, dt=1e-10, nsteps=2):
+    """tests/run_MMS_space.py: passive system, two steps, direct solves"""
+    mesh, sub, surf = kmesh.mms_mesh(r)
+    L = MMSLoads(mesh, sub, surf, dt)
+    mm, P = L.mm, L.P
+    params = namedtuple("params", "dt F psi C_phi C_M R temperature phi_M_init_type rho_sub")(
+        dt, 1.0, 1.0, 1.0 / dt, 1.0, 1.0, 1.0, "constant", {0: Constant(0), 1: Constant(0)})
+    exact = [mm.exact_field(P, "c", k, t=0.0) for k in range(3)]
+    ion_list = []
+    for k, name in enumerate("abc"):
+        ion_list.append({"c_init_sub": exact[k].ravel(), "c_init_sub_type": "function", "z": mm.z[k], "name": name,
+                         "D_sub": {1: Constant(mm.D1[k]), 0: Constant(mm.D2[k])},
+                         "C_sub": {1: Constant(mm.C1[k]), 0: Constant(mm.C2[k])}, "f_source": Constant(0)})
+    S = Solver(params, ion_list, mms=L, lib=lib)
+    S.setup_domain(mesh, sub, surf)
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    sp = SolverParams(True, True, r, None, None, None, None, None, None)
+    t = Constant(0.0)
+    uh, c_elim = S.solve_system_passive(nsteps * dt, t, sp, None)
+    errs = [mm.l2_error(P, uh[0].nodal(), "c", 0), mm.l2_error(P, uh[1].nodal(), "c", 1),
+            mm.l2_error(P, uh[2].nodal(), "phi", mean_free=True)]
+    return np.array(errs), S, L

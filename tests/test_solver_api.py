@@ -1,0 +1,42 @@
+"""Reference-facing API on the host-emulation library (CPU suite): the run-script flow of
+run_2D.py against the oracle, the output files, and the MMS convergence study of
+tests/run_MMS_space.py through the product code path."""
+import os
+
+import numpy as np
+
+import solver_checks as sc
+from common import rel_err
+
+
+def test_run_2d_flow_matches_oracle(emu_lib, tmp_path):
+    out = str(tmp_path) + "/"
+    S, O = sc.run_2d_neuron(emu_lib, 4, rtol_emi=1e-12, rtol_knp=1e-13, outdir=out)
+    assert rel_err(S.phi_M_prev_PDE.vector().get_local(), O.phi_M) < 1e-6      # north_star trace tolerance
+    for k in range(2):
+        assert rel_err(S.c.split()[k].nodal(), O.c[k]) < 1e-9
+    assert rel_err(S.ion_list[-1]["c"].nodal(), O.c_elim) < 1e-9
+    for k in range(3):
+        assert rel_err(S.ion_list[k]["E"].vector().get_local(), O.E[k]) < 1e-7
+    # membrane model tables and stimulus mask (membrane.py:92-104)
+    ode = S.mem_models[0]["ode"]
+    P = ode.parameters
+    col = ode.ode.parameter_indices("stim_amplitude")
+    assert np.array_equal(P[:, col] > 0, ode.dof_locations[:, 0] < 20e-6)
+    assert abs(ode.time - 4 * sc.DT) < 1e-15
+    # statistics files keep the reference's format (solver.py:1146-1198)
+    txt = open(os.path.join(out, "solver", "emi_niter_0.txt")).read().splitlines()
+    assert txt[0].startswith("num cells:") and txt[1].startswith("dofs:") and len(txt) == 2 + 4
+    assert os.path.exists(os.path.join(out, "results.npz"))
+
+
+def test_reference_tolerances_give_traces_within_solver_tolerance(emu_lib):
+    S, O = sc.run_2d_neuron(emu_lib, 3)                # rtol 1e-5 / 1e-7 as run_2D.py:185-192
+    assert rel_err(S.phi_M_prev_PDE.vector().get_local(), O.phi_M) < 5e-4
+    assert rel_err(S.c.split()[0].nodal(), O.c[0]) < 1e-5
+
+
+def test_mms_space_rates_through_the_product_path(emu_lib):
+    errs = np.array([sc.run_mms(emu_lib, r)[0] for r in (3, 4, 5)])
+    rates = np.log(errs[:-1] / errs[1:]) / np.log(2.0)
+    assert np.all(rates[-1] > 1.85) and np.all(rates[-1] < 2.2), rates
