@@ -414,7 +414,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
       // attainable accuracy: a tolerance below the fp64 floor of this system is treated as
       // reached once the preconditioned residual has stagnated at round-off level
       if (zn < best) { best = zn; best_it = it; }
-      else if (it - best_it >= 25 && best <= 1e-8 * bnorm) break;
+      else if (it - best_it >= 40 && best <= 1e-10 * bnorm) break;
       const double beta = d2[0] / rz;
       rz = d2[0];
       { AxpbyKernel k{1.0, z, beta, p}; parallel_for(s, n, k); }
