@@ -88,6 +88,7 @@ class Engine:
         self.stats = {"emi_niter": [], "knp_niter": []}
         self.rtol_emi, self.atol_emi = 1e-5, 1e-40
         self.rtol_knp, self.atol_knp = 1e-7, 1e-40
+        self.max_it = 1000                                             # ksp_max_it (solver.py:429, 687)
         self.ode_rtol, self.ode_atol = 1e-8, 0.0                       # membrane.py:112
         self.phi_M_init_type = "constant"
 
@@ -232,10 +233,10 @@ class Engine:
     def pde_phase(self):
         ctx = self.ctx
         ctx.assemble_emi()
-        it, _ = ctx.solve_emi(self.rtol_emi, self.atol_emi, 1000)
+        it, _ = ctx.solve_emi(self.rtol_emi, self.atol_emi, self.max_it)
         self.stats["emi_niter"].append(it)
         ctx.assemble_knp()
-        it, _ = ctx.solve_knp(self.rtol_knp, self.atol_knp, 1000)
+        it, _ = ctx.solve_knp(self.rtol_knp, self.atol_knp, self.max_it)
         self.stats["knp_niter"].append(it)
         ctx.post_step(_lib.POST_ALL)
         self.t += self.dt

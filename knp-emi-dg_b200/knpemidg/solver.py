@@ -173,6 +173,7 @@ class Solver:
         eng = self.engine
         eng.rtol_emi, eng.atol_emi = self.rtol_emi, self.atol_emi
         eng.rtol_knp, eng.atol_knp = self.rtol_knp, self.atol_knp
+        eng.max_it = 50000 if (self.direct_emi or self.direct_knp) else 1000
         if bool(eng.splitting) != bool(splitting):
             eng.set_splitting(splitting)
         self._update_loads()
