@@ -147,6 +147,48 @@ int knp_membrane_stimulus(knp_ctx* ctx, int handle, const uint8_t* mask, int nco
 int knp_ode_step(knp_ctx* ctx, int handle, double t0, double dt, double rtol, double atol,
                  int set_v, int64_t* stats /* [2]: max steps, total rhs evals; may be NULL */);
 
+/* ---- multi-GPU: cell-partitioned mesh, one context (= one process, one GPU) per part.
+ * Replaces what the reference gets from dolfin's distributed mesh + PETSc's MPI
+ * matrices/vectors when run_*.py is started under mpirun (ghosted DG facet
+ * integrals, src/knpemidg/solver.py:16 `parameters['ghost_mode'] = 'shared_vertex'`, MPI bbox reductions :387-388;
+ * VecScatter inside MatMult and MPI_Allreduce inside VecDot/VecNorm of KSPSolve,
+ * solver.py:509, 771).
+ *
+ * The mesh passed to knp_mesh_set is then the LOCAL mesh: the nc_owned cells of this
+ * part first, followed by its ghost cells (the face neighbours owned by other parts),
+ * grouped by owning rank in the order of neigh_rank[]; only facets with at least one
+ * owned cell are listed.  Rows are assembled and solved for owned cells only; ghost
+ * values of every field/vector are refreshed by halo exchanges.
+ *   send_ptr[nneigh+1], send_cells[]: owned cells whose dofs go to neighbour i,
+ *     in the order in which that rank numbers them as ghosts;
+ *   recv_ptr[nneigh+1]: ghost cells received from neighbour i are the local cells
+ *     nc_owned + recv_ptr[i] .. nc_owned + recv_ptr[i+1].
+ * Call after knp_mesh_set and before knp_params_set. */
+int knp_dist_set(knp_ctx* ctx, int rank, int world, int64_t nc_owned, int nneigh,
+                 const int32_t* neigh_rank, const int64_t* send_ptr, const int32_t* send_cells,
+                 const int64_t* recv_ptr);
+/* transport 1 (product): NCCL send/recv + allreduce over NVLink on the context's
+ * stream.  Rank 0 obtains an id with knp_nccl_unique_id, the host program hands the
+ * 128 bytes to the other ranks (torch.distributed broadcast in the Python layer),
+ * every rank calls knp_dist_init_nccl (collective). */
+int knp_nccl_unique_id(char out[128]);
+int knp_dist_init_nccl(knp_ctx* ctx, const char uid[128]);
+/* transport 2 (host-emulation build only, for the CPU test-suite under gloo): the
+ * exchanges are delegated to host callbacks.
+ *   exchange: send[send_off[i]..send_off[i+1]) goes to ranks[i], the message from
+ *     ranks[i] lands in recv[recv_off[i]..recv_off[i+1]);
+ *   allreduce: in-place sum of n doubles over all ranks (same bits on every rank). */
+typedef int (*knp_exchange_fn)(void* user, int nneigh, const int32_t* ranks, const double* send,
+                               const int64_t* send_off, double* recv, const int64_t* recv_off);
+typedef int (*knp_allreduce_fn)(void* user, double* buf, int64_t n);
+int knp_dist_set_callbacks(knp_ctx* ctx, knp_exchange_fn exchange, knp_allreduce_fn allreduce,
+                           void* user);
+/* info[0]=rank, [1]=world, [2]=owned cells, [3]=ghost cells, [4]=neighbours,
+ * [5]=halo exchanges issued so far, [6]=allreduces issued so far */
+int knp_dist_info(knp_ctx* ctx, int64_t info[8]);
+/* refresh the ghost values of a cell field from their owners (collective) */
+int knp_field_halo(knp_ctx* ctx, int which, int idx);
+
 /* ---- timers (solver.py:77-81): seconds accumulated since the last reset in
  * out[0..5] = emi assembly, emi solve, knp assembly, knp solve, ode, post. */
 int knp_timers_get(knp_ctx* ctx, double* out, int reset);

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["knp_api.cu", "knp_solve.cu"]
-HEADERS = ["knp_common.h", "knp_dg.h", "knp_ode.h", "knp_linalg.h", "knp_amg.h", "knp_ctx.h"]
+HEADERS = ["knp_common.h", "knp_comm.h", "knp_dg.h", "knp_ode.h", "knp_linalg.h", "knp_amg.h", "knp_ctx.h"]
 
 
 def generate_models():
@@ -39,6 +39,23 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def nccl_include():
+    """nccl.h (types only: the library resolves NCCL's functions from the already loaded
+    libnccl.so.2 at run time, see csrc/knp_comm.h)"""
+    try:
+        import nvidia.nccl as pkg
+        for base in list(getattr(pkg, "__path__", [])):
+            inc = os.path.join(base, "include")
+            if os.path.exists(os.path.join(inc, "nccl.h")):
+                return inc
+    except Exception:
+        pass
+    for inc in ("/usr/include", "/usr/local/cuda/include"):
+        if os.path.exists(os.path.join(inc, "nccl.h")):
+            return inc
+    raise RuntimeError("nccl.h not found")
+
+
 def build_cuda(force=False, verbose=False):
     gen = generate_models()
     out = os.path.join(HERE, "knpemidg", "libknpemi.so")
@@ -47,8 +64,8 @@ def build_cuda(force=False, verbose=False):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
-           "-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
+           "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-I", nccl_include(),
+           "-o", out] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

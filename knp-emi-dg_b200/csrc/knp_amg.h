@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <numeric>
 #include "knp_common.h"
+#include "knp_comm.h"
 #include "knp_linalg.h"
 
 namespace knp {
@@ -36,18 +37,24 @@ struct HostTransfer {         // P (n_f x n_c) and R = P^T in CSR
   bool unit = true;           // all weights 1 (pure aggregation)
 };
 
-inline HostTransfer transfer_from_aggregates(const std::vector<int32_t>& agg, int64_t ncoarse) {
+// agg[i] = coarse unknown of fine unknown i for ALL local fine unknowns (owned first, then
+// ghosts, whose coarse unknowns are ghosts of the coarse level); the restriction has one row
+// per OWNED coarse unknown and gathers owned fine unknowns only (aggregates never cross
+// a partition boundary).
+inline HostTransfer transfer_from_aggregates(const std::vector<int32_t>& agg, int64_t ncoarse,
+                                             int64_t nf_own = -1) {
   HostTransfer T;
   T.nf = (int64_t)agg.size(); T.ncoarse = ncoarse; T.unit = true;
+  if (nf_own < 0) nf_own = T.nf;
   T.pptr.resize(T.nf + 1); T.pidx.resize(T.nf);
   for (int64_t i = 0; i <= T.nf; ++i) T.pptr[i] = (int32_t)i;
   for (int64_t i = 0; i < T.nf; ++i) T.pidx[i] = agg[i];
   T.rptr.assign(ncoarse + 1, 0);
-  for (int64_t i = 0; i < T.nf; ++i) T.rptr[agg[i] + 1]++;
+  for (int64_t i = 0; i < nf_own; ++i) T.rptr[agg[i] + 1]++;
   for (int64_t I = 0; I < ncoarse; ++I) T.rptr[I + 1] += T.rptr[I];
-  T.ridx.resize(T.nf);
+  T.ridx.resize(nf_own);
   std::vector<int32_t> fill(T.rptr.begin(), T.rptr.end() - 1);
-  for (int64_t i = 0; i < T.nf; ++i) T.ridx[fill[agg[i]]++] = (int32_t)i;
+  for (int64_t i = 0; i < nf_own; ++i) T.ridx[fill[agg[i]]++] = (int32_t)i;
   return T;
 }
 
@@ -127,7 +134,7 @@ inline int64_t aggregate(const HostCsr& A, double theta, std::vector<int32_t>& a
   for (int64_t i = 0; i < n; ++i) {
     for (int32_t e = A.ptr[i]; e < A.ptr[i + 1]; ++e) {
       const int32_t j = A.col[e];
-      if (j == i) continue;
+      if (j == i || j >= n) continue;   // j >= n: ghost unknown, owned by another rank
       if (fabs(A.val[e]) >= theta * sqrt(diag[i] * diag[j]) && A.val[e] != 0.0) scol.push_back(j);
     }
     sptr[i + 1] = (int32_t)scol.size();
@@ -163,7 +170,9 @@ inline int64_t aggregate(const HostCsr& A, double theta, std::vector<int32_t>& a
 
 // ---- device side -----------------------------------------------------------------
 struct AmgLevelPlan {          // level l >= 1 (CSR)
-  int64_t n = 0, nnz = 0;
+  int64_t n = 0, nnz = 0;      // owned rows, stored entries
+  int64_t nloc = 0;            // owned + ghost unknowns (columns, vector length)
+  HaloPlan halo;               // ghost exchange of this level's vectors (multi-GPU)
   DevBuf<int32_t> ptr, col;
   // Galerkin gather from level l-1 values
   DevBuf<int32_t> gptr, gidx; DevBuf<double> gw; bool g_unit = true;
@@ -177,7 +186,10 @@ struct AmgPlan {
   bool ready = false;
   int64_t n0 = 0;
   std::vector<AmgLevelPlan> lev;   // lev[0] = level 1 ...
-  int64_t m_dense = 0;             // rows of the last level
+  int64_t m_dense = 0;             // rows of the last level (summed over all ranks)
+  int64_t dense_off = 0;           // global index of this rank's first last-level row
+  DevBuf<int32_t> dense_map;       // last level: local unknown (owned + ghost) -> global index
+  DevBuf<double> dense_b, dense_x; // last level: global right-hand side / solution
   DevBuf<double> x0, r0, t0;       // level-0 work vectors
   DevBuf<double> colbuf;
 };

@@ -71,6 +71,7 @@ int knp_ctx_destroy(knp_ctx* ctx) {
 #ifndef KNP_EMU
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm.nccl) { nccl_api().CommDestroy(ctx->comm.nccl); ctx->comm.nccl = nullptr; }
 #endif
   knp_stream_t s = ctx->stream;
   delete ctx;
@@ -97,6 +98,10 @@ static void build_mesh(knp_ctx* c, int64_t nc, int64_t nv, const double* coords,
                        const int32_t* fcells, const int32_t* ftag, int nmt, const int32_t* mtags) {
   constexpr int ND = D + 1;
   c->d = D; c->nd = ND; c->nc = nc; c->n = nc * ND;
+  c->nc_own = nc; c->n_own = c->n; c->n_global = (double)c->n;   // single part until knp_dist_set
+  c->comm.world = 1; c->comm.rank = 0; c->comm.nbr.clear();
+  c->halo0 = HaloPlan();
+  c->halo0.n_own = c->n;
   if (nc * ND * ND * (ND + 2) >= (int64_t)2147483647) fail("mesh too large for 32-bit value positions");
   // geometry: grad lambda_i, |K|, h = max edge (CellDiameter, solver.py:102-103)
   std::vector<double> grad((size_t)nc * ND * D), vol(nc), hh(nc);
@@ -351,7 +356,7 @@ static void assemble_emi_t(knp_ctx* c) {
   pre.grad = c->grad.p; pre.region = c->region.p; pre.kappa = c->kappa.p; pre.q = c->q.p;
   parallel_for(s, c->nc, pre, 128);
   EmiArgs<D> k;
-  k.P = c->P; k.nc = c->nc;
+  k.P = c->P; k.nc = c->nc; k.nw = c->nc_own;
   k.grad = c->grad.p; k.vol = c->vol.p; k.h = c->h.p;
   k.nbr = c->nbr.p; k.finfo = c->finfo.p; k.fmem = c->fmem.p;
   k.kappa = c->kappa.p; k.q = c->q.p; k.phiM = c->phiM.p;
@@ -359,10 +364,10 @@ static void assemble_emi_t(knp_ctx* c) {
   k.load = c->has_load_emi ? c->load_emi.p : nullptr;
   k.A = c->A_emi.p; k.Adiag = c->Adiag_emi(); k.rhs = c->rhs_emi.p;
 #ifdef KNP_EMU
-  parallel_for(s, c->nc, EmiCellKernel<D>{k}, 128);
+  parallel_for(s, c->nc_own, EmiCellKernel<D>{k}, 128);
 #else
   ++launch_counter();
-  emi_assemble_kernel<D><<<(unsigned)((c->nc + ASM_CPB - 1) / ASM_CPB), ASM_CPB*(D + 1), 0, s>>>(k);
+  emi_assemble_kernel<D><<<(unsigned)((c->nc_own + ASM_CPB - 1) / ASM_CPB), ASM_CPB*(D + 1), 0, s>>>(k);
   KNP_CUDA(cudaGetLastError());
 #endif
 }
@@ -375,7 +380,7 @@ static void assemble_knp_t(knp_ctx* c) {
   parallel_for(s, c->nc, gk, 128);
   {
     KnpArgs<D> k;
-    k.P = c->P; k.nc = c->nc; k.nion = c->P.N - 1;
+    k.P = c->P; k.nc = c->nc; k.nw = c->nc_own; k.nion = c->P.N - 1;
     k.grad = c->grad.p; k.vol = c->vol.p; k.h = c->h.p; k.region = c->region.p;
     k.nbr = c->nbr.p; k.finfo = c->finfo.p; k.gphi = c->gphi.p;
     for (int i = 0; i < MAX_IONS; ++i) { k.cn[i] = nullptr; k.load[i] = nullptr; k.A[i] = nullptr; k.rhs[i] = nullptr; }
@@ -385,10 +390,10 @@ static void assemble_knp_t(knp_ctx* c) {
       k.A[ion] = c->A_knp[ion].p; k.rhs[ion] = c->rhs_knp[ion].p;
     }
 #ifdef KNP_EMU
-    parallel_for(s, c->nc, KnpCellKernel<D>{k}, 128);
+    parallel_for(s, c->nc_own, KnpCellKernel<D>{k}, 128);
 #else
     ++launch_counter();
-    knp_assemble_kernel<D><<<(unsigned)((c->nc + ASM_CPB - 1) / ASM_CPB), ASM_CPB*(D + 1), 0, s>>>(k);
+    knp_assemble_kernel<D><<<(unsigned)((c->nc_own + ASM_CPB - 1) / ASM_CPB), ASM_CPB*(D + 1), 0, s>>>(k);
     KNP_CUDA(cudaGetLastError());
 #endif
   }
@@ -446,7 +451,7 @@ int knp_matrix_export(knp_ctx* ctx, int which, int64_t* rowptr, int32_t* col, do
   int64_t k = 0;
   rowptr[0] = 0;
   std::vector<std::pair<int32_t, int>> order;  // (neighbour cell, slot)
-  for (int64_t c = 0; c < nc; ++c) {
+  for (int64_t c = 0; c < ctx->nc_own; ++c) {
     order.clear();
     order.push_back({(int32_t)c, 0});
     for (int f = 0; f < nd; ++f) {
@@ -471,8 +476,9 @@ int knp_spmv(knp_ctx* ctx, int which, const double* x, double* y) {
   BellMat M = bell_of(ctx, which);
   DevBuf<double> dx, dy;
   dx.upload(x, ctx->n, ctx->stream); dy.alloc(ctx->n);
-  if (ctx->d == 2) { BellSpmvKernel<3> k{M, dx.p, nullptr, dy.p, 0}; parallel_for(ctx->stream, ctx->n, k); }
-  else { BellSpmvKernel<4> k{M, dx.p, nullptr, dy.p, 0}; parallel_for(ctx->stream, ctx->n, k); }
+  if (ctx->comm.active()) ctx->comm.halo(ctx->stream, ctx->halo0, dx.p);
+  if (ctx->d == 2) { BellSpmvKernel<3> k{M, dx.p, nullptr, dy.p, 0}; parallel_for(ctx->stream, ctx->n_own, k); }
+  else { BellSpmvKernel<4> k{M, dx.p, nullptr, dy.p, 0}; parallel_for(ctx->stream, ctx->n_own, k); }
   d2h(y, dy.p, ctx->n * sizeof(double), ctx->stream);
   KNP_CATCH
 }
@@ -675,6 +681,131 @@ int knp_ode_step(knp_ctx* ctx, int h, double t0, double dt, double rtol, double 
   KNP_CATCH
 }
 
+// ---------------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------------
+int knp_dist_set(knp_ctx* ctx, int rank, int world, int64_t nc_owned, int nneigh, const int32_t* neigh_rank,
+                 const int64_t* send_ptr, const int32_t* send_cells, const int64_t* recv_ptr) {
+  KNP_TRY
+  knp_ctx* c = ctx;
+  if (c->nc == 0) fail("knp_dist_set: set the mesh first");
+  if (c->params_set) fail("knp_dist_set: call before knp_params_set");
+  if (world < 1 || rank < 0 || rank >= world) fail("knp_dist_set: bad rank/world");
+  if (nc_owned < 1 || nc_owned > c->nc) fail("knp_dist_set: bad owned-cell count");
+  if (nneigh < 0 || (nneigh > 0 && (!neigh_rank || !send_ptr || !recv_ptr))) fail("knp_dist_set: bad neighbour lists");
+  const int nd = c->nd;
+  const int64_t nghost = c->nc - nc_owned;
+  if ((nneigh ? recv_ptr[nneigh] : 0) != nghost) fail("knp_dist_set: recv_ptr does not cover the ghost cells");
+  for (int64_t cell = 0; cell < nc_owned; ++cell)
+    for (int f = 0; f < nd; ++f)
+      if (c->h_nbr[(size_t)f * c->nc + cell] >= c->nc) fail("knp_dist_set: neighbour out of range");
+  c->comm.rank = rank; c->comm.world = world;
+  c->comm.nbr.assign(neigh_rank, neigh_rank + nneigh);
+  for (int i = 0; i < nneigh; ++i) {
+    if (neigh_rank[i] < 0 || neigh_rank[i] >= world || neigh_rank[i] == rank) fail("knp_dist_set: bad neighbour rank");
+    if (i > 0 && neigh_rank[i] <= neigh_rank[i - 1]) fail("knp_dist_set: neighbour ranks must ascend");
+  }
+  c->nc_own = nc_owned; c->n_own = nc_owned * nd;
+  HaloPlan& H = c->halo0;
+  H = HaloPlan();
+  H.n_own = c->n_own; H.n_ghost = nghost * nd;
+  H.send_off.assign(nneigh + 1, 0); H.recv_off.assign(nneigh + 1, 0);
+  for (int i = 0; i < nneigh; ++i) {
+    if (send_ptr[i + 1] < send_ptr[i] || recv_ptr[i + 1] < recv_ptr[i]) fail("knp_dist_set: pointers must ascend");
+    for (int64_t k = send_ptr[i]; k < send_ptr[i + 1]; ++k) {
+      const int32_t cell = send_cells[k];
+      if (cell < 0 || cell >= nc_owned) fail("knp_dist_set: send cell is not an owned cell");
+      for (int a = 0; a < nd; ++a) H.h_send_idx.push_back(cell * nd + a);
+    }
+    H.send_off[i + 1] = send_ptr[i + 1] * nd;
+    H.recv_off[i + 1] = recv_ptr[i + 1] * nd;
+    for (int64_t g = recv_ptr[i]; g < recv_ptr[i + 1]; ++g)
+      for (int a = 0; a < nd; ++a) { H.ghost_rank.push_back(neigh_rank[i]); H.ghost_id.push_back(-1); }
+  }
+  H.upload(c->stream);
+  // rows exist for owned cells only
+  int64_t nblocks = 0;
+  for (int64_t cell = 0; cell < nc_owned; ++cell) {
+    ++nblocks;
+    for (int f = 0; f < nd; ++f) nblocks += c->h_nbr[(size_t)f * c->nc + cell] >= 0;
+  }
+  c->nnz_export = nblocks * nd * nd;
+  {
+    std::vector<int32_t> mc;
+    for (int32_t v : c->h_mem_ci) if (v < nc_owned) mc.push_back(v);
+    for (int32_t v : c->h_mem_ce) if (v < nc_owned) mc.push_back(v);
+    std::sort(mc.begin(), mc.end());
+    mc.erase(std::unique(mc.begin(), mc.end()), mc.end());
+    c->nmc = (int64_t)mc.size();
+    c->memcell.upload(mc, c->stream);
+  }
+  c->amg.ready = false;
+  KNP_CATCH
+}
+
+int knp_nccl_unique_id(char out[128]) {
+  KNP_TRY
+#ifdef KNP_EMU
+  (void)out;
+  fail("knp_nccl_unique_id: the host-emulation build has no NCCL transport");
+#else
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  NcclApi& N = nccl_api();
+  N.load();
+  ncclUniqueId id;
+  N.check(N.GetUniqueId(&id), "ncclGetUniqueId");
+  memcpy(out, &id, 128);
+#endif
+  KNP_CATCH
+}
+
+int knp_dist_init_nccl(knp_ctx* ctx, const char uid[128]) {
+  KNP_TRY
+#ifdef KNP_EMU
+  (void)ctx; (void)uid;
+  fail("knp_dist_init_nccl: the host-emulation build has no NCCL transport");
+#else
+  if (ctx->comm.world < 2) fail("knp_dist_init_nccl: call knp_dist_set first (world >= 2)");
+  NcclApi& N = nccl_api();
+  N.load();
+  KNP_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->comm.nccl) { N.CommDestroy(ctx->comm.nccl); ctx->comm.nccl = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, uid, 128);
+  N.check(N.CommInitRank(&ctx->comm.nccl, ctx->comm.world, id, ctx->comm.rank), "ncclCommInitRank");
+#endif
+  KNP_CATCH
+}
+
+int knp_dist_set_callbacks(knp_ctx* ctx, knp_exchange_fn exchange, knp_allreduce_fn allreduce, void* user) {
+  KNP_TRY
+#ifndef KNP_EMU
+  (void)ctx; (void)exchange; (void)allreduce; (void)user;
+  fail("knp_dist_set_callbacks: host callbacks are a test transport of the emulation build; "
+       "the CUDA build communicates with NCCL (knp_dist_init_nccl)");
+#else
+  ctx->comm.xfn = exchange; ctx->comm.rfn = allreduce; ctx->comm.user = user;
+#endif
+  KNP_CATCH
+}
+
+int knp_dist_info(knp_ctx* ctx, int64_t info[8]) {
+  KNP_TRY
+  info[0] = ctx->comm.rank; info[1] = ctx->comm.world; info[2] = ctx->nc_own; info[3] = ctx->nc - ctx->nc_own;
+  info[4] = (int64_t)ctx->comm.nbr.size(); info[5] = ctx->comm.n_halo; info[6] = ctx->comm.n_allreduce; info[7] = 0;
+  KNP_CATCH
+}
+
+int knp_field_halo(knp_ctx* ctx, int which, int idx) {
+  KNP_TRY
+  int64_t cnt = 0;
+  double* p = field_ptr(ctx, which, idx, cnt, false);
+  if (cnt != ctx->n) fail("knp_field_halo: not a cell field");
+  ctx->comm.halo(ctx->stream, ctx->halo0, p);
+  stream_sync(ctx->stream);
+  KNP_CATCH
+}
+
 int knp_timers_get(knp_ctx* ctx, double* out, int reset) {
   KNP_TRY
   for (int i = 0; i < T_COUNT; ++i) { out[i] = ctx->timers[i]; if (reset) ctx->timers[i] = 0.0; }
@@ -717,7 +848,7 @@ int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* byt
   KNP_TRY
   if (!ctx->params_set) fail("knp_bench_kernel: context not set up");
   if (reps < 1) reps = 1;
-  const double nc = (double)ctx->nc, n = (double)ctx->n, nd = ctx->nd, d = ctx->d, bs = (double)ctx->bs();
+  const double nc = (double)ctx->nc_own, n = (double)ctx->n_own, nd = ctx->nd, d = ctx->d, bs = (double)ctx->bs();
   const double N = ctx->P.N;
   const double geom = 8.0 * nc * nd * d + 16.0 * nc + 4.0 * nc + 8.0 * nd * nc;  // grad, vol+h, region, nbr+finfo
   DevBuf<double> x, y;
@@ -729,16 +860,16 @@ int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* byt
     switch (kernel) {
       case 0: {
         BellMat M = bell_of(ctx, 0);
-        if (ctx->d == 2) { BellSpmvKernel<3> k{M, x.p, nullptr, y.p, 0}; parallel_for(ctx->stream, ctx->n, k); }
-        else { BellSpmvKernel<4> k{M, x.p, nullptr, y.p, 0}; parallel_for(ctx->stream, ctx->n, k); }
+        if (ctx->d == 2) { BellSpmvKernel<3> k{M, x.p, nullptr, y.p, 0}; parallel_for(ctx->stream, ctx->n_own, k); }
+        else { BellSpmvKernel<4> k{M, x.p, nullptr, y.p, 0}; parallel_for(ctx->stream, ctx->n_own, k); }
         break;
       }
       case 1: if (ctx->d == 2) assemble_emi_t<2>(ctx); else assemble_emi_t<3>(ctx); break;
       case 2: if (ctx->d == 2) assemble_knp_t<2>(ctx); else assemble_knp_t<3>(ctx); break;
       case 3: {
         BellMat M = bell_of(ctx, 1);
-        if (ctx->d == 2) { BellJacobiKernel<3> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->n, k, 192); }
-        else { BellJacobiKernel<4> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->n, k, 256); }
+        if (ctx->d == 2) { BellJacobiKernel<3> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->n_own, k, 192); }
+        else { BellJacobiKernel<4> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->n_own, k, 256); }
         break;
       }
       default: fail("unknown kernel id");

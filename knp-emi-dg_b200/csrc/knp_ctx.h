@@ -3,6 +3,7 @@
 #include <chrono>
 #include <memory>
 #include "knp_common.h"
+#include "knp_comm.h"
 #include "knp_dg.h"
 #include "knp_linalg.h"
 #include "knp_amg.h"
@@ -42,6 +43,12 @@ struct knp_ctx {
   // mesh
   int d = 0, nd = 0;
   int64_t nc = 0, n = 0, nm = 0, nnz_export = 0, nsip = 0;
+  // multi-GPU: nc/n count the LOCAL cells/dofs (owned + ghost, the stride and size of every
+  // per-cell array and vector); rows are assembled, solved and reduced over the owned ones
+  int64_t nc_own = 0, n_own = 0;
+  double n_global = 0.0;        // owned dofs summed over all ranks
+  knp::Comm comm;
+  knp::HaloPlan halo0;          // level-0 (DG dof) halo
   std::vector<int32_t> h_nbr, h_finfo, h_fmem;                 // [nd][nc]
   std::vector<int32_t> h_mem_facet, h_mem_ci, h_mem_ce, h_mem_tag, h_mem_fi;
   knp::DevBuf<double> grad, vol, h;

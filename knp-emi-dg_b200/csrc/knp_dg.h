@@ -181,7 +181,8 @@ template <int D>
 struct EmiArgs {
   static constexpr int ND = D + 1;
   Params P;
-  int64_t nc;
+  int64_t nc;                    // local cells (owned + ghost): stride of every per-cell array
+  int64_t nw;                    // cells whose rows are assembled (the owned ones, numbered first)
   const double* grad; const double* vol; const double* h;
   const int32_t* nbr; const int32_t* finfo; const int32_t* fmem;
   const double* kappa; const double* q;
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) emi_assemble_kernel(const 
   const int64_t cell0 = (int64_t)blockIdx.x * ASM_CPB;
   const int64_t cell = cell0 + cl;
   const int64_t nc = a.nc;
-  if (cell < nc) {
+  if (cell < a.nw) {
     double g[ND][D];
     #pragma unroll
     for (int i = 0; i < ND; ++i)
@@ -458,7 +459,7 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) emi_assemble_kernel(const 
     }
   }
   __syncthreads();
-  const int64_t ncell_blk = (nc - cell0 < ASM_CPB) ? (nc - cell0) : ASM_CPB;
+  const int64_t ncell_blk = (a.nw - cell0 < ASM_CPB) ? (a.nw - cell0) : ASM_CPB;
   const int nval = (int)ncell_blk * BS;
   // off-diagonal slots
   #pragma unroll
@@ -505,7 +506,8 @@ template <int D>
 struct KnpArgs {
   static constexpr int ND = D + 1;
   Params P;
-  int64_t nc;
+  int64_t nc;                    // local cells (stride)
+  int64_t nw;                    // owned cells (rows assembled)
   int nion;                      // number of solved ions (N-1)
   const double* grad; const double* vol; const double* h;
   const int32_t* region; const int32_t* nbr; const int32_t* finfo;
@@ -764,7 +766,7 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) knp_assemble_kernel(const 
   const int64_t cell0 = (int64_t)blockIdx.x * ASM_CPB;
   const int64_t cell = cell0 + cl;
   const int64_t nc = a.nc;
-  const bool active = cell < nc;
+  const bool active = cell < a.nw;
   double g[ND][D], gp[D];
   double K = 0.0, hK = 0.0;
   int reg = 0;
@@ -786,7 +788,7 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) knp_assemble_kernel(const 
       default: knp_facet_geom<D, D>(a, cell, g, K, hK, gp, G); break;
     }
   }
-  const int64_t ncell_blk = (nc - cell0 < ASM_CPB) ? (nc - cell0) : ASM_CPB;
+  const int64_t ncell_blk = (a.nw - cell0 < ASM_CPB) ? (a.nw - cell0) : ASM_CPB;
   const int nval = (int)ncell_blk * BS;
   const int nrow = (int)ncell_blk * ND;
   for (int ion = 0; ion < a.nion; ++ion) {

@@ -260,11 +260,25 @@ struct CoarseUpKernel {
   }
 };
 
-struct CsrToDenseKernel {  // dense[m*m] (zeroed before) <- CSR
-  CsrMat A; double* dense;
+// dense[m*m] (zeroed before) <- the owned rows of the last level's CSR; `map` (nullptr =
+// identity) sends a local unknown to its index in the global last-level numbering, `off` is
+// the global index of local row 0.
+struct CsrToDenseKernel {
+  CsrMat A; double* dense; int64_t m; int64_t off; const int32_t* map;
   KNP_HD void operator()(int64_t row) const {
-    for (int32_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) dense[row * A.n + A.col[k]] = A.val[k];
+    for (int32_t k = A.ptr[row]; k < A.ptr[row + 1]; ++k) {
+      const int64_t col = map ? map[A.col[k]] : A.col[k];
+      dense[(off + row) * m + col] = A.val[k];
+    }
   }
+};
+struct ScatterOffsetKernel {  // out[off + i] = x[i]
+  const double* x; double* out; int64_t off;
+  KNP_HD void operator()(int64_t i) const { out[off + i] = x[i]; }
+};
+struct GatherMapKernel {      // out[i] = x[map[i]]
+  const double* x; const int32_t* map; double* out;
+  KNP_HD void operator()(int64_t i) const { out[i] = x[map[i]]; }
 };
 
 struct DenseMatvecKernel {  // y = M x with M stored TRANSPOSED (MT[j*m + i] = M[i][j])
@@ -295,7 +309,7 @@ struct AddConstKernel {  // x += a
 };
 // w -= sum_i h_i V_i  (Gram-Schmidt update), V = k vectors of length n, contiguous
 struct GsUpdateKernel {
-  int64_t n; int k; const double* V; const double* h /*device, k entries*/; double* w;
+  int64_t n /*stride of V*/; int k; const double* V; const double* h /*device, k entries*/; double* w;
   KNP_HD void operator()(int64_t e) const {
     double acc = w[e];
     for (int i = 0; i < k; ++i) acc -= h[i] * V[(int64_t)i * n + e];
@@ -322,7 +336,8 @@ constexpr int RED_THREADS = 256;
 
 #ifndef KNP_EMU
 template <int K>
-__global__ void __launch_bounds__(RED_THREADS) multi_dot_partial(int64_t n, const double* __restrict__ V,
+__global__ void __launch_bounds__(RED_THREADS) multi_dot_partial(int64_t n, int64_t stride,
+                                                                 const double* __restrict__ V,
                                                                  const double* __restrict__ w,
                                                                  double* __restrict__ partial) {
   double acc[K];
@@ -332,7 +347,7 @@ __global__ void __launch_bounds__(RED_THREADS) multi_dot_partial(int64_t n, cons
        e += (int64_t)gridDim.x * blockDim.x) {
     const double we = w[e];
 #pragma unroll
-    for (int i = 0; i < K; ++i) acc[i] += V[(int64_t)i * n + e] * we;
+    for (int i = 0; i < K; ++i) acc[i] += V[(int64_t)i * stride + e] * we;
   }
   __shared__ double sm[K][RED_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -372,23 +387,23 @@ static __global__ void __launch_bounds__(RED_THREADS) multi_dot_final(int k, int
 }
 #endif
 
-// device-side dots; `out` (device, >= k doubles) receives the results, `partial` is a
-// scratch buffer of DOT_MAX*RED_BLOCKS doubles.
-inline void multi_dot_device(knp_stream_t s, int64_t n, int k, const double* V, const double* w,
+// device-side dots over the first n entries of k vectors `stride` apart; `out` (device,
+// >= k doubles) receives the results, `partial` is a scratch buffer of DOT_MAX*RED_BLOCKS doubles.
+inline void multi_dot_device(knp_stream_t s, int64_t n, int64_t stride, int k, const double* V, const double* w,
                              double* partial, double* out) {
   for (int base = 0; base < k; base += DOT_MAX) {
     const int kk = (k - base < DOT_MAX) ? k - base : DOT_MAX;
-    const double* Vb = V + (int64_t)base * n;
+    const double* Vb = V + (int64_t)base * stride;
 #ifdef KNP_EMU
     (void)s; (void)partial;
     for (int i = 0; i < kk; ++i) {
       double acc = 0.0;
-      for (int64_t e = 0; e < n; ++e) acc += Vb[(int64_t)i * n + e] * w[e];
+      for (int64_t e = 0; e < n; ++e) acc += Vb[(int64_t)i * stride + e] * w[e];
       out[base + i] = acc;
     }
 #else
     switch (kk) {
-#define KNP_CASE(K) case K: multi_dot_partial<K><<<RED_BLOCKS, RED_THREADS, 0, s>>>(n, Vb, w, partial); break;
+#define KNP_CASE(K) case K: multi_dot_partial<K><<<RED_BLOCKS, RED_THREADS, 0, s>>>(n, stride, Vb, w, partial); break;
       KNP_CASE(1) KNP_CASE(2) KNP_CASE(3) KNP_CASE(4) KNP_CASE(5) KNP_CASE(6) KNP_CASE(7) KNP_CASE(8)
 #undef KNP_CASE
     }

@@ -28,32 +28,49 @@ static double now_s() {
 }
 
 // ---- small helpers ---------------------------------------------------------------------
+// Multi-GPU: every kernel below runs over the OWNED rows (the first n_own entries of a
+// vector); the operators that read a vector through the matrix first refresh its ghost
+// entries from their owners (knp_comm.h).
+static void halo0(knp_ctx* c, const double* x) {
+  if (c->comm.active()) c->comm.halo(c->stream, c->halo0, const_cast<double*>(x));
+}
 template <int ND>
 static void bell_spmv(knp_ctx* c, const BellMat& A, const double* x, const double* b, double* y, int mode) {
   BellSpmvKernel<ND> k{A, x, b, y, mode};
-  parallel_for(c->stream, c->n, k, 256);
+  parallel_for(c->stream, c->n_own, k, 256);
 }
 static void bell_spmv(knp_ctx* c, const BellMat& A, const double* x, const double* b, double* y, int mode) {
+  halo0(c, x);
   if (c->nd == 3) bell_spmv<3>(c, A, x, b, y, mode); else bell_spmv<4>(c, A, x, b, y, mode);
 }
 static void block_apply(knp_ctx* c, const double* dinv, const double* r, double* out, double w, int mode) {
-  if (c->nd == 3) { BlockDiagApplyKernel<3> k{dinv, r, out, w, mode}; parallel_for(c->stream, c->n, k); }
-  else { BlockDiagApplyKernel<4> k{dinv, r, out, w, mode}; parallel_for(c->stream, c->n, k); }
+  if (c->nd == 3) { BlockDiagApplyKernel<3> k{dinv, r, out, w, mode}; parallel_for(c->stream, c->n_own, k); }
+  else { BlockDiagApplyKernel<4> k{dinv, r, out, w, mode}; parallel_for(c->stream, c->n_own, k); }
 }
 static void bell_jacobi(knp_ctx* c, const BellMat& A, const double* dinv, const double* b,
                         const double* xin, double* xout, double w) {
-  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n, k, 192); }
-  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n, k, 256); }
+  halo0(c, xin);
+  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n_own, k, 192); }
+  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n_own, k, 256); }
 }
 static void block_inverse(knp_ctx* c, const double* blocks, double* inv) {
-  if (c->nd == 3) { BlockInverseKernel<3> k{blocks, inv}; parallel_for(c->stream, c->nc, k, 128); }
-  else { BlockInverseKernel<4> k{blocks, inv}; parallel_for(c->stream, c->nc, k, 128); }
+  if (c->nd == 3) { BlockInverseKernel<3> k{blocks, inv}; parallel_for(c->stream, c->nc_own, k, 128); }
+  else { BlockInverseKernel<4> k{blocks, inv}; parallel_for(c->stream, c->nc_own, k, 128); }
 }
 
-// host-visible dot products (one sync each)
+// host-visible dot products over all ranks (one sync each)
 static void dots_host(knp_ctx* c, int k, const double* V, const double* w, double* out_host) {
-  multi_dot_device(c->stream, c->n, k, V, w, c->kr_partial.p, c->kr_scal.p);
+  multi_dot_device(c->stream, c->n_own, c->n, k, V, w, c->kr_partial.p, c->kr_scal.p);
+  c->comm.allreduce(c->stream, c->kr_scal.p, k);
   d2h(out_host, c->kr_scal.p, k * sizeof(double), c->stream);
+}
+// sum over ranks of a few host numbers (setup-time decisions must agree on every rank)
+static void global_sum(knp_ctx* c, double* v, int k) {
+  if (!c->comm.active()) return;
+  double* dev = c->kr_scal.p + 768;
+  h2d(dev, v, k * sizeof(double), c->stream);
+  c->comm.allreduce(c->stream, dev, k);
+  d2h(v, dev, k * sizeof(double), c->stream);
 }
 static double dot_host(knp_ctx* c, const double* x, const double* y) {
   double v;
@@ -70,10 +87,10 @@ static HostCsr level0_csr(knp_ctx* c) {
   const int nd = c->nd;
   const int64_t nc = c->nc, bs = c->bs(), ss = c->slot_stride();
   HostCsr A;
-  A.n = c->n;
+  A.n = c->n_own;
   A.ptr.assign(A.n + 1, 0);
   A.col.reserve((size_t)c->nnz_export); A.pos.reserve((size_t)c->nnz_export);
-  for (int64_t cell = 0; cell < nc; ++cell)
+  for (int64_t cell = 0; cell < c->nc_own; ++cell)
     for (int i = 0; i < nd; ++i) {
       const int64_t dbase = cell * bs + i * nd;
       for (int j = 0; j < nd; ++j) { A.col.push_back((int32_t)(cell * nd + j)); A.pos.push_back((int32_t)(dbase + j)); }
@@ -89,21 +106,23 @@ static HostCsr level0_csr(knp_ctx* c) {
 }
 
 // DG dof -> region-wise continuous vertex: union-find over matching dofs of tag-0 facets
+// (owned cells only: the gluing stops at partition boundaries, like at membranes, so that
+// every coarse unknown lives on one rank)
 static int64_t vertex_injection(knp_ctx* c, std::vector<int32_t>& agg) {
   const int nd = c->nd;
-  const int64_t nc = c->nc, n = c->n;
+  const int64_t nc = c->nc, n = c->n_own;
   std::vector<int32_t> parent(n);
   std::iota(parent.begin(), parent.end(), 0);
   auto find = [&](int32_t x) {
     while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
     return x;
   };
-  for (int64_t cell = 0; cell < nc; ++cell)
+  for (int64_t cell = 0; cell < c->nc_own; ++cell)
     for (int f = 0; f < nd; ++f) {
       const int w = c->h_finfo[(size_t)f * nc + cell];
       if (fi_kind(w) != FK_SIP) continue;
       const int32_t c2 = c->h_nbr[(size_t)f * nc + cell];
-      if (c2 < cell) continue;
+      if (c2 < cell || c2 >= c->nc_own) continue;
       for (int a = 0; a < nd; ++a) {
         if (a == f) continue;
         const int32_t x = find((int32_t)(cell * nd + a)), y = find(c2 * nd + fi_perm(w, a));
@@ -120,9 +139,60 @@ static int64_t vertex_injection(knp_ctx* c, std::vector<int32_t>& agg) {
   return na;
 }
 
+// Ghost side of a coarsening step.  `agg_own` maps the owned fine unknowns to owned coarse
+// unknowns 0..na_own-1.  Every rank sends the coarse index of its owned fine unknowns through
+// the fine level's halo; the distinct (owner, index) pairs received become the ghost unknowns
+// of the coarse level (numbered after the owned ones, grouped by owner, ascending index), and
+// the image of each fine send list is the coarse send list - the owner and the receiver sort
+// by the same key, so the two sides agree without a handshake.  Returns agg for ALL local
+// fine unknowns and fills the coarse level's halo plan Hc.
+static std::vector<int32_t> extend_aggregates(knp_ctx* c, HaloPlan& Hf, const std::vector<int32_t>& agg_own,
+                                              int64_t na_own, HaloPlan& Hc) {
+  const int64_t nf_own = Hf.n_own, nf_ghost = Hf.n_ghost;
+  const int nn = (int)c->comm.nbr.size();
+  std::vector<int32_t> agg((size_t)(nf_own + nf_ghost));
+  std::copy(agg_own.begin(), agg_own.begin() + nf_own, agg.begin());
+  Hc.n_own = na_own; Hc.n_ghost = 0;
+  Hc.send_off.assign(nn + 1, 0); Hc.recv_off.assign(nn + 1, 0);
+  Hc.h_send_idx.clear(); Hc.ghost_rank.clear(); Hc.ghost_id.clear();
+  if (!c->comm.active()) return agg;
+  std::vector<double> ids((size_t)(nf_own + nf_ghost), -1.0);
+  for (int64_t i = 0; i < nf_own; ++i) ids[i] = (double)agg_own[i];
+  DevBuf<double> tmp;
+  tmp.upload(ids, c->stream);
+  c->comm.halo(c->stream, Hf, tmp.p);
+  ids = tmp.download(c->stream);
+  int64_t ng = 0;
+  std::vector<int32_t> uniq;
+  for (int i = 0; i < nn; ++i) {
+    uniq.clear();
+    for (int64_t j = Hf.recv_off[i]; j < Hf.recv_off[i + 1]; ++j) uniq.push_back((int32_t)ids[nf_own + j]);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    if (!uniq.empty() && uniq.front() < 0) fail("extend_aggregates: a ghost unknown was not sent by its owner");
+    for (int64_t j = Hf.recv_off[i]; j < Hf.recv_off[i + 1]; ++j) {
+      const int32_t id = (int32_t)ids[nf_own + j];
+      agg[nf_own + j] = (int32_t)(na_own + ng + (std::lower_bound(uniq.begin(), uniq.end(), id) - uniq.begin()));
+    }
+    for (int32_t id : uniq) { Hc.ghost_rank.push_back(c->comm.nbr[i]); Hc.ghost_id.push_back(id); }
+    ng += (int64_t)uniq.size();
+    Hc.recv_off[i + 1] = ng;
+    uniq.clear();
+    for (int64_t k = Hf.send_off[i]; k < Hf.send_off[i + 1]; ++k) uniq.push_back(agg_own[Hf.h_send_idx[k]]);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    Hc.h_send_idx.insert(Hc.h_send_idx.end(), uniq.begin(), uniq.end());
+    Hc.send_off[i + 1] = (int64_t)Hc.h_send_idx.size();
+  }
+  Hc.n_ghost = ng;
+  Hc.upload(c->stream);
+  return agg;
+}
+
 static void upload_level(knp_ctx* c, AmgLevelPlan& L, const GalerkinPlan& G, const HostTransfer& T) {
   knp_stream_t s = c->stream;
   L.n = G.coarse.n; L.nnz = (int64_t)G.coarse.col.size();
+  L.nloc = L.n + L.halo.n_ghost;
   L.ptr.upload(G.coarse.ptr, s); L.col.upload(G.coarse.col, s);
   L.gptr.upload(G.gptr, s); L.gidx.upload(G.gidx, s);
   L.g_unit = G.gw.empty();
@@ -131,13 +201,13 @@ static void upload_level(knp_ctx* c, AmgLevelPlan& L, const GalerkinPlan& G, con
   L.rptr.upload(T.rptr, s); L.ridx.upload(T.ridx, s);
   L.t_unit = T.unit;
   if (!T.unit) { L.pw.upload(T.pw, s); L.rw.upload(T.rw, s); }
-  L.b.alloc(L.n); L.x.alloc(L.n); L.r.alloc(L.n); L.t.alloc(L.n);
+  L.b.alloc(L.nloc); L.x.alloc(L.nloc); L.r.alloc(L.nloc); L.t.alloc(L.nloc);
 }
 
 static void alloc_values(knp_ctx* c, AmgValues& V) {
   const size_t nl = c->amg.lev.size();
   V.val.resize(nl); V.dinv.resize(nl);
-  for (size_t l = 0; l < nl; ++l) { V.val[l].alloc(c->amg.lev[l].nnz); V.dinv[l].alloc(c->amg.lev[l].n); }
+  for (size_t l = 0; l < nl; ++l) { V.val[l].alloc(c->amg.lev[l].nnz); V.dinv[l].alloc(c->amg.lev[l].nloc); }
   V.dense.alloc((size_t)c->amg.m_dense * c->amg.m_dense);
   V.binv.alloc((size_t)c->slot_stride());
 }
@@ -154,29 +224,54 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
   // fine values of B (A's off-diagonal slots + Bdiag) for the setup-time strength graph
   std::vector<double> fine = ctx->A_emi.download(ctx->stream);
   HostCsr A0 = level0_csr(ctx);
-  std::vector<int32_t> agg;
-  int64_t ncoarse = vertex_injection(ctx, agg);
-  HostTransfer T = transfer_from_aggregates(agg, ncoarse);
+  std::vector<int32_t> agg_own;
+  int64_t ncoarse = vertex_injection(ctx, agg_own);
+  amg.lev.emplace_back();
+  std::vector<int32_t> agg = extend_aggregates(ctx, ctx->halo0, agg_own, ncoarse, amg.lev.back().halo);
+  HostTransfer T = transfer_from_aggregates(agg, ncoarse, ctx->n_own);
   GalerkinPlan G = galerkin_plan(A0, T);
   galerkin_numeric_host(G, fine);
-  amg.lev.emplace_back();
   upload_level(ctx, amg.lev.back(), G, T);
   { std::vector<int32_t>().swap(A0.col); std::vector<int32_t>().swap(A0.pos); }
-  while ((int)amg.lev.size() + 1 < max_levels && G.coarse.n > coarse_size) {
+  double gn = (double)G.coarse.n;          // rows of the current coarsest level over all ranks
+  global_sum(ctx, &gn, 1);
+  while ((int)amg.lev.size() + 1 < max_levels && gn > coarse_size) {
     std::vector<int32_t> ag2;
     const int64_t na = aggregate(G.coarse, theta, ag2);
-    if (na >= G.coarse.n * 0.9 || na < 1) break;  // coarsening stalled
-    HostTransfer T2 = transfer_from_aggregates(ag2, na);
+    double gna = (double)na;
+    global_sum(ctx, &gna, 1);
+    if (gna >= gn * 0.9 || gna < 1) break;  // coarsening stalled
+    amg.lev.emplace_back();
+    AmgLevelPlan& fineL = amg.lev[amg.lev.size() - 2];
+    std::vector<int32_t> ag2_all = extend_aggregates(ctx, fineL.halo, ag2, na, amg.lev.back().halo);
+    HostTransfer T2 = transfer_from_aggregates(ag2_all, na, G.coarse.n);
     std::vector<double> vals = G.coarse.val;
     GalerkinPlan G2 = galerkin_plan(G.coarse, T2);
     galerkin_numeric_host(G2, vals);
-    amg.lev.emplace_back();
     upload_level(ctx, amg.lev.back(), G2, T2);
     G = std::move(G2);
+    gn = gna;
   }
-  amg.m_dense = amg.lev.back().n;
+  // last level: dense inverse of the GLOBAL matrix, replicated on every rank
+  {
+    AmgLevelPlan& L = amg.lev.back();
+    const int world = ctx->comm.world, rank = ctx->comm.rank;
+    if (world > 256) fail("knp_amg_setup: at most 256 ranks");
+    std::vector<double> cnt(world, 0.0);
+    cnt[rank] = (double)L.n;
+    global_sum(ctx, cnt.data(), world);
+    std::vector<int64_t> off(world + 1, 0);
+    for (int r = 0; r < world; ++r) off[r + 1] = off[r] + (int64_t)cnt[r];
+    amg.m_dense = off[world];
+    amg.dense_off = off[rank];
+    std::vector<int32_t> map((size_t)L.nloc);
+    for (int64_t i = 0; i < L.n; ++i) map[i] = (int32_t)(off[rank] + i);
+    for (int64_t g = 0; g < L.halo.n_ghost; ++g) map[L.n + g] = (int32_t)(off[L.halo.ghost_rank[g]] + L.halo.ghost_id[g]);
+    amg.dense_map.upload(map, ctx->stream);
+  }
   if (amg.m_dense > 4096) fail("knp_amg_setup: coarsest level too large for the dense solve (" +
                                 std::to_string(amg.m_dense) + " rows); raise max_levels");
+  amg.dense_b.alloc(amg.m_dense); amg.dense_x.alloc(amg.m_dense);
   amg.x0.alloc(ctx->n); amg.r0.alloc(ctx->n); amg.t0.alloc(ctx->n);
   amg.colbuf.alloc(amg.m_dense);
   alloc_values(ctx, ctx->amg_emi);
@@ -189,7 +284,8 @@ extern "C" int knp_amg_info(knp_ctx* ctx, int64_t* nlevels, int64_t* rows, int64
   KNP_TRY
   if (!ctx->amg.ready) fail("AMG not set up");
   *nlevels = (int64_t)ctx->amg.lev.size() + 1;
-  if (cap > 0) { rows[0] = ctx->n; nnz[0] = ctx->nnz_export; }
+  // owned rows / stored entries of this rank per level
+  if (cap > 0) { rows[0] = ctx->n_own; nnz[0] = ctx->nnz_export; }
   for (size_t l = 0; l < ctx->amg.lev.size() && (int)l + 1 < cap; ++l) {
     rows[l + 1] = ctx->amg.lev[l].n; nnz[l + 1] = ctx->amg.lev[l].nnz;
   }
@@ -222,7 +318,7 @@ static CsrMat csr_of(const AmgLevelPlan& L, const AmgValues& V, size_t l) {
 // only every OMEGA_PERIOD refreshes)
 constexpr int OMEGA_PERIOD = 200;
 static double estimate_lambda_max(knp_ctx* c, const BellMat& A, const double* dinv) {
-  const int64_t n = c->n;
+  const int64_t n = c->n_own;
   double* v = c->amg.x0.p; double* w = c->amg.t0.p; double* u = c->amg.r0.p;
   std::vector<double> h(n);
   for (int64_t i = 0; i < n; ++i) h[i] = 1.0 + 0.5 * sin(1.7 * (double)i) + ((i * 2654435761u) % 1024) / 1024.0;
@@ -255,13 +351,16 @@ static void amg_refresh(knp_ctx* c, AmgValues& V, const BellMat& A0, const doubl
     parallel_for(s, L.nnz, g);
     CsrL1DiagKernel dk{csr_of(L, V, l), V.dinv[l].p};
     parallel_for(s, L.n, dk);
+    c->comm.halo(s, L.halo, V.dinv[l].p);   // the fused sweeps read dinv of ghost columns
     fine = V.val[l].p;
   }
   const size_t last = c->amg.lev.size() - 1;
   const int64_t m = c->amg.m_dense;
   dev_zero(V.dense.p, (size_t)m * m * sizeof(double), s);
-  CsrToDenseKernel tk{csr_of(c->amg.lev[last], V, last), V.dense.p};
-  parallel_for(s, m, tk);
+  CsrToDenseKernel tk{csr_of(c->amg.lev[last], V, last), V.dense.p, m, c->amg.dense_off,
+                      c->comm.active() ? c->amg.dense_map.p : nullptr};
+  parallel_for(s, c->amg.lev[last].n, tk);
+  c->comm.allreduce(s, V.dense.p, m * m);   // every rank contributes its rows
   dense_inverse_device(s, (int)m, V.dense.p, c->amg.colbuf.p);
 }
 
@@ -275,43 +374,68 @@ static void transfer(knp_ctx* c, int64_t nrows, const int32_t* ptr, const int32_
 }
 
 // solve level l (>= 1, index into lev = l-1) approximately: L.x <- cycle(L.b)
-static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li) {
+// On return the ghost entries of L.x are valid when ghost_x is set (the parent's fused
+// prolongation+smoothing sweep reads them).
+static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
   knp_stream_t s = c->stream;
   AmgLevelPlan& L = c->amg.lev[li];
+  Comm& comm = c->comm;
   if (li + 1 == c->amg.lev.size()) {
-    DenseMatvecKernel k{L.n, V.dense.p, L.b.p, L.x.p};
-    parallel_for(s, L.n, k, 64);
+    if (!comm.active()) {
+      DenseMatvecKernel k{L.n, V.dense.p, L.b.p, L.x.p};
+      parallel_for(s, L.n, k, 64);
+      return;
+    }
+    // the global right-hand side is summed over ranks, every rank applies the replicated
+    // inverse and picks its owned and ghost unknowns
+    AmgPlan& amg = c->amg;
+    const int64_t m = amg.m_dense;
+    dev_zero(amg.dense_b.p, (size_t)m * sizeof(double), s);
+    { ScatterOffsetKernel k{L.b.p, amg.dense_b.p, amg.dense_off}; parallel_for(s, L.n, k); }
+    comm.allreduce(s, amg.dense_b.p, m);
+    { DenseMatvecKernel k{m, V.dense.p, amg.dense_b.p, amg.dense_x.p}; parallel_for(s, m, k, 64); }
+    { GatherMapKernel k{amg.dense_x.p, amg.dense_map.p, L.x.p}; parallel_for(s, L.nloc, k); }
     return;
   }
   CsrMat A = csr_of(L, V, li);
   AmgLevelPlan& C = c->amg.lev[li + 1];
   if (c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1 && C.t_unit) {
     // fused V(1,1) path: two kernels down (smooth+residual, restrict), one up (prolong+smooth)
+    comm.halo(s, L.halo, L.b.p);
     { CoarseResidualKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.r.p}; parallel_rows<8>(s, L.n, k); }
+    if (L.halo.n_ghost > 0) {   // x = dinv b on the ghost unknowns too (read by the sweep up)
+      DiagScaleKernel k{V.dinv[li].p + L.n, L.b.p + L.n, L.x.p + L.n, 1.0};
+      parallel_for(s, L.halo.n_ghost, k);
+    }
     { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, L.r.p, C.b.p, 0}; parallel_rows<8>(s, C.n, k); }
-    coarse_cycle(c, V, li + 1);
+    coarse_cycle(c, V, li + 1, true);
     { CoarseUpKernel k{A, V.dinv[li].p, L.b.p, L.x.p, C.pidx.p, C.x.p, L.t.p}; parallel_rows<8>(s, L.n, k); }
     std::swap(L.x.p, L.t.p);
+    if (ghost_x) comm.halo(s, L.halo, L.x.p);
     return;
   }
   // pre-smoothing from a zero guess
   { DiagScaleKernel k{V.dinv[li].p, L.b.p, L.x.p, 1.0}; parallel_for(s, L.n, k); }
   for (int it = 1; it < c->opt.nu_pre; ++it) {
+    comm.halo(s, L.halo, L.x.p);
     CsrJacobiKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.t.p, 1.0};
     parallel_for(s, L.n, k);
     std::swap(L.x.p, L.t.p);
   }
   for (int g = 0; g < c->opt.gamma; ++g) {
+    comm.halo(s, L.halo, L.x.p);
     { CsrSpmvKernel k{A, L.x.p, L.b.p, L.r.p, 1}; parallel_for(s, L.n, k); }
     transfer(c, C.n, C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, L.r.p, C.b.p, 0);
-    coarse_cycle(c, V, li + 1);
+    coarse_cycle(c, V, li + 1, false);
     transfer(c, L.n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, C.x.p, L.x.p, 1);
   }
   for (int it = 0; it < c->opt.nu_post; ++it) {
+    comm.halo(s, L.halo, L.x.p);
     CsrJacobiKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.t.p, 1.0};
     parallel_for(s, L.n, k);
     std::swap(L.x.p, L.t.p);
   }
+  if (ghost_x) comm.halo(s, L.halo, L.x.p);
 }
 
 // z = M^-1 r
@@ -328,8 +452,8 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
   for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, V.binv.p, r, x, t, w); std::swap(x, t); }
   bell_spmv(c, A0, x, r, amg.r0.p, 1);
   { TransferRowsKernel k{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, amg.r0.p, C.b.p, 0}; parallel_rows<8>(c->stream, C.n, k); }
-  coarse_cycle(c, V, 0);
-  transfer(c, c->n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, C.x.p, x, 1);
+  coarse_cycle(c, V, 0, false);
+  transfer(c, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, C.x.p, x, 1);
   if (c->opt.nu_post == 0) { d2d(z, x, c->n * sizeof(double), c->stream); return; }
   for (int it = 0; it < c->opt.nu_post; ++it) {
     double* out = (it + 1 == c->opt.nu_post) ? z : t;
@@ -348,8 +472,8 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
 // along them, amplified by the mass-shifted preconditioner, puts a floor under ||M^-1 r||.
 static void remove_mean(knp_ctx* c, double* v) {
   const double s = dot_host(c, v, c->kr_ones.p);
-  AddConstKernel k{-s / (double)c->n, v};
-  parallel_for(c->stream, c->n, k);
+  AddConstKernel k{-s / c->n_global, v};
+  parallel_for(c->stream, c->n_own, k);
 }
 
 static void ensure_krylov(knp_ctx* c) {
@@ -362,6 +486,9 @@ static void ensure_krylov(knp_ctx* c) {
   }
   const size_t need = (size_t)(c->opt.restart + 1) * n;
   if (c->kr_V.n < need) c->kr_V.alloc(need);
+  double ng = (double)c->n_own;
+  global_sum(c, &ng, 1);
+  c->n_global = ng;
 }
 
 extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, int* niter, double* resid) {
@@ -372,7 +499,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   stream_sync(s);
   const double t0 = now_s();
   ensure_krylov(c);
-  const int64_t n = c->n;
+  const int64_t n = c->n, no = c->n_own;   // local vector length (stride) / owned rows
   BellMat A = bell_of(c, 0), B = bell_of(c, 1);
   // preconditioner refresh (the reference rebuilds BoomerAMG at every setOperators)
   if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_emi, B, c->A_emi.p, c->Bdiag());
@@ -404,7 +531,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
         fail("knp_solve_emi: operator or preconditioner is indefinite");
       }
       const double alpha = rz / pq;
-      { Axpy2Kernel k{alpha, p, q, x, r}; parallel_for(s, n, k); }
+      { Axpy2Kernel k{alpha, p, q, x, r}; parallel_for(s, no, k); }
       precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
       remove_mean(c, z);
       double d2[2];
@@ -417,11 +544,12 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
       else if (it - best_it >= 40 && best <= 1e-10 * bnorm) break;
       const double beta = d2[0] / rz;
       rz = d2[0];
-      { AxpbyKernel k{1.0, z, beta, p}; parallel_for(s, n, k); }
+      { AxpbyKernel k{1.0, z, beta, p}; parallel_for(s, no, k); }
     }
     if (it > maxit) fail("knp_solve_emi: CG did not converge in " + std::to_string(maxit) +
                          " iterations (ksp_error_if_not_converged, solver.py:428)");
   }
+  halo0(c, x);   // the assembly of the KNP system reads phi on the ghost cells
   stream_sync(s);
   if (niter) *niter = it;
   if (resid) *resid = zn;
@@ -434,7 +562,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
 // ---------------------------------------------------------------------------------
 static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, double* resid_out) {
   knp_stream_t s = c->stream;
-  const int64_t n = c->n;
+  const int64_t n = c->n, no = c->n_own;   // stride of the Krylov basis / owned rows
   const int m = c->opt.restart;
   BellMat A = bell_of(c, 2 + ion);
   AmgValues& Vv = c->amg_knp[ion];
@@ -457,7 +585,7 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
     const double beta = sqrt(dot_host(c, V, V));
     res = beta;
     if ((beta <= tol && it >= c->opt.knp_min_it) || it >= maxit || beta == 0.0) break;
-    { ScaleKernel k{1.0 / beta, V, V}; parallel_for(s, n, k); }
+    { ScaleKernel k{1.0 / beta, V, V}; parallel_for(s, no, k); }
     std::fill(g.begin(), g.end(), 0.0);
     g[0] = beta;
     int j = 0;
@@ -469,14 +597,16 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
       precondition(c, Vv, A, bj, r, w);            // w = M^-1 A v_j
       // classical Gram-Schmidt, one pass: h = V^T w stays on the device for the update,
       // ||w||^2 lands right behind it; one host read per iteration
-      multi_dot_device(s, n, j + 1, V, w, c->kr_partial.p, hdev);
-      { GsUpdateKernel k{n, j + 1, V, hdev, w}; parallel_for(s, n, k); }
-      multi_dot_device(s, n, 1, w, w, c->kr_partial.p, hdev + j + 1);
+      multi_dot_device(s, no, n, j + 1, V, w, c->kr_partial.p, hdev);
+      c->comm.allreduce(s, hdev, j + 1);
+      { GsUpdateKernel k{n, j + 1, V, hdev, w}; parallel_for(s, no, k); }
+      multi_dot_device(s, no, n, 1, w, w, c->kr_partial.p, hdev + j + 1);
+      c->comm.allreduce(s, hdev + j + 1, 1);
       d2h(hcol.data(), hdev, (j + 2) * sizeof(double), s);
       const double hn = sqrt(hcol[j + 1]);
       for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
       H[(size_t)(j + 1) * m + j] = hn;
-      if (hn > 0.0) { ScaleKernel k{1.0 / hn, w, vn}; parallel_for(s, n, k); }
+      if (hn > 0.0) { ScaleKernel k{1.0 / hn, w, vn}; parallel_for(s, no, k); }
       for (int i = 0; i < j; ++i) {                // apply previous rotations
         const double a = H[(size_t)i * m + j], bq = H[(size_t)(i + 1) * m + j];
         H[(size_t)i * m + j] = cs[i] * a + sn[i] * bq;
@@ -502,7 +632,7 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
     if (k > 0) {
       h2d(hdev, y.data(), k * sizeof(double), s);
       CombineKernel ck{n, k, V, hdev, x};
-      parallel_for(s, n, ck);
+      parallel_for(s, no, ck);
     }
     if (done || it >= maxit) {
       if (!done) { *resid_out = res; return -it; }
@@ -525,6 +655,7 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
     double res = 0.0;
     const int it = gmres_one(ctx, ion, rtol, atol, maxit, &res);
     if (it < 0) fail("knp_solve_knp: GMRES did not converge for ion " + std::to_string(ion));
+    halo0(ctx, ctx->c[ion].p);   // post-step and the next assembly read c on the ghost cells
     worst = it > worst ? it : worst;
     rmax = res > rmax ? res : rmax;
   }

@@ -26,6 +26,9 @@ _ip = C.POINTER(C.c_int32)
 _lp = C.POINTER(C.c_int64)
 _bp = C.POINTER(C.c_uint8)
 _ctx = C.c_void_p
+# transport callbacks of the host-emulation build (include/knpemi.h knp_exchange_fn / knp_allreduce_fn)
+XFN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _ip, _dp, _lp, _dp, _lp)
+RFN = C.CFUNCTYPE(C.c_int, C.c_void_p, _dp, C.c_int64)
 
 _PROTOS = {
     "knp_last_error": (C.c_char_p, []),
@@ -65,6 +68,12 @@ _PROTOS = {
     "knp_membrane_outputs": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _ip]),
     "knp_membrane_stimulus": (C.c_int, [_ctx, C.c_int, _bp, C.c_int, _ip, _dp]),
     "knp_ode_step": (C.c_int, [_ctx, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, _lp]),
+    "knp_dist_set": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int64, C.c_int, _ip, _lp, _ip, _lp]),
+    "knp_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "knp_dist_init_nccl": (C.c_int, [_ctx, C.c_char_p]),
+    "knp_dist_set_callbacks": (C.c_int, [_ctx, XFN, RFN, C.c_void_p]),
+    "knp_dist_info": (C.c_int, [_ctx, _lp]),
+    "knp_field_halo": (C.c_int, [_ctx, C.c_int, C.c_int]),
     "knp_timers_get": (C.c_int, [_ctx, _dp, C.c_int]),
     "knp_launch_count": (C.c_longlong, []),
     "knp_timer_start": (C.c_int, [_ctx]),
@@ -110,6 +119,11 @@ class Lib:
     def is_cuda(self):
         return bool(self.dll.knp_is_cuda_build())
 
+    def nccl_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self.check(self.dll.knp_nccl_unique_id(buf))
+        return buf.raw
+
     def models(self):
         out = {}
         for i in range(self.dll.knp_model_count()):
@@ -140,7 +154,10 @@ class Context:
         self.lib = lib or get()
         self.h = _ctx()
         self.lib.check(self.lib.dll.knp_ctx_create(int(device), C.byref(self.h)))
+        self.device = int(device)
         self.d = self.nc = self.n = self.nm = 0
+        self.nc_owned = self.n_owned = 0
+        self.rank, self.world = 0, 1
         self.N = 0
 
     def close(self):
@@ -174,6 +191,39 @@ class Context:
         self.d, self.nc, self.n, self.nm, self.nnz = (int(v) for v in info[:5])
         self.nd = self.d + 1
         self.nsip = int(info[5])
+        self.nc_owned, self.n_owned = self.nc, self.n
+        self.rank, self.world = 0, 1
+
+    # -- multi-GPU --------------------------------------------------------
+    def set_dist(self, rank, world, nc_owned, neigh, send_ptr, send_cells, recv_ptr):
+        """declare this context one part of a cell-partitioned mesh (knp_dist_set)"""
+        neigh = _i32(neigh)
+        sp = np.ascontiguousarray(send_ptr, dtype=np.int64)
+        sc = _i32(send_cells)
+        rp = np.ascontiguousarray(recv_ptr, dtype=np.int64)
+        self._call("knp_dist_set", int(rank), int(world), int(nc_owned), neigh.size, _p(neigh, _ip), _p(sp, _lp),
+                   _p(sc, _ip), _p(rp, _lp))
+        self.rank, self.world = int(rank), int(world)
+        self.nc_owned, self.n_owned = int(nc_owned), int(nc_owned) * self.nd
+        info = np.zeros(8, dtype=np.int64)
+        self._call("knp_mesh_info", _p(info, _lp))
+        self.nnz = int(info[4])
+
+    def init_nccl(self, uid):
+        assert len(uid) == 128
+        self._call("knp_dist_init_nccl", C.create_string_buffer(bytes(uid), 128))
+
+    def set_callbacks(self, exchange, allreduce):
+        self._call("knp_dist_set_callbacks", exchange, allreduce, None)
+
+    def dist_info(self):
+        info = np.zeros(8, dtype=np.int64)
+        self._call("knp_dist_info", _p(info, _lp))
+        return dict(zip(("rank", "world", "owned_cells", "ghost_cells", "neighbours", "halos", "allreduces"),
+                        (int(v) for v in info[:7])))
+
+    def field_halo(self, which, idx=0):
+        self._call("knp_field_halo", int(which), int(idx))
 
     def membrane_table(self):
         out = [np.zeros(self.nm, dtype=np.int32) for _ in range(4)]
@@ -216,11 +266,12 @@ class Context:
     def matrix(self, which):
         """scipy CSR copy of matrix `which` (0 A_emi, 1 B_emi, 2+k A_knp[k])."""
         import scipy.sparse as sp
-        ptr = np.zeros(self.n + 1, dtype=np.int64)
+        ptr = np.zeros(self.n_owned + 1, dtype=np.int64)
         col = np.zeros(self.nnz, dtype=np.int32)
         val = np.zeros(self.nnz)
         self._call("knp_matrix_export", which, _p(ptr, _lp), _p(col, _ip), _p(val, _dp))
-        return sp.csr_matrix((val, col, ptr), shape=(self.n, self.n))
+        # rows: owned dofs; columns: local dofs (owned + ghost)
+        return sp.csr_matrix((val, col, ptr), shape=(self.n_owned, self.n))
 
     def spmv(self, which, x):
         x = _f64(x).ravel()

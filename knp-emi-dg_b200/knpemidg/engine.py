@@ -51,16 +51,37 @@ def _simplex_rule(dim, n):
 
 class Engine:
     def __init__(self, mesh, cell_tags, facet_tags, *, F, R, T, C_M, C_phi, dt, z, D_sub, rho_sub=None,
-                 membrane_tags=(), degree=1, splitting=True, mms=False, C_sub=None, device=0, lib=None):
+                 membrane_tags=(), degree=1, splitting=True, mms=False, C_sub=None, device=0, lib=None,
+                 transport=None, part=None):
+        """`transport` (knpemidg.partition.TorchTransport of a torch.distributed job with
+        more than one rank): this engine then holds ONE part of the cell-partitioned mesh
+        (`part[cell]` = owning rank, default partition_cells) and every rank runs the same
+        sequence of calls; `mesh`, the tags and all set_* inputs stay GLOBAL arrays."""
         mesh.init_topology()
+        self.global_mesh = mesh
+        self.transport = transport if (transport is not None and transport.world > 1) else None
+        self.local = None
+        cell_tags = np.asarray(cell_tags)
+        facet_tags = np.asarray(facet_tags)
+        self.tags = np.unique(cell_tags)
+        self.nc_global = mesh.cells.shape[0]
+        self.global_membrane_facets = np.flatnonzero(
+            (mesh.facet_cells[:, 1] >= 0) & np.isin(facet_tags, [int(t) for t in membrane_tags]))
+        if self.transport is not None:
+            from . import partition
+            if part is None:
+                part = partition.partition_cells(mesh, self.transport.world)
+            self.local = partition.LocalPart(mesh, cell_tags, facet_tags, part, self.transport.rank)
+            mesh, cell_tags, facet_tags = self.local.mesh, self.local.cell_tags, self.local.facet_tags
         self.mesh = mesh
         self.ctx = _lib.Context(device, lib)
         ctx = self.ctx
-        cell_tags = np.asarray(cell_tags)
-        self.tags = np.unique(cell_tags)
         region = np.searchsorted(self.tags, cell_tags).astype(np.int32)
         ctx.set_mesh(mesh.coords, mesh.cells, region, mesh.facet_cells, np.asarray(facet_tags),
                      tuple(int(t) for t in membrane_tags))
+        if self.local is not None:
+            ctx.set_dist(**self.local.dist_args())
+            self.transport.attach(ctx)
         self.d, self.nd, self.nc, self.n, self.nm = ctx.d, ctx.nd, ctx.nc, ctx.n, ctx.nm
         self.N = len(z)
         self.dt = float(dt)
@@ -101,8 +122,14 @@ class Engine:
                 vals[self.cell_tags == t] = float(sub[int(t)])
             self.ctx.set_field(F_C, k, np.repeat(vals, self.nd))
 
+    def localize(self, nodal):
+        """global per-dof array [nc_global * nd] -> this rank's cells (owned + ghost)"""
+        if self.local is None:
+            return nodal
+        return np.asarray(nodal).reshape(self.nc_global, -1)[self.local.l2g]
+
     def set_concentration(self, k, nodal):
-        self.ctx.set_field(F_C, k, nodal)
+        self.ctx.set_field(F_C, k, self.localize(nodal))
 
     def membrane_midpoints(self):
         return self.mesh.facet_midpoints()[self.mem["facet"]]
@@ -250,15 +277,31 @@ class Engine:
         self.k += 1
 
     # -- observables ---------------------------------------------------------
-    def phi(self):
-        return self.ctx.get_field(F_PHI).reshape(self.nc, self.nd)
+    # Single part: the arrays of the whole mesh.  Partitioned: this rank's cells (owned first,
+    # then ghosts) unless gather=True, which assembles the global array on every rank
+    # (collective; tests and output only, never inside the time loop).
+    def _cells(self, local, gather):
+        local = local.reshape(self.nc, self.nd)
+        if self.local is None or not gather:
+            return local
+        no = self.local.nc_owned
+        return self.transport.gather_owned(local[:no], self.local.owned_global_cells(), self.nc_global)
 
-    def concentration(self, k):
-        return self.ctx.get_field(F_C, k).reshape(self.nc, self.nd)
+    def phi(self, gather=False):
+        return self._cells(self.ctx.get_field(F_PHI), gather)
 
-    def phi_M(self):
-        return self.ctx.get_field(F_PHIM)
+    def concentration(self, k, gather=False):
+        return self._cells(self.ctx.get_field(F_C, k), gather)
+
+    def phi_M(self, gather=False):
+        v = self.ctx.get_field(F_PHIM)
+        if self.local is None or not gather:
+            return v
+        mine = self.mem["cell_i"] < self.local.nc_owned           # the copy that counts: ICS cell owner
+        gfacet = self.local.facets[self.mem["facet"]]
+        rows = np.searchsorted(self.global_membrane_facets, gfacet)
+        return self.transport.gather_owned(v[mine], rows[mine], self.global_membrane_facets.size)
 
     def dofs(self):
-        """V_emi.dim() + V_knp.dim() (solver.py:1163-1164)."""
-        return self.N * self.n
+        """V_emi.dim() + V_knp.dim() (solver.py:1163-1164) of the whole mesh."""
+        return self.N * self.nd * self.nc_global
