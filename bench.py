@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""bench.py - KNP-EMI time-steps/s on the 3D axon-bundle workload (BASELINE.json configs[2]).
+"""bench.py - KNP-EMI DOF-steps/s (and time-steps/s) on the 3D axon-bundle workload
+(BASELINE.json configs[2]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling weak|strong]
 
 One "step" = one full time step of the reference's loop (solver.py:1072-1127): membrane
 ODE step -> EMI assembly + CG/AMG solve -> KNP assembly + GMRES/AMG solves -> post-step.
@@ -9,9 +10,15 @@ Workload: 32 x 0.9 x 0.9 um box with four axons (make_mesh_3D.py:81-111) at 96 x
 tetrahedra = 419,904 cells, 5.04 M DOFs (3 fields x 4 dofs x cells), Hodgkin-Huxley membranes
 with the synaptic stimulus of run_3D.py, dt = 0.1 ms, CG rtol 1e-5, GMRES(30) rtol 1e-7.
 
-Prints ONE JSON line (rank 0).  `value` = steps/s with everything resident in HBM;
-`e2e` = the same loop driven with HOST buffers through the C ABI (state uploaded from
-pinned memory before and downloaded after every step).
+N > 1 (one process per GPU, torchrun): the mesh is partitioned by cell, one part per GPU,
+DG halos over NCCL send/recv and Krylov dots over NCCL allreduce inside libknpemi.so.
+Weak scaling (default): the bundle is N x 32 um long with 96 N x 27 x 27 x 6 tetrahedra, so
+every GPU holds the N = 1 workload (5.04 M DOFs); `--scaling strong` keeps the N = 1 mesh.
+
+Prints ONE JSON line (rank 0).  `value` = DOF-steps/s = (DOFs of the whole mesh) x steps /
+time with everything resident in HBM (`steps_per_s` beside it); `e2e` = the same loop
+driven with HOST buffers through the C ABI (state uploaded from pinned memory before and
+downloaded after every step).
 """
 import argparse
 import json
@@ -38,6 +45,9 @@ NA_I, NA_E, K_I, K_E = 12.838513108648856, 100.71925900027354, 124.1539758349190
 C_INIT = [{1: K_I, 0: K_E}, {1: NA_I + K_I, 0: NA_E + K_E}, {1: NA_I, 0: NA_E}]   # K, Cl, Na (run_3D.py)
 ION_NAMES = ["K", "Cl", "Na"]
 STIMULUS = {"stim_amplitude": 10.0}
+# dram__bytes_read.sum + dram__bytes_write.sum of one BellSpmvKernel<4> launch on the N = 1 workload, from
+# the `ncu --set full` capture summarised in profiles/ (None until captured)
+TRAFFIC_SPMV = None
 
 
 def stim_locator(x):
@@ -97,12 +107,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_engine(dims, device):
+def build_engine(dims, device, transport=None, nblocks=1):
     from knpemidg import mesh as kmesh
     from knpemidg.engine import Engine
     from knpemidg.models import mm_hh, mm_hh_no_stim
-    mesh, sub, surf = kmesh.bundle_3d_mesh(dims=dims)
-    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), device=device, **PHYS)
+    mesh, sub, surf = kmesh.bundle_3d_mesh(dims=dims, nblocks=nblocks)
+    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), device=device, transport=transport,
+                 **PHYS)
     eng.set_concentrations_by_tag(C_INIT)
     eng.add_membrane_model(1, mm_hh, ION_NAMES, stimulus=STIMULUS, stimulus_locator=stim_locator)
     eng.add_membrane_model(2, mm_hh_no_stim, ION_NAMES, stimulus=STIMULUS, stimulus_locator=stim_locator)
@@ -129,33 +140,73 @@ def cpu_reference_steps(nsteps, dims=SAMPLE_DIMS):
     return dt, 3 * P.ndof, {"emi_niter": O.niter["emi"][-1:], "knp_niter": O.niter["knp"][-2:]}
 
 
-def workload_dofs(dims):
-    return 3 * 4 * 6 * dims[0] * dims[1] * dims[2]
+def workload_dofs(dims, nblocks=1):
+    return 3 * 4 * 6 * dims[0] * dims[1] * dims[2] * nblocks
+
+
+def _cpu_worker(nsteps, q):
+    try:
+        try:                                    # one thread per copy: the copies fill the cores
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(1)
+        except Exception:
+            pass
+        q.put(cpu_reference_steps(nsteps))
+    except Exception as e:  # pragma: no cover
+        q.put(e)
+
+
+def cpu_reference_parallel(nsteps, nproc):
+    """`nproc` independent copies of the CPU restatement stepping the sample at the same time
+    (what `mpirun -n nproc` of the reference could reach at best: perfect scaling, no
+    communication).  Returns aggregate DOF-steps/s, seconds per step of the slowest copy, dofs."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=(nsteps, q)) for _ in range(nproc)]
+    for p in procs:
+        p.start()
+    res = [q.get() for _ in procs]
+    for p in procs:
+        p.join()
+    for r in res:
+        if isinstance(r, Exception):
+            raise r
+    sec = max(r[0] for r in res)
+    dofs = res[0][1]
+    return nproc * dofs / sec, sec, dofs, res[0][2]
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def run_reference(args, rank):
+    """The reference's own path is dolfin + PETSc + numbalsoda, none of which exists in this
+    image: the reference arm times the CPU restatement (oracle/) of the same
+    time step on the host cores, one copy per core."""
     if rank != 0:
         return
     steps = max(1, min(args.steps, 3))
-    sec, dofs, info = cpu_reference_steps(steps)
+    cores = max(1, min(host_cores(), 32))
+    value, sec, dofs, info = cpu_reference_parallel(steps, cores)
+    sample = (f"{cores} independent copies (one per host core) of the oracle/ restatement on the bundle "
+              f"{SAMPLE_DIMS[0]}x{SAMPLE_DIMS[1]}x{SAMPLE_DIMS[2]}x6 tets ({dofs} DOFs each), {steps} steps of "
+              f"{sec:.2f} s after 1 warm-up step; DOF-steps/s summed over the copies")
     full = workload_dofs(WORKLOAD_DIMS)
-    value = (dofs / full) / sec                # steps/s on the full workload at equal DOF-steps/s
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        cores = os.cpu_count()
-    sample = (f"bundle {SAMPLE_DIMS[0]}x{SAMPLE_DIMS[1]}x{SAMPLE_DIMS[2]}x6 tets ({dofs} DOFs), {steps} steps of "
-              f"{sec:.2f} s; scaled to the {full}-DOF workload at equal DOF-steps/s")
-    line = {"impl": "reference", "metric": "time_steps_per_s", "value": value, "unit": "steps/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 / value,
+    line = {"impl": "reference", "metric": "dof_steps_per_s", "value": value, "unit": "DOF-steps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * full / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": "3D axon bundle 96x27x27x6 tets, 5.04M DOFs, HH membranes (BASELINE configs[2])",
-                       "note": "dolfin+PETSc cannot be installed here; CPU restatement (oracle/) on numpy/scipy"},
-            "dof_steps_per_s": dofs / sec,
-            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": 1, "kind": "port", "sample": sample,
-                             "host_cores_available": cores},
-            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                       "note": "dolfin+PETSc+numbalsoda cannot be installed here; CPU restatement (oracle/) on "
+                               "numpy/scipy on a bounded sample; ms_per_step = the full workload at this rate"},
+            "steps_per_s": value / full,
+            "cpu_baseline": {"value": value, "unit": "DOF-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "DOF-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "detail": info}
     print(json.dumps(line), flush=True)
 
@@ -166,6 +217,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--scaling", default="weak", choices=("weak", "strong"))
     ap.add_argument("--dims", default=None, help="nx,ny,nz override (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -180,10 +232,13 @@ def main():
 
     import torch
     dist = None
+    transport = None
     if world > 1:
         import torch.distributed as dist
+        from knpemidg.partition import TorchTransport
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        transport = TorchTransport()
 
     def barrier():
         if dist is not None:
@@ -197,8 +252,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    eng = build_engine(dims, local_rank)
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    nblocks = world if args.scaling == "weak" else 1
+    eng = build_engine(dims, local_rank, transport, nblocks)
     ctx = eng.ctx
+    dofs = eng.dofs()                                  # of the whole (partitioned) mesh
     for _ in range(warmup):
         eng.step()
     # ---- timed region: K steps, state resident in HBM -----------------------------
@@ -217,9 +281,11 @@ def main():
     barrier()
     launches = ctx.launch_count() - l0
     phase = ctx.timers()
+    comm_info = ctx.dist_info()
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms)
-    value = world * args.steps / (ms * 1e-3)
+    steps_per_s = args.steps / (ms * 1e-3)
+    value = dofs * steps_per_s
 
     # ---- e2e: the same loop with host buffers through the C ABI -------------------
     from knpemidg import _lib
@@ -253,8 +319,8 @@ def main():
     barrier()
     wall_e2e = time.perf_counter() - t0
     ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e * 1e3))
-    e2e_value = world * e2e_steps / (ms_e2e * 1e-3)
-    bytes_dir = 8 * ((N + 1) * n + nm)
+    e2e_value = dofs * e2e_steps / (ms_e2e * 1e-3)
+    bytes_dir = sum_over_ranks(8.0 * ((N + 1) * n + nm))
 
     # ---- roofline of the hot kernels (CUDA events on the library's stream) ----------
     peak, peak_src = read_peaks()
@@ -265,9 +331,11 @@ def main():
                       "frac": kbytes / (kms * 1e-3) / 1e9 / peak}
     dom = kern["bell_spmv"]
     roofline = {"bound": "hbm", "kernel": "knp::BellSpmvKernel<4> (block-ELL fp64 SpMV)",
-                "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": TRAFFIC_SPMV,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
                 "ms_per_launch": dom["ms"], "other_kernels": kern}
+    launches = int(sum_over_ranks(float(launches)))
+    barrier()
 
     if rank != 0:
         if dist is not None:
@@ -275,27 +343,28 @@ def main():
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        sec, dofs, info = cpu_reference_steps(2)
-        full = workload_dofs(dims)
-        cpu = {"value": (dofs / full) / sec, "unit": "steps/s", "cores": 1, "kind": "port",
-               "sample": f"oracle/ restatement, bundle {SAMPLE_DIMS} x6 tets ({dofs} DOFs), 2 steps of {sec:.2f} s, "
-                         f"scaled to the {full}-DOF workload at equal DOF-steps/s",
-               "dof_steps_per_s": dofs / sec}
-    dofs = eng.dofs()
-    line = {"metric": "time_steps_per_s", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        sec, sdofs, info = cpu_reference_steps(2)
+        cpu = {"value": sdofs / sec, "unit": "DOF-steps/s", "cores": 1, "kind": "port",
+               "sample": f"oracle/ restatement (numpy/scipy, one core), bundle {SAMPLE_DIMS} x6 tets ({sdofs} DOFs), "
+                         f"2 steps of {sec:.2f} s after 1 warm-up step",
+               "steps_per_s_on_workload": sdofs / sec / dofs}
+    nx = dims[0] * nblocks
+    line = {"metric": "dof_steps_per_s", "value": value, "unit": "DOF-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D axon bundle {dims[0]}x{dims[1]}x{dims[2]}x6 tets (BASELINE configs[2]), "
-                                   f"{eng.nc} cells, {dofs} DOFs, {eng.nm} HH membrane facets, dt=1e-4 s",
-                       "parallelism": "replicas" if world > 1 else "single",
-                       "l2_policy": "inputs larger than L2 (matrices 3 x %.0f MB)" % (ctx.nnz * 8 / 1e6),
+            "config": {"workload": f"3D axon bundle {nx}x{dims[1]}x{dims[2]}x6 tets (BASELINE configs[2]"
+                                   + (f", {nblocks} blocks of 32 um in a row" if nblocks > 1 else "") + "), "
+                                   f"{eng.nc_global} cells, {dofs} DOFs, HH membranes, dt=1e-4 s",
+                       "parallelism": (f"cell partition, {world} parts (recursive bisection), NCCL halo + allreduce"
+                                       if world > 1 else "single"),
+                       "l2_policy": "inputs larger than L2 (matrices 3 x %.0f MB per GPU)" % (ctx.nnz * 8 / 1e6),
                        "solver": "CG rtol 1e-5 / GMRES(30) rtol 1e-7, aggregation AMG (plan reused, Galerkin refreshed per step)"},
-            "dof_steps_per_s": value * dofs,
+            "steps_per_s": steps_per_s,
             "seconds_per_step": {k: v / args.steps for k, v in phase.items()},
             "iterations": {"emi": eng.stats["emi_niter"][-args.steps:], "knp": eng.stats["knp_niter"][-args.steps:]},
-            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": bytes_dir,
-                    "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "e2e": {"value": e2e_value, "unit": "DOF-steps/s", "h2d_bytes_per_step": bytes_dir,
+                    "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps, "steps_per_s": e2e_steps / (ms_e2e * 1e-3)},
+            "gpu_launches": launches, "comm": comm_info, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

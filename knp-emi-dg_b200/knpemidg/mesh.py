@@ -300,26 +300,29 @@ def neuron_2d_mesh(resolution):
     return mesh, sub, surf
 
 
-def bundle_3d_mesh(resolution=0, dims=None):
+def bundle_3d_mesh(resolution=0, dims=None, nblocks=1):
     """examples/idealized-geometries/make_mesh_3D.py:81-111: 32x0.9x0.9 um box,
     four axons (all cell tag 1), membrane tag 1 for the first axon and 2 for the
     other three, exterior 5, scaled to m.  `dims=(nx,ny,nz)` overrides the
-    2^r refinement (SURVEY.md 8d 'scale 3' = (96,27,27))."""
+    2^r refinement (SURVEY.md 8d 'scale 3' = (96,27,27)).  `nblocks` > 1 (weak-scaling
+    runs) lengthens the bundle: the box is 32*nblocks um long with nx*nblocks cells along
+    it, the axons keep their 5 um distance from both ends."""
     if dims is None:
         nx, ny, nz = 32 * 2 ** resolution, 9 * 2 ** resolution, 9 * 2 ** resolution
     else:
         nx, ny, nz = dims
-    mesh = box_mesh((0.0, 0.0, 0.0), (32.0, 0.9, 0.9), nx, ny, nz)
+    L = 32.0 * nblocks
+    mesh = box_mesh((0.0, 0.0, 0.0), (L, 0.9, 0.9), nx * nblocks, ny, nz)
     mesh.init_topology()
     tol = 1e-9
     sub = MeshFunction(mesh, 3, 0)
     surf = MeshFunction(mesh, 2, 0)
     cm = mesh.cell_midpoints()
     fm = mesh.facet_midpoints()
-    axons = [((5, 0.2, 0.2), (27, 0.4, 0.4), 1),
-             ((5, 0.5, 0.5), (27, 0.7, 0.7), 2),
-             ((5, 0.5, 0.2), (27, 0.7, 0.4), 2),
-             ((5, 0.2, 0.5), (27, 0.4, 0.7), 2)]
+    axons = [((5, 0.2, 0.2), (L - 5, 0.4, 0.4), 1),
+             ((5, 0.5, 0.5), (L - 5, 0.7, 0.7), 2),
+             ((5, 0.5, 0.2), (L - 5, 0.7, 0.4), 2),
+             ((5, 0.2, 0.5), (L - 5, 0.4, 0.7), 2)]
     for a, b, tag in axons:
         sub.array()[_inside(cm, a, b, tol)] = 1
         surf.array()[_on_box_surface(fm, a, b, tol)] = tag
