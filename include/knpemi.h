@@ -170,7 +170,11 @@ int knp_dist_set(knp_ctx* ctx, int rank, int world, int64_t nc_owned, int nneigh
 /* transport 1 (product): NCCL send/recv + allreduce over NVLink on the context's
  * stream.  Rank 0 obtains an id with knp_nccl_unique_id, the host program hands the
  * 128 bytes to the other ranks (torch.distributed broadcast in the Python layer),
- * every rank calls knp_dist_init_nccl (collective). */
+ * every rank calls knp_dist_init_nccl (collective).  The call also tries to map every
+ * rank's exchange arena with CUDA IPC; where that works the halo exchanges and the small
+ * allreduces run as the library's own peer-memory kernels (one launch each, NVLink
+ * stores + flags) and NCCL remains for setup and large reductions.  KNP_P2P=0 in the
+ * environment keeps everything on NCCL. */
 int knp_nccl_unique_id(char out[128]);
 int knp_dist_init_nccl(knp_ctx* ctx, const char uid[128]);
 /* transport 2 (host-emulation build only, for the CPU test-suite under gloo): the
@@ -184,7 +188,8 @@ typedef int (*knp_allreduce_fn)(void* user, double* buf, int64_t n);
 int knp_dist_set_callbacks(knp_ctx* ctx, knp_exchange_fn exchange, knp_allreduce_fn allreduce,
                            void* user);
 /* info[0]=rank, [1]=world, [2]=owned cells, [3]=ghost cells, [4]=neighbours,
- * [5]=halo exchanges issued so far, [6]=allreduces issued so far */
+ * [5]=halo exchanges issued so far, [6]=allreduces issued so far, [7]=how many of those
+ * were served by the library's own peer-memory (NVLink, CUDA IPC) kernels instead of NCCL */
 int knp_dist_info(knp_ctx* ctx, int64_t info[8]);
 /* refresh the ghost values of a cell field from their owners (collective) */
 int knp_field_halo(knp_ctx* ctx, int which, int idx);

@@ -71,6 +71,7 @@ int knp_ctx_destroy(knp_ctx* ctx) {
 #ifndef KNP_EMU
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  ctx->comm.close_p2p();
   if (ctx->comm.nccl) { nccl_api().CommDestroy(ctx->comm.nccl); ctx->comm.nccl = nullptr; }
 #endif
   knp_stream_t s = ctx->stream;
@@ -773,6 +774,7 @@ int knp_dist_init_nccl(knp_ctx* ctx, const char uid[128]) {
   ncclUniqueId id;
   memcpy(&id, uid, 128);
   N.check(N.CommInitRank(&ctx->comm.nccl, ctx->comm.world, id, ctx->comm.rank), "ncclCommInitRank");
+  ctx->comm.setup_p2p(ctx->stream);   // peer-memory kernels where CUDA IPC works, NCCL otherwise
 #endif
   KNP_CATCH
 }
@@ -792,7 +794,12 @@ int knp_dist_set_callbacks(knp_ctx* ctx, knp_exchange_fn exchange, knp_allreduce
 int knp_dist_info(knp_ctx* ctx, int64_t info[8]) {
   KNP_TRY
   info[0] = ctx->comm.rank; info[1] = ctx->comm.world; info[2] = ctx->nc_own; info[3] = ctx->nc - ctx->nc_own;
-  info[4] = (int64_t)ctx->comm.nbr.size(); info[5] = ctx->comm.n_halo; info[6] = ctx->comm.n_allreduce; info[7] = 0;
+  info[4] = (int64_t)ctx->comm.nbr.size(); info[5] = ctx->comm.n_halo; info[6] = ctx->comm.n_allreduce;
+#ifdef KNP_EMU
+  info[7] = 0;
+#else
+  info[7] = ctx->comm.n_p2p;
+#endif
   KNP_CATCH
 }
 

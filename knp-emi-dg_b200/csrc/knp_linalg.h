@@ -295,6 +295,10 @@ struct AxpbyKernel {  // y = a x + b y
   double a; const double* x; double b; double* y;
   KNP_HD void operator()(int64_t i) const { y[i] = a * x[i] + b * y[i]; }
 };
+struct DirectionKernel {  // p = (z - mu) + b p   (CG direction from the mean-free preconditioned residual)
+  const double* z; double mu; double b; double* p;
+  KNP_HD void operator()(int64_t i) const { p[i] = (z[i] - mu) + b * p[i]; }
+};
 struct Axpy2Kernel {  // x += a p ; r -= a q     (CG update)
   double a; const double* p; const double* q; double* x; double* r;
   KNP_HD void operator()(int64_t i) const { x[i] += a * p[i]; r[i] -= a * q[i]; }
@@ -314,6 +318,19 @@ struct GsUpdateKernel {
     double acc = w[e];
     for (int i = 0; i < k; ++i) acc -= h[i] * V[(int64_t)i * n + e];
     w[e] = acc;
+  }
+};
+// Gram-Schmidt update and normalisation in one pass: v = (v - sum_i h_i V_i) / hn with
+// hn^2 = h[k] - sum_i h_i^2, where h[k] = |v|^2 before the update (Pythagoras: one reduction
+// per Arnoldi step).  When the subtraction cancels too many digits (hn^2 < tol * |v|^2) the
+// vector is left unnormalised and the caller computes the norm explicitly.
+struct GsNormalizeKernel {
+  int64_t n /*stride of V*/; int k; const double* V; const double* h /*device, k+1 entries*/; double* v; double tol;
+  KNP_HD void operator()(int64_t e) const {
+    double acc = v[e], s = 0.0;
+    for (int i = 0; i < k; ++i) { acc -= h[i] * V[(int64_t)i * n + e]; s += h[i] * h[i]; }
+    const double hn2 = h[k] - s;
+    v[e] = (hn2 >= tol * h[k] && hn2 > 0.0) ? acc / sqrt(hn2) : acc;
   }
 };
 // x += sum_i y_i V_i
@@ -387,6 +404,38 @@ static __global__ void __launch_bounds__(RED_THREADS) multi_dot_final(int k, int
 }
 #endif
 
+// up to 4 independent dot products a_i . b_i in one pass (CG: r.z, z.z, 1.z, 1.r)
+struct DotPairs { const double* a[4]; const double* b[4]; };
+#ifndef KNP_EMU
+template <int K>
+__global__ void __launch_bounds__(RED_THREADS) pair_dot_partial(int64_t n, const DotPairs P,
+                                                                double* __restrict__ partial) {
+  double acc[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) acc[i] = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc[i] += P.a[i][e] * P.b[i][e];
+  }
+  __shared__ double sm[K][RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[i][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double v = 0.0;
+    for (int wv = 0; wv < RED_THREADS / 32; ++wv) v += sm[threadIdx.x][wv];
+    partial[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = v;
+  }
+}
+#endif
+
 // device-side dots over the first n entries of k vectors `stride` apart; `out` (device,
 // >= k doubles) receives the results, `partial` is a scratch buffer of DOT_MAX*RED_BLOCKS doubles.
 inline void multi_dot_device(knp_stream_t s, int64_t n, int64_t stride, int k, const double* V, const double* w,
@@ -413,6 +462,28 @@ inline void multi_dot_device(knp_stream_t s, int64_t n, int64_t stride, int k, c
     KNP_CUDA(cudaGetLastError());
 #endif
   }
+}
+
+inline void pair_dot_device(knp_stream_t s, int64_t n, int k, const DotPairs& P, double* partial, double* out) {
+#ifdef KNP_EMU
+  (void)s; (void)partial;
+  for (int i = 0; i < k; ++i) {
+    double acc = 0.0;
+    for (int64_t e = 0; e < n; ++e) acc += P.a[i][e] * P.b[i][e];
+    out[i] = acc;
+  }
+#else
+  switch (k) {
+    case 1: pair_dot_partial<1><<<RED_BLOCKS, RED_THREADS, 0, s>>>(n, P, partial); break;
+    case 2: pair_dot_partial<2><<<RED_BLOCKS, RED_THREADS, 0, s>>>(n, P, partial); break;
+    case 3: pair_dot_partial<3><<<RED_BLOCKS, RED_THREADS, 0, s>>>(n, P, partial); break;
+    default: pair_dot_partial<4><<<RED_BLOCKS, RED_THREADS, 0, s>>>(n, P, partial); break;
+  }
+  KNP_CUDA(cudaGetLastError());
+  launch_counter() += 2;
+  multi_dot_final<<<1, RED_THREADS, 0, s>>>(k, RED_BLOCKS, partial, out);
+  KNP_CUDA(cudaGetLastError());
+#endif
 }
 
 // inverse of the dense m x m coarsest-level matrix by Gauss-Jordan without pivoting (SPD

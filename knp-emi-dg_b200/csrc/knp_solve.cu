@@ -506,6 +506,20 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   else { if (c->bj_emi.n != (size_t)c->slot_stride()) c->bj_emi.alloc(c->slot_stride()); block_inverse(c, c->Bdiag(), c->bj_emi.p); }
   double* x = c->phi.p; double* r = c->kr_r.p; double* z = c->kr_r.p + n; double* p = c->kr_p.p; double* q = c->kr_q.p;
   const double* b = c->rhs_emi.p;
+  // r.z, z.z, 1.z and 1.r in one pass and one reduction; the mean of z is removed
+  // analytically: with mu = (1.z)/N,  r.(z-mu) = r.z - mu (1.r),  |z-mu|^2 = z.z - N mu^2
+  const double* ones = c->kr_ones.p;
+  const double Ng = c->n_global;
+  auto fused_dots = [&](double& rz_out, double& zz_out, double& mu_out) {
+    DotPairs P{{r, z, ones, ones}, {z, z, z, r}};
+    pair_dot_device(s, no, 4, P, c->kr_partial.p, c->kr_scal.p);
+    c->comm.allreduce(s, c->kr_scal.p, 4);
+    double d[4];
+    d2h(d, c->kr_scal.p, sizeof d, s);
+    mu_out = d[2] / Ng;
+    rz_out = d[0] - mu_out * d[3];
+    zz_out = fmax(d[1] - Ng * mu_out * mu_out, 0.0);
+  };
   // reference norm ||M^-1 b||
   precondition(c, c->amg_emi, B, c->bj_emi.p, b, z);
   remove_mean(c, z);
@@ -513,13 +527,13 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   const double tol = fmax(rtol * bnorm, atol);
   bell_spmv(c, A, x, b, r, 1);
   precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
-  remove_mean(c, z);
-  double zn = sqrt(dot_host(c, z, z));
+  double rz, zz, mu;
+  fused_dots(rz, zz, mu);
+  double zn = sqrt(zz);
   int it = 0, best_it = 0;
   double best = zn;
   if (zn > tol) {
-    d2d(p, z, n * sizeof(double), s);
-    double rz = dot_host(c, r, z);
+    { DirectionKernel k{z, mu, 0.0, p}; parallel_for(s, no, k); }
     for (it = 1; it <= maxit; ++it) {
       bell_spmv(c, A, p, nullptr, q, 0);
       const double pq = dot_host(c, p, q);
@@ -533,24 +547,26 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
       const double alpha = rz / pq;
       { Axpy2Kernel k{alpha, p, q, x, r}; parallel_for(s, no, k); }
       precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
-      remove_mean(c, z);
-      double d2[2];
-      dots_host(c, 2, r, z, d2);     // {r, z} are contiguous: r.z and z.z in one pass
-      zn = sqrt(d2[1]);
+      double rz_new;
+      fused_dots(rz_new, zz, mu);
+      zn = sqrt(zz);
       if (zn <= tol) break;
       // attainable accuracy: a tolerance below the fp64 floor of this system is treated as
       // reached once the preconditioned residual has stagnated at round-off level
       if (zn < best) { best = zn; best_it = it; }
       else if (it - best_it >= 40 && best <= 1e-10 * bnorm) break;
-      const double beta = d2[0] / rz;
-      rz = d2[0];
-      { AxpbyKernel k{1.0, z, beta, p}; parallel_for(s, no, k); }
+      const double beta = rz_new / rz;
+      rz = rz_new;
+      { DirectionKernel k{z, mu, beta, p}; parallel_for(s, no, k); }
     }
     if (it > maxit) fail("knp_solve_emi: CG did not converge in " + std::to_string(maxit) +
                          " iterations (ksp_error_if_not_converged, solver.py:428)");
   }
   halo0(c, x);   // the assembly of the KNP system reads phi on the ghost cells
   stream_sync(s);
+#ifndef KNP_EMU
+  c->comm.check_p2p(s);
+#endif
   if (niter) *niter = it;
   if (resid) *resid = zn;
   c->timers[T_EMI_SOLVE] += now_s() - t0;
@@ -594,19 +610,26 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
       double* vj = V + (int64_t)j * n;
       double* vn = V + (int64_t)(j + 1) * n;
       bell_spmv(c, A, vj, nullptr, r, 0);
-      precondition(c, Vv, A, bj, r, w);            // w = M^-1 A v_j
-      // classical Gram-Schmidt, one pass: h = V^T w stays on the device for the update,
-      // ||w||^2 lands right behind it; one host read per iteration
-      multi_dot_device(s, no, n, j + 1, V, w, c->kr_partial.p, hdev);
-      c->comm.allreduce(s, hdev, j + 1);
-      { GsUpdateKernel k{n, j + 1, V, hdev, w}; parallel_for(s, no, k); }
-      multi_dot_device(s, no, n, 1, w, w, c->kr_partial.p, hdev + j + 1);
-      c->comm.allreduce(s, hdev + j + 1, 1);
+      precondition(c, Vv, A, bj, r, vn);           // w = M^-1 A v_j, built in the next basis slot
+      // classical Gram-Schmidt with ONE reduction per step: h = V^T w and |w|^2 in the same
+      // pass (w is basis slot j+1), the new norm from Pythagoras, update + normalisation fused;
+      // h stays on the device for the update, the host reads it once for the Givens rotations
+      multi_dot_device(s, no, n, j + 2, V, vn, c->kr_partial.p, hdev);
+      c->comm.allreduce(s, hdev, j + 2);
+      const double cancel_tol = 1e-6;
+      { GsNormalizeKernel k{n, j + 1, V, hdev, vn, cancel_tol}; parallel_for(s, no, k); }
       d2h(hcol.data(), hdev, (j + 2) * sizeof(double), s);
-      const double hn = sqrt(hcol[j + 1]);
+      double hsum = 0.0;
+      for (int i = 0; i <= j; ++i) hsum += hcol[i] * hcol[i];
+      double hn2 = hcol[j + 1] - hsum;
+      if (!(hn2 >= cancel_tol * hcol[j + 1] && hn2 > 0.0)) {
+        // too much cancellation (w almost in span V): explicit norm of the updated vector
+        hn2 = dot_host(c, vn, vn);
+        if (hn2 > 0.0) { ScaleKernel k{1.0 / sqrt(hn2), vn, vn}; parallel_for(s, no, k); }
+      }
+      const double hn = hn2 > 0.0 ? sqrt(hn2) : 0.0;
       for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
       H[(size_t)(j + 1) * m + j] = hn;
-      if (hn > 0.0) { ScaleKernel k{1.0 / hn, w, vn}; parallel_for(s, no, k); }
       for (int i = 0; i < j; ++i) {                // apply previous rotations
         const double a = H[(size_t)i * m + j], bq = H[(size_t)(i + 1) * m + j];
         H[(size_t)i * m + j] = cs[i] * a + sn[i] * bq;
@@ -660,6 +683,9 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
     rmax = res > rmax ? res : rmax;
   }
   stream_sync(ctx->stream);
+#ifndef KNP_EMU
+  ctx->comm.check_p2p(ctx->stream);
+#endif
   if (niter) *niter = worst;
   if (resid) *resid = rmax;
   ctx->timers[T_KNP_SOLVE] += now_s() - t0;

@@ -219,8 +219,8 @@ class Context:
     def dist_info(self):
         info = np.zeros(8, dtype=np.int64)
         self._call("knp_dist_info", _p(info, _lp))
-        return dict(zip(("rank", "world", "owned_cells", "ghost_cells", "neighbours", "halos", "allreduces"),
-                        (int(v) for v in info[:7])))
+        return dict(zip(("rank", "world", "owned_cells", "ghost_cells", "neighbours", "halos", "allreduces",
+                         "peer_memory_ops"), (int(v) for v in info[:8])))
 
     def field_halo(self, which, idx=0):
         self._call("knp_field_halo", int(which), int(idx))
