@@ -12,8 +12,8 @@ with the synaptic stimulus of run_3D.py, dt = 0.1 ms, CG rtol 1e-5, GMRES(30) rt
 
 N > 1 (one process per GPU, torchrun): the mesh is partitioned by cell, one part per GPU,
 DG halos over NCCL send/recv and Krylov dots over NCCL allreduce inside libknpemi.so.
-Weak scaling (default): the bundle is N x 32 um long with 96 N x 27 x 27 x 6 tetrahedra, so
-every GPU holds the N = 1 workload (5.04 M DOFs); `--scaling strong` keeps the N = 1 mesh.
+Weak scaling (default): N copies of the four-axon block side by side (32 x 0.9 N x 0.9 um,
+96 x 27 N x 27 x 6 tetrahedra, 4 N axons), so every GPU holds the N = 1 workload (5.04 M DOFs); `--scaling strong` keeps the N = 1 mesh.
 
 Prints ONE JSON line (rank 0).  `value` = DOF-steps/s = (DOFs of the whole mesh) x steps /
 time with everything resident in HBM (`steps_per_s` beside it); `e2e` = the same loop
@@ -348,12 +348,11 @@ def main():
                "sample": f"oracle/ restatement (numpy/scipy, one core), bundle {SAMPLE_DIMS} x6 tets ({sdofs} DOFs), "
                          f"2 steps of {sec:.2f} s after 1 warm-up step",
                "steps_per_s_on_workload": sdofs / sec / dofs}
-    nx = dims[0] * nblocks
     line = {"metric": "dof_steps_per_s", "value": value, "unit": "DOF-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D axon bundle {nx}x{dims[1]}x{dims[2]}x6 tets (BASELINE configs[2]"
-                                   + (f", {nblocks} blocks of 32 um in a row" if nblocks > 1 else "") + "), "
+            "config": {"workload": f"3D axon bundle {dims[0]}x{dims[1] * nblocks}x{dims[2]}x6 tets (BASELINE configs[2]"
+                                   + (f", {nblocks} four-axon blocks side by side" if nblocks > 1 else "") + "), "
                                    f"{eng.nc_global} cells, {dofs} DOFs, HH membranes, dt=1e-4 s",
                        "parallelism": (f"cell partition, {world} parts (recursive bisection), NCCL halo + allreduce"
                                        if world > 1 else "single"),

@@ -186,6 +186,16 @@ struct AmgPlan {
   bool ready = false;
   int64_t n0 = 0;
   std::vector<AmgLevelPlan> lev;   // lev[0] = level 1 ...
+  // Multi-GPU: levels lev[0 .. rep_from-1] are distributed (owned rows + ghosts, halo per
+  // sweep).  Once a level has few enough rows over all ranks, its matrix and right-hand side
+  // are all-gathered and the REST of the hierarchy (lev[rep_from] = the global copy of
+  // lev[rep_from-1], then serial coarsening down to the dense level) is built and applied
+  // redundantly on every rank: one all-gather per cycle instead of two halos per level.
+  size_t rep_from = (size_t)-1;    // index of the first replicated level; -1: none
+  int64_t rep_vstride = 0, rep_bstride = 0;   // padded per-rank segment: matrix values / rows
+  DevBuf<double> rep_val, rep_b;   // all-gather buffers [world * stride]
+  DevBuf<int32_t> rep_bmap;        // global row of the replica -> position in rep_b
+  DevBuf<int32_t> rep_xmap;        // local unknown of lev[rep_from-1] -> global row of the replica
   int64_t m_dense = 0;             // rows of the last level (summed over all ranks)
   int64_t dense_off = 0;           // global index of this rank's first last-level row
   DevBuf<int32_t> dense_map;       // last level: local unknown (owned + ghost) -> global index

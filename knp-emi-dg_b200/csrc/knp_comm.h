@@ -67,6 +67,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool loaded = false;
   void load() {
@@ -87,6 +88,7 @@ struct NcclApi {
     Send = reinterpret_cast<decltype(Send)>(sym("ncclSend"));
     Recv = reinterpret_cast<decltype(Recv)>(sym("ncclRecv"));
     AllReduce = reinterpret_cast<decltype(AllReduce)>(sym("ncclAllReduce"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(sym("ncclAllGather"));
     GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
     loaded = true;
   }
@@ -380,6 +382,23 @@ struct Comm {
       if (nr > 0) N.check(N.Recv(x + H.n_own + H.recv_off[i], (size_t)nr, ncclDouble, nbr[i], nccl, s), "ncclRecv");
     }
     N.check(N.GroupEnd(), "ncclGroupEnd");
+#endif
+  }
+
+  // in-place all-gather: rank r's `count` doubles sit at buf + r*count on entry (own segment)
+  // and on every rank on return
+  void allgather(knp_stream_t s, double* buf, int64_t count) {
+    if (!active()) return;
+    require_transport();
+    ++n_allreduce;
+#ifdef KNP_EMU
+    (void)s;
+    for (int r = 0; r < world; ++r)
+      if (r != rank) memset(buf + (int64_t)r * count, 0, (size_t)count * sizeof(double));
+    if (rfn(user, buf, (int64_t)world * count)) fail("allgather callback failed");
+#else
+    NcclApi& N = nccl_api();
+    N.check(N.AllGather(buf + (int64_t)rank * count, buf, (size_t)count, ncclDouble, nccl, s), "ncclAllGather");
 #endif
   }
 

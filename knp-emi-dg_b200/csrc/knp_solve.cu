@@ -212,6 +212,93 @@ static void alloc_values(knp_ctx* c, AmgValues& V) {
   V.binv.alloc((size_t)c->slot_stride());
 }
 
+// rows (over all ranks) below which the rest of the hierarchy is replicated; 0 disables
+static int64_t replicate_threshold() {
+  const char* e = getenv("KNP_AMG_REPLICATE");
+  return e ? atoll(e) : 262144;
+}
+
+// gather `count` doubles per rank (padded) from every rank to every rank, on the host
+static std::vector<double> host_allgather(knp_ctx* c, const std::vector<double>& mine, int64_t count) {
+  DevBuf<double> buf;
+  buf.alloc((size_t)c->comm.world * count);
+  h2d(buf.p + (int64_t)c->comm.rank * count, mine.data(), mine.size() * sizeof(double), c->stream);
+  c->comm.allgather(c->stream, buf.p, count);
+  return buf.download(c->stream);
+}
+
+// Turn the current coarsest distributed level D = lev.back() (pattern + setup values in G.coarse,
+// owned rows, local columns) into a GLOBAL matrix known to every rank, appended as the
+// replicated level lev[rep_from]; G.coarse becomes that global matrix so that the serial
+// coarsening code continues on it unchanged.
+static void replicate_level(knp_ctx* c, GalerkinPlan& G) {
+  AmgPlan& amg = c->amg;
+  Comm& comm = c->comm;
+  const int world = comm.world, rank = comm.rank;
+  AmgLevelPlan& D = amg.lev.back();
+  const HostCsr& A = G.coarse;
+  // sizes of every rank's share
+  std::vector<double> cnt(2 * (size_t)world, 0.0);
+  cnt[2 * rank] = (double)D.n; cnt[2 * rank + 1] = (double)D.nnz;
+  global_sum(c, cnt.data(), 2 * world);
+  std::vector<int64_t> off(world + 1, 0);
+  int64_t bstride = 1, vstride = 1;
+  for (int r = 0; r < world; ++r) {
+    off[r + 1] = off[r] + (int64_t)cnt[2 * r];
+    bstride = std::max<int64_t>(bstride, (int64_t)cnt[2 * r]);
+    vstride = std::max<int64_t>(vstride, (int64_t)cnt[2 * r + 1]);
+  }
+  const int64_t m = off[world];
+  if (m >= 2147483647 / 64) fail("replicate_level: level too large");
+  // local unknown -> global row
+  std::vector<int32_t> xmap((size_t)D.nloc);
+  for (int64_t i = 0; i < D.n; ++i) xmap[i] = (int32_t)(off[rank] + i);
+  for (int64_t g = 0; g < D.halo.n_ghost; ++g) xmap[D.n + g] = (int32_t)(off[D.halo.ghost_rank[g]] + D.halo.ghost_id[g]);
+  // every rank's rows: lengths, global columns, setup values
+  std::vector<double> len((size_t)bstride, 0.0), col((size_t)vstride, 0.0), val((size_t)vstride, 0.0);
+  for (int64_t i = 0; i < D.n; ++i) len[i] = (double)(A.ptr[i + 1] - A.ptr[i]);
+  for (int64_t k = 0; k < D.nnz; ++k) { col[k] = (double)xmap[A.col[k]]; val[k] = A.val[k]; }
+  const std::vector<double> all_len = host_allgather(c, len, bstride);
+  const std::vector<double> all_col = host_allgather(c, col, vstride);
+  const std::vector<double> all_val = host_allgather(c, val, vstride);
+  GalerkinPlan R;
+  HostCsr& B = R.coarse;
+  B.n = m;
+  B.ptr.assign(m + 1, 0);
+  std::vector<int32_t> bmap((size_t)m);
+  R.gptr.push_back(0);
+  for (int r = 0; r < world; ++r) {
+    int64_t k = 0;
+    for (int64_t i = 0; i < (int64_t)cnt[2 * r]; ++i) {
+      const int64_t row = off[r] + i;
+      bmap[row] = (int32_t)(r * bstride + i);
+      const int64_t l = (int64_t)all_len[r * bstride + i];
+      for (int64_t e = 0; e < l; ++e, ++k) {
+        B.col.push_back((int32_t)all_col[r * vstride + k]);
+        B.val.push_back(all_val[r * vstride + k]);
+        R.gidx.push_back((int32_t)(r * vstride + k));     // position in the all-gathered value buffer
+        R.gptr.push_back((int32_t)R.gidx.size());
+      }
+      B.ptr[row + 1] = (int32_t)B.col.size();
+    }
+  }
+  B.pos.resize(B.col.size());
+  std::iota(B.pos.begin(), B.pos.end(), 0);
+  amg.rep_vstride = vstride; amg.rep_bstride = bstride;
+  amg.rep_val.alloc((size_t)world * vstride);
+  amg.rep_b.alloc((size_t)world * bstride);
+  amg.rep_bmap.upload(bmap, c->stream);
+  amg.rep_xmap.upload(xmap, c->stream);
+  amg.rep_from = amg.lev.size();
+  amg.lev.emplace_back();
+  AmgLevelPlan& T0 = amg.lev.back();
+  T0.halo.n_own = m; T0.halo.n_ghost = 0;
+  HostTransfer none;   // no transfer operator between a level and its replica (all-gather instead)
+  none.pptr.assign(1, 0); none.rptr.assign(1, 0);
+  upload_level(c, T0, R, none);
+  G = std::move(R);
+}
+
 extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coarse_size) {
   KNP_TRY
   if (!ctx->emi_assembled) fail("knp_amg_setup: assemble the EMI system first (strength of connection needs values)");
@@ -235,15 +322,24 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
   { std::vector<int32_t>().swap(A0.col); std::vector<int32_t>().swap(A0.pos); }
   double gn = (double)G.coarse.n;          // rows of the current coarsest level over all ranks
   global_sum(ctx, &gn, 1);
+  amg.rep_from = (size_t)-1;
+  bool replicated = false;                 // G.coarse is a global matrix held by every rank
   while ((int)amg.lev.size() + 1 < max_levels && gn > coarse_size) {
+    if (ctx->comm.active() && !replicated && gn <= (double)replicate_threshold()) {
+      replicate_level(ctx, G);             // appends the global copy of lev.back()
+      replicated = true;
+      continue;
+    }
     std::vector<int32_t> ag2;
     const int64_t na = aggregate(G.coarse, theta, ag2);
     double gna = (double)na;
-    global_sum(ctx, &gna, 1);
+    if (!replicated) global_sum(ctx, &gna, 1);
     if (gna >= gn * 0.9 || gna < 1) break;  // coarsening stalled
     amg.lev.emplace_back();
     AmgLevelPlan& fineL = amg.lev[amg.lev.size() - 2];
-    std::vector<int32_t> ag2_all = extend_aggregates(ctx, fineL.halo, ag2, na, amg.lev.back().halo);
+    std::vector<int32_t> ag2_all;
+    if (replicated) { ag2_all = ag2; amg.lev.back().halo.n_own = na; amg.lev.back().halo.n_ghost = 0; }
+    else ag2_all = extend_aggregates(ctx, fineL.halo, ag2, na, amg.lev.back().halo);
     HostTransfer T2 = transfer_from_aggregates(ag2_all, na, G.coarse.n);
     std::vector<double> vals = G.coarse.val;
     GalerkinPlan G2 = galerkin_plan(G.coarse, T2);
@@ -253,7 +349,10 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
     gn = gna;
   }
   // last level: dense inverse of the GLOBAL matrix, replicated on every rank
-  {
+  if (replicated) {
+    amg.m_dense = amg.lev.back().n;
+    amg.dense_off = 0;
+  } else {
     AmgLevelPlan& L = amg.lev.back();
     const int world = ctx->comm.world, rank = ctx->comm.rank;
     if (world > 256) fail("knp_amg_setup: at most 256 ranks");
@@ -345,22 +444,33 @@ static void amg_refresh(knp_ctx* c, AmgValues& V, const BellMat& A0, const doubl
     V.age = 0;
   }
   const double* fine = fine_values;
-  for (size_t l = 0; l < c->amg.lev.size(); ++l) {
-    AmgLevelPlan& L = c->amg.lev[l];
+  AmgPlan& amg = c->amg;
+  for (size_t l = 0; l < amg.lev.size(); ++l) {
+    AmgLevelPlan& L = amg.lev[l];
+    if (l == amg.rep_from) {
+      // the replica's values: every rank's share of the level above, all-gathered
+      AmgLevelPlan& D = amg.lev[l - 1];
+      d2d(amg.rep_val.p + (int64_t)c->comm.rank * amg.rep_vstride, V.val[l - 1].p, D.nnz * sizeof(double), s);
+      c->comm.allgather(s, amg.rep_val.p, amg.rep_vstride);
+      fine = amg.rep_val.p;
+    }
     GalerkinKernel g{L.gptr.p, L.gidx.p, L.g_unit ? nullptr : L.gw.p, fine, V.val[l].p};
     parallel_for(s, L.nnz, g);
-    CsrL1DiagKernel dk{csr_of(L, V, l), V.dinv[l].p};
-    parallel_for(s, L.n, dk);
-    c->comm.halo(s, L.halo, V.dinv[l].p);   // the fused sweeps read dinv of ghost columns
+    if (l + 1 != amg.rep_from) {             // the level that is replicated is never smoothed itself
+      CsrL1DiagKernel dk{csr_of(L, V, l), V.dinv[l].p};
+      parallel_for(s, L.n, dk);
+      if (l < amg.rep_from) c->comm.halo(s, L.halo, V.dinv[l].p);   // the fused sweeps read dinv of ghost columns
+    }
     fine = V.val[l].p;
   }
   const size_t last = c->amg.lev.size() - 1;
   const int64_t m = c->amg.m_dense;
   dev_zero(V.dense.p, (size_t)m * m * sizeof(double), s);
+  const bool dense_distributed = c->comm.active() && last < amg.rep_from;
   CsrToDenseKernel tk{csr_of(c->amg.lev[last], V, last), V.dense.p, m, c->amg.dense_off,
-                      c->comm.active() ? c->amg.dense_map.p : nullptr};
+                      dense_distributed ? c->amg.dense_map.p : nullptr};
   parallel_for(s, c->amg.lev[last].n, tk);
-  c->comm.allreduce(s, V.dense.p, m * m);   // every rank contributes its rows
+  if (dense_distributed) c->comm.allreduce(s, V.dense.p, m * m);   // every rank contributes its rows
   dense_inverse_device(s, (int)m, V.dense.p, c->amg.colbuf.p);
 }
 
@@ -380,8 +490,21 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
   knp_stream_t s = c->stream;
   AmgLevelPlan& L = c->amg.lev[li];
   Comm& comm = c->comm;
+  const bool dist = comm.active() && li < c->amg.rep_from;   // this level's vectors have ghosts
+  if (li + 1 == c->amg.rep_from) {
+    // hand over to the replicated rest of the hierarchy: all-gather the right-hand side, run
+    // the remaining cycle redundantly, pick this rank's owned and ghost unknowns
+    AmgPlan& amg = c->amg;
+    AmgLevelPlan& T0 = amg.lev[li + 1];
+    d2d(amg.rep_b.p + (int64_t)comm.rank * amg.rep_bstride, L.b.p, L.n * sizeof(double), s);
+    comm.allgather(s, amg.rep_b.p, amg.rep_bstride);
+    { GatherMapKernel k{amg.rep_b.p, amg.rep_bmap.p, T0.b.p}; parallel_for(s, T0.n, k); }
+    coarse_cycle(c, V, li + 1, false);
+    { GatherMapKernel k{T0.x.p, amg.rep_xmap.p, L.x.p}; parallel_for(s, L.nloc, k); }
+    return;
+  }
   if (li + 1 == c->amg.lev.size()) {
-    if (!comm.active()) {
+    if (!dist) {
       DenseMatvecKernel k{L.n, V.dense.p, L.b.p, L.x.p};
       parallel_for(s, L.n, k, 64);
       return;
@@ -401,7 +524,7 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
   AmgLevelPlan& C = c->amg.lev[li + 1];
   if (c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1 && C.t_unit) {
     // fused V(1,1) path: two kernels down (smooth+residual, restrict), one up (prolong+smooth)
-    comm.halo(s, L.halo, L.b.p);
+    if (dist) comm.halo(s, L.halo, L.b.p);
     { CoarseResidualKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.r.p}; parallel_rows<8>(s, L.n, k); }
     if (L.halo.n_ghost > 0) {   // x = dinv b on the ghost unknowns too (read by the sweep up)
       DiagScaleKernel k{V.dinv[li].p + L.n, L.b.p + L.n, L.x.p + L.n, 1.0};
@@ -411,31 +534,31 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
     coarse_cycle(c, V, li + 1, true);
     { CoarseUpKernel k{A, V.dinv[li].p, L.b.p, L.x.p, C.pidx.p, C.x.p, L.t.p}; parallel_rows<8>(s, L.n, k); }
     std::swap(L.x.p, L.t.p);
-    if (ghost_x) comm.halo(s, L.halo, L.x.p);
+    if (ghost_x && dist) comm.halo(s, L.halo, L.x.p);
     return;
   }
   // pre-smoothing from a zero guess
   { DiagScaleKernel k{V.dinv[li].p, L.b.p, L.x.p, 1.0}; parallel_for(s, L.n, k); }
   for (int it = 1; it < c->opt.nu_pre; ++it) {
-    comm.halo(s, L.halo, L.x.p);
+    if (dist) comm.halo(s, L.halo, L.x.p);
     CsrJacobiKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.t.p, 1.0};
     parallel_for(s, L.n, k);
     std::swap(L.x.p, L.t.p);
   }
   for (int g = 0; g < c->opt.gamma; ++g) {
-    comm.halo(s, L.halo, L.x.p);
+    if (dist) comm.halo(s, L.halo, L.x.p);
     { CsrSpmvKernel k{A, L.x.p, L.b.p, L.r.p, 1}; parallel_for(s, L.n, k); }
     transfer(c, C.n, C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, L.r.p, C.b.p, 0);
     coarse_cycle(c, V, li + 1, false);
     transfer(c, L.n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, C.x.p, L.x.p, 1);
   }
   for (int it = 0; it < c->opt.nu_post; ++it) {
-    comm.halo(s, L.halo, L.x.p);
+    if (dist) comm.halo(s, L.halo, L.x.p);
     CsrJacobiKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.t.p, 1.0};
     parallel_for(s, L.n, k);
     std::swap(L.x.p, L.t.p);
   }
-  if (ghost_x) comm.halo(s, L.halo, L.x.p);
+  if (ghost_x && dist) comm.halo(s, L.halo, L.x.p);
 }
 
 // z = M^-1 r
@@ -616,7 +739,9 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
       // h stays on the device for the update, the host reads it once for the Givens rotations
       multi_dot_device(s, no, n, j + 2, V, vn, c->kr_partial.p, hdev);
       c->comm.allreduce(s, hdev, j + 2);
-      const double cancel_tol = 1e-6;
+      // the Pythagorean norm carries a relative error of about eps |w|^2 / hn^2: keep it below
+      // the requested tolerance, otherwise fall back to the explicit norm
+      const double cancel_tol = fmax(1e-6, 100.0 * 2.2e-16 / fmax(rtol, 1e-16));
       { GsNormalizeKernel k{n, j + 1, V, hdev, vn, cancel_tol}; parallel_for(s, no, k); }
       d2h(hcol.data(), hdev, (j + 2) * sizeof(double), s);
       double hsum = 0.0;

@@ -305,27 +305,29 @@ def bundle_3d_mesh(resolution=0, dims=None, nblocks=1):
     four axons (all cell tag 1), membrane tag 1 for the first axon and 2 for the
     other three, exterior 5, scaled to m.  `dims=(nx,ny,nz)` overrides the
     2^r refinement (SURVEY.md 8d 'scale 3' = (96,27,27)).  `nblocks` > 1 (weak-scaling
-    runs) lengthens the bundle: the box is 32*nblocks um long with nx*nblocks cells along
-    it, the axons keep their 5 um distance from both ends."""
+    runs) puts that many copies of the four-axon block side by side in y: a
+    32 x 0.9*nblocks x 0.9 um box with nx x ny*nblocks x nz cells and 4*nblocks axons."""
     if dims is None:
         nx, ny, nz = 32 * 2 ** resolution, 9 * 2 ** resolution, 9 * 2 ** resolution
     else:
         nx, ny, nz = dims
-    L = 32.0 * nblocks
-    mesh = box_mesh((0.0, 0.0, 0.0), (L, 0.9, 0.9), nx * nblocks, ny, nz)
+    W = 0.9 * nblocks
+    mesh = box_mesh((0.0, 0.0, 0.0), (32.0, W, 0.9), nx, ny * nblocks, nz)
     mesh.init_topology()
     tol = 1e-9
     sub = MeshFunction(mesh, 3, 0)
     surf = MeshFunction(mesh, 2, 0)
     cm = mesh.cell_midpoints()
     fm = mesh.facet_midpoints()
-    axons = [((5, 0.2, 0.2), (L - 5, 0.4, 0.4), 1),
-             ((5, 0.5, 0.5), (L - 5, 0.7, 0.7), 2),
-             ((5, 0.5, 0.2), (L - 5, 0.7, 0.4), 2),
-             ((5, 0.2, 0.5), (L - 5, 0.4, 0.7), 2)]
-    for a, b, tag in axons:
-        sub.array()[_inside(cm, a, b, tol)] = 1
-        surf.array()[_on_box_surface(fm, a, b, tol)] = tag
+    for blk in range(nblocks):
+        y0 = 0.9 * blk
+        axons = [((5, y0 + 0.2, 0.2), (27, y0 + 0.4, 0.4), 1),
+                 ((5, y0 + 0.5, 0.5), (27, y0 + 0.7, 0.7), 2),
+                 ((5, y0 + 0.5, 0.2), (27, y0 + 0.7, 0.4), 2),
+                 ((5, y0 + 0.2, 0.5), (27, y0 + 0.4, 0.7), 2)]
+        for a, b, tag in axons:
+            sub.array()[_inside(cm, a, b, tol)] = 1
+            surf.array()[_on_box_surface(fm, a, b, tol)] = tag
     surf.array()[mesh.exterior_facets()] = 5
     mesh.scale(1e-6)
     return mesh, sub, surf
