@@ -57,8 +57,8 @@ def test_partitioned_run_matches_single_part(emu_lib, tmp_path, world, case):
     # aggregates never cross a partition boundary, so the hierarchy (and the iteration count)
     # depends on the partition: the default partition cuts across the weak (long) direction
     # of the bundle and changes little; the deliberately bad "quad" split cuts the strong
-    # transverse couplings of the 10:1 cells and costs about 2.5x
-    slack = 3 if case.endswith("_quad") else 1.5
+    # transverse couplings of the 10:1 cells and costs about 3x
+    slack = 4 if case.endswith("_quad") else 1.5
     for a, b in zip(res["iterations"]["emi_niter"], res["ref_iterations"]["emi_niter"]):
         assert a <= slack * b + 5
     for a, b in zip(res["iterations"]["knp_niter"], res["ref_iterations"]["knp_niter"]):
