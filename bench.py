@@ -329,6 +329,13 @@ def main():
         kms, kbytes = ctx.bench_kernel(kid, reps=20)
         kern[name] = {"ms": kms, "algorithmic_bytes": kbytes, "gbs": kbytes / (kms * 1e-3) / 1e9,
                       "frac": kbytes / (kms * 1e-3) / 1e9 / peak}
+    comm_us = None
+    if world > 1:       # latency of one exchange of each kind, back to back (collective)
+        comm_us = {}
+        for kid, name in ((4, "dg_halo"), (5, "allreduce_4"), (6, "amg_tail_allgather")):
+            barrier()
+            kms, kbytes = ctx.bench_kernel(kid, reps=200)
+            comm_us[name] = {"us": kms * 1e3, "bytes": kbytes}
     dom = kern["bell_spmv"]
     roofline = {"bound": "hbm", "kernel": "knp::BellSpmvKernel<4> (block-ELL fp64 SpMV)",
                 "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": TRAFFIC_SPMV,
@@ -363,7 +370,7 @@ def main():
             "iterations": {"emi": eng.stats["emi_niter"][-args.steps:], "knp": eng.stats["knp_niter"][-args.steps:]},
             "e2e": {"value": e2e_value, "unit": "DOF-steps/s", "h2d_bytes_per_step": bytes_dir,
                     "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps, "steps_per_s": e2e_steps / (ms_e2e * 1e-3)},
-            "gpu_launches": launches, "comm": comm_info, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": launches, "comm": comm_info, "comm_latency": comm_us, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -207,7 +207,9 @@ int knp_timers_get(knp_ctx* ctx, double* out, int reset);
  *   current state, timed with CUDA events; *ms = average per launch and
  *   *bytes = algorithmic bytes one launch moves.
  *   kernel ids: 0 block-ELL SpMV (A_emi), 1 EMI assembly (pre-pass + cells),
- *   2 KNP assembly (all solved ions), 3 block-Jacobi sweep (B_emi). */
+ *   2 KNP assembly (all solved ions), 3 block-Jacobi sweep (B_emi);
+ *   multi-GPU exchanges (collective; 0 ms on a single part): 4 DG halo of one field,
+ *   5 allreduce of 4 Krylov scalars, 6 all-gather of the replicated AMG level's rhs. */
 long long knp_launch_count(void);
 int knp_timer_start(knp_ctx* ctx);
 int knp_timer_stop(knp_ctx* ctx, double* ms);

@@ -860,6 +860,7 @@ int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* byt
   const double geom = 8.0 * nc * nd * d + 16.0 * nc + 4.0 * nc + 8.0 * nd * nc;  // grad, vol+h, region, nbr+finfo
   DevBuf<double> x, y;
   if (kernel == 0 || kernel == 3) { x.alloc(ctx->n); y.alloc(ctx->n); }
+  if (kernel >= 4 && !ctx->comm.active()) { *ms = 0.0; *bytes = 0.0; return 0; }
   stream_sync(ctx->stream);
   double t_ms = 0.0;
   knp_timer_start(ctx);
@@ -879,6 +880,11 @@ int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* byt
         else { BellJacobiKernel<4> k{M, ctx->Adiag_emi(), ctx->rhs_emi.p, x.p, y.p, 0.7}; parallel_for(ctx->stream, ctx->n_own, k, 256); }
         break;
       }
+      case 4: ctx->comm.halo(ctx->stream, ctx->halo0, ctx->phi.p); break;          // DG halo exchange
+      case 5: ctx->comm.allreduce(ctx->stream, ctx->kr_scal.p + 900, 4); break;    // Krylov scalars
+      case 6:                                                                      // AMG tail all-gather
+        if (ctx->amg.ready && ctx->amg.rep_from != (size_t)-1) ctx->comm.allgather(ctx->stream, ctx->amg.rep_b.p, ctx->amg.rep_bstride);
+        break;
       default: fail("unknown kernel id");
     }
   }
@@ -893,6 +899,9 @@ int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* byt
     case 2: b = /*grad*/ 8.0 * n + 8.0 * nc * nd * d + 8.0 * nc * d
               + geom + 8.0 * nc * d + (N - 1) * (8.0 * n + mat + 8.0 * n); break;
     case 3: b = mat + 8.0 * nc * bs + 4.0 * nd * nc + 24.0 * n; break;
+    case 4: b = 8.0 * (double)(ctx->halo0.nsend() + ctx->halo0.n_ghost); break;
+    case 5: b = 32.0; break;
+    case 6: b = 8.0 * (double)ctx->amg.rep_bstride * ctx->comm.world; break;
   }
   *bytes = b;
   KNP_CATCH
