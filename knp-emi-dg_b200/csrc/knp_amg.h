@@ -191,6 +191,8 @@ struct AmgPlan {
   // are all-gathered and the REST of the hierarchy (lev[rep_from] = the global copy of
   // lev[rep_from-1], then serial coarsening down to the dense level) is built and applied
   // redundantly on every rank: one all-gather per cycle instead of two halos per level.
+  size_t tail_from = (size_t)-1;   // first level handled by the single-launch coarse_tail_kernel; -1: none
+  int tail_blocks = 0;             // its (cooperative) grid
   size_t rep_from = (size_t)-1;    // index of the first replicated level; -1: none
   int64_t rep_vstride = 0, rep_bstride = 0;   // padded per-rank segment: matrix values / rows
   DevBuf<double> rep_val, rep_b;   // all-gather buffers [world * stride]

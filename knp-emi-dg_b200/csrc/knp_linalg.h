@@ -263,6 +263,106 @@ struct CoarseUpKernel {
 // dense[m*m] (zeroed before) <- the owned rows of the last level's CSR; `map` (nullptr =
 // identity) sends a local unknown to its index in the global last-level numbering, `off` is
 // the global index of local row 0.
+// ---- the small coarse levels in ONE launch ------------------------------------------------
+// Levels with 10^1..10^4 rows cost 5-7 us per launch (launch + drain) and three launches per
+// level and cycle; together they were 29 % of a time step (profiles/launches_r01_step.md).
+// coarse_tail_kernel runs the whole fused V(1,1) cycle of those levels - sweep down
+// (smooth + residual, restrict), dense solve, sweep up (prolong + smooth) - as one cooperative
+// launch with grid-wide barriers between the phases.  The arithmetic (lane assignment,
+// reduction order) is exactly that of CoarseResidualKernel / TransferRowsKernel /
+// DenseMatvecKernel / CoarseUpKernel above, so the result is bit-identical to the
+// launch-per-sweep path (which the host emulation and larger levels keep using).
+constexpr int TAIL_MAX_LEVELS = 12;
+constexpr int TAIL_MAX_ROWS = 40000;
+struct TailLevel {
+  int64_t n;
+  const int32_t* ptr; const int32_t* col; const double* val; const double* dinv;
+  double* b; double* x; double* r;
+  const int32_t* rptr; const int32_t* ridx;   // restriction INTO this level from the finer tail level
+  const int32_t* agg;                         // finer tail level's unknown -> unknown of this level
+};
+struct TailArgs {
+  int nlev;                // L[nlev-1] is the dense level
+  TailLevel L[TAIL_MAX_LEVELS];
+  const double* denseT;    // transposed inverse of the last level
+};
+
+#ifndef KNP_EMU
+}  // namespace knp
+#include <cooperative_groups.h>
+namespace knp {
+static __global__ void __launch_bounds__(256) coarse_tail_kernel(const TailArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  constexpr int LANES = 8;
+  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int lane = (int)(gt % LANES);
+  const int64_t nsub = nthreads / LANES;       // rows processed per pass
+  const int64_t sub = gt / LANES;
+  // sweep down
+  for (int k = 0; k + 1 < a.nlev; ++k) {
+    const TailLevel& L = a.L[k];
+    for (int64_t base = 0; base < L.n; base += nsub) {
+      const int64_t i = base + sub;
+      const bool ok = i < L.n;
+      double acc = 0.0;
+      if (ok)
+        for (int32_t e = L.ptr[i] + lane; e < L.ptr[i + 1]; e += LANES) {
+          const int32_t j = L.col[e];
+          acc += L.val[e] * L.dinv[j] * L.b[j];
+        }
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LANES);
+      if (ok && lane == 0) L.r[i] = L.b[i] - acc;
+    }
+    grid.sync();
+    const TailLevel& C = a.L[k + 1];
+    for (int64_t base = 0; base < C.n; base += nsub) {
+      const int64_t I = base + sub;
+      const bool ok = I < C.n;
+      double acc = 0.0;
+      if (ok)
+        for (int32_t e = C.rptr[I] + lane; e < C.rptr[I + 1]; e += LANES) acc += L.r[C.ridx[e]];
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LANES);
+      if (ok && lane == 0) C.b[I] = acc;
+    }
+    grid.sync();
+  }
+  // dense level
+  {
+    const TailLevel& D = a.L[a.nlev - 1];
+    const int64_t m = D.n;
+    for (int64_t row = gt; row < m; row += nthreads) {
+      double acc = 0.0;
+      for (int64_t j = 0; j < m; ++j) acc += a.denseT[j * m + row] * D.b[j];
+      D.x[row] = acc;
+    }
+    grid.sync();
+  }
+  // sweep up
+  for (int k = a.nlev - 2; k >= 0; --k) {
+    const TailLevel& L = a.L[k];
+    const TailLevel& C = a.L[k + 1];
+    for (int64_t base = 0; base < L.n; base += nsub) {
+      const int64_t i = base + sub;
+      const bool ok = i < L.n;
+      double acc = 0.0;
+      if (ok)
+        for (int32_t e = L.ptr[i] + lane; e < L.ptr[i + 1]; e += LANES) {
+          const int32_t j = L.col[e];
+          acc += L.val[e] * (__dmul_rn(L.dinv[j], L.b[j]) + C.x[C.agg[j]]);
+        }
+#pragma unroll
+      for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LANES);
+      if (ok && lane == 0) L.x[i] = __dmul_rn(L.dinv[i], L.b[i]) + C.x[C.agg[i]] + L.dinv[i] * (L.b[i] - acc);
+    }
+    if (k > 0) grid.sync();
+  }
+}
+#endif
+
 struct CsrToDenseKernel {
   CsrMat A; double* dense; int64_t m; int64_t off; const int32_t* map;
   KNP_HD void operator()(int64_t row) const {

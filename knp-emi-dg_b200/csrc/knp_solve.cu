@@ -370,6 +370,34 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
   }
   if (amg.m_dense > 4096) fail("knp_amg_setup: coarsest level too large for the dense solve (" +
                                 std::to_string(amg.m_dense) + " rows); raise max_levels");
+  // the small levels run as one cooperative launch per cycle (coarse_tail_kernel)
+  amg.tail_from = (size_t)-1; amg.tail_blocks = 0;
+#ifndef KNP_EMU
+  {
+    const char* e = getenv("KNP_AMG_TAIL");
+    if (!(e && e[0] == '0')) {
+      size_t first = amg.lev.size();
+      for (size_t l = amg.lev.size(); l-- > 0;) {
+        const bool local = !ctx->comm.active() || l >= amg.rep_from;   // no halos inside the tail
+        if (!local || amg.lev[l].n > TAIL_MAX_ROWS || !amg.lev[l].t_unit) break;
+        first = l;
+      }
+      if (first == amg.rep_from) ++first;   // the hand-over into the replica stays a regular step
+      int coop = 0, dev = 0, nsm = 0, per_sm = 0;
+      KNP_CUDA(cudaGetDevice(&dev));
+      KNP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+      KNP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+      KNP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_tail_kernel, 256, 0));
+      if (coop && per_sm > 0 && first + 2 <= amg.lev.size() && amg.lev.size() - first <= (size_t)TAIL_MAX_LEVELS) {
+        amg.tail_from = first;
+        int64_t want = (amg.lev[first].n * 8 + 255) / 256;     // 8 lanes per row
+        if (want > 64) want = 64;                              // few blocks: cheap grid barriers
+        if (want > (int64_t)nsm * per_sm) want = (int64_t)nsm * per_sm;
+        amg.tail_blocks = (int)(want < 1 ? 1 : want);
+      }
+    }
+  }
+#endif
   amg.dense_b.alloc(amg.m_dense); amg.dense_x.alloc(amg.m_dense);
   amg.x0.alloc(ctx->n); amg.r0.alloc(ctx->n); amg.t0.alloc(ctx->n);
   amg.colbuf.alloc(amg.m_dense);
@@ -491,6 +519,26 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
   AmgLevelPlan& L = c->amg.lev[li];
   Comm& comm = c->comm;
   const bool dist = comm.active() && li < c->amg.rep_from;   // this level's vectors have ghosts
+#ifndef KNP_EMU
+  if (li == c->amg.tail_from && c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1) {
+    AmgPlan& amg = c->amg;
+    TailArgs a;
+    a.nlev = (int)(amg.lev.size() - li);
+    for (int k = 0; k < a.nlev; ++k) {
+      AmgLevelPlan& T = amg.lev[li + k];
+      TailLevel& t = a.L[k];
+      t.n = T.n; t.ptr = T.ptr.p; t.col = T.col.p; t.val = V.val[li + k].p; t.dinv = V.dinv[li + k].p;
+      t.b = T.b.p; t.x = T.x.p; t.r = T.r.p;
+      t.rptr = T.rptr.p; t.ridx = T.ridx.p; t.agg = T.pidx.p;
+    }
+    a.denseT = V.dense.p;
+    void* params[] = {(void*)&a};
+    ++launch_counter();
+    KNP_CUDA(cudaLaunchCooperativeKernel((const void*)coarse_tail_kernel, dim3((unsigned)amg.tail_blocks), dim3(256),
+                                         params, 0, s));
+    return;
+  }
+#endif
   if (li + 1 == c->amg.rep_from) {
     // hand over to the replicated rest of the hierarchy: all-gather the right-hand side, run
     // the remaining cycle redundantly, pick this rank's owned and ghost unknowns
