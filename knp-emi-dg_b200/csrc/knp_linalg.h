@@ -266,14 +266,17 @@ struct CoarseUpKernel {
 // ---- the small coarse levels in ONE launch ------------------------------------------------
 // Levels with 10^1..10^4 rows cost 5-7 us per launch (launch + drain) and three launches per
 // level and cycle; together they were 29 % of a time step (profiles/launches_r01_step.md).
-// coarse_tail_kernel runs the whole fused V(1,1) cycle of those levels - sweep down
-// (smooth + residual, restrict), dense solve, sweep up (prolong + smooth) - as one cooperative
-// launch with grid-wide barriers between the phases.  The arithmetic (lane assignment,
+// coarse_tail_kernel runs the whole fused V(1,1) cycle of the smallest levels - sweep down
+// (smooth + residual, restrict), dense solve, sweep up (prolong + smooth) - as ONE launch of a
+// single thread-block cluster (8 CTAs x 1024 threads on 8 SMs) with the hardware cluster
+// barrier (~0.2 us, B300_MICROARCH.md) between the phases.  (A cooperative whole-grid version
+// with grid.sync() was measured SLOWER than the launches it replaced: ~5 us per grid barrier.)  The arithmetic (lane assignment,
 // reduction order) is exactly that of CoarseResidualKernel / TransferRowsKernel /
 // DenseMatvecKernel / CoarseUpKernel above, so the result is bit-identical to the
 // launch-per-sweep path (which the host emulation and larger levels keep using).
 constexpr int TAIL_MAX_LEVELS = 12;
-constexpr int TAIL_MAX_ROWS = 40000;
+constexpr int TAIL_MAX_ROWS = 4096;
+constexpr int TAIL_CTAS = 8, TAIL_THREADS = 1024;
 struct TailLevel {
   int64_t n;
   const int32_t* ptr; const int32_t* col; const double* val; const double* dinv;
@@ -291,9 +294,10 @@ struct TailArgs {
 }  // namespace knp
 #include <cooperative_groups.h>
 namespace knp {
-static __global__ void __launch_bounds__(256) coarse_tail_kernel(const TailArgs a) {
+static __global__ void __cluster_dims__(TAIL_CTAS, 1, 1) __launch_bounds__(TAIL_THREADS)
+coarse_tail_kernel(const TailArgs a) {
   namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+  cg::cluster_group grid = cg::this_cluster();   // the whole grid is one cluster
   constexpr int LANES = 8;
   const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -397,7 +401,11 @@ struct AxpbyKernel {  // y = a x + b y
 };
 struct DirectionKernel {  // p = (z - mu) + b p   (CG direction from the mean-free preconditioned residual)
   const double* z; double mu; double b; double* p;
-  KNP_HD void operator()(int64_t i) const { p[i] = (z[i] - mu) + b * p[i]; }
+  KNP_HD void operator()(int64_t i) const { p[i] = (b == 0.0) ? (z[i] - mu) : (z[i] - mu) + b * p[i]; }
+};
+struct Axpy2ProjKernel {  // x += a p ; r = r - a q - shift   (CG update; shift keeps r mean-free)
+  double a; const double* p; const double* q; double* x; double* r; double shift;
+  KNP_HD void operator()(int64_t i) const { x[i] += a * p[i]; r[i] = (r[i] - a * q[i]) - shift; }
 };
 struct Axpy2Kernel {  // x += a p ; r -= a q     (CG update)
   double a; const double* p; const double* q; double* x; double* r;

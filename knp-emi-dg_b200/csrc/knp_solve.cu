@@ -383,17 +383,9 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
         first = l;
       }
       if (first == amg.rep_from) ++first;   // the hand-over into the replica stays a regular step
-      int coop = 0, dev = 0, nsm = 0, per_sm = 0;
-      KNP_CUDA(cudaGetDevice(&dev));
-      KNP_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-      KNP_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-      KNP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, coarse_tail_kernel, 256, 0));
-      if (coop && per_sm > 0 && first + 2 <= amg.lev.size() && amg.lev.size() - first <= (size_t)TAIL_MAX_LEVELS) {
+      if (first + 2 <= amg.lev.size() && amg.lev.size() - first <= (size_t)TAIL_MAX_LEVELS) {
         amg.tail_from = first;
-        int64_t want = (amg.lev[first].n * 8 + 255) / 256;     // 8 lanes per row
-        if (want > 64) want = 64;                              // few blocks: cheap grid barriers
-        if (want > (int64_t)nsm * per_sm) want = (int64_t)nsm * per_sm;
-        amg.tail_blocks = (int)(want < 1 ? 1 : want);
+        amg.tail_blocks = TAIL_CTAS;
       }
     }
   }
@@ -532,10 +524,9 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
       t.rptr = T.rptr.p; t.ridx = T.ridx.p; t.agg = T.pidx.p;
     }
     a.denseT = V.dense.p;
-    void* params[] = {(void*)&a};
     ++launch_counter();
-    KNP_CUDA(cudaLaunchCooperativeKernel((const void*)coarse_tail_kernel, dim3((unsigned)amg.tail_blocks), dim3(256),
-                                         params, 0, s));
+    coarse_tail_kernel<<<TAIL_CTAS, TAIL_THREADS, 0, s>>>(a);
+    KNP_CUDA(cudaGetLastError());
     return;
   }
 #endif
@@ -677,10 +668,15 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   else { if (c->bj_emi.n != (size_t)c->slot_stride()) c->bj_emi.alloc(c->slot_stride()); block_inverse(c, c->Bdiag(), c->bj_emi.p); }
   double* x = c->phi.p; double* r = c->kr_r.p; double* z = c->kr_r.p + n; double* p = c->kr_p.p; double* q = c->kr_q.p;
   const double* b = c->rhs_emi.p;
-  // r.z, z.z, 1.z and 1.r in one pass and one reduction; the mean of z is removed
-  // analytically: with mu = (1.z)/N,  r.(z-mu) = r.z - mu (1.r),  |z-mu|^2 = z.z - N mu^2
+  // Two reductions per iteration.  (1) {p.q, 1.q}: with 1.r known, the mean of the updated
+  // residual is known before the update and is subtracted in the same pass, so r stays
+  // orthogonal to the null space to round-off of ITS OWN size (an unprojected r drifts by
+  // eps |b|, which the mass-shifted preconditioner amplifies until it dominates z).
+  // (2) {r.z, z.z, 1.z, 1.r}: the mean of z is then a small component and is removed
+  // analytically: mu = (1.z)/N,  r.(z-mu) = r.z - mu (1.r),  |z-mu|^2 = z.z - N mu^2.
   const double* ones = c->kr_ones.p;
   const double Ng = c->n_global;
+  double sum_r = 0.0;
   auto fused_dots = [&](double& rz_out, double& zz_out, double& mu_out) {
     DotPairs P{{r, z, ones, ones}, {z, z, z, r}};
     pair_dot_device(s, no, 4, P, c->kr_partial.p, c->kr_scal.p);
@@ -688,6 +684,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
     double d[4];
     d2h(d, c->kr_scal.p, sizeof d, s);
     mu_out = d[2] / Ng;
+    sum_r = d[3];
     rz_out = d[0] - mu_out * d[3];
     zz_out = fmax(d[1] - Ng * mu_out * mu_out, 0.0);
   };
@@ -697,6 +694,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   const double bnorm = sqrt(dot_host(c, z, z));
   const double tol = fmax(rtol * bnorm, atol);
   bell_spmv(c, A, x, b, r, 1);
+  remove_mean(c, r);
   precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
   double rz, zz, mu;
   fused_dots(rz, zz, mu);
@@ -707,7 +705,15 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
     { DirectionKernel k{z, mu, 0.0, p}; parallel_for(s, no, k); }
     for (it = 1; it <= maxit; ++it) {
       bell_spmv(c, A, p, nullptr, q, 0);
-      const double pq = dot_host(c, p, q);
+      double pq, sum_q;
+      {
+        DotPairs P{{p, ones, nullptr, nullptr}, {q, q, nullptr, nullptr}};
+        pair_dot_device(s, no, 2, P, c->kr_partial.p, c->kr_scal.p);
+        c->comm.allreduce(s, c->kr_scal.p, 2);
+        double d[2];
+        d2h(d, c->kr_scal.p, sizeof d, s);
+        pq = d[0]; sum_q = d[1];
+      }
       if (!(pq > 0.0)) {
         // at round-off level p can fall into the (constant) null space of A: the iteration
         // has converged as far as fp64 allows
@@ -716,7 +722,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
         fail("knp_solve_emi: operator or preconditioner is indefinite");
       }
       const double alpha = rz / pq;
-      { Axpy2Kernel k{alpha, p, q, x, r}; parallel_for(s, no, k); }
+      { Axpy2ProjKernel k{alpha, p, q, x, r, (sum_r - alpha * sum_q) / Ng}; parallel_for(s, no, k); }
       precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
       double rz_new;
       fused_dots(rz_new, zz, mu);
