@@ -50,8 +50,10 @@ def test_rest_state_is_preserved_at_scale(gpu_lib):
     pm = eng.phi_M()
     # 5 steps at the reference's KSP tolerances (CG rtol 1e-5): within 0.01 mV of rest
     assert np.abs(pm + 0.07438609374462003).max() < 1e-5
+    # no pumps in the HH model: the resting Na+/K+ leak currents move the concentrations next
+    # to the membranes by a few 1e-5 (relative) over 5 steps; anything larger is a solver fault
     for k in range(3):
-        assert rel_err(eng.concentration(k), c0[k]) < 1e-6
+        assert rel_err(eng.concentration(k), c0[k]) < 1e-4
     z = bench.PHYS["z"]
     total = sum(z[k] * eng.concentration(k) for k in range(3))
     assert np.abs(total).max() < 1e-9 * np.abs(c0[1]).max()
