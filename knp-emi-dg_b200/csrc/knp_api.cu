@@ -58,6 +58,7 @@ int knp_ctx_create(int device, knp_ctx** out) {
 #ifndef KNP_EMU
   KNP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 #endif
+  { const char* e = getenv("KNP_KNP_PRESMOOTH"); c->opt.knp_presmooth0 = !(e && e[0] == '0'); }
   c->kr_scal.alloc(1024);
   c->kr_partial.alloc((size_t)DOT_MAX * RED_BLOCKS);
   c->ode_stats.alloc(4);

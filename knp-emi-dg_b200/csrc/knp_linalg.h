@@ -72,23 +72,30 @@ struct BlockDiagApplyKernel {
 template <int ND>
 struct BellJacobiKernel {
   BellMat A; const double* dinv; const double* b; const double* xin; double* xout; double w;
+  // optional fused prolongation (post-smoothing of the V-cycle): the sweep runs on
+  // x' = xin + P xc with (P xc)_d = xc[agg[d]] (unit aggregation transfer); xin == nullptr
+  // means x' = P xc (no pre-smoothed iterate)
+  const int32_t* agg = nullptr; const double* xc = nullptr;
+  KNP_HD double xval(int64_t d) const {
+    double v = xin ? xin[d] : 0.0;
+    if (agg) v += xc[agg[d]];
+    return v;
+  }
   KNP_HD double row_residual(int64_t cell, int i) const {
     const int64_t bs = ND * ND;
     double acc = b[cell * ND + i];
     {
       const double* a = A.diag + cell * bs + i * ND;
-      const double* xc = xin + cell * ND;
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc -= a[j] * xc[j];
+      for (int j = 0; j < ND; ++j) acc -= a[j] * xval(cell * ND + j);
     }
 #pragma unroll
     for (int f = 0; f < ND; ++f) {
       const int64_t c2 = A.nbr[f * A.nc + cell];
       if (c2 < 0) continue;
       const double* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND;
-      const double* xc = xin + c2 * ND;
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc -= a[j] * xc[j];
+      for (int j = 0; j < ND; ++j) acc -= a[j] * xval(c2 * ND + j);
     }
     return acc;
   }
@@ -112,7 +119,7 @@ struct BellJacobiKernel {
     double acc = 0.0;
 #pragma unroll
     for (int j = 0; j < ND; ++j) acc += di[j] * r[j];
-    xout[row] = xin[row] + w * acc;
+    xout[row] = xval(row) + w * acc;
   }
 };
 

@@ -53,6 +53,13 @@ static void bell_jacobi(knp_ctx* c, const BellMat& A, const double* dinv, const 
   if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n_own, k, 192); }
   else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n_own, k, 256); }
 }
+// post-smoothing sweep fused with the prolongation: out = x' + w Dinv (b - A x'), x' = xin + P xc
+// (xin may be nullptr).  The ghost entries of xin (if any) and of xc must be valid.
+static void bell_jacobi_prolong(knp_ctx* c, const BellMat& A, const double* dinv, const double* b,
+                                const double* xin, const int32_t* agg, const double* xc, double* xout, double w) {
+  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w, agg, xc}; parallel_for(c->stream, c->n_own, k, 192); }
+  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w, agg, xc}; parallel_for(c->stream, c->n_own, k, 256); }
+}
 static void block_inverse(knp_ctx* c, const double* blocks, double* inv) {
   if (c->nd == 3) { BlockInverseKernel<3> k{blocks, inv}; parallel_for(c->stream, c->nc_own, k, 128); }
   else { BlockInverseKernel<4> k{blocks, inv}; parallel_for(c->stream, c->nc_own, k, 128); }
@@ -601,7 +608,11 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
 }
 
 // z = M^-1 r
-static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const double* bj, const double* r, double* z) {
+// `presmooth0` = false drops the pre-smoothing sweep of the DG level (a V(0,1) cycle there:
+// the right-hand side is restricted directly, one matrix pass less per application).  The
+// resulting operator is not symmetric: fine for GMRES (KNP), not used with CG (EMI).
+static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const double* bj, const double* r, double* z,
+                         bool presmooth0 = true) {
   if (c->opt.pc == 0 || !c->amg.ready) {
     block_apply(c, bj, r, z, 1.0, 0);
     return;
@@ -610,6 +621,19 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
   AmgLevelPlan& C = amg.lev[0];
   const double w = V.omega;
   double* x = amg.x0.p; double* t = amg.t0.p;
+  const bool fused_post = c->opt.nu_post == 1 && C.t_unit && c->opt.nu_pre == 1;
+  if (fused_post) {
+    const double* rr = r;
+    if (presmooth0) {
+      block_apply(c, V.binv.p, r, x, w, 0);
+      bell_spmv(c, A0, x, r, amg.r0.p, 1);          // refreshes the ghost entries of x as well
+      rr = amg.r0.p;
+    }
+    { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, rr, C.b.p, 0}; parallel_rows<8>(c->stream, C.n, k); }
+    coarse_cycle(c, V, 0, c->comm.active());        // ghost entries of C.x are read by the fused sweep
+    bell_jacobi_prolong(c, A0, V.binv.p, r, presmooth0 ? x : nullptr, C.pidx.p, C.x.p, z, w);
+    return;
+  }
   block_apply(c, V.binv.p, r, x, w, 0);
   for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, V.binv.p, r, x, t, w); std::swap(x, t); }
   bell_spmv(c, A0, x, r, amg.r0.p, 1);
@@ -766,7 +790,8 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
   const double* b = c->rhs_knp[ion].p;
   double* V = c->kr_V.p; double* w = c->kr_w.p; double* r = c->kr_r.p;
   double* hdev = c->kr_scal.p + 512;  // device copy of the current Hessenberg column / y
-  precondition(c, Vv, A, bj, b, w);
+  const bool pre0 = c->opt.knp_presmooth0;
+  precondition(c, Vv, A, bj, b, w, pre0);
   const double bnorm = sqrt(dot_host(c, w, w));
   const double tol = fmax(rtol * bnorm, atol);
   std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
@@ -774,7 +799,7 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
   double res = 0.0;
   while (true) {
     bell_spmv(c, A, x, b, r, 1);
-    precondition(c, Vv, A, bj, r, V);              // V0 = M^-1 (b - A x)
+    precondition(c, Vv, A, bj, r, V, pre0);        // V0 = M^-1 (b - A x)
     const double beta = sqrt(dot_host(c, V, V));
     res = beta;
     if ((beta <= tol && it >= c->opt.knp_min_it) || it >= maxit || beta == 0.0) break;
@@ -787,7 +812,7 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
       double* vj = V + (int64_t)j * n;
       double* vn = V + (int64_t)(j + 1) * n;
       bell_spmv(c, A, vj, nullptr, r, 0);
-      precondition(c, Vv, A, bj, r, vn);           // w = M^-1 A v_j, built in the next basis slot
+      precondition(c, Vv, A, bj, r, vn, pre0);     // w = M^-1 A v_j, built in the next basis slot
       // classical Gram-Schmidt with ONE reduction per step: h = V^T w and |w|^2 in the same
       // pass (w is basis slot j+1), the new norm from Pythagoras, update + normalisation fused;
       // h stays on the device for the update, the host reads it once for the Givens rotations
