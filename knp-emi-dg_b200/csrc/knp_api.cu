@@ -58,7 +58,8 @@ int knp_ctx_create(int device, knp_ctx** out) {
 #ifndef KNP_EMU
   KNP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 #endif
-  { const char* e = getenv("KNP_KNP_PRESMOOTH"); c->opt.knp_presmooth0 = !(e && e[0] == '0'); }
+  { const char* e = getenv("KNP_KNP_PRESMOOTH"); c->opt.knp_presmooth0 = (e && e[0] == '1'); }
+  { const char* e = getenv("KNP_FUSE_PROLONG"); c->opt.fuse_prolong = (e && e[0] == '1'); }
   c->kr_scal.alloc(1024);
   c->kr_partial.alloc((size_t)DOT_MAX * RED_BLOCKS);
   c->ode_stats.alloc(4);

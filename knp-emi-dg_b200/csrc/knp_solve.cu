@@ -621,7 +621,10 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
   AmgLevelPlan& C = amg.lev[0];
   const double w = V.omega;
   double* x = amg.x0.p; double* t = amg.t0.p;
-  const bool fused_post = c->opt.nu_post == 1 && C.t_unit && c->opt.nu_pre == 1;
+  // (measured on B200: the fused prolongation + sweep is ~2 % SLOWER than prolongation and sweep
+  // as two launches - 40 extra gathers per row in a kernel that otherwise runs at 0.9 of the
+  // HBM roofline - so it is opt-in)
+  const bool fused_post = c->opt.fuse_prolong && c->opt.nu_post == 1 && C.t_unit && c->opt.nu_pre == 1;
   if (fused_post) {
     const double* rr = r;
     if (presmooth0) {
@@ -634,12 +637,16 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
     bell_jacobi_prolong(c, A0, V.binv.p, r, presmooth0 ? x : nullptr, C.pidx.p, C.x.p, z, w);
     return;
   }
-  block_apply(c, V.binv.p, r, x, w, 0);
-  for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, V.binv.p, r, x, t, w); std::swap(x, t); }
-  bell_spmv(c, A0, x, r, amg.r0.p, 1);
-  { TransferRowsKernel k{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, amg.r0.p, C.b.p, 0}; parallel_rows<8>(c->stream, C.n, k); }
+  const double* rr = r;
+  if (presmooth0) {
+    block_apply(c, V.binv.p, r, x, w, 0);
+    for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, V.binv.p, r, x, t, w); std::swap(x, t); }
+    bell_spmv(c, A0, x, r, amg.r0.p, 1);
+    rr = amg.r0.p;
+  }
+  { TransferRowsKernel k{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, rr, C.b.p, 0}; parallel_rows<8>(c->stream, C.n, k); }
   coarse_cycle(c, V, 0, false);
-  transfer(c, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, C.x.p, x, 1);
+  transfer(c, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, C.x.p, x, presmooth0 ? 1 : 0);
   if (c->opt.nu_post == 0) { d2d(z, x, c->n * sizeof(double), c->stream); return; }
   for (int it = 0; it < c->opt.nu_post; ++it) {
     double* out = (it + 1 == c->opt.nu_post) ? z : t;
