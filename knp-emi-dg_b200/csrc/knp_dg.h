@@ -938,33 +938,66 @@ struct FacetTraceKernel {
 // inverse of the ND x ND diagonal blocks (element block-Jacobi), Gauss-Jordan with
 // partial pivoting, one block per index.
 template <int ND>
+KNP_HD void invert_block(const double* in, double* out) {   // in/out: ND*ND doubles, row major
+  double a[ND][ND], b[ND][ND];
+  for (int i = 0; i < ND; ++i)
+    for (int j = 0; j < ND; ++j) { a[i][j] = in[i * ND + j]; b[i][j] = (i == j); }
+  for (int col = 0; col < ND; ++col) {
+    int piv = col;
+    double best = fabs(a[col][col]);
+    for (int rr = col + 1; rr < ND; ++rr)
+      if (fabs(a[rr][col]) > best) { best = fabs(a[rr][col]); piv = rr; }
+    if (piv != col)
+      for (int j = 0; j < ND; ++j) {
+        double t = a[col][j]; a[col][j] = a[piv][j]; a[piv][j] = t;
+        t = b[col][j]; b[col][j] = b[piv][j]; b[piv][j] = t;
+      }
+    const double ip = 1.0 / a[col][col];
+    for (int j = 0; j < ND; ++j) { a[col][j] *= ip; b[col][j] *= ip; }
+    for (int rr = 0; rr < ND; ++rr) {
+      if (rr == col) continue;
+      const double fct = a[rr][col];
+      for (int j = 0; j < ND; ++j) { a[rr][j] -= fct * a[col][j]; b[rr][j] -= fct * b[col][j]; }
+    }
+  }
+  for (int i = 0; i < ND; ++i)
+    for (int j = 0; j < ND; ++j) out[i * ND + j] = b[i][j];
+}
+
+template <int ND>
 struct BlockInverseKernel {
   const double* blocks; double* inv;
-  KNP_HD void operator()(int64_t cell) const {
-    double a[ND][ND], b[ND][ND];
-    for (int i = 0; i < ND; ++i)
-      for (int j = 0; j < ND; ++j) { a[i][j] = blocks[cell * ND * ND + i * ND + j]; b[i][j] = (i == j); }
-    for (int col = 0; col < ND; ++col) {
-      int piv = col;
-      double best = fabs(a[col][col]);
-      for (int rr = col + 1; rr < ND; ++rr)
-        if (fabs(a[rr][col]) > best) { best = fabs(a[rr][col]); piv = rr; }
-      if (piv != col)
-        for (int j = 0; j < ND; ++j) {
-          double t = a[col][j]; a[col][j] = a[piv][j]; a[piv][j] = t;
-          t = b[col][j]; b[col][j] = b[piv][j]; b[piv][j] = t;
-        }
-      const double ip = 1.0 / a[col][col];
-      for (int j = 0; j < ND; ++j) { a[col][j] *= ip; b[col][j] *= ip; }
-      for (int rr = 0; rr < ND; ++rr) {
-        if (rr == col) continue;
-        const double fct = a[rr][col];
-        for (int j = 0; j < ND; ++j) { a[rr][j] -= fct * a[col][j]; b[rr][j] -= fct * b[col][j]; }
-      }
-    }
-    for (int i = 0; i < ND; ++i)
-      for (int j = 0; j < ND; ++j) inv[cell * ND * ND + i * ND + j] = b[i][j];
-  }
+  KNP_HD void operator()(int64_t cell) const { invert_block<ND>(blocks + cell * ND * ND, inv + cell * ND * ND); }
 };
+
+#ifndef KNP_EMU
+// CUDA driver of the same arithmetic: 128 cells per block, the blocks are read and written as
+// contiguous runs through shared memory (pitch ND*ND+1), one thread inverts one block there.
+// (The one-index-per-cell functor reads 128-byte strided: 81 us for 420k cells; this: coalesced.)
+template <int ND>
+__global__ void __launch_bounds__(128) block_inverse_kernel(int64_t nc, const double* __restrict__ blocks,
+                                                            double* __restrict__ inv) {
+  constexpr int BS = ND * ND, PITCH = BS + 1, CPB = 128;
+  __shared__ double sm[CPB][PITCH];
+  const int t = threadIdx.x;
+  const int64_t cell0 = (int64_t)blockIdx.x * CPB;
+  const int ncell = (int)((nc - cell0 < CPB) ? (nc - cell0) : CPB);
+  const int nval = ncell * BS;
+  const double* src = blocks + cell0 * BS;
+  for (int e = t; e < nval; e += CPB) sm[e / BS][e % BS] = src[e];
+  __syncthreads();
+  if (t < ncell) {
+    double in[BS], out[BS];
+#pragma unroll
+    for (int k = 0; k < BS; ++k) in[k] = sm[t][k];
+    invert_block<ND>(in, out);
+#pragma unroll
+    for (int k = 0; k < BS; ++k) sm[t][k] = out[k];
+  }
+  __syncthreads();
+  double* dst = inv + cell0 * BS;
+  for (int e = t; e < nval; e += CPB) dst[e] = sm[e / BS][e % BS];
+}
+#endif
 
 }  // namespace knp

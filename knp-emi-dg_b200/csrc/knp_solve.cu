@@ -61,8 +61,16 @@ static void bell_jacobi_prolong(knp_ctx* c, const BellMat& A, const double* dinv
   else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w, agg, xc}; parallel_for(c->stream, c->n_own, k, 256); }
 }
 static void block_inverse(knp_ctx* c, const double* blocks, double* inv) {
+#ifdef KNP_EMU
   if (c->nd == 3) { BlockInverseKernel<3> k{blocks, inv}; parallel_for(c->stream, c->nc_own, k, 128); }
   else { BlockInverseKernel<4> k{blocks, inv}; parallel_for(c->stream, c->nc_own, k, 128); }
+#else
+  const unsigned grid = (unsigned)((c->nc_own + 127) / 128);
+  ++launch_counter();
+  if (c->nd == 3) block_inverse_kernel<3><<<grid, 128, 0, c->stream>>>(c->nc_own, blocks, inv);
+  else block_inverse_kernel<4><<<grid, 128, 0, c->stream>>>(c->nc_own, blocks, inv);
+  KNP_CUDA(cudaGetLastError());
+#endif
 }
 
 // host-visible dot products over all ranks (one sync each)
@@ -222,7 +230,7 @@ static void alloc_values(knp_ctx* c, AmgValues& V) {
 // rows (over all ranks) below which the rest of the hierarchy is replicated; 0 disables
 static int64_t replicate_threshold() {
   const char* e = getenv("KNP_AMG_REPLICATE");
-  return e ? atoll(e) : 262144;
+  return e ? atoll(e) : 131072;
 }
 
 // gather `count` doubles per rank (padded) from every rank to every rank, on the host
