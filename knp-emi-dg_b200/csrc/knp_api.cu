@@ -350,6 +350,14 @@ int knp_field_get(knp_ctx* ctx, int which, int idx, double* dst, int64_t count) 
 // ---------------------------------------------------------------------------------
 // assembly
 // ---------------------------------------------------------------------------------
+#ifndef KNP_EMU
+static int asm_min_blocks() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("KNP_ASM_MINB"); v = e ? atoi(e) : 4; }
+  return v;
+}
+#endif
+
 template <int D>
 static void assemble_emi_t(knp_ctx* c) {
   knp_stream_t s = c->stream;
@@ -370,7 +378,14 @@ static void assemble_emi_t(knp_ctx* c) {
   parallel_for(s, c->nc_own, EmiCellKernel<D>{k}, 128);
 #else
   ++launch_counter();
-  emi_assemble_kernel<D><<<(unsigned)((c->nc_own + ASM_CPB - 1) / ASM_CPB), ASM_CPB*(D + 1), 0, s>>>(k);
+  {
+    const unsigned grid = (unsigned)((c->nc_own + ASM_CPB - 1) / ASM_CPB);
+    switch (asm_min_blocks()) {   // resident blocks per SM the register budget is compiled for
+      case 5: emi_assemble_kernel<D, 5><<<grid, ASM_CPB*(D + 1), 0, s>>>(k); break;
+      case 6: emi_assemble_kernel<D, 6><<<grid, ASM_CPB*(D + 1), 0, s>>>(k); break;
+      default: emi_assemble_kernel<D, 4><<<grid, ASM_CPB*(D + 1), 0, s>>>(k); break;
+    }
+  }
   KNP_CUDA(cudaGetLastError());
 #endif
 }
@@ -396,7 +411,14 @@ static void assemble_knp_t(knp_ctx* c) {
     parallel_for(s, c->nc_own, KnpCellKernel<D>{k}, 128);
 #else
     ++launch_counter();
-    knp_assemble_kernel<D><<<(unsigned)((c->nc_own + ASM_CPB - 1) / ASM_CPB), ASM_CPB*(D + 1), 0, s>>>(k);
+    {
+      const unsigned grid = (unsigned)((c->nc_own + ASM_CPB - 1) / ASM_CPB);
+      switch (asm_min_blocks()) {
+        case 5: knp_assemble_kernel<D, 5><<<grid, ASM_CPB*(D + 1), 0, s>>>(k); break;
+        case 6: knp_assemble_kernel<D, 6><<<grid, ASM_CPB*(D + 1), 0, s>>>(k); break;
+        default: knp_assemble_kernel<D, 4><<<grid, ASM_CPB*(D + 1), 0, s>>>(k); break;
+      }
+    }
     KNP_CUDA(cudaGetLastError());
 #endif
   }

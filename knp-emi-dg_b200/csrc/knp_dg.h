@@ -399,8 +399,8 @@ constexpr int ASM_CPB = 32;  // cells per thread block
 // thread (f, cl) computes facet f's blocks and row f of the cell integrals; the block's
 // results are staged in shared memory (pitch 17/10 doubles per ND x ND block: conflict
 // free) and written out slot by slot as contiguous runs of ASM_CPB * ND * ND doubles.
-template <int D>
-__global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) emi_assemble_kernel(const EmiArgs<D> a) {
+template <int D, int MINB>
+__global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) emi_assemble_kernel(const EmiArgs<D> a) {
   constexpr int ND = D + 1, BS = ND * ND, PITCH = BS + 1, NT = ASM_CPB * ND;
   __shared__ double sO[ND][ASM_CPB][PITCH];   // off-diagonal blocks per facet
   __shared__ double sD[ND][ASM_CPB][PITCH];   // diagonal-block contributions per facet thread
@@ -755,8 +755,8 @@ struct KnpCellKernel {   // one index per cell, all solved ions (host emulation 
 };
 
 #ifndef KNP_EMU
-template <int D>
-__global__ void __launch_bounds__(ASM_CPB*(D + 1), 4) knp_assemble_kernel(const KnpArgs<D> a) {
+template <int D, int MINB>
+__global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) knp_assemble_kernel(const KnpArgs<D> a) {
   constexpr int ND = D + 1, BS = ND * ND, PITCH = BS + 1, NT = ASM_CPB * ND;
   __shared__ double sO[ND][ASM_CPB][PITCH];
   __shared__ double sD[ND][ASM_CPB][PITCH];
