@@ -46,8 +46,8 @@ C_INIT = [{1: K_I, 0: K_E}, {1: NA_I + K_I, 0: NA_E + K_E}, {1: NA_I, 0: NA_E}] 
 ION_NAMES = ["K", "Cl", "Na"]
 STIMULUS = {"stim_amplitude": 10.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of one BellSpmvKernel<4> launch on the N = 1 workload, from
-# the `ncu --set full` capture summarised in profiles/ (None until captured)
-TRAFFIC_SPMV = None
+# the `ncu --set full` capture summarised in profiles/kernels_r01_solver.md
+TRAFFIC_SPMV = 3.119e8     # 299.4 MB read + 12.5 MB written (profiles/kernels_r01_solver.md, launch #1)
 
 
 def stim_locator(x):
@@ -294,11 +294,11 @@ def main():
     host["phi"] = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
     host["phiM"] = torch.empty(nm, dtype=torch.float64).pin_memory().numpy()
 
-    def download():
+    def download():                       # device -> pinned host buffers, no staging copy
         for k in range(N):
-            host[("c", k)][:] = ctx.get_field(_lib.F_C, k)
-        host["phi"][:] = ctx.get_field(_lib.F_PHI)
-        host["phiM"][:] = ctx.get_field(_lib.F_PHIM)
+            ctx.get_field(_lib.F_C, k, out=host[("c", k)])
+        ctx.get_field(_lib.F_PHI, out=host["phi"])
+        ctx.get_field(_lib.F_PHIM, out=host["phiM"])
 
     def upload():
         for k in range(N):

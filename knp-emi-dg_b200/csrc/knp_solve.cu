@@ -227,6 +227,11 @@ static void alloc_values(knp_ctx* c, AmgValues& V) {
   V.binv.alloc((size_t)c->slot_stride());
 }
 
+static int64_t double_coarsening_rows() {
+  const char* e = getenv("KNP_AMG_DOUBLE");
+  return e ? atoll(e) : 0;
+}
+
 // rows (over all ranks) below which the rest of the hierarchy is replicated; 0 disables
 static int64_t replicate_threshold() {
   const char* e = getenv("KNP_AMG_REPLICATE");
@@ -346,7 +351,23 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
       continue;
     }
     std::vector<int32_t> ag2;
-    const int64_t na = aggregate(G.coarse, theta, ag2);
+    int64_t na = aggregate(G.coarse, theta, ag2);
+    // Small levels are latency-bound (each costs three sweeps of a few microseconds per cycle,
+    // whatever its size): below `double_rows` rows a level is coarsened TWICE in one step (the
+    // aggregates of the aggregates), which halves the number of small levels.  Local levels
+    // only (single part, or the replicated tail).
+    if ((replicated || !ctx->comm.active()) && G.coarse.n <= double_coarsening_rows() && na > coarse_size) {
+      HostTransfer Tm = transfer_from_aggregates(ag2, na);
+      std::vector<double> vm = G.coarse.val;
+      GalerkinPlan Gm = galerkin_plan(G.coarse, Tm);
+      galerkin_numeric_host(Gm, vm);
+      std::vector<int32_t> ag3;
+      const int64_t nb = aggregate(Gm.coarse, theta, ag3);
+      if (nb >= 1 && nb < na * 0.9) {
+        for (auto& a : ag2) a = ag3[a];
+        na = nb;
+      }
+    }
     double gna = (double)na;
     if (!replicated) global_sum(ctx, &gna, 1);
     if (gna >= gn * 0.9 || gna < 1) break;  // coarsening stalled

@@ -251,9 +251,15 @@ class Context:
         v = _f64(values).ravel()
         self._call("knp_field_set", which, idx, _p(v, _dp), v.size)
 
-    def get_field(self, which, idx=0):
-        out = np.empty(self._count(which))
-        self._call("knp_field_get", which, idx, _p(out, _dp), out.size)
+    def get_field(self, which, idx=0, out=None):
+        """copy a field to the host; `out` (contiguous float64, e.g. a pinned buffer) receives it
+        directly when given"""
+        n = self._count(which)
+        if out is None:
+            out = np.empty(n)
+        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.size != n:
+            raise ValueError("get_field: out must be a contiguous float64 array of the field's size")
+        self._call("knp_field_get", which, idx, _p(out, _dp), n)
         return out
 
     # -- assembly ---------------------------------------------------------
