@@ -64,7 +64,7 @@ def build_cuda(force=False, verbose=False):
         return out
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc, "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-I", nccl_include(),
+           "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "--expt-relaxed-constexpr", "-I", nccl_include(),
            "-o", out] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
@@ -80,7 +80,7 @@ def build_emu(force=False):
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [gen, os.path.join(ROOT, "include", "knpemi.h")]
     if not force and not _stale(out, deps):
         return out
-    cmd = ["g++", "-std=c++17", "-O2", "-DKNP_EMU", "-fPIC", "-shared", "-o", out]
+    cmd = ["g++", "-std=c++17", "-O2", "-DKNP_EMU", "-fPIC", "-pthread", "-shared", "-o", out]
     for f in SOURCES:
         cmd += ["-x", "c++", os.path.join(CSRC, f)]
     subprocess.run(cmd, check=True)

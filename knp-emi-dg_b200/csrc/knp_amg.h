@@ -178,9 +178,9 @@ struct AmgLevelPlan {          // level l >= 1 (CSR)
   DevBuf<int32_t> gptr, gidx; DevBuf<double> gw; bool g_unit = true;
   // transfer between l-1 (fine) and l (coarse)
   DevBuf<int32_t> pptr, pidx, rptr, ridx; DevBuf<double> pw, rw; bool t_unit = true;
-  // work vectors of this level
-  DevBuf<double> b, x, r, t;
 };
+
+struct LevelVectors { DevBuf<double> b, x, r, t; };   // work vectors of one level of one system
 
 struct AmgPlan {
   bool ready = false;
@@ -195,15 +195,14 @@ struct AmgPlan {
   int tail_blocks = 0;             // its (cooperative) grid
   size_t rep_from = (size_t)-1;    // index of the first replicated level; -1: none
   int64_t rep_vstride = 0, rep_bstride = 0;   // padded per-rank segment: matrix values / rows
-  DevBuf<double> rep_val, rep_b;   // all-gather buffers [world * stride]
+  DevBuf<double> rep_val;          // all-gather buffer of the matrix values [world * stride]
   DevBuf<int32_t> rep_bmap;        // global row of the replica -> position in rep_b
   DevBuf<int32_t> rep_xmap;        // local unknown of lev[rep_from-1] -> global row of the replica
   int64_t m_dense = 0;             // rows of the last level (summed over all ranks)
   int64_t dense_off = 0;           // global index of this rank's first last-level row
   DevBuf<int32_t> dense_map;       // last level: local unknown (owned + ghost) -> global index
-  DevBuf<double> dense_b, dense_x; // last level: global right-hand side / solution
-  DevBuf<double> x0, r0, t0;       // level-0 work vectors
-  DevBuf<double> colbuf;
+
+
 };
 
 struct AmgValues {                 // numeric part, one per linear system
@@ -211,6 +210,12 @@ struct AmgValues {                 // numeric part, one per linear system
   std::vector<DevBuf<double>> dinv;  // l1-Jacobi diagonals
   DevBuf<double> dense;              // inverse of the last level
   DevBuf<double> binv;               // level-0 inverse diagonal blocks [nc][ND][ND]
+  // work vectors (per system: independent systems are solved concurrently)
+  std::vector<LevelVectors> vec;     // per level >= 1
+  DevBuf<double> x0, r0, t0;         // level-0 work vectors
+  DevBuf<double> colbuf;             // dense inverse scratch
+  DevBuf<double> dense_b, dense_x;   // last level (distributed): global right-hand side / solution
+  DevBuf<double> rep_b;              // replicated tail: all-gather buffer of the right-hand side
   double omega = 0.0;                // level-0 damping 4/(3 lambda_max(Dinv A)), estimated
   int age = 0;                       // refreshes since the last estimate
 };

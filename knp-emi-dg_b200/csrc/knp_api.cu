@@ -60,8 +60,9 @@ int knp_ctx_create(int device, knp_ctx** out) {
 #endif
   { const char* e = getenv("KNP_KNP_PRESMOOTH"); c->opt.knp_presmooth0 = (e && e[0] == '1'); }
   { const char* e = getenv("KNP_FUSE_PROLONG"); c->opt.fuse_prolong = (e && e[0] == '1'); }
-  c->kr_scal.alloc(1024);
-  c->kr_partial.alloc((size_t)DOT_MAX * RED_BLOCKS);
+  c->kr0.stream = c->stream;
+  c->kr0.scal.alloc(1024);
+  c->kr0.partial.alloc((size_t)DOT_MAX * RED_BLOCKS);
   c->ode_stats.alloc(4);
   *out = c.release();
   KNP_CATCH
@@ -77,6 +78,9 @@ int knp_ctx_destroy(knp_ctx* ctx) {
   if (ctx->comm.nccl) { nccl_api().CommDestroy(ctx->comm.nccl); ctx->comm.nccl = nullptr; }
 #endif
   knp_stream_t s = ctx->stream;
+#ifndef KNP_EMU
+  for (auto& k : ctx->kr_ion) if (k.own_stream) { cudaStreamSynchronize(k.stream); cudaStreamDestroy(k.stream); }
+#endif
   delete ctx;
 #ifndef KNP_EMU
   cudaStreamDestroy(s);
@@ -905,9 +909,9 @@ int knp_bench_kernel(knp_ctx* ctx, int kernel, int reps, double* ms, double* byt
         break;
       }
       case 4: ctx->comm.halo(ctx->stream, ctx->halo0, ctx->phi.p); break;          // DG halo exchange
-      case 5: ctx->comm.allreduce(ctx->stream, ctx->kr_scal.p + 900, 4); break;    // Krylov scalars
+      case 5: ctx->comm.allreduce(ctx->stream, ctx->kr0.scal.p + 900, 4); break;    // Krylov scalars
       case 6:                                                                      // AMG tail all-gather
-        if (ctx->amg.ready && ctx->amg.rep_from != (size_t)-1) ctx->comm.allgather(ctx->stream, ctx->amg.rep_b.p, ctx->amg.rep_bstride);
+        if (ctx->amg.ready && ctx->amg.rep_from != (size_t)-1) ctx->comm.allgather(ctx->stream, ctx->amg_emi.rep_b.p, ctx->amg.rep_bstride);
         break;
       default: fail("unknown kernel id");
     }

@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 #include <stdexcept>
+#include <atomic>
 
 #ifdef KNP_EMU
 #define KNP_HD inline
@@ -151,8 +152,8 @@ struct DevBuf {
 };
 
 // number of kernel launches issued by this library (bench.py reports it as gpu_launches)
-inline long long& launch_counter() {
-  static long long n = 0;
+inline std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> n{0};
   return n;
 }
 

@@ -39,6 +39,15 @@ struct SolverOptions {
 
 enum { T_EMI_ASM = 0, T_EMI_SOLVE, T_KNP_ASM, T_KNP_SOLVE, T_ODE, T_POST, T_COUNT };
 
+// Mutable state of ONE running Krylov solve (vectors, scalar scratch, the stream it is issued
+// on).  The context owns one for the main stream and one per solved ion, so that the
+// independent KNP systems can be solved concurrently on separate streams.
+struct KrylovWs {
+  knp_stream_t stream = 0;
+  bool own_stream = false;
+  DevBuf<double> r, p, q, w, V, scal, partial;
+};
+
 }  // namespace knp
 
 struct knp_ctx {
@@ -74,7 +83,9 @@ struct knp_ctx {
   bool emi_assembled = false, knp_assembled = false;
   // solver
   knp::SolverOptions opt;
-  knp::DevBuf<double> kr_r, kr_z, kr_p, kr_q, kr_V, kr_w, kr_scal, kr_partial, kr_ones;
+  knp::KrylovWs kr0;                               // main-stream workspace
+  knp::KrylovWs kr_ion[knp::MAX_IONS];             // concurrent KNP solves (single-GPU)
+  knp::DevBuf<double> kr_ones;
   knp::AmgPlan amg;
   knp::AmgValues amg_emi, amg_knp[knp::MAX_IONS];
   knp::DevBuf<double> bj_emi, bj_knp[knp::MAX_IONS];   // block-Jacobi inverses

@@ -8,6 +8,7 @@
 // ||M^-1 r|| <= max(rtol * ||M^-1 b||, atol), nonzero initial guess.
 #include "../../include/knpemi.h"
 #include "knp_ctx.h"
+#include <thread>
 
 using namespace knp;
 
@@ -27,65 +28,73 @@ static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// ---- per-solve workspace -----------------------------------------------------------------
+// Every helper below issues on the stream of the CURRENT workspace and uses its scratch
+// buffers: the context's main workspace by default, a per-ion workspace inside the worker
+// threads that solve the independent KNP systems concurrently.
+static thread_local KrylovWs* tl_ws = nullptr;
+static KrylovWs& ws(knp_ctx* c) { return tl_ws ? *tl_ws : c->kr0; }
+static knp_stream_t cs(knp_ctx* c) { return ws(c).stream; }
+
 // ---- small helpers ---------------------------------------------------------------------
 // Multi-GPU: every kernel below runs over the OWNED rows (the first n_own entries of a
 // vector); the operators that read a vector through the matrix first refresh its ghost
 // entries from their owners (knp_comm.h).
 static void halo0(knp_ctx* c, const double* x) {
-  if (c->comm.active()) c->comm.halo(c->stream, c->halo0, const_cast<double*>(x));
+  if (c->comm.active()) c->comm.halo(cs(c), c->halo0, const_cast<double*>(x));
 }
 template <int ND>
 static void bell_spmv(knp_ctx* c, const BellMat& A, const double* x, const double* b, double* y, int mode) {
   BellSpmvKernel<ND> k{A, x, b, y, mode};
-  parallel_for(c->stream, c->n_own, k, 256);
+  parallel_for(cs(c), c->n_own, k, 256);
 }
 static void bell_spmv(knp_ctx* c, const BellMat& A, const double* x, const double* b, double* y, int mode) {
   halo0(c, x);
   if (c->nd == 3) bell_spmv<3>(c, A, x, b, y, mode); else bell_spmv<4>(c, A, x, b, y, mode);
 }
 static void block_apply(knp_ctx* c, const double* dinv, const double* r, double* out, double w, int mode) {
-  if (c->nd == 3) { BlockDiagApplyKernel<3> k{dinv, r, out, w, mode}; parallel_for(c->stream, c->n_own, k); }
-  else { BlockDiagApplyKernel<4> k{dinv, r, out, w, mode}; parallel_for(c->stream, c->n_own, k); }
+  if (c->nd == 3) { BlockDiagApplyKernel<3> k{dinv, r, out, w, mode}; parallel_for(cs(c), c->n_own, k); }
+  else { BlockDiagApplyKernel<4> k{dinv, r, out, w, mode}; parallel_for(cs(c), c->n_own, k); }
 }
 static void bell_jacobi(knp_ctx* c, const BellMat& A, const double* dinv, const double* b,
                         const double* xin, double* xout, double w) {
   halo0(c, xin);
-  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n_own, k, 192); }
-  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w}; parallel_for(c->stream, c->n_own, k, 256); }
+  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 192); }
+  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 256); }
 }
 // post-smoothing sweep fused with the prolongation: out = x' + w Dinv (b - A x'), x' = xin + P xc
 // (xin may be nullptr).  The ghost entries of xin (if any) and of xc must be valid.
 static void bell_jacobi_prolong(knp_ctx* c, const BellMat& A, const double* dinv, const double* b,
                                 const double* xin, const int32_t* agg, const double* xc, double* xout, double w) {
-  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w, agg, xc}; parallel_for(c->stream, c->n_own, k, 192); }
-  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w, agg, xc}; parallel_for(c->stream, c->n_own, k, 256); }
+  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w, agg, xc}; parallel_for(cs(c), c->n_own, k, 192); }
+  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w, agg, xc}; parallel_for(cs(c), c->n_own, k, 256); }
 }
 static void block_inverse(knp_ctx* c, const double* blocks, double* inv) {
 #ifdef KNP_EMU
-  if (c->nd == 3) { BlockInverseKernel<3> k{blocks, inv}; parallel_for(c->stream, c->nc_own, k, 128); }
-  else { BlockInverseKernel<4> k{blocks, inv}; parallel_for(c->stream, c->nc_own, k, 128); }
+  if (c->nd == 3) { BlockInverseKernel<3> k{blocks, inv}; parallel_for(cs(c), c->nc_own, k, 128); }
+  else { BlockInverseKernel<4> k{blocks, inv}; parallel_for(cs(c), c->nc_own, k, 128); }
 #else
   const unsigned grid = (unsigned)((c->nc_own + 127) / 128);
   ++launch_counter();
-  if (c->nd == 3) block_inverse_kernel<3><<<grid, 128, 0, c->stream>>>(c->nc_own, blocks, inv);
-  else block_inverse_kernel<4><<<grid, 128, 0, c->stream>>>(c->nc_own, blocks, inv);
+  if (c->nd == 3) block_inverse_kernel<3><<<grid, 128, 0, cs(c)>>>(c->nc_own, blocks, inv);
+  else block_inverse_kernel<4><<<grid, 128, 0, cs(c)>>>(c->nc_own, blocks, inv);
   KNP_CUDA(cudaGetLastError());
 #endif
 }
 
 // host-visible dot products over all ranks (one sync each)
 static void dots_host(knp_ctx* c, int k, const double* V, const double* w, double* out_host) {
-  multi_dot_device(c->stream, c->n_own, c->n, k, V, w, c->kr_partial.p, c->kr_scal.p);
-  c->comm.allreduce(c->stream, c->kr_scal.p, k);
-  d2h(out_host, c->kr_scal.p, k * sizeof(double), c->stream);
+  multi_dot_device(cs(c), c->n_own, c->n, k, V, w, ws(c).partial.p, ws(c).scal.p);
+  c->comm.allreduce(cs(c), ws(c).scal.p, k);
+  d2h(out_host, ws(c).scal.p, k * sizeof(double), cs(c));
 }
 // sum over ranks of a few host numbers (setup-time decisions must agree on every rank)
 static void global_sum(knp_ctx* c, double* v, int k) {
   if (!c->comm.active()) return;
-  double* dev = c->kr_scal.p + 768;
-  h2d(dev, v, k * sizeof(double), c->stream);
-  c->comm.allreduce(c->stream, dev, k);
-  d2h(v, dev, k * sizeof(double), c->stream);
+  double* dev = ws(c).scal.p + 768;
+  h2d(dev, v, k * sizeof(double), cs(c));
+  c->comm.allreduce(cs(c), dev, k);
+  d2h(v, dev, k * sizeof(double), cs(c));
 }
 static double dot_host(knp_ctx* c, const double* x, const double* y) {
   double v;
@@ -174,9 +183,9 @@ static std::vector<int32_t> extend_aggregates(knp_ctx* c, HaloPlan& Hf, const st
   std::vector<double> ids((size_t)(nf_own + nf_ghost), -1.0);
   for (int64_t i = 0; i < nf_own; ++i) ids[i] = (double)agg_own[i];
   DevBuf<double> tmp;
-  tmp.upload(ids, c->stream);
-  c->comm.halo(c->stream, Hf, tmp.p);
-  ids = tmp.download(c->stream);
+  tmp.upload(ids, cs(c));
+  c->comm.halo(cs(c), Hf, tmp.p);
+  ids = tmp.download(cs(c));
   int64_t ng = 0;
   std::vector<int32_t> uniq;
   for (int i = 0; i < nn; ++i) {
@@ -200,12 +209,12 @@ static std::vector<int32_t> extend_aggregates(knp_ctx* c, HaloPlan& Hf, const st
     Hc.send_off[i + 1] = (int64_t)Hc.h_send_idx.size();
   }
   Hc.n_ghost = ng;
-  Hc.upload(c->stream);
+  Hc.upload(cs(c));
   return agg;
 }
 
 static void upload_level(knp_ctx* c, AmgLevelPlan& L, const GalerkinPlan& G, const HostTransfer& T) {
-  knp_stream_t s = c->stream;
+  knp_stream_t s = cs(c);
   L.n = G.coarse.n; L.nnz = (int64_t)G.coarse.col.size();
   L.nloc = L.n + L.halo.n_ghost;
   L.ptr.upload(G.coarse.ptr, s); L.col.upload(G.coarse.col, s);
@@ -216,7 +225,6 @@ static void upload_level(knp_ctx* c, AmgLevelPlan& L, const GalerkinPlan& G, con
   L.rptr.upload(T.rptr, s); L.ridx.upload(T.ridx, s);
   L.t_unit = T.unit;
   if (!T.unit) { L.pw.upload(T.pw, s); L.rw.upload(T.rw, s); }
-  L.b.alloc(L.nloc); L.x.alloc(L.nloc); L.r.alloc(L.nloc); L.t.alloc(L.nloc);
 }
 
 static void alloc_values(knp_ctx* c, AmgValues& V) {
@@ -225,6 +233,15 @@ static void alloc_values(knp_ctx* c, AmgValues& V) {
   for (size_t l = 0; l < nl; ++l) { V.val[l].alloc(c->amg.lev[l].nnz); V.dinv[l].alloc(c->amg.lev[l].nloc); }
   V.dense.alloc((size_t)c->amg.m_dense * c->amg.m_dense);
   V.binv.alloc((size_t)c->slot_stride());
+  V.vec.clear(); V.vec.resize(nl);
+  for (size_t l = 0; l < nl; ++l) {
+    const size_t m = (size_t)c->amg.lev[l].nloc;
+    V.vec[l].b.alloc(m); V.vec[l].x.alloc(m); V.vec[l].r.alloc(m); V.vec[l].t.alloc(m);
+  }
+  V.x0.alloc(c->n); V.r0.alloc(c->n); V.t0.alloc(c->n);
+  V.colbuf.alloc(c->amg.m_dense);
+  V.dense_b.alloc(c->amg.m_dense); V.dense_x.alloc(c->amg.m_dense);
+  if (c->amg.rep_from != (size_t)-1) V.rep_b.alloc((size_t)c->comm.world * c->amg.rep_bstride);
 }
 
 static int64_t double_coarsening_rows() {
@@ -242,9 +259,9 @@ static int64_t replicate_threshold() {
 static std::vector<double> host_allgather(knp_ctx* c, const std::vector<double>& mine, int64_t count) {
   DevBuf<double> buf;
   buf.alloc((size_t)c->comm.world * count);
-  h2d(buf.p + (int64_t)c->comm.rank * count, mine.data(), mine.size() * sizeof(double), c->stream);
-  c->comm.allgather(c->stream, buf.p, count);
-  return buf.download(c->stream);
+  h2d(buf.p + (int64_t)c->comm.rank * count, mine.data(), mine.size() * sizeof(double), cs(c));
+  c->comm.allgather(cs(c), buf.p, count);
+  return buf.download(cs(c));
 }
 
 // Turn the current coarsest distributed level D = lev.back() (pattern + setup values in G.coarse,
@@ -306,9 +323,8 @@ static void replicate_level(knp_ctx* c, GalerkinPlan& G) {
   std::iota(B.pos.begin(), B.pos.end(), 0);
   amg.rep_vstride = vstride; amg.rep_bstride = bstride;
   amg.rep_val.alloc((size_t)world * vstride);
-  amg.rep_b.alloc((size_t)world * bstride);
-  amg.rep_bmap.upload(bmap, c->stream);
-  amg.rep_xmap.upload(xmap, c->stream);
+  amg.rep_bmap.upload(bmap, cs(c));
+  amg.rep_xmap.upload(xmap, cs(c));
   amg.rep_from = amg.lev.size();
   amg.lev.emplace_back();
   AmgLevelPlan& T0 = amg.lev.back();
@@ -426,9 +442,6 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
     }
   }
 #endif
-  amg.dense_b.alloc(amg.m_dense); amg.dense_x.alloc(amg.m_dense);
-  amg.x0.alloc(ctx->n); amg.r0.alloc(ctx->n); amg.t0.alloc(ctx->n);
-  amg.colbuf.alloc(amg.m_dense);
   alloc_values(ctx, ctx->amg_emi);
   for (int k = 0; k < ctx->P.N - 1; ++k) alloc_values(ctx, ctx->amg_knp[k]);
   amg.ready = true;
@@ -472,12 +485,12 @@ static CsrMat csr_of(const AmgLevelPlan& L, const AmgValues& V, size_t l) {
 // omega * lambda_max < 2; the matrices change slowly in time, so the estimate is redone
 // only every OMEGA_PERIOD refreshes)
 constexpr int OMEGA_PERIOD = 200;
-static double estimate_lambda_max(knp_ctx* c, const BellMat& A, const double* dinv) {
+static double estimate_lambda_max(knp_ctx* c, AmgValues& V, const BellMat& A, const double* dinv) {
   const int64_t n = c->n_own;
-  double* v = c->amg.x0.p; double* w = c->amg.t0.p; double* u = c->amg.r0.p;
+  double* v = V.x0.p; double* w = V.t0.p; double* u = V.r0.p;
   std::vector<double> h(n);
   for (int64_t i = 0; i < n; ++i) h[i] = 1.0 + 0.5 * sin(1.7 * (double)i) + ((i * 2654435761u) % 1024) / 1024.0;
-  h2d(v, h.data(), n * sizeof(double), c->stream);
+  h2d(v, h.data(), n * sizeof(double), cs(c));
   double lam = 1.0;
   for (int it = 0; it < 12; ++it) {
     bell_spmv(c, A, v, nullptr, u, 0);
@@ -486,17 +499,17 @@ static double estimate_lambda_max(knp_ctx* c, const BellMat& A, const double* di
     if (!(nv > 0.0) || !(nw > 0.0)) break;
     lam = nw / nv;
     ScaleKernel k{1.0 / nw, w, v};
-    parallel_for(c->stream, n, k);
+    parallel_for(cs(c), n, k);
   }
   return lam;
 }
 
 static void amg_refresh(knp_ctx* c, AmgValues& V, const BellMat& A0, const double* fine_values, const double* diag_blocks) {
-  knp_stream_t s = c->stream;
+  knp_stream_t s = cs(c);
   block_inverse(c, diag_blocks, V.binv.p);
   if (c->opt.omega > 0.0) V.omega = c->opt.omega;
   else if (V.omega <= 0.0 || ++V.age >= OMEGA_PERIOD) {
-    V.omega = 4.0 / (3.0 * 1.05 * estimate_lambda_max(c, A0, V.binv.p));
+    V.omega = 4.0 / (3.0 * 1.05 * estimate_lambda_max(c, V, A0, V.binv.p));
     V.age = 0;
   }
   const double* fine = fine_values;
@@ -527,7 +540,7 @@ static void amg_refresh(knp_ctx* c, AmgValues& V, const BellMat& A0, const doubl
                       dense_distributed ? c->amg.dense_map.p : nullptr};
   parallel_for(s, c->amg.lev[last].n, tk);
   if (dense_distributed) c->comm.allreduce(s, V.dense.p, m * m);   // every rank contributes its rows
-  dense_inverse_device(s, (int)m, V.dense.p, c->amg.colbuf.p);
+  dense_inverse_device(s, (int)m, V.dense.p, V.colbuf.p);
 }
 
 // ---------------------------------------------------------------------------------
@@ -536,15 +549,16 @@ static void amg_refresh(knp_ctx* c, AmgValues& V, const BellMat& A0, const doubl
 static void transfer(knp_ctx* c, int64_t nrows, const int32_t* ptr, const int32_t* idx, const double* w,
                      const double* x, double* y, int add) {
   TransferKernel k{nrows, ptr, idx, w, x, y, add};
-  parallel_for(c->stream, nrows, k);
+  parallel_for(cs(c), nrows, k);
 }
 
 // solve level l (>= 1, index into lev = l-1) approximately: L.x <- cycle(L.b)
 // On return the ghost entries of L.x are valid when ghost_x is set (the parent's fused
 // prolongation+smoothing sweep reads them).
 static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
-  knp_stream_t s = c->stream;
+  knp_stream_t s = cs(c);
   AmgLevelPlan& L = c->amg.lev[li];
+  LevelVectors& Lv = V.vec[li];
   Comm& comm = c->comm;
   const bool dist = comm.active() && li < c->amg.rep_from;   // this level's vectors have ghosts
 #ifndef KNP_EMU
@@ -556,7 +570,7 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
       AmgLevelPlan& T = amg.lev[li + k];
       TailLevel& t = a.L[k];
       t.n = T.n; t.ptr = T.ptr.p; t.col = T.col.p; t.val = V.val[li + k].p; t.dinv = V.dinv[li + k].p;
-      t.b = T.b.p; t.x = T.x.p; t.r = T.r.p;
+      t.b = V.vec[li + k].b.p; t.x = V.vec[li + k].x.p; t.r = V.vec[li + k].r.p;
       t.rptr = T.rptr.p; t.ridx = T.ridx.p; t.agg = T.pidx.p;
     }
     a.denseT = V.dense.p;
@@ -571,16 +585,17 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
     // the remaining cycle redundantly, pick this rank's owned and ghost unknowns
     AmgPlan& amg = c->amg;
     AmgLevelPlan& T0 = amg.lev[li + 1];
-    d2d(amg.rep_b.p + (int64_t)comm.rank * amg.rep_bstride, L.b.p, L.n * sizeof(double), s);
-    comm.allgather(s, amg.rep_b.p, amg.rep_bstride);
-    { GatherMapKernel k{amg.rep_b.p, amg.rep_bmap.p, T0.b.p}; parallel_for(s, T0.n, k); }
+    LevelVectors& T0v = V.vec[li + 1];
+    d2d(V.rep_b.p + (int64_t)comm.rank * amg.rep_bstride, Lv.b.p, L.n * sizeof(double), s);
+    comm.allgather(s, V.rep_b.p, amg.rep_bstride);
+    { GatherMapKernel k{V.rep_b.p, amg.rep_bmap.p, T0v.b.p}; parallel_for(s, T0.n, k); }
     coarse_cycle(c, V, li + 1, false);
-    { GatherMapKernel k{T0.x.p, amg.rep_xmap.p, L.x.p}; parallel_for(s, L.nloc, k); }
+    { GatherMapKernel k{T0v.x.p, amg.rep_xmap.p, Lv.x.p}; parallel_for(s, L.nloc, k); }
     return;
   }
   if (li + 1 == c->amg.lev.size()) {
     if (!dist) {
-      DenseMatvecKernel k{L.n, V.dense.p, L.b.p, L.x.p};
+      DenseMatvecKernel k{L.n, V.dense.p, Lv.b.p, Lv.x.p};
       parallel_for(s, L.n, k, 64);
       return;
     }
@@ -588,52 +603,53 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
     // inverse and picks its owned and ghost unknowns
     AmgPlan& amg = c->amg;
     const int64_t m = amg.m_dense;
-    dev_zero(amg.dense_b.p, (size_t)m * sizeof(double), s);
-    { ScatterOffsetKernel k{L.b.p, amg.dense_b.p, amg.dense_off}; parallel_for(s, L.n, k); }
-    comm.allreduce(s, amg.dense_b.p, m);
-    { DenseMatvecKernel k{m, V.dense.p, amg.dense_b.p, amg.dense_x.p}; parallel_for(s, m, k, 64); }
-    { GatherMapKernel k{amg.dense_x.p, amg.dense_map.p, L.x.p}; parallel_for(s, L.nloc, k); }
+    dev_zero(V.dense_b.p, (size_t)m * sizeof(double), s);
+    { ScatterOffsetKernel k{Lv.b.p, V.dense_b.p, amg.dense_off}; parallel_for(s, L.n, k); }
+    comm.allreduce(s, V.dense_b.p, m);
+    { DenseMatvecKernel k{m, V.dense.p, V.dense_b.p, V.dense_x.p}; parallel_for(s, m, k, 64); }
+    { GatherMapKernel k{V.dense_x.p, amg.dense_map.p, Lv.x.p}; parallel_for(s, L.nloc, k); }
     return;
   }
   CsrMat A = csr_of(L, V, li);
   AmgLevelPlan& C = c->amg.lev[li + 1];
+  LevelVectors& Cv = V.vec[li + 1];
   if (c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1 && C.t_unit) {
     // fused V(1,1) path: two kernels down (smooth+residual, restrict), one up (prolong+smooth)
-    if (dist) comm.halo(s, L.halo, L.b.p);
-    { CoarseResidualKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.r.p}; parallel_rows<8>(s, L.n, k); }
+    if (dist) comm.halo(s, L.halo, Lv.b.p);
+    { CoarseResidualKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, Lv.r.p}; parallel_rows<8>(s, L.n, k); }
     if (L.halo.n_ghost > 0) {   // x = dinv b on the ghost unknowns too (read by the sweep up)
-      DiagScaleKernel k{V.dinv[li].p + L.n, L.b.p + L.n, L.x.p + L.n, 1.0};
+      DiagScaleKernel k{V.dinv[li].p + L.n, Lv.b.p + L.n, Lv.x.p + L.n, 1.0};
       parallel_for(s, L.halo.n_ghost, k);
     }
-    { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, L.r.p, C.b.p, 0}; parallel_rows<8>(s, C.n, k); }
+    { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, Lv.r.p, Cv.b.p, 0}; parallel_rows<8>(s, C.n, k); }
     coarse_cycle(c, V, li + 1, true);
-    { CoarseUpKernel k{A, V.dinv[li].p, L.b.p, L.x.p, C.pidx.p, C.x.p, L.t.p}; parallel_rows<8>(s, L.n, k); }
-    std::swap(L.x.p, L.t.p);
-    if (ghost_x && dist) comm.halo(s, L.halo, L.x.p);
+    { CoarseUpKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, C.pidx.p, Cv.x.p, Lv.t.p}; parallel_rows<8>(s, L.n, k); }
+    std::swap(Lv.x.p, Lv.t.p);
+    if (ghost_x && dist) comm.halo(s, L.halo, Lv.x.p);
     return;
   }
   // pre-smoothing from a zero guess
-  { DiagScaleKernel k{V.dinv[li].p, L.b.p, L.x.p, 1.0}; parallel_for(s, L.n, k); }
+  { DiagScaleKernel k{V.dinv[li].p, Lv.b.p, Lv.x.p, 1.0}; parallel_for(s, L.n, k); }
   for (int it = 1; it < c->opt.nu_pre; ++it) {
-    if (dist) comm.halo(s, L.halo, L.x.p);
-    CsrJacobiKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.t.p, 1.0};
+    if (dist) comm.halo(s, L.halo, Lv.x.p);
+    CsrJacobiKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, Lv.t.p, 1.0};
     parallel_for(s, L.n, k);
-    std::swap(L.x.p, L.t.p);
+    std::swap(Lv.x.p, Lv.t.p);
   }
   for (int g = 0; g < c->opt.gamma; ++g) {
-    if (dist) comm.halo(s, L.halo, L.x.p);
-    { CsrSpmvKernel k{A, L.x.p, L.b.p, L.r.p, 1}; parallel_for(s, L.n, k); }
-    transfer(c, C.n, C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, L.r.p, C.b.p, 0);
+    if (dist) comm.halo(s, L.halo, Lv.x.p);
+    { CsrSpmvKernel k{A, Lv.x.p, Lv.b.p, Lv.r.p, 1}; parallel_for(s, L.n, k); }
+    transfer(c, C.n, C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, Lv.r.p, Cv.b.p, 0);
     coarse_cycle(c, V, li + 1, false);
-    transfer(c, L.n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, C.x.p, L.x.p, 1);
+    transfer(c, L.n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, Cv.x.p, Lv.x.p, 1);
   }
   for (int it = 0; it < c->opt.nu_post; ++it) {
-    if (dist) comm.halo(s, L.halo, L.x.p);
-    CsrJacobiKernel k{A, V.dinv[li].p, L.b.p, L.x.p, L.t.p, 1.0};
+    if (dist) comm.halo(s, L.halo, Lv.x.p);
+    CsrJacobiKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, Lv.t.p, 1.0};
     parallel_for(s, L.n, k);
-    std::swap(L.x.p, L.t.p);
+    std::swap(Lv.x.p, Lv.t.p);
   }
-  if (ghost_x && dist) comm.halo(s, L.halo, L.x.p);
+  if (ghost_x && dist) comm.halo(s, L.halo, Lv.x.p);
 }
 
 // z = M^-1 r
@@ -648,8 +664,9 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
   }
   AmgPlan& amg = c->amg;
   AmgLevelPlan& C = amg.lev[0];
+  LevelVectors& Cv = V.vec[0];
   const double w = V.omega;
-  double* x = amg.x0.p; double* t = amg.t0.p;
+  double* x = V.x0.p; double* t = V.t0.p;
   // (measured on B200: the fused prolongation + sweep is ~2 % SLOWER than prolongation and sweep
   // as two launches - 40 extra gathers per row in a kernel that otherwise runs at 0.9 of the
   // HBM roofline - so it is opt-in)
@@ -658,32 +675,32 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
     const double* rr = r;
     if (presmooth0) {
       block_apply(c, V.binv.p, r, x, w, 0);
-      bell_spmv(c, A0, x, r, amg.r0.p, 1);          // refreshes the ghost entries of x as well
-      rr = amg.r0.p;
+      bell_spmv(c, A0, x, r, V.r0.p, 1);          // refreshes the ghost entries of x as well
+      rr = V.r0.p;
     }
-    { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, rr, C.b.p, 0}; parallel_rows<8>(c->stream, C.n, k); }
+    { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, rr, Cv.b.p, 0}; parallel_rows<8>(cs(c), C.n, k); }
     coarse_cycle(c, V, 0, c->comm.active());        // ghost entries of C.x are read by the fused sweep
-    bell_jacobi_prolong(c, A0, V.binv.p, r, presmooth0 ? x : nullptr, C.pidx.p, C.x.p, z, w);
+    bell_jacobi_prolong(c, A0, V.binv.p, r, presmooth0 ? x : nullptr, C.pidx.p, Cv.x.p, z, w);
     return;
   }
   const double* rr = r;
   if (presmooth0) {
     block_apply(c, V.binv.p, r, x, w, 0);
     for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, V.binv.p, r, x, t, w); std::swap(x, t); }
-    bell_spmv(c, A0, x, r, amg.r0.p, 1);
-    rr = amg.r0.p;
+    bell_spmv(c, A0, x, r, V.r0.p, 1);
+    rr = V.r0.p;
   }
-  { TransferRowsKernel k{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, rr, C.b.p, 0}; parallel_rows<8>(c->stream, C.n, k); }
+  { TransferRowsKernel k{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, rr, Cv.b.p, 0}; parallel_rows<8>(cs(c), C.n, k); }
   coarse_cycle(c, V, 0, false);
-  transfer(c, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, C.x.p, x, presmooth0 ? 1 : 0);
-  if (c->opt.nu_post == 0) { d2d(z, x, c->n * sizeof(double), c->stream); return; }
+  transfer(c, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, Cv.x.p, x, presmooth0 ? 1 : 0);
+  if (c->opt.nu_post == 0) { d2d(z, x, c->n * sizeof(double), cs(c)); return; }
   for (int it = 0; it < c->opt.nu_post; ++it) {
     double* out = (it + 1 == c->opt.nu_post) ? z : t;
     bell_jacobi(c, A0, V.binv.p, r, x, out, w);
     if (out != z) std::swap(x, t);
   }
   // keep the plan's buffers in their slots for the next call
-  if (x != amg.x0.p) std::swap(amg.x0.p, amg.t0.p);
+  if (x != V.x0.p) std::swap(V.x0.p, V.t0.p);
 }
 
 // ---------------------------------------------------------------------------------
@@ -695,19 +712,21 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
 static void remove_mean(knp_ctx* c, double* v) {
   const double s = dot_host(c, v, c->kr_ones.p);
   AddConstKernel k{-s / c->n_global, v};
-  parallel_for(c->stream, c->n_own, k);
+  parallel_for(cs(c), c->n_own, k);
 }
 
 static void ensure_krylov(knp_ctx* c) {
   const size_t n = c->n;
-  if (c->kr_r.n != 2 * n) { c->kr_r.alloc(2 * n); c->kr_p.alloc(n); c->kr_q.alloc(n); c->kr_w.alloc(n); }
+  KrylovWs& K = ws(c);
+  if (K.scal.n == 0) { K.scal.alloc(1024); K.partial.alloc((size_t)DOT_MAX * RED_BLOCKS); }
+  if (K.r.n != 2 * n) { K.r.alloc(2 * n); K.p.alloc(n); K.q.alloc(n); K.w.alloc(n); }
   if (c->kr_ones.n != n) {
     c->kr_ones.alloc(n);
     std::vector<double> one(n, 1.0);
-    h2d(c->kr_ones.p, one.data(), n * sizeof(double), c->stream);
+    h2d(c->kr_ones.p, one.data(), n * sizeof(double), cs(c));
   }
   const size_t need = (size_t)(c->opt.restart + 1) * n;
-  if (c->kr_V.n < need) c->kr_V.alloc(need);
+  if (K.V.n < need) K.V.alloc(need);
   double ng = (double)c->n_own;
   global_sum(c, &ng, 1);
   c->n_global = ng;
@@ -717,7 +736,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   KNP_TRY
   if (!ctx->emi_assembled) fail("knp_solve_emi: assemble first");
   knp_ctx* c = ctx;
-  knp_stream_t s = c->stream;
+  knp_stream_t s = cs(c);
   stream_sync(s);
   const double t0 = now_s();
   ensure_krylov(c);
@@ -726,7 +745,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   // preconditioner refresh (the reference rebuilds BoomerAMG at every setOperators)
   if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_emi, B, c->A_emi.p, c->Bdiag());
   else { if (c->bj_emi.n != (size_t)c->slot_stride()) c->bj_emi.alloc(c->slot_stride()); block_inverse(c, c->Bdiag(), c->bj_emi.p); }
-  double* x = c->phi.p; double* r = c->kr_r.p; double* z = c->kr_r.p + n; double* p = c->kr_p.p; double* q = c->kr_q.p;
+  double* x = c->phi.p; double* r = ws(c).r.p; double* z = ws(c).r.p + n; double* p = ws(c).p.p; double* q = ws(c).q.p;
   const double* b = c->rhs_emi.p;
   // Two reductions per iteration.  (1) {p.q, 1.q}: with 1.r known, the mean of the updated
   // residual is known before the update and is subtracted in the same pass, so r stays
@@ -739,10 +758,10 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   double sum_r = 0.0;
   auto fused_dots = [&](double& rz_out, double& zz_out, double& mu_out) {
     DotPairs P{{r, z, ones, ones}, {z, z, z, r}};
-    pair_dot_device(s, no, 4, P, c->kr_partial.p, c->kr_scal.p);
-    c->comm.allreduce(s, c->kr_scal.p, 4);
+    pair_dot_device(s, no, 4, P, ws(c).partial.p, ws(c).scal.p);
+    c->comm.allreduce(s, ws(c).scal.p, 4);
     double d[4];
-    d2h(d, c->kr_scal.p, sizeof d, s);
+    d2h(d, ws(c).scal.p, sizeof d, s);
     mu_out = d[2] / Ng;
     sum_r = d[3];
     rz_out = d[0] - mu_out * d[3];
@@ -768,10 +787,10 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
       double pq, sum_q;
       {
         DotPairs P{{p, ones, nullptr, nullptr}, {q, q, nullptr, nullptr}};
-        pair_dot_device(s, no, 2, P, c->kr_partial.p, c->kr_scal.p);
-        c->comm.allreduce(s, c->kr_scal.p, 2);
+        pair_dot_device(s, no, 2, P, ws(c).partial.p, ws(c).scal.p);
+        c->comm.allreduce(s, ws(c).scal.p, 2);
         double d[2];
-        d2h(d, c->kr_scal.p, sizeof d, s);
+        d2h(d, ws(c).scal.p, sizeof d, s);
         pq = d[0]; sum_q = d[1];
       }
       if (!(pq > 0.0)) {
@@ -814,7 +833,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
 // GMRES (KNP), one ion at a time
 // ---------------------------------------------------------------------------------
 static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, double* resid_out) {
-  knp_stream_t s = c->stream;
+  knp_stream_t s = cs(c);
   const int64_t n = c->n, no = c->n_own;   // stride of the Krylov basis / owned rows
   const int m = c->opt.restart;
   BellMat A = bell_of(c, 2 + ion);
@@ -824,8 +843,8 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
   const double* bj = c->bj_knp[ion].p;
   double* x = c->c[ion].p;
   const double* b = c->rhs_knp[ion].p;
-  double* V = c->kr_V.p; double* w = c->kr_w.p; double* r = c->kr_r.p;
-  double* hdev = c->kr_scal.p + 512;  // device copy of the current Hessenberg column / y
+  double* V = ws(c).V.p; double* w = ws(c).w.p; double* r = ws(c).r.p;
+  double* hdev = ws(c).scal.p + 512;  // device copy of the current Hessenberg column / y
   const bool pre0 = c->opt.knp_presmooth0;
   precondition(c, Vv, A, bj, b, w, pre0);
   const double bnorm = sqrt(dot_host(c, w, w));
@@ -852,7 +871,7 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
       // classical Gram-Schmidt with ONE reduction per step: h = V^T w and |w|^2 in the same
       // pass (w is basis slot j+1), the new norm from Pythagoras, update + normalisation fused;
       // h stays on the device for the update, the host reads it once for the Givens rotations
-      multi_dot_device(s, no, n, j + 2, V, vn, c->kr_partial.p, hdev);
+      multi_dot_device(s, no, n, j + 2, V, vn, ws(c).partial.p, hdev);
       c->comm.allreduce(s, hdev, j + 2);
       // the Pythagorean norm carries a relative error of about eps |w|^2 / hn^2: keep it below
       // the requested tolerance, otherwise fall back to the explicit norm
@@ -914,7 +933,53 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
   ensure_krylov(ctx);
   int worst = 0;
   double rmax = 0.0;
-  for (int ion = 0; ion < ctx->P.N - 1; ++ion) {
+  const int nion = ctx->P.N - 1;
+  bool concurrent = false;
+#ifndef KNP_EMU
+  {
+    // The ions' systems are independent (solver.py:550-594).  On one GPU they are solved
+    // CONCURRENTLY: one host thread and one stream per ion, so the latency-bound parts of one
+    // solve (small AMG levels, host round trips of the Krylov scalars) overlap the
+    // bandwidth-bound kernels of the other.  (Multi-GPU runs keep them in sequence: the
+    // exchange kernels of a plan must be issued in the same order on every rank.)
+    const char* e = getenv("KNP_CONCURRENT_IONS");
+    concurrent = nion > 1 && !ctx->comm.active() && !(e && e[0] == '0');
+  }
+  if (concurrent) {
+    cudaEvent_t ready;
+    KNP_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    KNP_CUDA(cudaEventRecord(ready, ctx->stream));
+    std::vector<std::thread> th;
+    std::vector<int> its(nion, 0);
+    std::vector<double> ress(nion, 0.0);
+    std::vector<std::string> errs(nion);
+    for (int ion = 0; ion < nion; ++ion) {
+      KrylovWs& K = ctx->kr_ion[ion];
+      if (!K.own_stream) { KNP_CUDA(cudaStreamCreateWithFlags(&K.stream, cudaStreamNonBlocking)); K.own_stream = true; }
+      KNP_CUDA(cudaStreamWaitEvent(K.stream, ready, 0));
+      th.emplace_back([ctx, ion, rtol, atol, maxit, &its, &ress, &errs, &K]() {
+        try {
+          KNP_CUDA(cudaSetDevice(ctx->device));
+          tl_ws = &K;
+          ensure_krylov(ctx);
+          its[ion] = gmres_one(ctx, ion, rtol, atol, maxit, &ress[ion]);
+          stream_sync(K.stream);
+        } catch (const std::exception& ex) { errs[ion] = ex.what(); }
+        catch (...) { errs[ion] = "unknown error"; }
+        tl_ws = nullptr;
+      });
+    }
+    for (auto& t : th) t.join();
+    cudaEventDestroy(ready);
+    for (int ion = 0; ion < nion; ++ion) {
+      if (!errs[ion].empty()) fail(errs[ion]);
+      if (its[ion] < 0) fail("knp_solve_knp: GMRES did not converge for ion " + std::to_string(ion));
+      worst = its[ion] > worst ? its[ion] : worst;
+      rmax = ress[ion] > rmax ? ress[ion] : rmax;
+    }
+  }
+#endif
+  for (int ion = 0; ion < nion && !concurrent; ++ion) {
     double res = 0.0;
     const int it = gmres_one(ctx, ion, rtol, atol, maxit, &res);
     if (it < 0) fail("knp_solve_knp: GMRES did not converge for ion " + std::to_string(ion));
