@@ -196,6 +196,8 @@ struct AmgPlan {
   size_t rep_from = (size_t)-1;    // index of the first replicated level; -1: none
   int64_t rep_vstride = 0, rep_bstride = 0;   // padded per-rank segment: matrix values / rows
   DevBuf<double> rep_val;          // all-gather buffer of the matrix values [world * stride]
+  HaloPlan rep_plan;               // the all-gather of the right-hand side as a peer-memory exchange
+                                   // with every rank (self included): one kernel, usable from worker threads
   DevBuf<int32_t> rep_bmap;        // global row of the replica -> position in rep_b
   DevBuf<int32_t> rep_xmap;        // local unknown of lev[rep_from-1] -> global row of the replica
   int64_t m_dense = 0;             // rows of the last level (summed over all ranks)

@@ -31,15 +31,21 @@ namespace knp {
 constexpr int P2P_MAX_NB = 16;      // neighbours per halo plan served by the peer-memory kernel
 constexpr int P2P_MAX_WORLD = 16;   // ranks served by the peer-memory allreduce
 constexpr int P2P_AR_MAX = 64;      // doubles per peer-memory allreduce (larger ones use NCCL)
+constexpr int P2P_MAX_WS = 7;       // independent exchange channels (one per concurrently running solve)
 
-struct HaloPlan {
-  int64_t n_own = 0, n_ghost = 0;
-  // peer-memory transport (filled by P2P::register_plan)
-  bool p2p_ready = false;
-  unsigned long long seq = 0;                        // exchanges done on this plan
+// peer-memory state of one halo plan on one channel (filled by Comm::register_plan)
+struct P2PChannel {
+  bool ready = false;
+  unsigned long long seq = 0;                        // exchanges done on this channel
   size_t local_flag_off[P2P_MAX_NB] = {0}, local_data_off[P2P_MAX_NB] = {0};    // in my arena
   size_t remote_flag_off[P2P_MAX_NB] = {0}, remote_data_off[P2P_MAX_NB] = {0};  // in the neighbour's arena
   size_t counter_off = 0;
+};
+
+struct HaloPlan {
+  int64_t n_own = 0, n_ghost = 0;
+  std::vector<int32_t> ranks;                // partner ranks of THIS plan; empty = the DG neighbours
+  P2PChannel ch[P2P_MAX_WS];
   std::vector<int64_t> send_off, recv_off;   // [nneigh+1], in entries
   std::vector<int32_t> h_send_idx;           // owned entries to pack, neighbour by neighbour
   std::vector<int32_t> ghost_rank, ghost_id; // per ghost entry: owning rank and its index there
@@ -193,12 +199,14 @@ struct P2P {
   char* arena = nullptr;
   size_t bytes = 0, bump = 0;
   char* peer[P2P_MAX_WORLD] = {nullptr};
-  p2p_u64 ar_seq = 0;
-  // fixed header (same offsets on every rank): error word, allreduce flags and slots
+  p2p_u64 ar_seq[P2P_MAX_WS] = {0};
+  // fixed header (same offsets on every rank): error word, allreduce flags and slots per channel
   static constexpr size_t ERR_OFF = 0;
-  static constexpr size_t AR_FLAG_OFF = 256;                                   // [2][P2P_MAX_WORLD] u64
-  static constexpr size_t AR_DATA_OFF = 1024;                                  // [2][P2P_MAX_WORLD][P2P_AR_MAX] f64
-  static constexpr size_t HEADER = AR_DATA_OFF + 2 * P2P_MAX_WORLD * P2P_AR_MAX * sizeof(double);
+  static constexpr size_t AR_FLAG_OFF = 256;                                   // [WS][2][P2P_MAX_WORLD] u64
+  static constexpr size_t AR_FLAG_WS = 2 * P2P_MAX_WORLD * sizeof(p2p_u64);
+  static constexpr size_t AR_DATA_OFF = AR_FLAG_OFF + P2P_MAX_WS * AR_FLAG_WS; // [WS][2][P2P_MAX_WORLD][P2P_AR_MAX] f64
+  static constexpr size_t AR_DATA_WS = 2 * P2P_MAX_WORLD * P2P_AR_MAX * sizeof(double);
+  static constexpr size_t HEADER = AR_DATA_OFF + P2P_MAX_WS * AR_DATA_WS;
   size_t alloc(size_t nbytes) {
     const size_t o = (bump + 255) & ~(size_t)255;
     if (o + nbytes > bytes) fail("peer-memory arena exhausted");
@@ -214,12 +222,13 @@ struct Comm {
   knp_exchange_fn xfn = nullptr;
   knp_allreduce_fn rfn = nullptr;
   void* user = nullptr;
-  int64_t n_halo = 0, n_allreduce = 0;
+  std::atomic<int64_t> n_halo{0}, n_allreduce{0};
 #ifndef KNP_EMU
   ncclComm_t nccl = nullptr;
   P2P p2p;
-  int64_t n_p2p = 0;                         // exchanges served by the peer-memory kernels
+  std::atomic<int64_t> n_p2p{0};             // exchanges served by the peer-memory kernels
 #endif
+  const std::vector<int32_t>& partners(const HaloPlan& H) const { return H.ranks.empty() ? nbr : H.ranks; }
   bool active() const { return world > 1; }
 
 #ifndef KNP_EMU
@@ -236,7 +245,7 @@ struct Comm {
     if (world > P2P_MAX_WORLD || p2p.on) return;
     P2P& P = p2p;
     int ok = 1;
-    P.bytes = (size_t)64 << 20;
+    P.bytes = (size_t)160 << 20;
     if (cudaMalloc((void**)&P.arena, P.bytes) != cudaSuccess) { cudaGetLastError(); P.arena = nullptr; ok = 0; }
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
@@ -284,33 +293,46 @@ struct Comm {
     P.arena = nullptr; P.on = false;
   }
 
-  // staging buffers and flags of one halo plan; the neighbours learn where to write through
-  // one small NCCL exchange (collective among the plan's neighbours, first use of the plan)
-  void register_plan(knp_stream_t s, HaloPlan& H) {
+  // staging buffers and flags of one halo plan on one channel; the partners learn where to
+  // write through one small NCCL exchange (collective among the plan's partners; main thread)
+  void register_plan(knp_stream_t s, HaloPlan& H, int w) {
     P2P& P = p2p;
-    const int nn = (int)nbr.size();
+    P2PChannel& C = H.ch[w];
+    const std::vector<int32_t>& R = partners(H);
+    const int nn = (int)R.size();
     std::vector<double> mine(2 * (size_t)nn + 2, 0.0), theirs(2 * (size_t)nn + 2, 0.0);
     for (int i = 0; i < nn; ++i) {
       const int64_t nr = H.recv_off[i + 1] - H.recv_off[i];
-      H.local_flag_off[i] = P.alloc(2 * sizeof(p2p_u64));
-      H.local_data_off[i] = P.alloc(2 * (size_t)nr * sizeof(double));
-      mine[2 * i] = (double)H.local_flag_off[i]; mine[2 * i + 1] = (double)H.local_data_off[i];
+      C.local_flag_off[i] = P.alloc(2 * sizeof(p2p_u64));
+      C.local_data_off[i] = P.alloc(2 * (size_t)nr * sizeof(double));
+      mine[2 * i] = (double)C.local_flag_off[i]; mine[2 * i + 1] = (double)C.local_data_off[i];
     }
-    H.counter_off = P.alloc(sizeof(unsigned int));
+    C.counter_off = P.alloc(sizeof(unsigned int));
     DevBuf<double> sb, rb;
     sb.upload(mine, s); rb.upload(theirs, s);
     NcclApi& N = nccl_api();
     N.check(N.GroupStart(), "ncclGroupStart");
     for (int i = 0; i < nn; ++i) {
-      N.check(N.Send(sb.p + 2 * i, 2, ncclDouble, nbr[i], nccl, s), "ncclSend");
-      N.check(N.Recv(rb.p + 2 * i, 2, ncclDouble, nbr[i], nccl, s), "ncclRecv");
+      if (R[i] == rank) continue;
+      N.check(N.Send(sb.p + 2 * i, 2, ncclDouble, R[i], nccl, s), "ncclSend");
+      N.check(N.Recv(rb.p + 2 * i, 2, ncclDouble, R[i], nccl, s), "ncclRecv");
     }
     N.check(N.GroupEnd(), "ncclGroupEnd");
     theirs = rb.download(s);
-    for (int i = 0; i < nn; ++i) { H.remote_flag_off[i] = (size_t)theirs[2 * i]; H.remote_data_off[i] = (size_t)theirs[2 * i + 1]; }
-    H.seq = 0;
-    H.p2p_ready = true;
+    for (int i = 0; i < nn; ++i) {
+      if (R[i] == rank) { C.remote_flag_off[i] = C.local_flag_off[i]; C.remote_data_off[i] = C.local_data_off[i]; }
+      else { C.remote_flag_off[i] = (size_t)theirs[2 * i]; C.remote_data_off[i] = (size_t)theirs[2 * i + 1]; }
+    }
+    C.seq = 0;
+    C.ready = true;
   }
+  // make channels 0..nws-1 of a plan usable from worker threads (no NCCL on first use there)
+  void prepare_plan(knp_stream_t s, HaloPlan& H, int nws) {
+    if (!p2p.on || (int)partners(H).size() > P2P_MAX_NB) return;
+    for (int w = 0; w < nws && w < P2P_MAX_WS; ++w)
+      if (!H.ch[w].ready) register_plan(s, H, w);
+  }
+  static bool& in_worker() { static thread_local bool v = false; return v; }
 
   void check_p2p(knp_stream_t s) {
     if (!p2p.on) return;
@@ -329,33 +351,38 @@ struct Comm {
   }
 
   // ghost entries of x (x + H.n_own ...) <- the owners' values
-  void halo(knp_stream_t s, HaloPlan& H, double* x) {
+  void halo(knp_stream_t s, HaloPlan& H, double* x, int w = 0) {
     if (!active()) return;
     require_transport();
     ++n_halo;
+    const std::vector<int32_t>& nbr = partners(H);   // (shadows the DG neighbour list on purpose)
     const int nn = (int)nbr.size();
 #ifndef KNP_EMU
-    if (p2p.on && nn <= P2P_MAX_NB) {
+    if (p2p.on && nn <= P2P_MAX_NB && w < P2P_MAX_WS) {
       if (nn == 0) return;
-      if (!H.p2p_ready) register_plan(s, H);
+      if (!H.ch[w].ready) {
+        if (in_worker()) fail("halo plan was not prepared for concurrent use");
+        register_plan(s, H, w);
+      }
       P2P& P = p2p;
+      P2PChannel& C = H.ch[w];
       P2PHaloArgs a;
       a.nn = nn; a.x = x; a.send_idx = H.send_idx.p; a.n_own = H.n_own;
-      const p2p_u64 seq = ++H.seq;
+      const p2p_u64 seq = ++C.seq;
       const size_t par = (size_t)(seq & 1);
       int64_t most = 1;
       for (int i = 0; i <= nn; ++i) { a.send_off[i] = H.send_off[i]; a.recv_off[i] = H.recv_off[i]; }
       for (int i = 0; i < nn; ++i) {
         const int64_t ns = H.send_off[i + 1] - H.send_off[i], nr = H.recv_off[i + 1] - H.recv_off[i];
         char* pb = P.peer[nbr[i]];
-        a.remote_data[i] = reinterpret_cast<double*>(pb + H.remote_data_off[i]) + par * (size_t)ns;
-        a.remote_flag[i] = reinterpret_cast<p2p_u64*>(pb + H.remote_flag_off[i]) + par;
-        a.local_data[i] = reinterpret_cast<const double*>(P.arena + H.local_data_off[i]) + par * (size_t)nr;
-        a.local_flag[i] = reinterpret_cast<volatile p2p_u64*>(P.arena + H.local_flag_off[i]) + par;
+        a.remote_data[i] = reinterpret_cast<double*>(pb + C.remote_data_off[i]) + par * (size_t)ns;
+        a.remote_flag[i] = reinterpret_cast<p2p_u64*>(pb + C.remote_flag_off[i]) + par;
+        a.local_data[i] = reinterpret_cast<const double*>(P.arena + C.local_data_off[i]) + par * (size_t)nr;
+        a.local_flag[i] = reinterpret_cast<volatile p2p_u64*>(P.arena + C.local_flag_off[i]) + par;
         most = ns > most ? ns : most; most = nr > most ? nr : most;
       }
       a.seq = seq;
-      a.counter = reinterpret_cast<unsigned int*>(P.arena + H.counter_off);
+      a.counter = reinterpret_cast<unsigned int*>(P.arena + C.counter_off);
       a.err = reinterpret_cast<int*>(P.arena + P2P::ERR_OFF);
       int64_t grid = (most + 255) / 256;
       if (grid < 1) grid = 1;
@@ -365,6 +392,9 @@ struct Comm {
       KNP_CUDA(cudaGetLastError());
       return;
     }
+#endif
+#ifndef KNP_EMU
+    if (in_worker()) fail("NCCL exchange requested from a worker thread");
 #endif
     if (H.nsend() > 0) {
       PackKernel k{H.send_idx.p, x, H.sendbuf.p};
@@ -403,7 +433,7 @@ struct Comm {
   }
 
   // in-place sum over ranks of n doubles (device memory; host memory in the emulation)
-  void allreduce(knp_stream_t s, double* buf, int64_t n) {
+  void allreduce(knp_stream_t s, double* buf, int64_t n, int w = 0) {
     if (!active()) return;
     require_transport();
     ++n_allreduce;
@@ -411,18 +441,19 @@ struct Comm {
     (void)s;
     if (rfn(user, buf, n)) fail("allreduce callback failed");
 #else
-    if (p2p.on && n <= P2P_AR_MAX) {
+    if (p2p.on && n <= P2P_AR_MAX && w < P2P_MAX_WS) {
       P2P& P = p2p;
       P2PArArgs a;
       a.world = world; a.rank = rank; a.n = (int)n; a.buf = buf;
-      const p2p_u64 seq = ++P.ar_seq;
+      const p2p_u64 seq = ++P.ar_seq[w];
       const size_t par = (size_t)(seq & 1);
+      const size_t doff = P2P::AR_DATA_OFF + (size_t)w * P2P::AR_DATA_WS, foff = P2P::AR_FLAG_OFF + (size_t)w * P2P::AR_FLAG_WS;
       for (int r = 0; r < world; ++r) {
-        a.peer_data[r] = reinterpret_cast<double*>(P.peer[r] + P2P::AR_DATA_OFF) + par * P2P_MAX_WORLD * P2P_AR_MAX;
-        a.peer_flag[r] = reinterpret_cast<p2p_u64*>(P.peer[r] + P2P::AR_FLAG_OFF) + par * P2P_MAX_WORLD;
+        a.peer_data[r] = reinterpret_cast<double*>(P.peer[r] + doff) + par * P2P_MAX_WORLD * P2P_AR_MAX;
+        a.peer_flag[r] = reinterpret_cast<p2p_u64*>(P.peer[r] + foff) + par * P2P_MAX_WORLD;
       }
-      a.my_data = reinterpret_cast<const double*>(P.arena + P2P::AR_DATA_OFF) + par * P2P_MAX_WORLD * P2P_AR_MAX;
-      a.my_flag = reinterpret_cast<volatile p2p_u64*>(P.arena + P2P::AR_FLAG_OFF) + par * P2P_MAX_WORLD;
+      a.my_data = reinterpret_cast<const double*>(P.arena + doff) + par * P2P_MAX_WORLD * P2P_AR_MAX;
+      a.my_flag = reinterpret_cast<volatile p2p_u64*>(P.arena + foff) + par * P2P_MAX_WORLD;
       a.seq = seq;
       a.err = reinterpret_cast<int*>(P.arena + P2P::ERR_OFF);
       ++launch_counter(); ++n_p2p;
@@ -430,6 +461,7 @@ struct Comm {
       KNP_CUDA(cudaGetLastError());
       return;
     }
+    if (in_worker()) fail("NCCL allreduce requested from a worker thread");
     nccl_allreduce(s, buf, n);
 #endif
   }

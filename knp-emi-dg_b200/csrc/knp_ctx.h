@@ -45,6 +45,7 @@ enum { T_EMI_ASM = 0, T_EMI_SOLVE, T_KNP_ASM, T_KNP_SOLVE, T_ODE, T_POST, T_COUN
 struct KrylovWs {
   knp_stream_t stream = 0;
   bool own_stream = false;
+  int id = 0;                  // exchange channel of this workspace (knp_comm.h)
   DevBuf<double> r, p, q, w, V, scal, partial;
 };
 

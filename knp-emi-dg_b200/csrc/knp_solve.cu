@@ -41,7 +41,7 @@ static knp_stream_t cs(knp_ctx* c) { return ws(c).stream; }
 // vector); the operators that read a vector through the matrix first refresh its ghost
 // entries from their owners (knp_comm.h).
 static void halo0(knp_ctx* c, const double* x) {
-  if (c->comm.active()) c->comm.halo(cs(c), c->halo0, const_cast<double*>(x));
+  if (c->comm.active()) c->comm.halo(cs(c), c->halo0, const_cast<double*>(x), ws(c).id);
 }
 template <int ND>
 static void bell_spmv(knp_ctx* c, const BellMat& A, const double* x, const double* b, double* y, int mode) {
@@ -85,7 +85,7 @@ static void block_inverse(knp_ctx* c, const double* blocks, double* inv) {
 // host-visible dot products over all ranks (one sync each)
 static void dots_host(knp_ctx* c, int k, const double* V, const double* w, double* out_host) {
   multi_dot_device(cs(c), c->n_own, c->n, k, V, w, ws(c).partial.p, ws(c).scal.p);
-  c->comm.allreduce(cs(c), ws(c).scal.p, k);
+  c->comm.allreduce(cs(c), ws(c).scal.p, k, ws(c).id);
   d2h(out_host, ws(c).scal.p, k * sizeof(double), cs(c));
 }
 // sum over ranks of a few host numbers (setup-time decisions must agree on every rank)
@@ -323,6 +323,22 @@ static void replicate_level(knp_ctx* c, GalerkinPlan& G) {
   std::iota(B.pos.begin(), B.pos.end(), 0);
   amg.rep_vstride = vstride; amg.rep_bstride = bstride;
   amg.rep_val.alloc((size_t)world * vstride);
+  {
+    // the right-hand side all-gather as an exchange plan: every rank (self included) receives
+    // this rank's padded segment; segment r of the buffer comes from rank r
+    HaloPlan& G = amg.rep_plan;
+    G = HaloPlan();
+    G.n_own = 0; G.n_ghost = (int64_t)world * bstride;
+    G.ranks.resize(world);
+    G.send_off.assign(world + 1, 0); G.recv_off.assign(world + 1, 0);
+    for (int r = 0; r < world; ++r) {
+      G.ranks[r] = r;
+      for (int64_t k = 0; k < bstride; ++k) G.h_send_idx.push_back((int32_t)(rank * bstride + k));
+      G.send_off[r + 1] = (int64_t)(r + 1) * bstride;
+      G.recv_off[r + 1] = (int64_t)(r + 1) * bstride;
+    }
+    G.upload(cs(c));
+  }
   amg.rep_bmap.upload(bmap, cs(c));
   amg.rep_xmap.upload(xmap, cs(c));
   amg.rep_from = amg.lev.size();
@@ -440,6 +456,16 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
         amg.tail_blocks = TAIL_CTAS;
       }
     }
+  }
+#endif
+#ifndef KNP_EMU
+  if (ctx->comm.active() && ctx->comm.p2p.on) {
+    // every exchange channel a concurrently running solve may use is registered now, on the
+    // main thread (registration talks NCCL; the worker threads must not)
+    const int nws = ctx->P.N;   // main + one per solved ion
+    ctx->comm.prepare_plan(ctx->stream, ctx->halo0, nws);
+    for (size_t l = 0; l < amg.lev.size() && l < amg.rep_from; ++l) ctx->comm.prepare_plan(ctx->stream, amg.lev[l].halo, nws);
+    if (amg.rep_from != (size_t)-1) ctx->comm.prepare_plan(ctx->stream, amg.rep_plan, nws);
   }
 #endif
   alloc_values(ctx, ctx->amg_emi);
@@ -560,6 +586,7 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
   AmgLevelPlan& L = c->amg.lev[li];
   LevelVectors& Lv = V.vec[li];
   Comm& comm = c->comm;
+  const int wid = ws(c).id;
   const bool dist = comm.active() && li < c->amg.rep_from;   // this level's vectors have ghosts
 #ifndef KNP_EMU
   if (li == c->amg.tail_from && c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1) {
@@ -587,7 +614,11 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
     AmgLevelPlan& T0 = amg.lev[li + 1];
     LevelVectors& T0v = V.vec[li + 1];
     d2d(V.rep_b.p + (int64_t)comm.rank * amg.rep_bstride, Lv.b.p, L.n * sizeof(double), s);
-    comm.allgather(s, V.rep_b.p, amg.rep_bstride);
+#ifndef KNP_EMU
+    if (comm.p2p.on && comm.world <= P2P_MAX_NB) comm.halo(s, amg.rep_plan, V.rep_b.p, wid);
+    else
+#endif
+      comm.allgather(s, V.rep_b.p, amg.rep_bstride);
     { GatherMapKernel k{V.rep_b.p, amg.rep_bmap.p, T0v.b.p}; parallel_for(s, T0.n, k); }
     coarse_cycle(c, V, li + 1, false);
     { GatherMapKernel k{T0v.x.p, amg.rep_xmap.p, Lv.x.p}; parallel_for(s, L.nloc, k); }
@@ -605,7 +636,7 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
     const int64_t m = amg.m_dense;
     dev_zero(V.dense_b.p, (size_t)m * sizeof(double), s);
     { ScatterOffsetKernel k{Lv.b.p, V.dense_b.p, amg.dense_off}; parallel_for(s, L.n, k); }
-    comm.allreduce(s, V.dense_b.p, m);
+    comm.allreduce(s, V.dense_b.p, m, wid);
     { DenseMatvecKernel k{m, V.dense.p, V.dense_b.p, V.dense_x.p}; parallel_for(s, m, k, 64); }
     { GatherMapKernel k{V.dense_x.p, amg.dense_map.p, Lv.x.p}; parallel_for(s, L.nloc, k); }
     return;
@@ -615,7 +646,7 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
   LevelVectors& Cv = V.vec[li + 1];
   if (c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1 && C.t_unit) {
     // fused V(1,1) path: two kernels down (smooth+residual, restrict), one up (prolong+smooth)
-    if (dist) comm.halo(s, L.halo, Lv.b.p);
+    if (dist) comm.halo(s, L.halo, Lv.b.p, wid);
     { CoarseResidualKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, Lv.r.p}; parallel_rows<8>(s, L.n, k); }
     if (L.halo.n_ghost > 0) {   // x = dinv b on the ghost unknowns too (read by the sweep up)
       DiagScaleKernel k{V.dinv[li].p + L.n, Lv.b.p + L.n, Lv.x.p + L.n, 1.0};
@@ -625,31 +656,31 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
     coarse_cycle(c, V, li + 1, true);
     { CoarseUpKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, C.pidx.p, Cv.x.p, Lv.t.p}; parallel_rows<8>(s, L.n, k); }
     std::swap(Lv.x.p, Lv.t.p);
-    if (ghost_x && dist) comm.halo(s, L.halo, Lv.x.p);
+    if (ghost_x && dist) comm.halo(s, L.halo, Lv.x.p, wid);
     return;
   }
   // pre-smoothing from a zero guess
   { DiagScaleKernel k{V.dinv[li].p, Lv.b.p, Lv.x.p, 1.0}; parallel_for(s, L.n, k); }
   for (int it = 1; it < c->opt.nu_pre; ++it) {
-    if (dist) comm.halo(s, L.halo, Lv.x.p);
+    if (dist) comm.halo(s, L.halo, Lv.x.p, wid);
     CsrJacobiKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, Lv.t.p, 1.0};
     parallel_for(s, L.n, k);
     std::swap(Lv.x.p, Lv.t.p);
   }
   for (int g = 0; g < c->opt.gamma; ++g) {
-    if (dist) comm.halo(s, L.halo, Lv.x.p);
+    if (dist) comm.halo(s, L.halo, Lv.x.p, wid);
     { CsrSpmvKernel k{A, Lv.x.p, Lv.b.p, Lv.r.p, 1}; parallel_for(s, L.n, k); }
     transfer(c, C.n, C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, Lv.r.p, Cv.b.p, 0);
     coarse_cycle(c, V, li + 1, false);
     transfer(c, L.n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, Cv.x.p, Lv.x.p, 1);
   }
   for (int it = 0; it < c->opt.nu_post; ++it) {
-    if (dist) comm.halo(s, L.halo, Lv.x.p);
+    if (dist) comm.halo(s, L.halo, Lv.x.p, wid);
     CsrJacobiKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, Lv.t.p, 1.0};
     parallel_for(s, L.n, k);
     std::swap(Lv.x.p, Lv.t.p);
   }
-  if (ghost_x && dist) comm.halo(s, L.halo, Lv.x.p);
+  if (ghost_x && dist) comm.halo(s, L.halo, Lv.x.p, wid);
 }
 
 // z = M^-1 r
@@ -727,9 +758,11 @@ static void ensure_krylov(knp_ctx* c) {
   }
   const size_t need = (size_t)(c->opt.restart + 1) * n;
   if (K.V.n < need) K.V.alloc(need);
-  double ng = (double)c->n_own;
-  global_sum(c, &ng, 1);
-  c->n_global = ng;
+  if (tl_ws == nullptr) {     // (worker threads find it set by the main thread)
+    double ng = (double)c->n_own;
+    global_sum(c, &ng, 1);
+    c->n_global = ng;
+  }
 }
 
 extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, int* niter, double* resid) {
@@ -832,14 +865,21 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
 // ---------------------------------------------------------------------------------
 // GMRES (KNP), one ion at a time
 // ---------------------------------------------------------------------------------
-static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, double* resid_out) {
+// preconditioner of ion's system after a re-assembly (the reference rebuilds BoomerAMG at
+// every setOperators, solver.py:767)
+static void knp_refresh(knp_ctx* c, int ion) {
+  BellMat A = bell_of(c, 2 + ion);
+  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_knp[ion], A, c->A_knp[ion].p, c->A_knp[ion].p);
+  else { if (c->bj_knp[ion].n != (size_t)c->slot_stride()) c->bj_knp[ion].alloc(c->slot_stride()); block_inverse(c, c->A_knp[ion].p, c->bj_knp[ion].p); }
+}
+
+static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, double* resid_out, bool refresh = true) {
   knp_stream_t s = cs(c);
   const int64_t n = c->n, no = c->n_own;   // stride of the Krylov basis / owned rows
   const int m = c->opt.restart;
   BellMat A = bell_of(c, 2 + ion);
   AmgValues& Vv = c->amg_knp[ion];
-  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, Vv, A, c->A_knp[ion].p, c->A_knp[ion].p);
-  else { if (c->bj_knp[ion].n != (size_t)c->slot_stride()) c->bj_knp[ion].alloc(c->slot_stride()); block_inverse(c, c->A_knp[ion].p, c->bj_knp[ion].p); }
+  if (refresh) knp_refresh(c, ion);
   const double* bj = c->bj_knp[ion].p;
   double* x = c->c[ion].p;
   const double* b = c->rhs_knp[ion].p;
@@ -872,7 +912,7 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
       // pass (w is basis slot j+1), the new norm from Pythagoras, update + normalisation fused;
       // h stays on the device for the update, the host reads it once for the Givens rotations
       multi_dot_device(s, no, n, j + 2, V, vn, ws(c).partial.p, hdev);
-      c->comm.allreduce(s, hdev, j + 2);
+      c->comm.allreduce(s, hdev, j + 2, ws(c).id);
       // the Pythagorean norm carries a relative error of about eps |w|^2 / hn^2: keep it below
       // the requested tolerance, otherwise fall back to the explicit norm
       const double cancel_tol = fmax(1e-6, 100.0 * 2.2e-16 / fmax(rtol, 1e-16));
@@ -942,10 +982,20 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
     // solve (small AMG levels, host round trips of the Krylov scalars) overlap the
     // bandwidth-bound kernels of the other.  (Multi-GPU runs keep them in sequence: the
     // exchange kernels of a plan must be issued in the same order on every rank.)
+    // Multi-GPU: every worker talks to its peers on its own exchange channel (peer-memory
+    // kernels only - NCCL calls must come from one thread in one order); the preconditioner
+    // refresh, which all-gathers matrix values with NCCL, is done up front on the main thread.
     const char* e = getenv("KNP_CONCURRENT_IONS");
-    concurrent = nion > 1 && !ctx->comm.active() && !(e && e[0] == '0');
+    const bool dist = ctx->comm.active();
+    const bool dist_ok = !dist || (ctx->comm.p2p.on && ctx->comm.world <= P2P_MAX_NB && nion + 1 <= P2P_MAX_WS &&
+                                   ctx->opt.pc == 1 && ctx->amg.ready &&
+                                   (ctx->amg.rep_from != (size_t)-1 || ctx->amg.m_dense <= P2P_AR_MAX));
+    concurrent = nion > 1 && dist_ok && !(e && e[0] == '0');
   }
   if (concurrent) {
+    const bool refresh_in_worker = !ctx->comm.active();
+    if (!refresh_in_worker)
+      for (int ion = 0; ion < nion; ++ion) knp_refresh(ctx, ion);
     cudaEvent_t ready;
     KNP_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     KNP_CUDA(cudaEventRecord(ready, ctx->stream));
@@ -955,17 +1005,21 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
     std::vector<std::string> errs(nion);
     for (int ion = 0; ion < nion; ++ion) {
       KrylovWs& K = ctx->kr_ion[ion];
+      K.id = 1 + ion;
       if (!K.own_stream) { KNP_CUDA(cudaStreamCreateWithFlags(&K.stream, cudaStreamNonBlocking)); K.own_stream = true; }
       KNP_CUDA(cudaStreamWaitEvent(K.stream, ready, 0));
-      th.emplace_back([ctx, ion, rtol, atol, maxit, &its, &ress, &errs, &K]() {
+      th.emplace_back([ctx, ion, rtol, atol, maxit, refresh_in_worker, &its, &ress, &errs, &K]() {
         try {
           KNP_CUDA(cudaSetDevice(ctx->device));
           tl_ws = &K;
+          Comm::in_worker() = true;
           ensure_krylov(ctx);
-          its[ion] = gmres_one(ctx, ion, rtol, atol, maxit, &ress[ion]);
+          its[ion] = gmres_one(ctx, ion, rtol, atol, maxit, &ress[ion], refresh_in_worker);
+          if (its[ion] >= 0) halo0(ctx, ctx->c[ion].p);   // ghost cells of the new concentration
           stream_sync(K.stream);
         } catch (const std::exception& ex) { errs[ion] = ex.what(); }
         catch (...) { errs[ion] = "unknown error"; }
+        Comm::in_worker() = false;
         tl_ws = nullptr;
       });
     }
