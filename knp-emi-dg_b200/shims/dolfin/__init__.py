@@ -1,0 +1,277 @@
+"""`dolfin` stand-in for hosts WITHOUT legacy FEniCS.
+
+The reference's run scripts and mesh scripts start with `from dolfin import *`
+(examples/idealized-geometries/run_2D.py:3, make_mesh_2D.py:15) and use a small part of
+dolfin for SETUP only: `Constant`, `Point`, `RectangleMesh`/`BoxMesh`, `MeshFunction`,
+`SubDomain`/`CompiledSubDomain`, the `cells`/`facets`/`SubsetIterator` entity iterators,
+`near`, and `File`/`Mesh` for dolfin-XML files.  This package provides exactly that on top of
+`knpemidg.mesh`, so that those scripts execute UNCHANGED with the B200 `knpemidg` package:
+put `knp-emi-dg_b200/shims` on `sys.path` (tests/test_reference_scripts.py does) - never when
+a real dolfin is installed, which `knpemidg.dolfin_adapter` handles instead.
+
+Everything here is host-side, once-per-run setup code; nothing is on the time-step path.
+Mesh numbering follows knpemidg.mesh, not dolfin's internals: files
+written and read back here are dolfin-XML in form and self-consistent, physics does not
+depend on the numbering.
+"""
+from __future__ import annotations
+
+import os
+import re
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+from knpemidg import mesh as _kmesh
+from knpemidg.frontend import Constant  # noqa: F401  (re-exported: `from dolfin import *`)
+
+DOLFIN_EPS = 3.0e-16
+
+
+def near(a, b, eps=DOLFIN_EPS):
+    return abs(a - b) < eps
+
+
+class Point:
+    def __init__(self, *xs):
+        if len(xs) == 1 and hasattr(xs[0], "__len__"):
+            xs = tuple(xs[0])
+        self._x = np.zeros(3)
+        self._x[: len(xs)] = xs
+
+    def x(self):
+        return float(self._x[0])
+
+    def y(self):
+        return float(self._x[1])
+
+    def z(self):
+        return float(self._x[2])
+
+    def array(self):
+        return self._x.copy()
+
+    def __getitem__(self, i):
+        return float(self._x[i])
+
+    def __len__(self):
+        return 3
+
+
+class Mesh(_kmesh.SimplexMesh):
+    """SimplexMesh with dolfin's constructor `Mesh(path_to_xml)`."""
+
+    def __init__(self, arg=None, cells=None):
+        if isinstance(arg, (str, os.PathLike)):
+            coords, cells = _read_mesh_xml(str(arg))
+            super().__init__(coords, cells)
+        elif isinstance(arg, _kmesh.SimplexMesh):
+            super().__init__(arg.coords, arg.cells)
+        else:
+            super().__init__(arg, cells)
+
+    def num_entities(self, dim):
+        if dim == self.gdim:
+            return self.num_cells()
+        if dim == self.gdim - 1:
+            return self.num_facets()
+        if dim == 0:
+            return self.num_vertices()
+        raise NotImplementedError(dim)
+
+
+def RectangleMesh(p0, p1, nx, ny, diagonal="right"):
+    m = _kmesh.rectangle_mesh((p0[0], p0[1]), (p1[0], p1[1]), nx, ny, diagonal)
+    return Mesh(m)
+
+
+def BoxMesh(p0, p1, nx, ny, nz):
+    m = _kmesh.box_mesh((p0[0], p0[1], p0[2]), (p1[0], p1[1], p1[2]), nx, ny, nz)
+    return Mesh(m)
+
+
+class _Entity:
+    def __init__(self, mesh, dim, index):
+        self._mesh, self._dim, self._index = mesh, dim, int(index)
+
+    def index(self):
+        return self._index
+
+    def dim(self):
+        return self._dim
+
+    def midpoint(self):
+        m = self._mesh
+        if self._dim == m.gdim:
+            return Point(m.coords[m.cells[self._index]].mean(axis=0))
+        m.init_topology()
+        return Point(m.coords[m.facet_verts[self._index]].mean(axis=0))
+
+
+def cells(mesh):
+    for i in range(mesh.num_cells()):
+        yield _Entity(mesh, mesh.gdim, i)
+
+
+def facets(mesh):
+    for i in range(mesh.num_facets()):
+        yield _Entity(mesh, mesh.gdim - 1, i)
+
+
+class MeshFunction(_kmesh.MeshFunction):
+    """dolfin's signatures: MeshFunction('size_t', mesh, dim[, value]) and
+    MeshFunction('size_t', mesh, path_to_xml)."""
+
+    def __init__(self, value_type, mesh, dim_or_path, value=0):
+        assert value_type in ("size_t", "int", "uint"), value_type
+        if isinstance(dim_or_path, (str, os.PathLike)):
+            dim, vals = _read_meshfunction_xml(str(dim_or_path), mesh)
+            super().__init__(mesh, dim, 0)
+            self._a[:] = vals
+        else:
+            super().__init__(mesh, int(dim_or_path), value)
+
+    @staticmethod
+    def _idx(i):
+        return i.index() if isinstance(i, _Entity) else i
+
+    def __getitem__(self, i):
+        return int(self._a[self._idx(i)])
+
+    def __setitem__(self, i, v):
+        self._a[self._idx(i)] = int(v)
+
+    def set_all(self, v):
+        self._a[:] = int(v)
+
+
+def SubsetIterator(mf, value):
+    for i in np.flatnonzero(mf.array() == value):
+        yield _Entity(mf.mesh(), mf.dim(), i)
+
+
+class SubDomain:
+    def inside(self, x, on_boundary):
+        raise NotImplementedError
+
+    def mark(self, mf, value):
+        """mark the entities whose midpoint is inside (dolfin also tests the vertices; the
+        reference's sub-domains are decided by the midpoint or by `on_boundary` alone)"""
+        mesh = mf.mesh()
+        mesh.init_topology()
+        d = mesh.gdim
+        if mf.dim() == d:
+            mids = mesh.cell_midpoints()
+            onb = np.zeros(len(mids), dtype=bool)
+        else:
+            mids = mesh.facet_midpoints()
+            onb = mesh.facet_cells[:, 1] < 0
+        for i, (x, b) in enumerate(zip(mids, onb)):
+            if self.inside(x, bool(b)):
+                mf[i] = value
+
+
+class CompiledSubDomain(SubDomain):
+    """C++ boolean expression in x[i], on_boundary, near(a, b) and DOLFIN_EPS, evaluated in Python."""
+
+    def __init__(self, cpp, **params):
+        expr = cpp.replace("&&", " and ").replace("||", " or ")
+        expr = re.sub(r"!(?!=)", " not ", expr)
+        expr = " ".join(expr.split())
+        self._code = compile(expr, "<CompiledSubDomain>", "eval")
+        self._params = dict(params)
+
+    def inside(self, x, on_boundary):
+        env = {"x": x, "on_boundary": on_boundary, "near": near, "DOLFIN_EPS": DOLFIN_EPS,
+               "true": True, "false": False, "fabs": abs, "abs": abs}
+        env.update(self._params)
+        return bool(eval(self._code, {"__builtins__": {}}, env))
+
+
+class File:
+    """`File(path) << mesh|mesh_function` (dolfin XML)."""
+
+    def __init__(self, path):
+        self.path = str(path)
+
+    def __lshift__(self, obj):
+        os.makedirs(os.path.dirname(self.path) or ".", exist_ok=True)
+        if isinstance(obj, _kmesh.MeshFunction):
+            _write_meshfunction_xml(self.path, obj)
+        elif isinstance(obj, _kmesh.SimplexMesh):
+            _write_mesh_xml(self.path, obj)
+        else:
+            raise NotImplementedError(type(obj))
+        return self
+
+    def __rshift__(self, obj):
+        raise NotImplementedError("use Mesh(path) / MeshFunction('size_t', mesh, path)")
+
+
+# ---- dolfin XML -------------------------------------------------------------------------
+_CELL = {2: "triangle", 3: "tetrahedron"}
+
+
+def _write_mesh_xml(path, mesh):
+    d = mesh.gdim
+    with open(path, "w") as f:
+        f.write('<?xml version="1.0"?>\n<dolfin xmlns:dolfin="http://fenicsproject.org">\n')
+        f.write(f'  <mesh celltype="{_CELL[d]}" dim="{d}">\n    <vertices size="{mesh.num_vertices()}">\n')
+        for i, x in enumerate(mesh.coords):
+            xyz = " ".join(f'{ax}="{float(v)!r}"' for ax, v in zip("xyz", x))
+            f.write(f'      <vertex index="{i}" {xyz} />\n')
+        f.write(f'    </vertices>\n    <cells size="{mesh.num_cells()}">\n')
+        for i, c in enumerate(mesh.cells):
+            vs = " ".join(f'v{k}="{int(v)}"' for k, v in enumerate(c))
+            f.write(f'      <{_CELL[d]} index="{i}" {vs} />\n')
+        f.write("    </cells>\n  </mesh>\n</dolfin>\n")
+
+
+def _read_mesh_xml(path):
+    root = ET.parse(path).getroot()
+    m = root.find("mesh")
+    d = int(m.get("dim"))
+    verts = m.find("vertices")
+    coords = np.zeros((int(verts.get("size")), d))
+    for v in verts:
+        coords[int(v.get("index"))] = [float(v.get(ax)) for ax in "xyz"[:d]]
+    cs = m.find("cells")
+    cells = np.zeros((int(cs.get("size")), d + 1), dtype=np.int32)
+    for c in cs:
+        cells[int(c.get("index"))] = [int(c.get(f"v{k}")) for k in range(d + 1)]
+    return coords, cells
+
+
+def _write_meshfunction_xml(path, mf):
+    """mesh_value_collection form (cell_index, local_entity, value), as dolfin writes it"""
+    mesh = mf.mesh()
+    mesh.init_topology()
+    d, dim = mesh.gdim, mf.dim()
+    a = mf.array()
+    with open(path, "w") as f:
+        f.write('<?xml version="1.0"?>\n<dolfin xmlns:dolfin="http://fenicsproject.org">\n  <mesh_function>\n')
+        f.write(f'    <mesh_value_collection name="f" type="uint" dim="{dim}" size="{len(a)}">\n')
+        if dim == d:
+            for i, v in enumerate(a):
+                f.write(f'      <value cell_index="{i}" local_entity="0" value="{int(v)}" />\n')
+        else:
+            for i, v in enumerate(a):
+                f.write(f'      <value cell_index="{int(mesh.facet_cells[i, 0])}" '
+                        f'local_entity="{int(mesh.facet_local[i, 0])}" value="{int(v)}" />\n')
+        f.write("    </mesh_value_collection>\n  </mesh_function>\n</dolfin>\n")
+
+
+def _read_meshfunction_xml(path, mesh):
+    root = ET.parse(path).getroot()
+    col = root.find("mesh_function").find("mesh_value_collection")
+    dim = int(col.get("dim"))
+    mesh.init_topology()
+    n = mesh.num_cells() if dim == mesh.gdim else mesh.num_facets()
+    vals = np.zeros(n, dtype=np.int64)
+    for v in col:
+        c, le, val = int(v.get("cell_index")), int(v.get("local_entity")), int(v.get("value"))
+        if dim == mesh.gdim:
+            vals[c] = val
+        else:
+            vals[mesh.cell_facets[c, le]] = val
+    return dim, vals

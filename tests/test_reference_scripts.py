@@ -1,0 +1,87 @@
+"""The reference's own scripts, executed UNCHANGED against this package (north_star: "the
+examples' run_*.py scripts drop in unchanged").
+
+`/root/reference/examples/idealized-geometries/{run_2D.py, make_mesh_2D.py, mm_hh.py}` are
+copied byte for byte into a temporary directory at test time (never into the repo) and run
+with `runpy` as `__main__`.  What stands in for the parts of the reference's environment that
+do not exist in this image: the `dolfin` shim (knp-emi-dg_b200/shims/dolfin: setup-only
+surface - meshes, mesh functions, sub-domains, XML files), the `numbalsoda` signature shim,
+and - because there is no GPU in the build container - the host-emulation build of the
+library injected as the library instance (the product itself has no CPU path).
+
+Skipped where /root/reference does not exist (the GPU box); the same flow runs on the GPU
+from tests/solver_checks.py (tests/test_gpu_solver.py).
+"""
+import os
+import runpy
+import shutil
+import sys
+
+import numpy as np
+import pytest
+
+from common import PKG, kmesh
+
+REF = "/root/reference/examples/idealized-geometries"
+SHIMS = os.path.join(PKG, "shims")
+
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+
+
+@pytest.fixture
+def ref_env(tmp_path, monkeypatch, emu_lib):
+    for name in ("run_2D.py", "make_mesh_2D.py", "make_mesh_3D.py", "mm_hh.py", "mm_hh_no_stim.py"):
+        shutil.copy(os.path.join(REF, name), tmp_path / name)
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(SHIMS)
+    monkeypatch.syspath_prepend(str(tmp_path))
+    if not hasattr(np, "float_"):                      # the reference predates numpy 2
+        monkeypatch.setattr(np, "float_", np.float64, raising=False)
+    from knpemidg import _lib
+    monkeypatch.setattr(_lib, "_instance", emu_lib)    # no GPU here: see module docstring
+    for mod in ("mm_hh", "mm_hh_no_stim", "make_mesh_2D", "make_mesh_3D", "dolfin"):
+        monkeypatch.delitem(sys.modules, mod, raising=False)
+    yield tmp_path
+    for mod in ("mm_hh", "mm_hh_no_stim", "make_mesh_2D", "make_mesh_3D", "dolfin"):
+        sys.modules.pop(mod, None)
+
+
+def test_run_2d_script_unchanged(ref_env):
+    """run_2D.py: generates its mesh with make_mesh_2D.main (dolfin XML files), reads them back,
+    runs 200 time steps of the 2D neuron with the reference's own mm_hh module and writes
+    fields + solver statistics.  The neuron must fire one action potential."""
+    g = runpy.run_path(str(ref_env / "run_2D.py"), run_name="__main__")
+    S = g["S"]
+    assert S.engine.k == 200
+    assert (ref_env / "meshes/2D/mesh_2.xml").exists() and (ref_env / "meshes/2D/surfaces_2.xml").exists()
+    out = ref_env / "results/data/2D"
+    stats = sorted(os.listdir(out / "solver"))
+    assert stats == sorted(f"{a}_{b}_2.txt" for a in ("emi", "knp") for b in ("assem", "solve", "niter"))
+    d = np.load(out / "results.npz", allow_pickle=True)
+    phi, sub = d["potential"], d["subdomains"]
+    assert phi.shape[0] == 200
+    ics = sub == 1
+    trace = np.array([p[ics].mean() - p[~ics].mean() for p in phi])          # ~ membrane potential
+    peak = int(np.argmax(trace))
+    assert 0.030 < trace[peak] < 0.060 and 15 < peak < 45                     # one action potential ...
+    assert trace.min() < -0.085                                                # ... after-hyperpolarisation ...
+    assert abs(trace[-1] + 0.0755) < 0.002                                     # ... and back to rest
+    # electroneutrality of the eliminated ion, concentrations stay physiological
+    c = d["concentrations"][-1]
+    assert np.isfinite(c).all() and c.min() > 0
+
+
+def test_make_mesh_3d_script_matches_native_generator(ref_env):
+    """make_mesh_3D.py (per-entity dolfin loops) and knpemidg.mesh.bundle_3d_mesh (vectorised
+    restatement used by bench.py) tag the same cells and facets."""
+    import make_mesh_3D
+    make_mesh_3D.main(["-r", "0", "-d", str(ref_env / "m3")])
+    import dolfin
+    mesh = dolfin.Mesh(str(ref_env / "m3/mesh_0.xml"))
+    sub = dolfin.MeshFunction("size_t", mesh, str(ref_env / "m3/subdomains_0.xml"))
+    surf = dolfin.MeshFunction("size_t", mesh, str(ref_env / "m3/surfaces_0.xml"))
+    nm, nsub, nsurf = kmesh.bundle_3d_mesh(0)
+    assert np.allclose(mesh.coords, nm.coords, rtol=0, atol=1e-18)
+    assert np.array_equal(mesh.cells, nm.cells)
+    assert np.array_equal(sub.array(), nsub.array())
+    assert np.array_equal(surf.array(), nsurf.array())
