@@ -220,6 +220,30 @@ KNP_HD void emi_cell_row(const EmiArgs<D>& a, const double (&g)[D + 1][D], doubl
   }
 }
 
+// Where a facet routine puts its block entries.  RegBlocks: plain arrays (one-index-per-cell
+// drivers, host emulation).  SmemBlocks: straight into the shared-memory staging rows of the
+// CUDA drivers - the entries never live in registers, which is what keeps those kernels'
+// register footprint down; the column map is applied in the store address.
+template <int ND>
+struct RegBlocks {
+  double (&O)[ND][ND]; double (&dg)[ND][ND];
+  KNP_HD void zeroO() const {
+#pragma unroll
+    for (int i = 0; i < ND; ++i)
+#pragma unroll
+      for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
+  }
+  KNP_HD void setO(int i, int j, double v) const { O[i][j] = v; }
+  KNP_HD void addD(int i, int j, double v) const { dg[i][j] += v; }
+};
+template <int ND>
+struct SmemBlocks {   // O, D: rows of ND*ND (+pad) doubles, zeroed by the caller; w: facet info word
+  double* O; double* D; int w;
+  KNP_HD void zeroO() const {}
+  KNP_HD void setO(int i, int j, double v) const { O[i * ND + fi_perm(w, j)] = v; }
+  KNP_HD void addD(int i, int j, double v) const { D[i * ND + j] += v; }
+};
+
 // facet F of `cell`.  Outputs are in the cell's OWN vertex numbering: O[i][j] couples my
 // dof i with the neighbour dof that sits at my vertex j (neighbour local index
 // fi_perm(w, j)); column F, which has no counterpart on my side, holds the coupling with
@@ -227,20 +251,17 @@ KNP_HD void emi_cell_row(const EmiArgs<D>& a, const double (&g)[D + 1][D], doubl
 // writer applies that column map in the store address, so no register array is ever
 // indexed dynamically.  dg += share of the diagonal block, r += share of the rhs.
 // Returns the facet info word (column map).
-template <int D, int F>
+template <int D, int F, class Blocks>
 KNP_HD int emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1][D], double K,
                      double hK, const double (&kap)[D + 1], const double (&qc)[D],
-                     double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1], double (&r)[D + 1]) {
+                     const Blocks& B, double (&r)[D + 1]) {
   constexpr int ND = D + 1;
   constexpr double c_m2 = 1.0 / (D * (D + 1));                  // facet mass
   constexpr double c_m3 = (D == 3) ? 1.0 / 60.0 : 1.0 / 24.0;   // facet cubic moment
   const int64_t nc = a.nc;
   const int w = a.finfo[F * nc + cell];
   const int kind = fi_kind(w);
-#pragma unroll
-  for (int i = 0; i < ND; ++i)
-#pragma unroll
-    for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
+  B.zeroO();
   if (kind == FK_NONE) return w;
   const int64_t c2 = a.nbr[F * nc + cell];
   double gn2 = 0.0;
@@ -296,8 +317,8 @@ KNP_HD int emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1]
           }
           pen *= pscale;
         }
-        dg[i][j] += -0.5 * gn_me[j] * S_me[i] - 0.5 * gn_me[i] * S_me[j] + pen;
-        O[i][j] = -0.5 * gn_nb[j] * S_nb[i] + ((j != F) ? 0.5 * gn_me[i] * S_me[j] - pen : 0.0);
+        B.addD(i, j, -0.5 * gn_me[j] * S_me[i] - 0.5 * gn_me[i] * S_me[j] + pen);
+        B.setO(i, j, -0.5 * gn_nb[j] * S_nb[i] + ((j != F) ? 0.5 * gn_me[i] * S_me[j] - pen : 0.0));
       }
     }
     // rhs: avg(q).n+ jump(v)  (solver.py:310)
@@ -317,8 +338,8 @@ KNP_HD int emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1]
       for (int j = 0; j < ND; ++j) {
         if (j == F) continue;
         const double v = cm * ((i == j) ? 2.0 : 1.0);
-        dg[i][j] += v;
-        O[i][j] = -v;
+        B.addD(i, j, v);
+        B.setO(i, j, -v);
       }
     }
     if (!a.P.mms) {
@@ -367,10 +388,10 @@ struct EmiCellKernel {
     for (int f = 0; f < ND; ++f) {
       double O[ND][ND];
       int w;
-      if (f == 0) w = emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, O, dg, r);
-      else if (f == 1) w = emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, O, dg, r);
-      else if (f == 2) w = emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, O, dg, r);
-      else w = emi_facet<D, D>(a, cell, g, K, hK, kap, qc, O, dg, r);
+      if (f == 0) w = emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, RegBlocks<ND>{O, dg}, r);
+      else if (f == 1) w = emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, RegBlocks<ND>{O, dg}, r);
+      else if (f == 2) w = emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, RegBlocks<ND>{O, dg}, r);
+      else w = emi_facet<D, D>(a, cell, g, K, hK, kap, qc, RegBlocks<ND>{O, dg}, r);
       double* Of = a.A + (int64_t)(1 + f) * a.nc * bs + cell * bs;
       #pragma unroll
       for (int i = 0; i < ND; ++i)
@@ -425,38 +446,32 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) emi_assemble_kernel(con
     kbar /= ND;
     #pragma unroll
     for (int x = 0; x < D; ++x) qc[x] = a.q[x * a.nc + cell];
-    double dg[ND][ND], r[ND], O[ND][ND];
+    double r[ND];
     #pragma unroll
-    for (int i = 0; i < ND; ++i) { r[i] = 0.0; for (int j = 0; j < ND; ++j) dg[i][j] = 0.0; }
-    // facet f and row f of the cell integrals (f is warp uniform)
-    double bdrow[ND];
-    int w;
+    for (int i = 0; i < ND; ++i) r[i] = 0.0;
+    // facet f and row f of the cell integrals (f is warp uniform); the block entries go
+    // straight into this thread's staging rows
+    double* myO = sO[f][cl];
+    double* myD = sD[f][cl];
+    #pragma unroll
+    for (int k = 0; k < BS; ++k) { myO[k] = 0.0; myD[k] = 0.0; }
+    const SmemBlocks<ND> blk{myO, myD, a.finfo[f * nc + cell]};
+    double bdrow[ND], row[ND], ri;
     switch (f) {
-      case 0: w = emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, O, dg, r);
-              { double row[ND], ri; emi_cell_row<D, 0>(a, g, K, kap, kbar, qc, row, bdrow, ri);
-                #pragma unroll
-                for (int j = 0; j < ND; ++j) dg[0][j] += row[j]; r[0] += ri; } break;
-      case 1: w = emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, O, dg, r);
-              { double row[ND], ri; emi_cell_row<D, 1>(a, g, K, kap, kbar, qc, row, bdrow, ri);
-                #pragma unroll
-                for (int j = 0; j < ND; ++j) dg[1][j] += row[j]; r[1] += ri; } break;
-      case 2: w = emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, O, dg, r);
-              { double row[ND], ri; emi_cell_row<D, 2>(a, g, K, kap, kbar, qc, row, bdrow, ri);
-                #pragma unroll
-                for (int j = 0; j < ND; ++j) dg[2][j] += row[j]; r[2] += ri; } break;
-      default: w = emi_facet<D, D>(a, cell, g, K, hK, kap, qc, O, dg, r);
-              { double row[ND], ri; emi_cell_row<D, D>(a, g, K, kap, kbar, qc, row, bdrow, ri);
-                #pragma unroll
-                for (int j = 0; j < ND; ++j) dg[D][j] += row[j]; r[D] += ri; } break;
+      case 0: emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, blk, r);
+              emi_cell_row<D, 0>(a, g, K, kap, kbar, qc, row, bdrow, ri); break;
+      case 1: emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, blk, r);
+              emi_cell_row<D, 1>(a, g, K, kap, kbar, qc, row, bdrow, ri); break;
+      case 2: emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, blk, r);
+              emi_cell_row<D, 2>(a, g, K, kap, kbar, qc, row, bdrow, ri); break;
+      default: emi_facet<D, D>(a, cell, g, K, hK, kap, qc, blk, r);
+              emi_cell_row<D, D>(a, g, K, kap, kbar, qc, row, bdrow, ri); break;
     }
+    r[f] += ri;
     #pragma unroll
-    for (int j = 0; j < ND; ++j) sB[cl][f * ND + j] = bdrow[j];
+    for (int j = 0; j < ND; ++j) { myD[f * ND + j] += row[j]; sB[cl][f * ND + j] = bdrow[j]; }
     #pragma unroll
-    for (int i = 0; i < ND; ++i) {
-      #pragma unroll
-      for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + fi_perm(w, j)] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
-      sR[f][cl][i] = r[i];
-    }
+    for (int i = 0; i < ND; ++i) sR[f][cl][i] = r[i];
   }
   __syncthreads();
   const int64_t ncell_blk = (a.nw - cell0 < ASM_CPB) ? (a.nw - cell0) : ASM_CPB;
@@ -590,15 +605,11 @@ KNP_HD void knp_facet_geom(const KnpArgs<D>& a, int64_t cell, const double (&g)[
 
 // per-ion part of facet F: O (own vertex order, column F = neighbour's opposite vertex),
 // dg += share of the diagonal block (solver.py:583-594)
-template <int D, int F>
-KNP_HD void knp_facet_ion(const Params& P, int ion, const KnpFacetGeom<D>& G, double Dme,
-                          double (&O)[D + 1][D + 1], double (&dg)[D + 1][D + 1]) {
+template <int D, int F, class Blocks>
+KNP_HD void knp_facet_ion(const Params& P, int ion, const KnpFacetGeom<D>& G, double Dme, const Blocks& B) {
   constexpr int ND = D + 1;
   constexpr double c_m2 = 1.0 / (D * (D + 1));
-#pragma unroll
-  for (int i = 0; i < ND; ++i)
-#pragma unroll
-    for (int j = 0; j < ND; ++j) O[i][j] = 0.0;
+  B.zeroO();
   if (G.kind != FK_SIP) return;
   const double zpsi = P.z[ion] * P.psi;
   const double Dnb = P.D[ion][G.regnb];
@@ -619,8 +630,8 @@ KNP_HD void knp_facet_ion(const Params& P, int ion, const KnpFacetGeom<D>& G, do
         v += pm * m2;
         o += pn * m2;
       }
-      dg[i][j] += v;
-      O[i][j] = o;
+      B.addD(i, j, v);
+      B.setO(i, j, o);
     }
   }
 }
@@ -737,10 +748,10 @@ struct KnpCellKernel {   // one index per cell, all solved ions (host emulation 
       if constexpr (D == 3) knp_cell_row<D, D>(a.P, ion, g, K, Dme, gp, cnl, dg[D], r[D]);
       for (int f = 0; f < ND; ++f) {
         double O[ND][ND];
-        if (f == 0) knp_facet_ion<D, 0>(a.P, ion, G[0], Dme, O, dg);
-        else if (f == 1) knp_facet_ion<D, 1>(a.P, ion, G[1], Dme, O, dg);
-        else if (f == 2) knp_facet_ion<D, 2>(a.P, ion, G[2], Dme, O, dg);
-        else knp_facet_ion<D, D>(a.P, ion, G[D], Dme, O, dg);
+        if (f == 0) knp_facet_ion<D, 0>(a.P, ion, G[0], Dme, RegBlocks<ND>{O, dg});
+        else if (f == 1) knp_facet_ion<D, 1>(a.P, ion, G[1], Dme, RegBlocks<ND>{O, dg});
+        else if (f == 2) knp_facet_ion<D, 2>(a.P, ion, G[2], Dme, RegBlocks<ND>{O, dg});
+        else knp_facet_ion<D, D>(a.P, ion, G[D], Dme, RegBlocks<ND>{O, dg});
         double* Of = a.A[ion] + (int64_t)(1 + f) * a.nc * bs + cell * bs;
         for (int i = 0; i < ND; ++i)
           for (int j = 0; j < ND; ++j) Of[i * ND + fi_perm(G[f].w, j)] = O[i][j];
@@ -796,29 +807,24 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) knp_assemble_kernel(con
       const double Dme = a.P.D[ion][reg];
       double cnl[ND];
       load_cell<ND>(a.cn[ion], cell, cnl);
-      double dg[ND][ND], O[ND][ND], row[ND], ri;
+      double row[ND], ri;
+      double* myO = sO[f][cl];
+      double* myD = sD[f][cl];
 #pragma unroll
-      for (int i = 0; i < ND; ++i)
-#pragma unroll
-        for (int j = 0; j < ND; ++j) dg[i][j] = 0.0;
+      for (int k = 0; k < BS; ++k) { myO[k] = 0.0; myD[k] = 0.0; }
+      const SmemBlocks<ND> blk{myO, myD, G.w};
       switch (f) {
-        case 0: knp_facet_ion<D, 0>(a.P, ion, G, Dme, O, dg);
-                knp_cell_row<D, 0>(a.P, ion, g, K, Dme, gp, cnl, row, ri);
-                for (int j = 0; j < ND; ++j) dg[0][j] += row[j]; break;
-        case 1: knp_facet_ion<D, 1>(a.P, ion, G, Dme, O, dg);
-                knp_cell_row<D, 1>(a.P, ion, g, K, Dme, gp, cnl, row, ri);
-                for (int j = 0; j < ND; ++j) dg[1][j] += row[j]; break;
-        case 2: knp_facet_ion<D, 2>(a.P, ion, G, Dme, O, dg);
-                knp_cell_row<D, 2>(a.P, ion, g, K, Dme, gp, cnl, row, ri);
-                for (int j = 0; j < ND; ++j) dg[2][j] += row[j]; break;
-        default: knp_facet_ion<D, D>(a.P, ion, G, Dme, O, dg);
-                knp_cell_row<D, D>(a.P, ion, g, K, Dme, gp, cnl, row, ri);
-                for (int j = 0; j < ND; ++j) dg[D][j] += row[j]; break;
+        case 0: knp_facet_ion<D, 0>(a.P, ion, G, Dme, blk);
+                knp_cell_row<D, 0>(a.P, ion, g, K, Dme, gp, cnl, row, ri); break;
+        case 1: knp_facet_ion<D, 1>(a.P, ion, G, Dme, blk);
+                knp_cell_row<D, 1>(a.P, ion, g, K, Dme, gp, cnl, row, ri); break;
+        case 2: knp_facet_ion<D, 2>(a.P, ion, G, Dme, blk);
+                knp_cell_row<D, 2>(a.P, ion, g, K, Dme, gp, cnl, row, ri); break;
+        default: knp_facet_ion<D, D>(a.P, ion, G, Dme, blk);
+                knp_cell_row<D, D>(a.P, ion, g, K, Dme, gp, cnl, row, ri); break;
       }
 #pragma unroll
-      for (int i = 0; i < ND; ++i)
-#pragma unroll
-        for (int j = 0; j < ND; ++j) { sO[f][cl][i * ND + fi_perm(G.w, j)] = O[i][j]; sD[f][cl][i * ND + j] = dg[i][j]; }
+      for (int j = 0; j < ND; ++j) myD[f * ND + j] += row[j];
       sR[cl][f] = ri;   // the facets add nothing to the KNP rhs (membrane part: KnpMembraneRhsKernel)
     }
     __syncthreads();
