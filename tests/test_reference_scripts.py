@@ -30,7 +30,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checko
 
 @pytest.fixture
 def ref_env(tmp_path, monkeypatch, emu_lib):
-    for name in ("run_2D.py", "make_mesh_2D.py", "make_mesh_3D.py", "mm_hh.py", "mm_hh_no_stim.py"):
+    for name in ("run_2D.py", "run_3D.py", "make_mesh_2D.py", "make_mesh_3D.py", "mm_hh.py", "mm_hh_no_stim.py"):
         shutil.copy(os.path.join(REF, name), tmp_path / name)
     monkeypatch.chdir(tmp_path)
     monkeypatch.syspath_prepend(SHIMS)
@@ -69,6 +69,24 @@ def test_run_2d_script_unchanged(ref_env):
     # electroneutrality of the eliminated ion, concentrations stay physiological
     c = d["concentrations"][-1]
     assert np.isfinite(c).all() and c.min() > 0
+
+
+@pytest.mark.skipif(os.environ.get("KNP_SLOW_TESTS") != "1",
+                    reason="~2 min on the host emulation (seconds on a GPU): set KNP_SLOW_TESTS=1")
+def test_run_3d_script_unchanged(ref_env):
+    """run_3D.py: four axons (15 552 tetrahedra), mm_hh on the stimulated axon and mm_hh_no_stim
+    on the other three, 200 steps.  Last verified in the build container: the stimulated axon
+    fires (mean ICS-ECS potential over all four axons peaks at -44 mV at step 15), CG 1 and
+    GMRES 5 iterations per step at the end."""
+    g = runpy.run_path(str(ref_env / "run_3D.py"), run_name="__main__")
+    S = g["S"]
+    assert S.engine.k == 200
+    d = np.load(ref_env / "results/data/3D/results.npz", allow_pickle=True)
+    phi, sub = d["potential"], d["subdomains"]
+    ics = sub == 1
+    trace = np.array([p[ics].mean() - p[~ics].mean() for p in phi])
+    assert -0.050 < trace.max() < -0.035 and 8 < int(np.argmax(trace)) < 30
+    assert abs(trace[-1] + 0.0747) < 0.002
 
 
 def test_make_mesh_3d_script_matches_native_generator(ref_env):
