@@ -60,6 +60,7 @@ int knp_ctx_create(int device, knp_ctx** out) {
 #endif
   { const char* e = getenv("KNP_KNP_PRESMOOTH"); c->opt.knp_presmooth0 = (e && e[0] == '1'); }
   { const char* e = getenv("KNP_FUSE_PROLONG"); c->opt.fuse_prolong = (e && e[0] == '1'); }
+  { const char* e = getenv("KNP_EXTRAPOLATE"); c->opt.extrapolate_phi = !(e && e[0] == '0'); }
   c->kr0.stream = c->stream;
   c->kr0.scal.alloc(1024);
   c->kr0.partial.alloc((size_t)DOT_MAX * RED_BLOCKS);
@@ -231,6 +232,7 @@ static void build_mesh(knp_ctx* c, int64_t nc, int64_t nv, const double* coords,
   c->A_emi.alloc((size_t)(ND + 2) * nc * ND * ND);
   c->trace_tmp.alloc(nm);
   c->emi_assembled = c->knp_assembled = false;
+  c->phi_old_valid = false;
   c->amg.ready = false;
   c->membranes.clear();
 }
@@ -338,6 +340,7 @@ int knp_field_set(knp_ctx* ctx, int which, int idx, const double* src, int64_t c
   int64_t n = 0;
   double* p = field_ptr(ctx, which, idx, n, true);
   if (count != n) fail("knp_field_set: wrong element count");
+  if (which == KNP_F_PHI) ctx->phi_old_valid = false;
   h2d(p, src, n * sizeof(double), ctx->stream);
   KNP_CATCH
 }

@@ -35,6 +35,10 @@ struct SolverOptions {
   // bench workload (profiles/); KNP_KNP_PRESMOOTH=1 in the environment restores V(1,1)
   bool knp_presmooth0 = false;
   bool fuse_prolong = false;    // KNP_FUSE_PROLONG=1
+  // initial guess of the EMI solve = 2 phi_n - phi_{n-1} instead of phi_n (the reference starts
+  // from phi_n, solver.py:431 `ksp_initial_guess_nonzero`); same stopping test, fewer iterations.
+  // KNP_EXTRAPOLATE=0 restores the reference's guess
+  bool extrapolate_phi = true;
 };
 
 enum { T_EMI_ASM = 0, T_EMI_SOLVE, T_KNP_ASM, T_KNP_SOLVE, T_ODE, T_POST, T_COUNT };
@@ -78,6 +82,9 @@ struct knp_ctx {
   knp::DevBuf<double> rhs_emi, rhs_knp[knp::MAX_IONS], load_emi, load_knp[knp::MAX_IONS];
   bool has_load_emi = false, has_load_knp[knp::MAX_IONS] = {false};
   knp::DevBuf<double> kappa, q, gphi;
+  knp::DevBuf<double> phi_old;   // potential of the previous time step (initial guess extrapolation)
+  bool phi_old_valid = false;
+  int phi_hist = 0;
   // matrices: A_emi = (nd+1) slots (slot 0 holds the diagonal blocks of B_emi, so the AMG
   // Galerkin plan addresses EMI and KNP matrices alike) followed by A_emi's own diagonal blocks
   knp::DevBuf<double> A_emi, A_knp[knp::MAX_IONS];

@@ -402,9 +402,9 @@ struct DenseMatvecKernel {  // y = M x with M stored TRANSPOSED (MT[j*m + i] = M
 };
 
 // ---- vector kernels ---------------------------------------------------------------
-struct AxpbyKernel {  // y = a x + b y
-  double a; const double* x; double b; double* y;
-  KNP_HD void operator()(int64_t i) const { y[i] = a * x[i] + b * y[i]; }
+struct ExtrapolateKernel {  // x <- 2 x - old, old <- x   (linear extrapolation in time of the initial guess)
+  double* x; double* old;
+  KNP_HD void operator()(int64_t i) const { const double t = x[i]; x[i] = 2.0 * t - old[i]; old[i] = t; }
 };
 struct DirectionKernel {  // p = (z - mu) + b p   (CG direction from the mean-free preconditioned residual)
   const double* z; double mu; double b; double* p;
@@ -414,10 +414,6 @@ struct Axpy2ProjKernel {  // x += a p ; r = r - a q - shift   (CG update; shift 
   double a; const double* p; const double* q; double* x; double* r; double shift;
   KNP_HD void operator()(int64_t i) const { x[i] += a * p[i]; r[i] = (r[i] - a * q[i]) - shift; }
 };
-struct Axpy2Kernel {  // x += a p ; r -= a q     (CG update)
-  double a; const double* p; const double* q; double* x; double* r;
-  KNP_HD void operator()(int64_t i) const { x[i] += a * p[i]; r[i] -= a * q[i]; }
-};
 struct ScaleKernel {  // y = a x
   double a; const double* x; double* y;
   KNP_HD void operator()(int64_t i) const { y[i] = a * x[i]; }
@@ -425,15 +421,6 @@ struct ScaleKernel {  // y = a x
 struct AddConstKernel {  // x += a
   double a; double* x;
   KNP_HD void operator()(int64_t i) const { x[i] += a; }
-};
-// w -= sum_i h_i V_i  (Gram-Schmidt update), V = k vectors of length n, contiguous
-struct GsUpdateKernel {
-  int64_t n /*stride of V*/; int k; const double* V; const double* h /*device, k entries*/; double* w;
-  KNP_HD void operator()(int64_t e) const {
-    double acc = w[e];
-    for (int i = 0; i < k; ++i) acc -= h[i] * V[(int64_t)i * n + e];
-    w[e] = acc;
-  }
 };
 // Gram-Schmidt update and normalisation in one pass: v = (v - sum_i h_i V_i) / hn with
 // hn^2 = h[k] - sum_i h_i^2, where h[k] = |v|^2 before the update (Pythagoras: one reduction

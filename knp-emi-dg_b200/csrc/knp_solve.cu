@@ -780,6 +780,15 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   else { if (c->bj_emi.n != (size_t)c->slot_stride()) c->bj_emi.alloc(c->slot_stride()); block_inverse(c, c->Bdiag(), c->bj_emi.p); }
   double* x = c->phi.p; double* r = ws(c).r.p; double* z = ws(c).r.p + n; double* p = ws(c).p.p; double* q = ws(c).q.p;
   const double* b = c->rhs_emi.p;
+  if (c->opt.extrapolate_phi) {
+    if (c->phi_old.n != (size_t)n) { c->phi_old.alloc(n); c->phi_old_valid = false; }
+    // the first stored field is an initial condition, not a solution: extrapolate only once two
+    // consecutive solutions exist (third solve on)
+    if (!c->phi_old_valid) c->phi_hist = 0;
+    if (c->phi_hist >= 2) { ExtrapolateKernel k{x, c->phi_old.p}; parallel_for(s, n, k); }
+    else { d2d(c->phi_old.p, x, n * sizeof(double), s); c->phi_hist++; }
+    c->phi_old_valid = true;
+  }
   // Two reductions per iteration.  (1) {p.q, 1.q}: with 1.r known, the mean of the updated
   // residual is known before the update and is subtracted in the same pass, so r stays
   // orthogonal to the null space to round-off of ITS OWN size (an unprojected r drifts by
