@@ -74,8 +74,8 @@ class MMSLoads:
     (solver.py:365-374, 645-657) computed by the oracle's sympy restatement of
     tests/mms_space.py, plus the exact fields for the error norms."""
 
-    def __init__(self, mesh, sub, surf, dt):
-        self.mm = omms.MMS("space", dt=dt)
+    def __init__(self, mesh, sub, surf, dt, kind="space"):
+        self.mm = omms.MMS(kind, dt=dt)
         self.P = forms.Problem(mesh, sub.array(), surf.array(), **self.mm.problem_kwargs())
 
     def load_emi(self, t):
@@ -107,6 +107,35 @@ def run_mms(lib, r, dt=1e-10, nsteps=2):
     sp = SolverParams(True, True, r, None, None, None, None, None, None)
     t = Constant(0.0)
     uh, c_elim = S.solve_system_passive(nsteps * dt, t, sp, None)
+    errs = [mm.l2_error(P, uh[0].nodal(), "c", 0), mm.l2_error(P, uh[1].nodal(), "c", 1),
+            mm.l2_error(P, uh[2].nodal(), "phi", mean_free=True)]
+    return np.array(errs), S, L
+
+
+def run_mms_time(lib, i, r=3, dt0=1.0e-2):
+    """tests/run_MMS_time.py: fixed mesh, dt = dt0 / 2^i, Tstop = 2 dt0, passive system, direct
+    solves; the exact solution is linear in space, so the error is the time error"""
+    dt = dt0 / 2 ** i
+    nsteps = int(round(2 * dt0 / dt))
+    mesh, sub, surf = kmesh.mms_mesh(r)
+    L = MMSLoads(mesh, sub, surf, dt, kind="time")
+    mm, P = L.mm, L.P
+    params = namedtuple("params", "dt F psi C_phi C_M R temperature phi_M_init_type rho_sub")(
+        dt, 1.0, 1.0, 1.0 / dt, 1.0, 1.0, 1.0, "expression", {0: Constant(0), 1: Constant(0)})
+    exact = [mm.exact_field(P, "c", k, t=0.0) for k in range(3)]
+    ion_list = []
+    for k, name in enumerate("abc"):
+        ion_list.append({"c_init_sub": exact[k].ravel(), "c_init_sub_type": "function", "z": mm.z[k], "name": name,
+                         "D_sub": {1: Constant(mm.D1[k]), 0: Constant(mm.D2[k])},
+                         "C_sub": {1: Constant(mm.C1[k]), 0: Constant(mm.C2[k])}, "f_source": Constant(0)})
+    S = Solver(params, ion_list, mms=L, lib=lib)
+    S.setup_domain(mesh, sub, surf)
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    sp = SolverParams(True, True, r, None, None, None, None, None, None)
+    t = Constant(0.0)
+    uh, c_elim = S.solve_system_passive(nsteps * dt, t, sp, None)
+    mm.t = float(t)
     errs = [mm.l2_error(P, uh[0].nodal(), "c", 0), mm.l2_error(P, uh[1].nodal(), "c", 1),
             mm.l2_error(P, uh[2].nodal(), "phi", mean_free=True)]
     return np.array(errs), S, L

@@ -30,6 +30,12 @@ def test_mms_space_rates(gpu_lib):
     assert np.all(rates[-1] > 1.9) and np.all(rates[-1] < 2.1), rates
 
 
+def test_mms_time_rates(gpu_lib):
+    errs = np.array([sc.run_mms_time(gpu_lib, i, r=4)[0] for i in (2, 3, 4, 5)])
+    rates = np.log(errs[:-1] / errs[1:]) / np.log(2.0)
+    assert np.all(rates[-1] > 0.93) and np.all(rates[-1] < 1.07), rates
+
+
 def test_rest_state_is_preserved_at_scale(gpu_lib):
     """with no stimulus the coupled system stays at rest (phi_M = -74.386 mV,
     concentrations constant); also electroneutrality of the eliminated ion.  Bundle mesh

@@ -40,3 +40,11 @@ def test_mms_space_rates_through_the_product_path(emu_lib):
     errs = np.array([sc.run_mms(emu_lib, r)[0] for r in (3, 4, 5)])
     rates = np.log(errs[:-1] / errs[1:]) / np.log(2.0)
     assert np.all(rates[-1] > 1.85) and np.all(rates[-1] < 2.2), rates
+
+
+def test_mms_time_rates_through_the_product_path(emu_lib):
+    """tests/run_MMS_time.py: first order in time (the reference prints the rates, expected ~1)"""
+    errs = np.array([sc.run_mms_time(emu_lib, i)[0] for i in (2, 3, 4, 5)])
+    rates = np.log(errs[:-1] / errs[1:]) / np.log(2.0)
+    assert np.all(rates[-1] > 0.93) and np.all(rates[-1] < 1.07), rates
+    assert np.all(np.diff(rates, axis=0) > 0)          # approaching 1 from below
