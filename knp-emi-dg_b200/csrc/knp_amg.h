@@ -220,6 +220,9 @@ struct AmgValues {                 // numeric part, one per linear system
   DevBuf<double> rep_b;              // replicated tail: all-gather buffer of the right-hand side
   double omega = 0.0;                // level-0 damping 4/(3 lambda_max(Dinv A)), estimated
   int age = 0;                       // refreshes since the last estimate
+  bool refreshed_now = true;         // did the current solve refresh the values
+  long long solves = 0;              // solves since the values were last refreshed (lagged refresh)
+  int last_iters = 0, fresh_iters = 0;   // iterations of the last solve / of the solve right after a refresh
 };
 
 }  // namespace knp

@@ -39,6 +39,13 @@ struct SolverOptions {
   // from phi_n, solver.py:431 `ksp_initial_guess_nonzero`); same stopping test, fewer iterations.
   // KNP_EXTRAPOLATE=0 restores the reference's guess
   bool extrapolate_phi = true;
+  // Preconditioner refresh: the reference rebuilds BoomerAMG at every solve (setOperators,
+  // solver.py:505, 767).  With refresh_period = P > 1 the hierarchy VALUES (Galerkin products,
+  // smoother diagonals, block inverses, dense inverse) are recomputed only every P-th solve of a
+  // system, or earlier when the Krylov iteration count has grown by more than 50 % (+2) since
+  // the last refresh; the Krylov solve itself still runs on the freshly assembled operator to
+  // the reference's tolerance.  KNP_AMG_REFRESH_PERIOD in the environment, default 1.
+  int refresh_period = 1;
 };
 
 enum { T_EMI_ASM = 0, T_EMI_SOLVE, T_KNP_ASM, T_KNP_SOLVE, T_ODE, T_POST, T_COUNT };

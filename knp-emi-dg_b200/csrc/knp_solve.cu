@@ -569,6 +569,19 @@ static void amg_refresh(knp_ctx* c, AmgValues& V, const BellMat& A0, const doubl
   dense_inverse_device(s, (int)m, V.dense.p, V.colbuf.p);
 }
 
+// lagged refresh policy (SolverOptions::refresh_period)
+static bool refresh_due(knp_ctx* c, AmgValues& V) {
+  const int P = c->opt.refresh_period;
+  if (P <= 1 || V.solves == 0) return true;
+  if (V.solves % P == 0) return true;
+  return V.last_iters > V.fresh_iters + V.fresh_iters / 2 + 2;   // the stale hierarchy has become costly
+}
+static void note_solve(AmgValues& V, bool refreshed, int iters) {
+  if (refreshed) { V.fresh_iters = iters; V.solves = 0; }
+  V.last_iters = iters;
+  V.solves++;
+}
+
 // ---------------------------------------------------------------------------------
 // cycle
 // ---------------------------------------------------------------------------------
@@ -776,8 +789,11 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   const int64_t n = c->n, no = c->n_own;   // local vector length (stride) / owned rows
   BellMat A = bell_of(c, 0), B = bell_of(c, 1);
   // preconditioner refresh (the reference rebuilds BoomerAMG at every setOperators)
-  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_emi, B, c->A_emi.p, c->Bdiag());
-  else { if (c->bj_emi.n != (size_t)c->slot_stride()) c->bj_emi.alloc(c->slot_stride()); block_inverse(c, c->Bdiag(), c->bj_emi.p); }
+  const bool refreshed = refresh_due(c, c->amg_emi);
+  if (refreshed) {
+    if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_emi, B, c->A_emi.p, c->Bdiag());
+    else { if (c->bj_emi.n != (size_t)c->slot_stride()) c->bj_emi.alloc(c->slot_stride()); block_inverse(c, c->Bdiag(), c->bj_emi.p); }
+  }
   double* x = c->phi.p; double* r = ws(c).r.p; double* z = ws(c).r.p + n; double* p = ws(c).p.p; double* q = ws(c).q.p;
   const double* b = c->rhs_emi.p;
   if (c->opt.extrapolate_phi) {
@@ -860,6 +876,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
     if (it > maxit) fail("knp_solve_emi: CG did not converge in " + std::to_string(maxit) +
                          " iterations (ksp_error_if_not_converged, solver.py:428)");
   }
+  note_solve(c->amg_emi, refreshed, it);
   halo0(c, x);   // the assembly of the KNP system reads phi on the ghost cells
   stream_sync(s);
 #ifndef KNP_EMU
@@ -877,8 +894,11 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
 // preconditioner of ion's system after a re-assembly (the reference rebuilds BoomerAMG at
 // every setOperators, solver.py:767)
 static void knp_refresh(knp_ctx* c, int ion) {
+  AmgValues& V = c->amg_knp[ion];
+  V.refreshed_now = refresh_due(c, V);
+  if (!V.refreshed_now) return;
   BellMat A = bell_of(c, 2 + ion);
-  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_knp[ion], A, c->A_knp[ion].p, c->A_knp[ion].p);
+  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, V, A, c->A_knp[ion].p, c->A_knp[ion].p);
   else { if (c->bj_knp[ion].n != (size_t)c->slot_stride()) c->bj_knp[ion].alloc(c->slot_stride()); block_inverse(c, c->A_knp[ion].p, c->bj_knp[ion].p); }
 }
 
@@ -971,6 +991,7 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
     }
   }
   *resid_out = res;
+  note_solve(Vv, Vv.refreshed_now, it);
   return it;
 }
 
