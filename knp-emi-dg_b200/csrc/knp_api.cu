@@ -61,7 +61,7 @@ int knp_ctx_create(int device, knp_ctx** out) {
   { const char* e = getenv("KNP_KNP_PRESMOOTH"); c->opt.knp_presmooth0 = (e && e[0] == '1'); }
   { const char* e = getenv("KNP_FUSE_PROLONG"); c->opt.fuse_prolong = (e && e[0] == '1'); }
   { const char* e = getenv("KNP_EXTRAPOLATE"); c->opt.extrapolate_phi = !(e && e[0] == '0'); }
-  { const char* e = getenv("KNP_AMG_REFRESH_PERIOD"); c->opt.refresh_period = e ? std::max(1, atoi(e)) : 1; }
+  { const char* e = getenv("KNP_AMG_REFRESH_PERIOD"); c->opt.refresh_period = e ? std::max(1, atoi(e)) : 4; }
   c->kr0.stream = c->stream;
   c->kr0.scal.alloc(1024);
   c->kr0.partial.alloc((size_t)DOT_MAX * RED_BLOCKS);
@@ -303,6 +303,8 @@ int knp_params_set(knp_ctx* ctx, double F, double R, double T, double C_M, doubl
       ctx->A_knp[k].alloc((size_t)(ctx->nd + 1) * ctx->slot_stride());
   }
   ctx->params_set = true;
+  ctx->amg_emi.solves = 0;                       // new coefficients: the next solves refresh their preconditioners
+  for (int k = 0; k < MAX_IONS; ++k) ctx->amg_knp[k].solves = 0;
   KNP_CATCH
 }
 

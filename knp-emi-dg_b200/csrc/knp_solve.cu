@@ -233,6 +233,7 @@ static void alloc_values(knp_ctx* c, AmgValues& V) {
   for (size_t l = 0; l < nl; ++l) { V.val[l].alloc(c->amg.lev[l].nnz); V.dinv[l].alloc(c->amg.lev[l].nloc); }
   V.dense.alloc((size_t)c->amg.m_dense * c->amg.m_dense);
   V.binv.alloc((size_t)c->slot_stride());
+  V.solves = 0; V.omega = 0.0; V.age = 0;   // fresh buffers: the next solve must refresh the values
   V.vec.clear(); V.vec.resize(nl);
   for (size_t l = 0; l < nl; ++l) {
     const size_t m = (size_t)c->amg.lev[l].nloc;
@@ -491,8 +492,8 @@ extern "C" int knp_solver_options(knp_ctx* ctx, int pc, int nu_pre, int nu_post,
   KNP_TRY
   if (pc < 0 || pc > 1) fail("pc must be 0 (block-Jacobi) or 1 (AMG)");
   if (nu_pre < 1 || nu_post < 0 || gamma < 1 || gamma > 2) fail("bad cycle parameters");
-  ctx->amg_emi.omega = 0.0;
-  for (int k = 0; k < MAX_IONS; ++k) ctx->amg_knp[k].omega = 0.0;
+  ctx->amg_emi.omega = 0.0; ctx->amg_emi.solves = 0;
+  for (int k = 0; k < MAX_IONS; ++k) { ctx->amg_knp[k].omega = 0.0; ctx->amg_knp[k].solves = 0; }
   if (gmres_restart < 1 || gmres_restart > 200) fail("bad GMRES restart");
   ctx->opt.pc = pc; ctx->opt.nu_pre = nu_pre; ctx->opt.nu_post = nu_post; ctx->opt.gamma = gamma;
   ctx->opt.omega = omega; ctx->opt.restart = gmres_restart; ctx->opt.knp_min_it = knp_min_it;
