@@ -445,10 +445,12 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
   {
     const char* e = getenv("KNP_AMG_TAIL");
     if (!(e && e[0] == '0')) {
+      const char* tr = getenv("KNP_TAIL_ROWS");
+      const int64_t tail_rows = tr ? atoll(tr) : TAIL_MAX_ROWS;
       size_t first = amg.lev.size();
       for (size_t l = amg.lev.size(); l-- > 0;) {
         const bool local = !ctx->comm.active() || l >= amg.rep_from;   // no halos inside the tail
-        if (!local || amg.lev[l].n > TAIL_MAX_ROWS || !amg.lev[l].t_unit) break;
+        if (!local || amg.lev[l].n > tail_rows || !amg.lev[l].t_unit) break;
         first = l;
       }
       if (first == amg.rep_from) ++first;   // the hand-over into the replica stays a regular step
@@ -1024,6 +1026,19 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
     concurrent = nion > 1 && dist_ok && !(e && e[0] == '0');
   }
   if (concurrent) {
+    // Streams and workspace buffers are created HERE, on the main thread, while this device is
+    // idle: cudaMalloc / cudaFree / stream creation may synchronise the whole device, and a
+    // device-wide wait issued while a peer-memory exchange kernel of the other worker is spinning
+    // on a neighbour rank (whose matching kernel may sit behind ITS allocation) can deadlock
+    // across ranks.
+    for (int ion = 0; ion < nion; ++ion) {
+      KrylovWs& K = ctx->kr_ion[ion];
+      K.id = 1 + ion;
+      if (!K.own_stream) { KNP_CUDA(cudaStreamCreateWithFlags(&K.stream, cudaStreamNonBlocking)); K.own_stream = true; }
+      tl_ws = &K;
+      ensure_krylov(ctx);
+      tl_ws = nullptr;
+    }
     const bool refresh_in_worker = !ctx->comm.active();
     if (!refresh_in_worker)
       for (int ion = 0; ion < nion; ++ion) knp_refresh(ctx, ion);
@@ -1036,15 +1051,12 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
     std::vector<std::string> errs(nion);
     for (int ion = 0; ion < nion; ++ion) {
       KrylovWs& K = ctx->kr_ion[ion];
-      K.id = 1 + ion;
-      if (!K.own_stream) { KNP_CUDA(cudaStreamCreateWithFlags(&K.stream, cudaStreamNonBlocking)); K.own_stream = true; }
       KNP_CUDA(cudaStreamWaitEvent(K.stream, ready, 0));
       th.emplace_back([ctx, ion, rtol, atol, maxit, refresh_in_worker, &its, &ress, &errs, &K]() {
         try {
           KNP_CUDA(cudaSetDevice(ctx->device));
           tl_ws = &K;
           Comm::in_worker() = true;
-          ensure_krylov(ctx);
           its[ion] = gmres_one(ctx, ion, rtol, atol, maxit, &ress[ion], refresh_in_worker);
           if (its[ion] >= 0) halo0(ctx, ctx->c[ion].p);   // ghost cells of the new concentration
           stream_sync(K.stream);
