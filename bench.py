@@ -259,12 +259,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    def progress(msg):                 # stderr breadcrumbs: where a run was if it is ever killed by a timeout
+        print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     nblocks = world if args.scaling == "weak" else 1
+    progress("building the engine")
     eng = build_engine(dims, local_rank, transport, nblocks)
+    progress("engine ready")
     ctx = eng.ctx
     dofs = eng.dofs()                                  # of the whole (partitioned) mesh
     for _ in range(warmup):
         eng.step()
+    progress("warm-up done")
     # ---- timed region: K steps, state resident in HBM -----------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -280,6 +286,7 @@ def main():
     ctx.sync()
     barrier()
     launches = ctx.launch_count() - l0
+    progress("timed steps done")
     phase = ctx.timers()
     comm_info = ctx.dist_info()
     clocks = sampler.stop() if rank == 0 else None
@@ -321,6 +328,7 @@ def main():
     ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e * 1e3))
     e2e_value = dofs * e2e_steps / (ms_e2e * 1e-3)
     bytes_dir = sum_over_ranks(8.0 * ((N + 1) * n + nm))
+    progress("e2e steps done")
 
     # ---- roofline of the hot kernels (CUDA events on the library's stream) ----------
     peak, peak_src = read_peaks()
@@ -343,6 +351,7 @@ def main():
                 "ms_per_launch": dom["ms"], "other_kernels": kern}
     launches = int(sum_over_ranks(float(launches)))
     barrier()
+    progress("kernel microbenchmarks done")
 
     if rank != 0:
         if dist is not None:

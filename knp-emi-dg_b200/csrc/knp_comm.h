@@ -128,6 +128,7 @@ struct P2PHaloArgs {
 // in the neighbours' memory (NVLink stores); the last block to finish raises the flags.
 // Phase B: wait for each neighbour's flag, copy its entries into the ghost tail of x.
 static __global__ void __launch_bounds__(256) p2p_halo_kernel(const P2PHaloArgs a) {
+  if (*(volatile int*)a.err) return;   // an earlier exchange timed out: drain the queue quickly, the host reports it
   const int64_t ns = a.send_off[a.nn];
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < ns; k += (int64_t)gridDim.x * blockDim.x) {
     int i = 0;
@@ -172,6 +173,7 @@ struct P2PArArgs {
 // in slot [rank] of every peer, raises flag [rank] there, waits for all flags in its own
 // arena and sums the slots in rank order (same bits on every rank).
 static __global__ void __launch_bounds__(128) p2p_allreduce_kernel(const P2PArArgs a) {
+  if (*(volatile int*)a.err) return;
   const int t = threadIdx.x;
   if (t < a.n) {
     const double v = a.buf[t];

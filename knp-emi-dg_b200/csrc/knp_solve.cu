@@ -1018,10 +1018,15 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
     // Multi-GPU: every worker talks to its peers on its own exchange channel (peer-memory
     // kernels only - NCCL calls must come from one thread in one order); the preconditioner
     // refresh, which all-gathers matrix values with NCCL, is done up front on the main thread.
+    // KNP_CONCURRENT_IONS: unset = concurrent on a single GPU only; 0 = never; 1 = also across
+    // ranks.  The multi-rank mode is OPT-IN: it measured -16 % at N=2, but 3 of 6 runs at N=2
+    // hung once the per-solve preconditioner refresh (whose NCCL all-gather had kept the ranks
+    // in step) became lagged - an unresolved race, so the default keeps the ions in sequence
+    // on more than one GPU.
     const char* e = getenv("KNP_CONCURRENT_IONS");
     const bool dist = ctx->comm.active();
-    const bool dist_ok = !dist || (ctx->comm.p2p.on && ctx->comm.world <= P2P_MAX_NB && nion + 1 <= P2P_MAX_WS &&
-                                   ctx->opt.pc == 1 && ctx->amg.ready &&
+    const bool dist_ok = !dist || (e && e[0] == '1' && ctx->comm.p2p.on && ctx->comm.world <= P2P_MAX_NB &&
+                                   nion + 1 <= P2P_MAX_WS && ctx->opt.pc == 1 && ctx->amg.ready &&
                                    (ctx->amg.rep_from != (size_t)-1 || ctx->amg.m_dense <= P2P_AR_MAX));
     concurrent = nion > 1 && dist_ok && !(e && e[0] == '0');
   }
