@@ -48,3 +48,46 @@ def test_mms_time_rates_through_the_product_path(emu_lib):
     rates = np.log(errs[:-1] / errs[1:]) / np.log(2.0)
     assert np.all(rates[-1] > 0.93) and np.all(rates[-1] < 1.07), rates
     assert np.all(np.diff(rates, axis=0) > 0)          # approaching 1 from below
+
+
+def _bundle_run(lib, env, nsteps=6):
+    """a few steps of the small 3D bundle under the given library environment switches"""
+    import os
+    import bench
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_hh, mm_hh_no_stim
+    from common import kmesh
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        mesh, sub, surf = kmesh.bundle_3d_mesh(0)
+        eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), lib=lib, **bench.PHYS)
+        eng.set_concentrations_by_tag(bench.C_INIT)
+        eng.add_membrane_model(1, mm_hh, bench.ION_NAMES, stimulus=bench.STIMULUS, stimulus_locator=bench.stim_locator)
+        eng.add_membrane_model(2, mm_hh_no_stim, bench.ION_NAMES, stimulus=bench.STIMULUS,
+                               stimulus_locator=bench.stim_locator)
+        eng.rtol_emi, eng.rtol_knp = 1e-10, 1e-11
+        for _ in range(nsteps):
+            eng.step()
+        return eng.phi_M().copy(), [eng.concentration(k).copy() for k in range(3)], dict(eng.stats)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_solver_engineering_switches_do_not_change_the_solution(emu_lib):
+    """lagged preconditioner refresh, time-extrapolated initial guess, V(0,1) inside GMRES: all
+    of them change HOW a system is solved, none may change WHAT a solve returns beyond the
+    Krylov tolerance (the switches are read when a context is created)"""
+    ref_pm, ref_c, ref_st = _bundle_run(emu_lib, {"KNP_AMG_REFRESH_PERIOD": "1", "KNP_EXTRAPOLATE": "0",
+                                                  "KNP_KNP_PRESMOOTH": "1"})
+    pm, c, st = _bundle_run(emu_lib, {"KNP_AMG_REFRESH_PERIOD": "4", "KNP_EXTRAPOLATE": "1",
+                                      "KNP_KNP_PRESMOOTH": "0"})
+    assert rel_err(pm, ref_pm) < 1e-7
+    for k in range(3):
+        assert rel_err(c[k], ref_c[k]) < 1e-8
+    # and they must not cost iterations on this case
+    assert sum(st["emi_niter"]) <= sum(ref_st["emi_niter"]) + 6
