@@ -108,9 +108,10 @@ def test_cuda_build_rejects_host_callbacks_and_emu_rejects_nccl(emu_lib):
 
 
 def test_bisection_cuts_the_weak_couplings():
-    """a 1 x 4 x 1 box with cells 0.5 x 0.0625 x 0.25: y is the longest extent, but a cut across y
-    severs the strong (short-distance, large-area) couplings; the partitioner must cut across x"""
-    mesh = kmesh.box_mesh((0, 0, 0), (1, 4, 1), 2, 64, 4)
+    """a 1 x 1.5 x 1 box with cells 0.5 x 0.0625 x 0.25: y is the longest extent, but a cut across y
+    severs the strong (short-distance, large-area) couplings - 16 facets of weight ~0.44 against
+    192 facets of weight ~0.03 across x; the partitioner must cut across x"""
+    mesh = kmesh.box_mesh((0, 0, 0), (1, 1.5, 1), 2, 24, 4)
     mesh.init_topology()
     part = partition.partition_cells(mesh, 2, refine=False)
     mid = mesh.cell_midpoints()
