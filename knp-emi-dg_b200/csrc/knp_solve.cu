@@ -250,6 +250,59 @@ static int64_t double_coarsening_rows() {
   return e ? atoll(e) : 0;
 }
 
+#ifndef KNP_EMU
+// CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY is the default since 12.2): the first
+// launch of a kernel may have to wait until the kernels that are running have finished.  A
+// worker thread that launches a not-yet-loaded kernel while the OTHER worker's exchange kernel
+// is spinning on a neighbour rank - which may be stuck the same way - is a cross-rank deadlock.
+// Every kernel the concurrent solves can launch is therefore loaded up front
+// (cudaFuncGetAttributes loads the function).
+template <class K>
+static void touch_kernel(K kernel) {
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, (const void*)kernel) != cudaSuccess) cudaGetLastError();   // best effort
+}
+template <int ND>
+static void preload_solver_kernels_nd() {
+  touch_kernel(pf_kernel<BellSpmvKernel<ND>>);
+  touch_kernel(pf_kernel<BlockDiagApplyKernel<ND>>);
+  touch_kernel(pf_kernel<BellJacobiKernel<ND>>);
+  touch_kernel(block_inverse_kernel<ND>);
+}
+static void preload_solver_kernels(knp_ctx* c) {
+  if (c->nd == 3) preload_solver_kernels_nd<3>(); else preload_solver_kernels_nd<4>();
+  touch_kernel(pf_kernel<TransferKernel>);
+  touch_kernel(pf_kernel<GalerkinKernel>);
+  touch_kernel(pf_kernel<CsrL1DiagKernel>);
+  touch_kernel(pf_kernel<CsrToDenseKernel>);
+  touch_kernel(pf_kernel<CsrSpmvKernel>);
+  touch_kernel(pf_kernel<CsrJacobiKernel>);
+  touch_kernel(pf_kernel<DiagScaleKernel>);
+  touch_kernel(pf_kernel<DenseMatvecKernel>);
+  touch_kernel(pf_kernel<ScatterOffsetKernel>);
+  touch_kernel(pf_kernel<GatherMapKernel>);
+  touch_kernel(pf_kernel<ScaleKernel>);
+  touch_kernel(pf_kernel<CombineKernel>);
+  touch_kernel(pf_kernel<GsNormalizeKernel>);
+  touch_kernel(pf_kernel<AddConstKernel>);
+  touch_kernel(pf_kernel<PackKernel>);
+  touch_kernel(subwarp_kernel<8, CoarseResidualKernel>);
+  touch_kernel(subwarp_kernel<8, TransferRowsKernel>);
+  touch_kernel(subwarp_kernel<8, CoarseUpKernel>);
+  touch_kernel(coarse_tail_kernel);
+  touch_kernel(dense_inverse_smem_kernel);
+  touch_kernel(dense_inverse_kernel);
+  touch_kernel(multi_dot_final);
+  touch_kernel(multi_dot_partial<1>); touch_kernel(multi_dot_partial<2>); touch_kernel(multi_dot_partial<3>);
+  touch_kernel(multi_dot_partial<4>); touch_kernel(multi_dot_partial<5>); touch_kernel(multi_dot_partial<6>);
+  touch_kernel(multi_dot_partial<7>); touch_kernel(multi_dot_partial<8>);
+  touch_kernel(pair_dot_partial<1>); touch_kernel(pair_dot_partial<2>);
+  touch_kernel(pair_dot_partial<3>); touch_kernel(pair_dot_partial<4>);
+  touch_kernel(p2p_halo_kernel);
+  touch_kernel(p2p_allreduce_kernel);
+}
+#endif
+
 // rows (over all ranks) below which the rest of the hierarchy is replicated; 0 disables
 static int64_t replicate_threshold() {
   const char* e = getenv("KNP_AMG_REPLICATE");
@@ -470,6 +523,9 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
     for (size_t l = 0; l < amg.lev.size() && l < amg.rep_from; ++l) ctx->comm.prepare_plan(ctx->stream, amg.lev[l].halo, nws);
     if (amg.rep_from != (size_t)-1) ctx->comm.prepare_plan(ctx->stream, amg.rep_plan, nws);
   }
+#endif
+#ifndef KNP_EMU
+  preload_solver_kernels(ctx);
 #endif
   alloc_values(ctx, ctx->amg_emi);
   for (int k = 0; k < ctx->P.N - 1; ++k) alloc_values(ctx, ctx->amg_knp[k]);

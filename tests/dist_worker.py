@@ -14,6 +14,10 @@ import json
 import os
 import sys
 
+# spin-waiting exchange kernels and lazily loaded CUDA modules do not mix (csrc/knp_solve.cu,
+# preload_solver_kernels): ask for eager loading before anything initialises CUDA
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
