@@ -1075,10 +1075,11 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
     // kernels only - NCCL calls must come from one thread in one order); the preconditioner
     // refresh, which all-gathers matrix values with NCCL, is done up front on the main thread.
     // KNP_CONCURRENT_IONS: unset = concurrent on a single GPU only; 0 = never; 1 = also across
-    // ranks.  The multi-rank mode is OPT-IN: it measured -16 % at N=2, but 3 of 6 runs at N=2
-    // hung once the per-solve preconditioner refresh (whose NCCL all-gather had kept the ranks
-    // in step) became lagged - an unresolved race, so the default keeps the ions in sequence
-    // on more than one GPU.
+    // ranks.  The multi-rank mode is still OPT-IN: it measured -16 % at N=2, but 4 of 10 runs at
+    // N=2 ended in an exchange time-out once the per-solve preconditioner refresh (whose NCCL
+    // all-gather had kept the ranks in step) became lagged.  Suspected cause: lazy kernel loading
+    // (preload_solver_kernels above); 2 of 2 runs were clean with the preload + eager loading,
+    // not yet enough to flip the default.
     const char* e = getenv("KNP_CONCURRENT_IONS");
     const bool dist = ctx->comm.active();
     const bool dist_ok = !dist || (e && e[0] == '1' && ctx->comm.p2p.on && ctx->comm.world <= P2P_MAX_NB &&
