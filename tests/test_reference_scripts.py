@@ -32,6 +32,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checko
 def ref_env(tmp_path, monkeypatch, emu_lib):
     for name in ("run_2D.py", "run_3D.py", "make_mesh_2D.py", "make_mesh_3D.py", "mm_hh.py", "mm_hh_no_stim.py"):
         shutil.copy(os.path.join(REF, name), tmp_path / name)
+    shutil.copy("/root/reference/tests/make_mesh_MMS.py", tmp_path / "make_mesh_MMS.py")
     monkeypatch.chdir(tmp_path)
     monkeypatch.syspath_prepend(SHIMS)
     monkeypatch.syspath_prepend(str(tmp_path))
@@ -39,10 +40,11 @@ def ref_env(tmp_path, monkeypatch, emu_lib):
         monkeypatch.setattr(np, "float_", np.float64, raising=False)
     from knpemidg import _lib
     monkeypatch.setattr(_lib, "_instance", emu_lib)    # no GPU here: see module docstring
-    for mod in ("mm_hh", "mm_hh_no_stim", "make_mesh_2D", "make_mesh_3D", "dolfin"):
+    mods = ("mm_hh", "mm_hh_no_stim", "make_mesh_2D", "make_mesh_3D", "make_mesh_MMS", "dolfin")
+    for mod in mods:
         monkeypatch.delitem(sys.modules, mod, raising=False)
     yield tmp_path
-    for mod in ("mm_hh", "mm_hh_no_stim", "make_mesh_2D", "make_mesh_3D", "dolfin"):
+    for mod in mods:
         sys.modules.pop(mod, None)
 
 
@@ -100,6 +102,32 @@ def test_make_mesh_3d_script_matches_native_generator(ref_env):
     surf = dolfin.MeshFunction("size_t", mesh, str(ref_env / "m3/surfaces_0.xml"))
     nm, nsub, nsurf = kmesh.bundle_3d_mesh(0)
     assert np.allclose(mesh.coords, nm.coords, rtol=0, atol=1e-18)
+    assert np.array_equal(mesh.cells, nm.cells)
+    assert np.array_equal(sub.array(), nsub.array())
+    assert np.array_equal(surf.array(), nsurf.array())
+
+
+@pytest.mark.parametrize("script,args,native", [
+    ("make_mesh_2D", ["-r", "1"], lambda: kmesh.neuron_2d_mesh(1)),
+    ("make_mesh_2D", ["-r", "2"], lambda: kmesh.neuron_2d_mesh(2)),
+    ("make_mesh_MMS", ["-r", "3"], lambda: kmesh.mms_mesh(3)),
+    ("make_mesh_MMS", ["-r", "4"], lambda: kmesh.mms_mesh(4)),
+])
+def test_mesh_scripts_match_native_generators(ref_env, script, args, native):
+    """the reference's mesh scripts (examples/idealized-geometries/make_mesh_2D.py, tests/make_mesh_MMS.py),
+    run unchanged on the dolfin shim, and the vectorised generators of knpemidg.mesh that the tests and
+    the benchmark use give the same cells and the same cell / facet tags"""
+    import importlib
+    mod = importlib.import_module(script)
+    out = ref_env / "m"
+    mod.main(args + ["-d", str(out)])
+    import dolfin
+    r = args[1]
+    mesh = dolfin.Mesh(str(out / f"mesh_{r}.xml"))
+    sub = dolfin.MeshFunction("size_t", mesh, str(out / f"subdomains_{r}.xml"))
+    surf = dolfin.MeshFunction("size_t", mesh, str(out / f"surfaces_{r}.xml"))
+    nm, nsub, nsurf = native()
+    assert np.allclose(mesh.coords, nm.coords, rtol=0, atol=1e-15 * max(1.0, np.abs(nm.coords).max()))
     assert np.array_equal(mesh.cells, nm.cells)
     assert np.array_equal(sub.array(), nsub.array())
     assert np.array_equal(surf.array(), nsurf.array())
