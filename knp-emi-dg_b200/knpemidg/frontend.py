@@ -15,10 +15,17 @@ from . import _lib
 
 
 class Constant:
-    """dolfin.Constant look-alike (scalar or small vector)."""
+    """dolfin.Constant look-alike (scalar or small vector).
+
+    A scalar Constant is also a SYMBOL: arithmetic with it (or passing it to the symbolic
+    sin/cos/... of knpemidg.symbolic) yields a sympy expression in which the Constant stays
+    a free symbol whose CURRENT value is substituted whenever the expression is evaluated -
+    that is how the time `t` of the reference's manufactured solutions (tests/mms_time.py:28-43)
+    keeps following `t.assign`.  `float(c)` and `as_float(expr)` give numbers."""
 
     def __init__(self, value):
-        self._v = np.asarray(value, dtype=float)
+        self._v = np.asarray(float(value) if np.ndim(value) == 0 else value, dtype=float)
+        self._sym = None
 
     def assign(self, value):
         self._v = np.asarray(float(value) if np.ndim(value) == 0 else value, dtype=float)
@@ -29,23 +36,44 @@ class Constant:
     def __float__(self):
         return float(self._v)
 
-    def __add__(self, o):
-        return float(self) + float(o)
+    def _sympy_(self):
+        if self._v.ndim != 0:
+            raise TypeError("a vector Constant is not a scalar symbol")
+        if self._sym is None:
+            from . import symbolic
+            self._sym = symbolic.constant_symbol(self)
+        return self._sym
 
-    __radd__ = __add__
+    def _bin(self, o, f):
+        from . import symbolic
+        if isinstance(o, symbolic.Vec):
+            return NotImplemented
+        return f(self._sympy_(), symbolic.to_sym(o))
 
-    def __mul__(self, o):
-        return float(self) * float(o)
-
-    __rmul__ = __mul__
+    def __add__(self, o): return self._bin(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._bin(o, lambda a, b: b + a)
+    def __sub__(self, o): return self._bin(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._bin(o, lambda a, b: b - a)
+    def __mul__(self, o): return self._bin(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._bin(o, lambda a, b: b * a)
+    def __truediv__(self, o): return self._bin(o, lambda a, b: a / b)
+    def __rtruediv__(self, o): return self._bin(o, lambda a, b: b / a)
+    def __pow__(self, o): return self._bin(o, lambda a, b: a ** b)
+    def __neg__(self): return -self._sympy_()
+    def __pos__(self): return self._sympy_()
 
     def __repr__(self):
         return f"Constant({self._v})"
 
 
 def as_float(v):
-    """float of a number, a Constant (ours or dolfin's) or a 0-d array"""
-    return float(v)
+    """float of a number, a Constant (ours or dolfin's), a 0-d array, or a symbolic expression
+    of Constants (their current values)"""
+    try:
+        return float(v)
+    except TypeError:
+        from . import symbolic
+        return symbolic.numeric(v)
 
 
 class _Vector:
@@ -79,6 +107,10 @@ class FunctionSpace:
         return self.engine.n if self.kind == "DG1" else self.engine.nm
 
 
+from .symbolic import field_ops  # noqa: E402
+
+
+@field_ops
 class CellField:
     """DG-P1 field on the device: field id (which, idx) of include/knpemi.h."""
 

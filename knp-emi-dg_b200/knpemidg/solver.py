@@ -184,9 +184,16 @@ class Solver:
         evaluated at the OLD time (t.assign comes last, :845)."""
         eng = self.engine
         if self.mms is not None:
-            eng.ctx.set_field(_lib.F_LOAD_EMI, 0, self.mms.load_emi(float(self._t)))
+            loads = self.mms
+            if not hasattr(loads, "load_emi"):
+                # the reference's own MMSData (tests/mms_space.py, mms_time.py): symbolic sources
+                if getattr(self, "_mms_loads", None) is None:
+                    from .mms_loads import ReferenceMMSLoads
+                    self._mms_loads = ReferenceMMSLoads(self)
+                loads = self._mms_loads
+            eng.ctx.set_field(_lib.F_LOAD_EMI, 0, loads.load_emi(float(self._t)))
             for k in range(self.N_ions):
-                eng.ctx.set_field(_lib.F_LOAD_KNP, k, self.mms.load_knp(k, float(self._t)))
+                eng.ctx.set_field(_lib.F_LOAD_KNP, k, loads.load_knp(k, float(self._t)))
             return
         for k, ion in enumerate(self.ion_list[:-1]):
             f = ion.get("f_source", None)

@@ -4,7 +4,9 @@ The reference's run scripts and mesh scripts start with `from dolfin import *`
 (examples/idealized-geometries/run_2D.py:3, make_mesh_2D.py:15) and use a small part of
 dolfin for SETUP only: `Constant`, `Point`, `RectangleMesh`/`BoxMesh`, `MeshFunction`,
 `SubDomain`/`CompiledSubDomain`, the `cells`/`facets`/`SubsetIterator` entity iterators,
-`near`, and `File`/`Mesh` for dolfin-XML files.  This package provides exactly that on top of
+`near`, and `File`/`Mesh` for dolfin-XML files; the manufactured-solution tests additionally
+use UFL symbolics (`SpatialCoordinate`, `sin/cos`, `grad/div/dot/inner`, `Expression`,
+`Measure`/`assemble` for the error norms), provided by knpemidg.symbolic on top of sympy.  This package provides exactly that on top of
 `knpemidg.mesh`, so that those scripts execute UNCHANGED with the B200 `knpemidg` package:
 put `knp-emi-dg_b200/shims` on `sys.path` (tests/test_reference_scripts.py does) - never when
 a real dolfin is installed, which `knpemidg.dolfin_adapter` handles instead.
@@ -24,6 +26,11 @@ import numpy as np
 
 from knpemidg import mesh as _kmesh
 from knpemidg.frontend import Constant  # noqa: F401  (re-exported: `from dolfin import *`)
+# symbolic stand-ins for the UFL the reference's MMS tests use (tests/mms_space.py, run_MMS_*.py)
+from knpemidg.symbolic import (Expression, Measure, SpatialCoordinate, assemble, cos, div, dot, exp,  # noqa: F401
+                               grad, inner, ln, pi, sin, sqrt)
+
+parameters = {}           # `parameters['ghost_mode'] = 'shared_vertex'` (solver.py:16): accepted, no effect
 
 DOLFIN_EPS = 3.0e-16
 
@@ -69,6 +76,12 @@ class Mesh(_kmesh.SimplexMesh):
             super().__init__(arg.coords, arg.cells)
         else:
             super().__init__(arg, cells)
+
+    class _Comm:
+        rank, size = 0, 1
+
+    def mpi_comm(self):
+        return Mesh._Comm()
 
     def num_entities(self, dim):
         if dim == self.gdim:

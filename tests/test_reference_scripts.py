@@ -32,7 +32,8 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference checko
 def ref_env(tmp_path, monkeypatch, emu_lib):
     for name in ("run_2D.py", "run_3D.py", "make_mesh_2D.py", "make_mesh_3D.py", "mm_hh.py", "mm_hh_no_stim.py"):
         shutil.copy(os.path.join(REF, name), tmp_path / name)
-    shutil.copy("/root/reference/tests/make_mesh_MMS.py", tmp_path / "make_mesh_MMS.py")
+    for name in ("make_mesh_MMS.py", "run_MMS_space.py", "run_MMS_time.py", "mms_space.py", "mms_time.py"):
+        shutil.copy(os.path.join("/root/reference/tests", name), tmp_path / name)
     monkeypatch.chdir(tmp_path)
     monkeypatch.syspath_prepend(SHIMS)
     monkeypatch.syspath_prepend(str(tmp_path))
@@ -40,7 +41,7 @@ def ref_env(tmp_path, monkeypatch, emu_lib):
         monkeypatch.setattr(np, "float_", np.float64, raising=False)
     from knpemidg import _lib
     monkeypatch.setattr(_lib, "_instance", emu_lib)    # no GPU here: see module docstring
-    mods = ("mm_hh", "mm_hh_no_stim", "make_mesh_2D", "make_mesh_3D", "make_mesh_MMS", "dolfin")
+    mods = ("mm_hh", "mm_hh_no_stim", "make_mesh_2D", "make_mesh_3D", "make_mesh_MMS", "mms_space", "mms_time", "dolfin")
     for mod in mods:
         monkeypatch.delitem(sys.modules, mod, raising=False)
     yield tmp_path
@@ -105,6 +106,33 @@ def test_make_mesh_3d_script_matches_native_generator(ref_env):
     assert np.array_equal(mesh.cells, nm.cells)
     assert np.array_equal(sub.array(), nsub.array())
     assert np.array_equal(surf.array(), nsurf.array())
+
+
+def test_run_mms_space_script_unchanged(ref_env):
+    """tests/run_MMS_space.py + tests/mms_space.py, the reference's spatial convergence test (it
+    prints the rates and asserts nothing): resolutions 2..7, passive system, "direct" solves.  The
+    UFL expressions of mms_space.py become sympy expressions (knpemidg.symbolic), the MMS load
+    vectors are integrated from the script's own data (knpemidg.mms_loads), the L2 errors are
+    assembled by the script's own `inner(ca1 - uh_ca, ...)*dX(1, ...)` forms.  Second order."""
+    g = runpy.run_path(str(ref_env / "run_MMS_space.py"), run_name="__main__")
+    for key in ("rates_ca", "rates_cb", "rates_cc", "rates_phi"):
+        rates = np.array(g[key], dtype=float)
+        assert len(rates) == 5
+        assert 1.95 < rates[-1] < 2.05, (key, rates)
+        assert np.all(np.diff(rates) > 0), (key, rates)        # approaching 2 from below
+    assert abs(g["errors_ca"][3] - 7.846295e-4) < 1e-9          # r = 5, as through the oracle's data (solver_checks.run_mms)
+
+
+@pytest.mark.skipif(os.environ.get("KNP_SLOW_TESTS") != "1",
+                    reason="~8 min on the host emulation (resolution 6, up to 256 steps): set KNP_SLOW_TESTS=1")
+def test_run_mms_time_script_unchanged(ref_env):
+    """tests/run_MMS_time.py + tests/mms_time.py: first order in time.  Last verified in the build
+    container: rates 0.88, 0.94, 0.975, 0.989, 0.995, 0.997 (concentrations) and
+    0.75, 0.91, 0.96, 0.98, 0.99, 0.996 (potential) for dt = 1e-2 / 2^i, i = 1..7."""
+    g = runpy.run_path(str(ref_env / "run_MMS_time.py"), run_name="__main__")
+    for key in ("rates_ca", "rates_cb", "rates_cc", "rates_phi"):
+        rates = np.array(g[key], dtype=float)
+        assert 0.98 < rates[-1] < 1.02, (key, rates)
 
 
 @pytest.mark.parametrize("script,args,native", [
