@@ -319,15 +319,19 @@ def bundle_3d_mesh(resolution=0, dims=None, nblocks=1):
     surf = MeshFunction(mesh, 2, 0)
     cm = mesh.cell_midpoints()
     fm = mesh.facet_midpoints()
-    for blk in range(nblocks):
-        y0 = 0.9 * blk
-        axons = [((5, y0 + 0.2, 0.2), (27, y0 + 0.4, 0.4), 1),
-                 ((5, y0 + 0.5, 0.5), (27, y0 + 0.7, 0.7), 2),
-                 ((5, y0 + 0.5, 0.2), (27, y0 + 0.7, 0.4), 2),
-                 ((5, y0 + 0.2, 0.5), (27, y0 + 0.4, 0.7), 2)]
-        for a, b, tag in axons:
-            sub.array()[_inside(cm, a, b, tol)] = 1
-            surf.array()[_on_box_surface(fm, a, b, tol)] = tag
+    if nblocks > 1:
+        # every block is a y-translate of the first: fold y into the first block and tag once
+        # (the axon surfaces lie at y in [0.2, 0.7] of a block, never on a block boundary)
+        cm, fm = cm.copy(), fm.copy()
+        for m in (cm, fm):
+            m[:, 1] -= 0.9 * np.clip(np.floor(m[:, 1] / 0.9), 0, nblocks - 1)
+    axons = [((5, 0.2, 0.2), (27, 0.4, 0.4), 1),
+             ((5, 0.5, 0.5), (27, 0.7, 0.7), 2),
+             ((5, 0.5, 0.2), (27, 0.7, 0.4), 2),
+             ((5, 0.2, 0.5), (27, 0.4, 0.7), 2)]
+    for a, b, tag in axons:
+        sub.array()[_inside(cm, a, b, tol)] = 1
+        surf.array()[_on_box_surface(fm, a, b, tol)] = tag
     surf.array()[mesh.exterior_facets()] = 5
     mesh.scale(1e-6)
     return mesh, sub, surf
