@@ -268,6 +268,40 @@ class Engine:
         ctx.post_step(_lib.POST_ALL)
         self.t += self.dt
 
+    def pde_phase_picard(self, tol=1.0e-4, max_iter=25):
+        """solve_for_time_step_picard (solver.py:850-927; present but not called in the reference):
+        EMI and KNP are re-solved with the conductivities / fractions of the latest Picard iterate
+        c_prev_k until max |c_prev_k - c| <= tol, the time derivative always refers to c_prev_n.
+        Returns the number of Picard iterations."""
+        ctx = self.ctx
+        nsolved = self.N - 1
+        c_n = [ctx.get_field(F_C, k) for k in range(nsolved)]
+        for k in range(nsolved):
+            ctx.set_field(F_CN, k, c_n[k])                 # c_prev_n stays fixed during the iteration
+        prev = c_n
+        it = 0
+        eps = 2.0 * tol
+        while eps > tol:
+            it += 1
+            ctx.assemble_emi()
+            n_emi, _ = ctx.solve_emi(self.rtol_emi, self.atol_emi, self.max_it)
+            ctx.assemble_knp()
+            n_knp, _ = ctx.solve_knp(self.rtol_knp, self.atol_knp, self.max_it)
+            self.stats["emi_niter"].append(n_emi)
+            self.stats["knp_niter"].append(n_knp)
+            cur = [ctx.get_field(F_C, k) for k in range(nsolved)]
+            eps = max(float(np.abs(a - b).max()) for a, b in zip(prev, cur))   # inf-norm, solver.py:883-884
+            prev = cur
+            ctx.post_step(_lib.POST_ELIMINATED | _lib.POST_NERNST)              # solver.py:892-913
+            if it > max_iter:
+                raise _lib.KnpError("Picard solver diverged (solver.py:916-918)")
+        for k in range(nsolved):
+            ctx.set_field(F_CN, k, prev[k])                                     # c_prev_n <- c_prev_k (:921)
+        ctx.post_step(_lib.POST_PHIM)                                           # :924-925
+        self.t += self.dt
+        self.picard_iterations = it
+        return it
+
     def step(self):
         if not getattr(self, "_initialized", False):
             self.initialize()

@@ -217,6 +217,22 @@ class Solver:
         eng.pde_phase()
         t.assign(float(t) + float(self.dt))
 
+    def solve_for_time_step_picard(self, k, t):
+        """one global PDE step with Picard iterations (solver.py:850-927; the reference keeps the
+        call commented out at :996, 1123); note the reference advances t BEFORE the solves here"""
+        eng = self.engine
+        t.assign(float(t) + float(self.dt))
+        self._t = t
+        if self.mms is not None or any(callable(ion.get("f_source", None)) for ion in self.ion_list[:-1]):
+            self._update_loads()
+        try:
+            eng.pde_phase_picard()
+        except _lib.KnpError as e:
+            if "Picard" in str(e):
+                print("Picard solver diverged")
+                sys.exit(2)
+            raise
+
     def _ode_phase(self, k):
         eng = self.engine
         for mem_model in self.mem_models:                                  # solver.py:1077-1113

@@ -91,3 +91,33 @@ def test_solver_engineering_switches_do_not_change_the_solution(emu_lib):
         assert rel_err(c[k], ref_c[k]) < 1e-8
     # and they must not cost iterations on this case
     assert sum(st["emi_niter"]) <= sum(ref_st["emi_niter"]) + 6
+
+
+def test_picard_variant(emu_lib):
+    """solve_for_time_step_picard (solver.py:850-927): converges in a few iterations at the
+    reference's time step and stays close to the split step it refines"""
+    import bench
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_hh
+    from common import kmesh
+
+    def make():
+        mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+        eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1,), lib=emu_lib, **bench.PHYS)
+        eng.set_concentrations_by_tag(bench.C_INIT)
+        eng.add_membrane_model(1, mm_hh, bench.ION_NAMES, stimulus=bench.STIMULUS, stimulus_locator=bench.stim_locator)
+        eng.rtol_emi, eng.rtol_knp = 1e-10, 1e-11
+        eng.initialize(pc=1)
+        return eng
+    a, b = make(), make()
+    for _ in range(3):
+        a.step()
+        b.ode_phase()
+        it = b.pde_phase_picard()
+        b.k += 1
+        assert 1 <= it <= 6
+    assert rel_err(b.phi_M(), a.phi_M()) < 1e-3
+    for k in range(3):
+        assert rel_err(b.concentration(k), a.concentration(k)) < 1e-4
+    # the fixed point: one more Picard sweep from the converged state changes nothing above tol
+    assert b.picard_iterations <= 3
