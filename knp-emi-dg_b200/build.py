@@ -87,6 +87,53 @@ def build_emu(force=False):
     return out
 
 
+def build_variant(user_modules, emu=False, cache_dir=None):
+    """A copy of the library that carries, besides the bundled membrane models, the given
+    user ODE modules (anything that follows the reference's mm_*.py protocol: the Python source
+    of `rhs_numba` is translated to a device function by knpemidg.odegen).  Returns
+    (path of the .so, {module: model name}).  Cached by content."""
+    import hashlib
+    sys.path.insert(0, HERE)
+    from knpemidg import odegen
+    from knpemidg.models import BUNDLED
+    mods = [(name, importlib.import_module("knpemidg.models." + name)) for name in BUNDLED]
+    names = {}
+    for m in user_modules:
+        src = odegen.python_rhs_source(m)
+        tables = repr((list(m.init_state_values()), list(m.init_parameter_values())))
+        tag = hashlib.sha1((src + tables).encode()).hexdigest()[:10]
+        base = "".join(ch if ch.isalnum() else "_" for ch in m.__name__.split(".")[-1])
+        names[m] = f"user_{base}_{tag}"
+        mods.append((names[m], m))
+    text = odegen.models_header(mods)
+    text = text.replace('#include "../knp_ode.h"', f'#include "{os.path.join(CSRC, "knp_ode.h")}"')
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, "include", "knpemi.h")]
+    stamp = hashlib.sha1((text + "".join(open(d).read() for d in deps) + ("emu" if emu else "cuda")).encode()).hexdigest()[:16]
+    cache_dir = cache_dir or os.environ.get("KNPEMIDG_VARIANT_DIR") or os.path.join(HERE, "knpemidg", "_variants")
+    vdir = os.path.join(cache_dir, stamp)
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, "libknpemi_emu.so" if emu else "libknpemi.so")
+    if os.path.exists(out):
+        return out, names
+    header = os.path.join(vdir, "models_gen.h")
+    with open(header, "w") as f:
+        f.write(text)
+    define = f'-DKNP_MODELS_HEADER="{header}"'
+    tmp = out + ".tmp"
+    if emu:
+        cmd = ["g++", "-std=c++17", "-O2", "-DKNP_EMU", define, "-fPIC", "-pthread", "-shared", "-o", tmp]
+        for f in SOURCES:
+            cmd += ["-x", "c++", os.path.join(CSRC, f)]
+    else:
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        cmd = [nvcc, "-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", define,
+               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared", "--expt-relaxed-constexpr",
+               "-I", nccl_include(), "-o", tmp] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
+    subprocess.run(cmd, check=True)
+    os.replace(tmp, out)
+    return out, names
+
+
 if __name__ == "__main__":
     if "--emu" in sys.argv:
         print(build_emu(force="--force" in sys.argv))

@@ -3,7 +3,11 @@
 #include "../../include/knpemi.h"
 #include <algorithm>
 #include "knp_ctx.h"
+#ifdef KNP_MODELS_HEADER      // a library variant that also carries user-supplied membrane models (build.py)
+#include KNP_MODELS_HEADER
+#else
 #include "generated/models_gen.h"
+#endif
 
 using namespace knp;
 

@@ -147,6 +147,21 @@ def get():
     return _instance
 
 
+def variant_with(lib, user_modules):
+    """A library that also carries the given user ODE modules (the reference accepts ANY module
+    with the mm_*.py protocol, membrane.py:88; here its right-hand side has to become device
+    code): the same sources are rebuilt with the modules' translated right-hand sides added
+    (knp-emi-dg_b200/build.py:build_variant; nvcc for the CUDA library, g++ for the emulation
+    build of the CPU tests; cached in knpemidg/_variants, git-ignored).  Returns (Lib, {module: name})."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(_HERE), "build.py")
+    spec = importlib.util.spec_from_file_location("knp_build", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    so, names = mod.build_variant(list(user_modules), emu=not lib.is_cuda())
+    return Lib(so), names
+
+
 class Context:
     """One device context; thin numpy-facing wrapper over the C ABI."""
 

@@ -49,6 +49,46 @@ def _simplex_rule(dim, n):
             (WU * WV * WW * (1 - U) ** 2 * (1 - V)).ravel() * 6.0)
 
 
+def find_compiled_model(lib, ode):
+    """name of the model compiled into `lib` that implements the ODE module `ode`: same table
+    sizes, same defaults and the same right-hand side on probe inputs (two different example
+    directories of the reference ship different modules called mm_hh); None if there is none"""
+    import importlib
+    from .models import BUNDLED
+    s0 = np.asarray(ode.init_state_values(), dtype=float)
+    p0 = np.asarray(ode.init_parameter_values(), dtype=float)
+    f = getattr(ode, "rhs_numba", None)
+    user_rhs = None
+    for attr in ("py_func", "_pyfunc"):
+        if f is not None and hasattr(f, attr):
+            user_rhs = getattr(f, attr)
+    rng = np.random.default_rng(7)
+    probes = [(0.01 * i, s0 * (1 + 0.1 * rng.uniform(-1, 1, s0.size)), p0 + 0.1 * rng.uniform(0.5, 1, p0.size))
+              for i in range(3)]
+    compiled = lib.models()
+    for name in BUNDLED:
+        if name not in compiled:
+            continue
+        mod = importlib.import_module("knpemidg.models." + name)
+        if mod is ode:
+            return name
+        if len(mod.init_state_values()) != s0.size or len(mod.init_parameter_values()) != p0.size:
+            continue
+        if not (np.array_equal(mod.init_state_values(), s0) and np.array_equal(mod.init_parameter_values(), p0)):
+            continue
+        if user_rhs is None:
+            return name
+        ok = True
+        for t, y, p in probes:
+            d1, d2, p1, p2 = np.zeros_like(y), np.zeros_like(y), p.copy(), p.copy()
+            user_rhs(t, y, d1, p1)
+            mod.rhs_numba.py_func(t, y, d2, p2)
+            ok &= np.allclose(d1, d2, rtol=1e-12, atol=0) and np.allclose(p1, p2, rtol=1e-12, atol=0)
+        if ok:
+            return name
+    return None
+
+
 class Engine:
     def __init__(self, mesh, cell_tags, facet_tags, *, F, R, T, C_M, C_phi, dt, z, D_sub, rho_sub=None,
                  membrane_tags=(), degree=1, splitting=True, mms=False, C_sub=None, device=0, lib=None,
@@ -103,6 +143,7 @@ class Engine:
         self.cell_tags = cell_tags
         self.mem = ctx.membrane_table()
         self.members = []
+        self.user_models = {}            # ODE module -> model name in a library variant (_lib.variant_with)
         self.k = 0
         self.t = 0.0
         self.amg_ready = False
@@ -157,44 +198,13 @@ class Engine:
         self.ctx.set_field(_lib.F_LOAD_KNP, k, load)
 
     def resolve_model(self, ode):
-        """name of the compiled model that implements the user's ODE module: same table
-        sizes, same defaults and the same right-hand side on probe inputs (two different
-        example directories of the reference ship different modules called mm_hh)."""
-        import importlib
-        from .models import BUNDLED
-        s0 = np.asarray(ode.init_state_values(), dtype=float)
-        p0 = np.asarray(ode.init_parameter_values(), dtype=float)
-        f = getattr(ode, "rhs_numba", None)
-        user_rhs = None
-        for attr in ("py_func", "_pyfunc"):
-            if f is not None and hasattr(f, attr):
-                user_rhs = getattr(f, attr)
-        rng = np.random.default_rng(7)
-        probes = [(0.01 * i, s0 * (1 + 0.1 * rng.uniform(-1, 1, s0.size)), p0 + 0.1 * rng.uniform(0.5, 1, p0.size))
-                  for i in range(3)]
-        compiled = self.ctx.lib.models()
-        for name in BUNDLED:
-            if name not in compiled:
-                continue
-            mod = importlib.import_module("knpemidg.models." + name)
-            if mod is ode:
-                return name
-            if len(mod.init_state_values()) != s0.size or len(mod.init_parameter_values()) != p0.size:
-                continue
-            if not (np.array_equal(mod.init_state_values(), s0) and np.array_equal(mod.init_parameter_values(), p0)):
-                continue
-            if user_rhs is None:
-                return name
-            ok = True
-            for t, y, p in probes:
-                d1, d2, p1, p2 = np.zeros_like(y), np.zeros_like(y), p.copy(), p.copy()
-                user_rhs(t, y, d1, p1)
-                mod.rhs_numba.py_func(t, y, d2, p2)
-                ok &= np.allclose(d1, d2, rtol=1e-12, atol=0) and np.allclose(p1, p2, rtol=1e-12, atol=0)
-            if ok:
-                return name
-        raise _lib.KnpError(f"membrane model '{ode.__name__}' has no compiled counterpart in libknpemi.so "
-                            f"(available: {sorted(compiled)}); add it to knpemidg/models and rebuild")
+        """name of the compiled model that implements the user's ODE module"""
+        name = self.user_models.get(ode) or find_compiled_model(self.ctx.lib, ode)
+        if name is None:
+            raise _lib.KnpError(f"membrane model '{ode.__name__}' has no compiled counterpart in the library "
+                                f"(available: {sorted(self.ctx.lib.models())}); add it to knpemidg/models and "
+                                "rebuild, or let Solver.setup_membrane_model build a library variant for it")
+        return name
 
     # -- membrane models -----------------------------------------------------
     def add_membrane_model(self, tag, module, ion_names, stimulus=None, stimulus_locator=None,
@@ -205,8 +215,11 @@ class Engine:
         name = module.__name__.split(".")[-1]
         models = lib.models()
         if name not in models:
-            raise _lib.KnpError(f"membrane model '{name}' is not compiled into libknpemi.so "
-                                f"(available: {sorted(models)})")
+            try:
+                name = self.resolve_model(module)
+            except (_lib.KnpError, AttributeError):
+                raise _lib.KnpError(f"membrane model '{name}' is not compiled into libknpemi.so "
+                                    f"(available: {sorted(models)})") from None
         mid, ns, npar = models[name]
         rows = np.flatnonzero(self.mem["tag"] == tag).astype(np.int32)   # ascending facet index
         m = MembraneHandle(self, tag, module, rows, mid, ns, npar)

@@ -140,8 +140,19 @@ class Solver:
     def setup_membrane_model(self, stim_params, odes):
         self.stimulus = stim_params.stimulus
         self.stimulus_locator = stim_params.stimulus_locator
+        user_names = {}
+        if self.engine is None:
+            # ODE modules without a compiled counterpart: build (once, cached) a library variant that
+            # carries their right-hand sides as device code, before the device context is created
+            from .engine import find_compiled_model
+            lib = self._lib or _lib.get()
+            missing = [ode for ode in odes.values() if find_compiled_model(lib, ode) is None]
+            if missing:
+                print(f"knpemidg: compiling {len(missing)} user membrane model(s) into a library variant ...")
+                self._lib, user_names = _lib.variant_with(lib, missing)
         self._ensure_engine(tuple(int(t) for t in odes), splitting=True)
         eng = self.engine
+        eng.user_models.update(user_names)
         self.mem_models = []
         for tag, ode in odes.items():
             ode_model = MembraneModel(ode, facet_f=self.surfaces, tag=int(tag), V=self.Q)
