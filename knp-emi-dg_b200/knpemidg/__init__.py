@@ -9,7 +9,7 @@ _LAZY = {
     "Solver": "knpemidg.solver", "MembraneModel": "knpemidg.membrane",
     "interface_normal": "knpemidg.utils", "plus": "knpemidg.utils", "minus": "knpemidg.utils",
     "pcws_constant_project": "knpemidg.utils", "subdomain_marking_foo": "knpemidg.utils",
-    "Constant": "knpemidg.frontend", "Expression": "knpemidg.frontend",
+    "Constant": "knpemidg.frontend", "Expression": "knpemidg.symbolic",
 }
 
 __all__ = ["Solver", "MembraneModel", "subdomain_marking_foo", "interface_normal", "plus",
