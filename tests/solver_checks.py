@@ -37,7 +37,7 @@ def _ion(name, z, D, ci, ce):
             "f_source": Constant(0)}
 
 
-def run_2d_neuron(lib, nsteps, rtol_emi=1e-5, rtol_knp=1e-7, outdir=None, g_syn=10.0):
+def run_2d_neuron(lib, nsteps, rtol_emi=1e-5, rtol_knp=1e-7, outdir=None, g_syn=10.0, resolution=0, trace=None):
     params = namedtuple("params", "dt n_steps_ODE F psi phi_M_init C_phi C_M R temperature phi_M_init_type "
                                   "rho_sub")(DT, 25, F, F / (R * T), Constant(-0.0743), C_M / DT, C_M, R, T,
                                              "constant", {0: Constant(0), 1: Constant(0)})
@@ -46,7 +46,7 @@ def run_2d_neuron(lib, nsteps, rtol_emi=1e-5, rtol_knp=1e-7, outdir=None, g_syn=
     stim = namedtuple("membrane_params", "g_syn_bar stimulus stimulus_locator")(
         g_syn, {"stim_amplitude": g_syn}, lambda x: x[0] < 20e-6)
     sp = SolverParams(False, False, 0, rtol_emi, rtol_knp, 1e-40, 1e-40, None, None)
-    mesh, sub, surf = kmesh.neuron_2d_mesh(0)
+    mesh, sub, surf = kmesh.neuron_2d_mesh(resolution)
     S = Solver2D(params, ion_list, lib=lib)
     S.setup_domain(mesh, sub, surf)
     S.setup_parameters()
@@ -65,7 +65,12 @@ def run_2d_neuron(lib, nsteps, rtol_emi=1e-5, rtol_knp=1e-7, outdir=None, g_syn=
     c0 = np.stack([np.where((sub.array() == 1)[:, None], ci[1], ci[0]) * np.ones((P.nc, P.nd)) for ci in cinit])
     O = stepper.OracleSolver(P, c0, models={1: mm_hh}, stimulus={"stim_amplitude": g_syn},
                              stimulus_locator=lambda x: x[0] < 20e-6, ion_names=["K", "Cl", "Na"])
-    O.run(nsteps)
+    if trace is None:
+        O.run(nsteps)
+    else:                                    # membrane-potential trace of the oracle, step by step
+        for _ in range(nsteps):
+            O.step()
+            trace.append(O.phi_M.copy())
     return S, O
 
 

@@ -1,0 +1,22 @@
+"""GPU: the complete run of examples/idealized-geometries/run_2D.py against the oracle (added after the
+last GPU session of round 1; its CPU twin, tests/test_solver_api.py::
+test_traces_over_an_action_potential_match_oracle, and a 200-step run on the host emulation - 6e-8 on the
+membrane potential - pass).  Runs last so that a surprise here cannot hide the rest of the GPU suite."""
+import pytest
+
+import solver_checks as sc
+from common import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_full_run_traces_match_oracle(gpu_lib):
+    """the run of examples/idealized-geometries/run_2D.py (Tstop = 20 ms, 200 steps, one action
+    potential) on the resolved 2D neuron: final membrane potential and concentrations against the
+    oracle within the north_star trace tolerance (1e-6 relative)"""
+    S, O = sc.run_2d_neuron(gpu_lib, 200, rtol_emi=1e-12, rtol_knp=1e-13, resolution=1)
+    assert abs(O.phi_M.mean() + 0.07515) < 2e-4                      # back at rest after the spike
+    assert rel_err(S.phi_M_prev_PDE.vector().get_local(), O.phi_M) < 1e-6
+    for k in range(2):
+        assert rel_err(S.c.split()[k].nodal(), O.c[k]) < 1e-9
+    assert rel_err(S.ion_list[-1]["c"].nodal(), O.c_elim) < 1e-9

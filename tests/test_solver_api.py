@@ -121,3 +121,16 @@ def test_picard_variant(emu_lib):
         assert rel_err(b.concentration(k), a.concentration(k)) < 1e-4
     # the fixed point: one more Picard sweep from the converged state changes nothing above tol
     assert b.picard_iterations <= 3
+
+
+def test_traces_over_an_action_potential_match_oracle(emu_lib):
+    """north_star: "membrane-potential and concentration traces over a full run must agree within
+    1e-6 relative".  100 steps (10 ms: stimulus, action potential, after-hyperpolarisation) on the
+    resolved 2D neuron; both sides solve to tight Krylov tolerances, the ODE integrators differ
+    (adaptive Dormand-Prince on the device, scipy LSODA in the oracle, both rtol 1e-8)."""
+    S, O = sc.run_2d_neuron(emu_lib, 100, rtol_emi=1e-12, rtol_knp=1e-13, resolution=1)
+    assert O.phi_M.max() < -0.07 and O.phi_M.min() < -0.08          # past the spike, in the after-hyperpolarisation
+    assert rel_err(S.phi_M_prev_PDE.vector().get_local(), O.phi_M) < 1e-6
+    for k in range(2):
+        assert rel_err(S.c.split()[k].nodal(), O.c[k]) < 1e-9
+    assert rel_err(S.ion_list[-1]["c"].nodal(), O.c_elim) < 1e-9
