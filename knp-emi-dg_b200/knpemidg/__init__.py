@@ -6,13 +6,13 @@ library raises."""
 from knpemidg.mesh import SimplexMesh, MeshFunction  # noqa: F401
 
 _LAZY = {
-    "Solver": "knpemidg.solver", "MembraneModel": "knpemidg.membrane",
+    "Solver": "knpemidg.solver", "SolverEMI": "knpemidg.solver_emi", "MembraneModel": "knpemidg.membrane",
     "interface_normal": "knpemidg.utils", "plus": "knpemidg.utils", "minus": "knpemidg.utils",
     "pcws_constant_project": "knpemidg.utils", "subdomain_marking_foo": "knpemidg.utils",
     "Constant": "knpemidg.frontend", "Expression": "knpemidg.symbolic",
 }
 
-__all__ = ["Solver", "MembraneModel", "subdomain_marking_foo", "interface_normal", "plus",
+__all__ = ["Solver", "SolverEMI", "MembraneModel", "subdomain_marking_foo", "interface_normal", "plus",
            "minus", "pcws_constant_project", "SimplexMesh", "MeshFunction"]
 
 

@@ -134,3 +134,40 @@ def test_traces_over_an_action_potential_match_oracle(emu_lib):
     for k in range(2):
         assert rel_err(S.c.split()[k].nodal(), O.c[k]) < 1e-9
     assert rel_err(S.ion_list[-1]["c"].nodal(), O.c_elim) < 1e-9
+
+
+def test_solver_emi_keeps_concentrations_frozen(emu_lib):
+    """SolverEMI (solver_emi.py): the run-script flow with the EMI sub-problem only - the
+    membrane fires, the concentrations never move"""
+    from collections import namedtuple
+    from knpemidg import SolverEMI
+    from knpemidg.frontend import Constant
+    from knpemidg.models import mm_hh
+    from common import kmesh
+
+    class EMI2D(SolverEMI):
+        def update_ode(self, ode_model):
+            sc.Solver2D.update_ode(self, ode_model)
+
+    params = namedtuple("params", "dt n_steps_ODE F psi phi_M_init C_phi C_M R temperature phi_M_init_type "
+                                  "rho_sub")(sc.DT, 25, sc.F, sc.F / (sc.R * sc.T), Constant(-0.0743), sc.C_M / sc.DT,
+                                             sc.C_M, sc.R, sc.T, "constant", {0: Constant(0), 1: Constant(0)})
+    ion_list = [sc._ion("K", 1.0, 1.96e-9, sc.K_I, sc.K_E), sc._ion("Cl", -1.0, 2.03e-9, sc.NA_I + sc.K_I, sc.NA_E + sc.K_E),
+                sc._ion("Na", 1.0, 1.33e-9, sc.NA_I, sc.NA_E)]
+    stim = namedtuple("membrane_params", "g_syn_bar stimulus stimulus_locator")(
+        10.0, {"stim_amplitude": 10.0}, lambda x: x[0] < 20e-6)
+    sp = sc.SolverParams(False, False, 0, 1e-5, 1e-7, 1e-40, 1e-40, None, None)
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    S = EMI2D(params, ion_list, lib=emu_lib)
+    S.setup_domain(mesh, sub, surf)
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    S.setup_membrane_model(stim, {1: mm_hh})
+    c0 = [S.c.split()[k].nodal().copy() for k in range(2)]
+    t = Constant(0.0)
+    S.solve_system_active(30 * sc.DT, t, sp)
+    pm = S.phi_M_prev_PDE.vector().get_local()
+    assert pm.max() > 0.0                                         # the spike (peak at step ~29 in the full model)
+    for k in range(2):
+        assert np.array_equal(S.c.split()[k].nodal(), c0[k])
+    assert all(n == 0 for n in S.engine.stats["knp_niter"]) and abs(float(t) - 30 * sc.DT) < 1e-15
