@@ -60,7 +60,58 @@ def make_mesh(name):
         return kmesh.bundle_3d_mesh(0) + ((1, 2),)
     if name == "emix":
         return kmesh.emix_like_mesh(10, n_cells=6) + ((1, 2),)
+    if name in ("unstr2d", "unstr3d"):
+        return unstructured_mesh(2 if name.endswith("2d") else 3) + ((1,),)
     raise ValueError(name)
+
+
+def unstructured_mesh(d, n=None, seed=3):
+    """UNSTRUCTURED simplex mesh with an embedded cell (scaled to um): cells whose midpoint lies in
+    [0.3, 0.7]^d get tag 1, the interface facets membrane tag 1, exterior facets 5.
+    2D: scipy Delaunay triangulation of jittered points (irregular valences).  3D: Delaunay of
+    near-grid points produces slivers, on which the SIP form with h = max edge (the reference's
+    CellDiameter) loses coercivity - so the 6-tets-per-box mesh with jittered interior vertices.
+    In both, the vertex numbering, the cell numbering and every cell's local vertex order are
+    randomly permuted: neighbour tables, facet permutations and orientations are arbitrary, which
+    the structured generators never produce."""
+    rng = np.random.default_rng(seed)
+    m = n or (14 if d == 2 else 7)
+    if d == 2:
+        from scipy.spatial import Delaunay
+        g = np.linspace(0.0, 1.0, m + 1)
+        pts = np.stack(np.meshgrid(*([g] * d), indexing="ij"), axis=-1).reshape(-1, d)
+        interior = np.all((pts > 1e-12) & (pts < 1 - 1e-12), axis=1)
+        pts[interior] += rng.uniform(-0.3, 0.3, (int(interior.sum()), d)) / m
+        cells = Delaunay(pts).simplices.astype(np.int32)
+        X = pts[cells]
+        vol = np.abs(np.linalg.det(X[:, 1:, :] - X[:, :1, :]))
+        cells = cells[vol > 1e-9 * vol.max()]
+    else:
+        base = kmesh.box_mesh((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), m, m, m)
+        pts, cells = base.coords.copy(), base.cells.copy()
+        interior = np.all((pts > 1e-12) & (pts < 1 - 1e-12), axis=1)
+        pts[interior] += rng.uniform(-0.15, 0.15, (int(interior.sum()), d)) / m
+    vperm = rng.permutation(len(pts))                            # new vertex numbering
+    inv = np.empty_like(vperm)
+    inv[vperm] = np.arange(len(pts))
+    pts = pts[vperm]
+    cells = inv[cells]
+    cells = cells[rng.permutation(len(cells))]                   # new cell numbering
+    for k in range(len(cells)):                                  # arbitrary local vertex order
+        cells[k] = cells[k][rng.permutation(d + 1)]
+    mesh = kmesh.SimplexMesh(pts * 1e-6, cells.astype(np.int32))
+    mesh.init_topology()
+    sub = kmesh.MeshFunction(mesh, d, 0)
+    surf = kmesh.MeshFunction(mesh, d - 1, 0)
+    mid = mesh.cell_midpoints() / 1e-6
+    sub.array()[np.all((mid > 0.3) & (mid < 0.7), axis=1)] = 1
+    fc = mesh.facet_cells
+    inter = fc[:, 1] >= 0
+    t0 = sub.array()[fc[:, 0]]
+    t1 = np.where(inter, sub.array()[np.maximum(fc[:, 1], 0)], t0)
+    surf.array()[inter & (t0 != t1)] = 1
+    surf.array()[~inter] = 5
+    return mesh, sub, surf
 
 
 class Case:

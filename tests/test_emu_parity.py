@@ -29,6 +29,15 @@ def test_solvers_3d_amg(emu_lib):
     pc.check_solvers(emu_lib, "emix", pcs=(1,), max_emi_it=25)
 
 
+@pytest.mark.parametrize("name", ["unstr2d", "unstr3d"])
+def test_unstructured_mesh_with_permuted_numbering(emu_lib, name):
+    """Delaunay (2D) / jittered (3D) mesh with random vertex, cell and local-vertex numbering
+    (tests/common.py:unstructured_mesh): assembly, post-step and both solvers against the oracle."""
+    pc.check_assembly(emu_lib, name, splitting=True, D_scale=(1.0, 0.5))
+    pc.check_post_step(emu_lib, name)
+    pc.check_solvers(emu_lib, name, pcs=(1,))
+
+
 def test_ode_models(emu_lib):
     pc.check_ode(emu_lib, ["mm_hh", "mm_glial_emix", "mm_leak"], nsteps=3)
 

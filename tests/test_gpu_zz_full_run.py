@@ -4,6 +4,7 @@ test_traces_over_an_action_potential_match_oracle, and a 200-step run on the hos
 membrane potential - pass).  Runs last so that a surprise here cannot hide the rest of the GPU suite."""
 import pytest
 
+import parity_checks as pc
 import solver_checks as sc
 from common import rel_err
 
@@ -20,3 +21,12 @@ def test_full_run_traces_match_oracle(gpu_lib):
     for k in range(2):
         assert rel_err(S.c.split()[k].nodal(), O.c[k]) < 1e-9
     assert rel_err(S.ion_list[-1]["c"].nodal(), O.c_elim) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["unstr2d", "unstr3d"])
+def test_unstructured_mesh_with_permuted_numbering(gpu_lib, name):
+    """GPU twin of tests/test_emu_parity.py::test_unstructured_mesh_with_permuted_numbering (added
+    after the last GPU session of round 1, hence in this last-running file)"""
+    pc.check_assembly(gpu_lib, name, splitting=True, D_scale=(1.0, 0.5))
+    pc.check_post_step(gpu_lib, name)
+    pc.check_solvers(gpu_lib, name, pcs=(1,))
