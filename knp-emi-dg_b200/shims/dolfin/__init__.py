@@ -69,7 +69,9 @@ class Mesh(_kmesh.SimplexMesh):
     """SimplexMesh with dolfin's constructor `Mesh(path_to_xml)`."""
 
     def __init__(self, arg=None, cells=None):
-        if isinstance(arg, (str, os.PathLike)):
+        if arg is None and cells is None:                 # `mesh = Mesh()`, filled by XDMFFile.read
+            super().__init__(np.zeros((0, 3)), np.zeros((0, 4), dtype=np.int32))
+        elif isinstance(arg, (str, os.PathLike)):
             coords, cells = _read_mesh_xml(str(arg))
             super().__init__(coords, cells)
         elif isinstance(arg, _kmesh.SimplexMesh):
@@ -82,6 +84,9 @@ class Mesh(_kmesh.SimplexMesh):
 
     def mpi_comm(self):
         return Mesh._Comm()
+
+    def init(self, *dims):
+        self.init_topology()
 
     def num_entities(self, dim):
         if dim == self.gdim:
@@ -112,6 +117,19 @@ class _Entity:
 
     def dim(self):
         return self._dim
+
+    def entities(self, dim):
+        """facet -> its cells (one on the boundary), cell -> its facets / vertices"""
+        m = self._mesh
+        m.init_topology()
+        if self._dim == m.gdim - 1 and dim == m.gdim:
+            c = m.facet_cells[self._index]
+            return c[c >= 0]
+        if self._dim == m.gdim and dim == m.gdim - 1:
+            return m.cell_facets[self._index]
+        if dim == 0:
+            return m.cells[self._index] if self._dim == m.gdim else m.facet_verts[self._index]
+        raise NotImplementedError((self._dim, dim))
 
     def midpoint(self):
         m = self._mesh
@@ -157,6 +175,12 @@ class MeshFunction(_kmesh.MeshFunction):
     def set_all(self, v):
         self._a[:] = int(v)
 
+    def rename(self, name, label=""):
+        self._name = str(name)
+
+    def name(self):
+        return getattr(self, "_name", "f")
+
 
 def SubsetIterator(mf, value):
     for i in np.flatnonzero(mf.array() == value):
@@ -184,6 +208,11 @@ class SubDomain:
                 mf[i] = value
 
 
+class DomainBoundary(SubDomain):
+    def inside(self, x, on_boundary):
+        return on_boundary
+
+
 class CompiledSubDomain(SubDomain):
     """C++ boolean expression in x[i], on_boundary, near(a, b) and DOLFIN_EPS, evaluated in Python."""
 
@@ -202,14 +231,17 @@ class CompiledSubDomain(SubDomain):
 
 
 class File:
-    """`File(path) << mesh|mesh_function` (dolfin XML)."""
+    """`File(path) << mesh|mesh_function` (dolfin XML; `.pvd` paths get a ParaView collection
+    with one ASCII .vtu piece)."""
 
     def __init__(self, path):
         self.path = str(path)
 
     def __lshift__(self, obj):
         os.makedirs(os.path.dirname(self.path) or ".", exist_ok=True)
-        if isinstance(obj, _kmesh.MeshFunction):
+        if self.path.endswith(".pvd"):
+            _write_pvd(self.path, obj)
+        elif isinstance(obj, _kmesh.MeshFunction):
             _write_meshfunction_xml(self.path, obj)
         elif isinstance(obj, _kmesh.SimplexMesh):
             _write_mesh_xml(self.path, obj)
@@ -219,6 +251,144 @@ class File:
 
     def __rshift__(self, obj):
         raise NotImplementedError("use Mesh(path) / MeshFunction('size_t', mesh, path)")
+
+
+class XDMFFile:
+    """`XDMFFile([comm,] path)`: `read(mesh)`, `read(mesh_function, name)`, `write(obj)`; also a
+    context manager (examples/emix-simulations/run_EMIx_simulation.py:160-193,
+    examples/rat-neuron/run_rat_neuron.py:156-164, 204-205).  Heavy data in HDF5 is read with
+    knpemidg.h5lite (gzip-chunked meshio files included), inline `Format="XML"` items as text;
+    `write` produces XDMF with inline data (no HDF5 writer here)."""
+
+    def __init__(self, *args):
+        self.path = str(args[-1])
+        self.parameters = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def close(self):
+        pass
+
+    def _item(self, node):
+        """numpy array of a <DataItem>"""
+        item = node if node.tag == "DataItem" else node.find("DataItem")
+        dims = [int(v) for v in item.get("Dimensions").split()]
+        text = (item.text or "").strip()
+        if item.get("Format", "XML").upper() == "HDF":
+            fname, dset = text.split(":", 1)
+            from knpemidg import h5lite
+            path = os.path.join(os.path.dirname(self.path), fname)
+            cache = self.__dict__.setdefault("_h5", {})
+            if path not in cache:
+                cache[path] = h5lite.File(path)
+            return cache[path][dset].read().reshape(dims)
+        kind = item.get("NumberType", item.get("DataType", "Float"))
+        return np.array(text.split(), dtype=float if kind == "Float" else np.int64).reshape(dims)
+
+    def _grids(self):
+        return list(ET.parse(self.path).getroot().iter("Grid"))
+
+    def read(self, obj, name=None):
+        grids = self._grids()
+        if isinstance(obj, _kmesh.MeshFunction):
+            return self._read_function(obj, name, grids)
+        g = grids[0]
+        topo = g.find("Topology")
+        nd = {"triangle": 3, "tetrahedron": 4}.get(topo.get("TopologyType").lower())
+        if nd is None:
+            raise NotImplementedError("XDMF topology " + topo.get("TopologyType"))
+        coords = self._item(g.find("Geometry"))[:, :nd - 1]
+        _kmesh.SimplexMesh.__init__(obj, coords, self._item(topo).reshape(-1, nd))
+
+    def _read_function(self, mf, name, grids):
+        mesh = mf.mesh()
+        for g in grids:
+            for att in g.findall("Attribute"):
+                if name is None or att.get("Name") == name:
+                    vals = self._item(att).reshape(-1)
+                    ents = np.sort(self._item(g.find("Topology")).reshape(len(vals), -1), axis=1)
+                    break
+            else:
+                continue
+            break
+        else:
+            raise RuntimeError(f"{self.path}: no attribute named {name!r}")
+        mesh.init_topology()
+        if ents.shape[1] != mf.dim() + 1:
+            raise RuntimeError(f"{self.path}: '{name}' lives on {ents.shape[1] - 1}-dimensional entities, "
+                               f"the MeshFunction on {mf.dim()}-dimensional ones")
+        mine = np.sort(mesh.cells if mf.dim() == mesh.gdim else mesh.facet_verts, axis=1).astype(np.int64)
+        if mine.shape == ents.shape and np.array_equal(mine, ents):
+            mf.array()[:] = np.rint(vals).astype(np.int64)
+            return
+        # match entities by their vertex sets (the file's ordering need not be the mesh's)
+        both = np.concatenate([mine, ents.astype(np.int64)])
+        _, inv = np.unique(both, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        slot = np.full(inv.max() + 1, -1, dtype=np.int64)
+        slot[inv[:len(mine)]] = np.arange(len(mine))
+        where = slot[inv[len(mine):]]
+        if (where < 0).any():
+            raise RuntimeError(f"{self.path}: '{name}' holds entities that are not in the mesh")
+        mf.array()[where] = np.rint(vals).astype(np.int64)
+
+    def write(self, obj, *a):
+        os.makedirs(os.path.dirname(self.path) or ".", exist_ok=True)
+        mesh = obj.mesh() if isinstance(obj, _kmesh.MeshFunction) else obj
+        mesh.init_topology()
+        d = mesh.gdim
+        ents = mesh.cells
+        if isinstance(obj, _kmesh.MeshFunction) and obj.dim() == d - 1:
+            ents = mesh.facet_verts
+        kind = {2: "PolyLine", 3: "Triangle", 4: "Tetrahedron"}[ents.shape[1]]
+
+        def block(a, fmt):
+            return "\n".join(" ".join(fmt % v for v in row) for row in np.atleast_2d(a))
+        with open(self.path, "w") as f:
+            f.write('<?xml version="1.0"?>\n<Xdmf Version="3.0"><Domain><Grid Name="mesh" GridType="Uniform">\n')
+            f.write(f'<Topology NumberOfElements="{len(ents)}" TopologyType="{kind}" '
+                    f'NodesPerElement="{ents.shape[1]}"><DataItem Dimensions="{len(ents)} {ents.shape[1]}" '
+                    f'NumberType="UInt" Format="XML">\n{block(ents, "%d")}\n</DataItem></Topology>\n')
+            f.write(f'<Geometry GeometryType="{"XY" if d == 2 else "XYZ"}"><DataItem Dimensions="{len(mesh.coords)} {d}" '
+                    f'Format="XML">\n{block(mesh.coords, "%.17g")}\n</DataItem></Geometry>\n')
+            if isinstance(obj, _kmesh.MeshFunction):
+                v = obj.array()
+                f.write(f'<Attribute Name="{getattr(obj, "_name", "f")}" AttributeType="Scalar" Center="Cell"><DataItem Dimensions="{len(v)} 1" '
+                        f'NumberType="UInt" Format="XML">\n{block(v.reshape(-1, 1), "%d")}\n</DataItem></Attribute>\n')
+            f.write("</Grid></Domain></Xdmf>\n")
+
+
+def _write_pvd(path, obj):
+    mesh = obj.mesh() if isinstance(obj, _kmesh.MeshFunction) else obj
+    d = mesh.gdim
+    piece = os.path.splitext(path)[0] + "000000.vtu"
+    cells = mesh.cells
+    with open(piece, "w") as f:
+        f.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="0.1">\n<UnstructuredGrid>\n')
+        f.write(f'<Piece NumberOfPoints="{len(mesh.coords)}" NumberOfCells="{len(cells)}">\n<Points>\n'
+                '<DataArray type="Float64" NumberOfComponents="3" format="ascii">\n')
+        pts = np.zeros((len(mesh.coords), 3))
+        pts[:, :d] = mesh.coords
+        f.write("\n".join(" ".join("%.17g" % v for v in p) for p in pts))
+        f.write('\n</DataArray>\n</Points>\n<Cells>\n<DataArray type="UInt32" Name="connectivity" format="ascii">\n')
+        f.write("\n".join(" ".join(str(int(v)) for v in c) for c in cells))
+        f.write('\n</DataArray>\n<DataArray type="UInt32" Name="offsets" format="ascii">\n')
+        f.write(" ".join(str((i + 1) * (d + 1)) for i in range(len(cells))))
+        f.write('\n</DataArray>\n<DataArray type="UInt8" Name="types" format="ascii">\n')
+        f.write(" ".join([str(5 if d == 2 else 10)] * len(cells)))
+        f.write("\n</DataArray>\n</Cells>\n")
+        if isinstance(obj, _kmesh.MeshFunction) and obj.dim() == d:
+            f.write('<CellData Scalars="f">\n<DataArray type="UInt32" Name="f" format="ascii">\n')
+            f.write(" ".join(str(int(v)) for v in obj.array()))
+            f.write("\n</DataArray>\n</CellData>\n")
+        f.write("</Piece>\n</UnstructuredGrid>\n</VTKFile>\n")
+    with open(path, "w") as f:
+        f.write('<?xml version="1.0"?>\n<VTKFile type="Collection" version="0.1">\n<Collection>\n'
+                f'<DataSet timestep="0" part="0" file="{os.path.basename(piece)}" />\n</Collection>\n</VTKFile>\n')
 
 
 # ---- dolfin XML -------------------------------------------------------------------------

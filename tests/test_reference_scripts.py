@@ -159,3 +159,89 @@ def test_mesh_scripts_match_native_generators(ref_env, script, args, native):
     assert np.array_equal(mesh.cells, nm.cells)
     assert np.array_equal(sub.array(), nsub.array())
     assert np.array_equal(surf.array(), nsurf.array())
+
+
+# ---- the EMIx example on the mesh the reference ships ---------------------------------------
+EMIX = "/root/reference/examples/emix-simulations"
+EMIX_MESH = "meshes/emix_meshes/volume_ncells_5_size_5000/"
+
+
+def _emix_mesh_dir(tmp_path):
+    """mesh.xdmf + mesh.h5 as shipped (linked, not copied), plus a tags.xdmf: the reference ships
+    tags.xdmf WITHOUT the tags.h5 it points to, so the facet labels are rebuilt the way
+    run_rat_neuron.py:187-201 does (interface facet <- label of its ICS cell, exterior > 10) and
+    written through the shim's XDMFFile with the attribute name the script reads."""
+    import dolfin
+    dst = tmp_path / EMIX_MESH
+    os.makedirs(dst)
+    for n in ("mesh.h5", "mesh.xdmf"):
+        os.symlink(os.path.join(EMIX, EMIX_MESH, n), dst / n)
+    mesh = dolfin.Mesh()
+    with dolfin.XDMFFile(str(dst / "mesh.xdmf")) as x:
+        x.read(mesh)
+        lab = dolfin.MeshFunction("size_t", mesh, 3)
+        x.read(lab, "label")
+    mesh.init_topology()
+    fc = mesh.facet_cells
+    inter = fc[:, 1] >= 0
+    a = lab.array()[fc[:, 0]]
+    b = np.where(inter, lab.array()[np.maximum(fc[:, 1], 0)], a)
+    surf = dolfin.MeshFunction("size_t", mesh, 2, 0)
+    surf.array()[inter & (a != b)] = np.maximum(a, b)[inter & (a != b)]
+    surf.array()[~inter] = 11
+    surf.rename("boundaries", "")
+    dolfin.XDMFFile(str(dst / "tags.xdmf")).write(surf)
+    return mesh, lab, surf
+
+
+def test_xdmf_hdf5_mesh_of_the_emix_example(ref_env):
+    """XDMFFile.read on the gzip-chunked meshio file of the EMIx example (knpemidg.h5lite: no
+    libhdf5 in this image): sizes as the .xdmf declares them, every tetrahedron positively
+    oriented, the six labels of the file, a closed ECS/ICS interface, and the facet function
+    survives a write/read cycle through XDMF."""
+    import dolfin
+    mesh, lab, surf = _emix_mesh_dir(ref_env)
+    assert mesh.coords.shape == (22419, 3) and mesh.cells.shape == (121617, 4)
+    X = mesh.coords[mesh.cells]
+    vol = np.linalg.det(X[:, 1:] - X[:, :1]) / 6.0
+    assert vol.min() > 0 and abs(vol.sum() - 1.0152937932e11) < 1e3          # nm^3
+    labels, counts = np.unique(lab.array(), return_counts=True)
+    assert labels.tolist() == [1, 2, 3, 4, 5, 6] and counts.tolist() == [73664, 6148, 3030, 5524, 25353, 7898]
+    assert mesh.num_facets() == 246206                                        # what the shipped tags.xdmf declares
+    back = dolfin.MeshFunction("size_t", mesh, 2)
+    dolfin.XDMFFile(str(ref_env / EMIX_MESH / "tags.xdmf")).read(back, "boundaries")
+    assert np.array_equal(back.array(), surf.array())
+    assert {int(k): int(v) for k, v in zip(*np.unique(surf.array(), return_counts=True))} == \
+        {0: 216079, 2: 3337, 3: 1157, 4: 2854, 5: 14940, 6: 1895, 11: 5944}
+    with pytest.raises(RuntimeError, match="no attribute named"):
+        dolfin.XDMFFile(str(ref_env / EMIX_MESH / "mesh.xdmf")).read(lab, "nonexistent")
+
+
+@pytest.mark.skipif(os.environ.get("KNP_SLOW_TESTS") != "1",
+                    reason="~2 min on the host emulation (121 617 tetrahedra): set KNP_SLOW_TESTS=1")
+def test_run_emix_script_unchanged_on_its_own_mesh(ref_env):
+    """run_EMIx_simulation.py with its mm_hh / mm_glial modules on the UNSTRUCTURED mesh the
+    reference ships (5 cells, slivers down to 4e-4 of the largest cell volume; ms / cm / mV units):
+    10 steps, glia at rest near -83 mV, the stimulated neurons fire.  Last verified in the build
+    container: CG 31-48 and GMRES 7-9 iterations per step."""
+    for name in ("run_EMIx_simulation.py", "mm_hh.py", "mm_glial.py"):
+        shutil.copy(os.path.join(EMIX, name), ref_env / name)
+    for mod in ("mm_hh", "mm_glial"):
+        sys.modules.pop(mod, None)
+    _emix_mesh_dir(ref_env)
+    try:
+        g = runpy.run_path(str(ref_env / "run_EMIx_simulation.py"), run_name="__main__")
+    finally:
+        for mod in ("mm_hh", "mm_glial"):
+            sys.modules.pop(mod, None)
+    S = g["S"]
+    assert S.engine.k == 10
+    assert max(S.engine.stats["emi_niter"]) < 80 and max(S.engine.stats["knp_niter"]) < 15
+    d = np.load(ref_env / "results/data/EMIx/results.npz", allow_pickle=True)
+    phi, sub = d["potential"], d["subdomains"]
+    mean = lambda k: np.array([p[sub == k].mean() for p in phi])
+    glia, neuron = mean(1) - mean(0), mean(2) - mean(0)
+    assert np.all(np.abs(glia + 83.2) < 1.5)                                  # mV
+    assert neuron[0] < -45 and neuron.max() > 40
+    c = d["concentrations"][-1]
+    assert np.isfinite(c).all() and c.min() > 3.0
