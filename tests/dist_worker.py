@@ -44,6 +44,13 @@ def build(case, lib, device, transport, tight=True):
         mesh, sub, surf = kmesh.neuron_2d_mesh(1)
         mtags, models = (1,), {1: mm_hh}
         phys, cinit, names = bench.PHYS, bench.C_INIT, bench.ION_NAMES
+    elif case == "unstr3d":
+        # jittered tetrahedra, random vertex / cell / local-vertex numbering (tests/common.py): the
+        # general graph partitioner, irregular halos and membrane facets cut by part boundaries
+        from common import unstructured_mesh
+        mesh, sub, surf = unstructured_mesh(3, n=8)
+        mtags, models = (1,), {1: mm_hh}
+        phys, cinit, names = bench.PHYS, bench.C_INIT, bench.ION_NAMES
     else:
         raise ValueError(case)
     part = None

@@ -45,7 +45,7 @@ def launch(world, kind, case, nsteps, out, timeout=600):
     return json.load(open(out))
 
 
-@pytest.mark.parametrize("world,case", [(2, "bundle_r0"), (4, "bundle_r0_quad"), (3, "neuron2d")])
+@pytest.mark.parametrize("world,case", [(2, "bundle_r0"), (4, "bundle_r0_quad"), (3, "neuron2d"), (3, "unstr3d")])
 def test_partitioned_run_matches_single_part(emu_lib, tmp_path, world, case):
     """two time steps (HH membranes with stimulus, CG+AMG, GMRES+AMG, tight tolerances):
     potentials, concentrations and membrane potentials of the partitioned run agree with the
@@ -58,7 +58,8 @@ def test_partitioned_run_matches_single_part(emu_lib, tmp_path, world, case):
     # depends on the partition: the default partition cuts across the weak (long) direction
     # of the bundle and changes little; the deliberately bad "quad" split cuts the strong
     # transverse couplings of the 10:1 cells and costs about 3x
-    slack = 4 if case.endswith("_quad") else 1.5
+    # (the 3 072-cell unstructured case: ~1 000 cells per part, a third of them on a part boundary)
+    slack = 4 if case.endswith("_quad") else 2 if case == "unstr3d" else 1.5
     for a, b in zip(res["iterations"]["emi_niter"], res["ref_iterations"]["emi_niter"]):
         assert a <= slack * b + 5
     for a, b in zip(res["iterations"]["knp_niter"], res["ref_iterations"]["knp_niter"]):
