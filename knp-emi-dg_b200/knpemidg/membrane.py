@@ -13,27 +13,69 @@ from . import _lib
 from .frontend import FacetField, FacetMean, HostFacetField
 
 
+def _table_engine(ode, n, lib=None):
+    """Device context for FREE-STANDING ODE tables (MembraneModel without a Solver, as in
+    examples/emix-simulations/run_calibration.py:13-22): the C ABI registers tables against the
+    membrane rows of a mesh, so a strip of 2 x n squares whose mid line has exactly n interface
+    facets carries them.  ODE modules without a compiled counterpart get a library variant first."""
+    from . import mesh as kmesh
+    from .engine import Engine, find_compiled_model
+    lib, names = lib or _lib.get(), {}
+    if find_compiled_model(lib, ode) is None:
+        print(f"knpemidg: compiling membrane model '{ode.__name__}' into a library variant ...")
+        lib, names = _lib.variant_with(lib, [ode])
+    m = kmesh.rectangle_mesh((0.0, 0.0), (float(n), 2.0), n, 2)
+    m.init_topology()
+    ctags = (m.cell_midpoints()[:, 1] > 1.0).astype(np.int64)
+    fc = m.facet_cells
+    ftags = ((fc[:, 1] >= 0) & (ctags[fc[:, 0]] != ctags[np.maximum(fc[:, 1], 0)])).astype(np.int64)
+    one = {0: 1.0, 1: 1.0}
+    eng = Engine(m, ctags, ftags, F=1.0, R=1.0, T=1.0, C_M=1.0, C_phi=1.0, dt=1.0, z=[1.0, -1.0],
+                 D_sub=[one, one], membrane_tags=(1,), lib=lib)
+    eng.user_models.update(names)
+    assert eng.nm == n
+    return eng
+
+
 class MembraneModel:
     def __init__(self, ode, facet_f, tag, V):
         """facets with facet_f == tag are governed by `ode`; V is the solver's Q space
-        (it carries the engine that owns the device context)."""
+        (it carries the engine that owns the device context) or, for free-standing tables, any
+        facet space of facet_f's mesh."""
         assert isinstance(tag, int)
-        engine = V.engine
+        engine = getattr(V, "engine", None)
+        standalone = engine is None
+        if standalone:
+            mesh = facet_f.mesh()
+            mesh.init_topology()
+            facets = np.flatnonzero(np.asarray(facet_f.array()) == tag)
+            engine = _table_engine(ode, len(facets), getattr(V, "lib", None))
         self.engine, self.V = engine, V
         self.ode, self.tag = ode, tag
         self.prefix = ode.__name__
         lib = engine.ctx.lib
         self._model_name = engine.resolve_model(ode)
         self.model_id, self.ns, self.np_ = lib.models()[self._model_name]
-        rows = np.flatnonzero(engine.mem["tag"] == tag).astype(np.int32)   # ascending facet index
+        if standalone:
+            rows = np.arange(len(facets), dtype=np.int32)
+            self.facets = facets
+            self.dof_locations = mesh.facet_midpoints()[facets]
+        else:
+            rows = np.flatnonzero(engine.mem["tag"] == tag).astype(np.int32)   # ascending facet index
+            self.facets = engine.mem["facet"][rows]
+            self.dof_locations = engine.membrane_midpoints()[rows]
         self.indices = rows                                   # rows of Q used by this model
-        self.facets = engine.mem["facet"][rows]
-        self.dof_locations = engine.membrane_midpoints()[rows]
         self.nodes = len(rows)
         states = np.array([ode.init_state_values() for _ in range(self.nodes)], dtype=float).reshape(self.nodes, self.ns)
         params = np.array([ode.init_parameter_values() for _ in range(self.nodes)], dtype=float).reshape(self.nodes, self.np_)
         self.handle = engine.ctx.membrane_register(self.model_id, rows, states, params)
-        engine.ctx.membrane_outputs(self.handle, ode.state_indices("V"), [])
+        try:
+            v_col = ode.state_indices("V")
+        except ValueError:                                    # mm_calibration: V_n, V_g - no PDE coupling
+            if not standalone:
+                raise
+            v_col = 0
+        engine.ctx.membrane_outputs(self.handle, v_col, [])
         self.time = 0
         self._set_v = False
         self._stim_key = None

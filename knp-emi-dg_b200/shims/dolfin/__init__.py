@@ -103,6 +103,25 @@ def RectangleMesh(p0, p1, nx, ny, diagonal="right"):
     return Mesh(m)
 
 
+def UnitSquareMesh(nx, ny, diagonal="right"):
+    return Mesh(_kmesh.rectangle_mesh((0.0, 0.0), (1.0, 1.0), nx, ny, diagonal))
+
+
+class FunctionSpace:
+    """what user code builds itself: the facet space handed to a free-standing MembraneModel
+    (run_calibration.py:13-14); the Solver's spaces are knpemidg.frontend.FunctionSpace"""
+
+    def __init__(self, mesh, family, degree=0):
+        self._mesh, self.family, self.degree = mesh, family, degree
+
+    def mesh(self):
+        return self._mesh
+
+
+def info(msg):
+    print(msg)
+
+
 def BoxMesh(p0, p1, nx, ny, nz):
     m = _kmesh.box_mesh((p0[0], p0[1], p0[2]), (p1[0], p1[1], p1[2]), nx, ny, nz)
     return Mesh(m)

@@ -32,8 +32,9 @@ MODULES = {
     "emix-simulations/mm_glial.py": "mm_glial_emix",
     "local-astrocyte-depolarization/mm_hh.py": "mm_hh_astro",
     "local-astrocyte-depolarization/mm_glial.py": "mm_glial_astro",
+    "emix-simulations/mm_calibration.py": "mm_calibration",          # appended last: the seeded stream above is unchanged
 }
-STATE_NAMES = ["m", "h", "n", "V"]
+STATE_NAMES = ["m", "h", "n", "V", "V_n", "V_g", "K_e", "K_n", "K_g", "Na_e", "Na_n", "Na_g"]
 
 
 def load(path):
@@ -58,7 +59,8 @@ PARAM_CANDIDATES = ["g_Na_bar", "g_K_bar", "g_leak_Na", "g_leak_K", "g_leak_Cl",
                     "K_e_init", "K_i_init", "Na_i_init", "g_Kir", "E_K_init", "rho_pump", "P_Nai", "P_Ke",
                     "k_dec", "Cl_i", "Cl_e", "K_i", "Na_e", "g_Cl_leak", "g_K_leak", "g_Na_leak", "stim_start",
                     "stim_end", "g_syn_bar", "T", "F", "R", "z_K", "z_Na", "z_Cl", "psi", "E_Kir", "g_KCC1",
-                    "i_pump", "g_leak", "E_leak", "phi_rest", "phi_M_init"]
+                    "i_pump", "g_leak", "E_leak", "phi_rest", "phi_M_init",
+                    "g_leak_Na_n", "g_leak_K_n", "g_leak_Na_g", "g_leak_K_g", "I_max_n", "I_max_g"]
 
 
 def main():

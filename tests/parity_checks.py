@@ -201,3 +201,38 @@ def check_ode_links(lib):
     # rows that carry no ODE point keep their phi_M
     others = np.setdiff1d(np.arange(nm), rows)
     assert np.array_equal(ctx.get_field(_lib.F_PHIM)[others], phiM[others])
+
+
+def check_calibration_kat(lib, nsteps=100000):
+    """KNOWN ANSWER from the reference's own run: examples/emix-simulations/run_calibration.py
+    integrates mm_calibration for 100 000 steps of 0.1 ms (LSODA, rtol 1e-8) and its outcome is
+    hard-coded as the initial state of examples/emix-simulations/mm_hh.py:11-14 (m, h, n, phi_M),
+    restated in knpemidg.models.mm_hh_emix and pinned to the reference file by
+    tests/golden/ode_rhs_golden.json.  The same run through the library's ODE kernel (a
+    free-standing MembraneModel, one ODE point) must land on those numbers."""
+    from knpemidg import mesh as kmesh
+    from knpemidg.membrane import MembraneModel
+    from knpemidg.models import mm_calibration, mm_hh_emix
+
+    class Space:                                  # any facet space of the mesh; carries the library under test
+        pass
+    V = Space()
+    V.lib = lib
+    mesh = kmesh.rectangle_mesh((0.0, 0.0), (1.0, 1.0), 1, 1)
+    facet_f = kmesh.MeshFunction(mesh, 1, 7)
+    facet_f.array()[0] = 0
+    m = MembraneModel(mm_calibration, facet_f=facet_f, tag=0, V=V)
+    assert m.nodes == 1
+    m.step_lsoda(dt=0.1, stimulus={"stim_amplitude": 0})
+    ctx = m.engine.ctx
+    for k in range(1, nsteps):
+        ctx.ode_step(m.handle, 0.1 * k, 0.1, 1e-8, 0.0, False)
+    got = m.states[0]
+    want = mm_hh_emix.init_state_values()                        # m, h, n, V
+    assert rel_err(got[:4], want) < 1e-11, (got[:4], want)
+    assert np.abs(got[:4] / want - 1.0).max() < 1e-10            # each component, not only the norm
+    # the remaining steady-state values as run_calibration.py prints them (this build, 12 digits)
+    assert abs(got[4] + 83.08244665955735) < 1e-8                # phi_M glia
+    assert np.abs(got[5:] / np.array([3.3236743806989133, 124.1417480555213, 102.74303871910962,
+                                      100.70633053050948, 12.8382384023078, 12.396954489036373]) - 1.0).max() < 1e-8
+    return got

@@ -44,3 +44,7 @@ def test_ode_models(emu_lib):
 
 def test_ode_links_and_stimulus(emu_lib):
     pc.check_ode_links(emu_lib)
+
+
+def test_calibration_run_lands_on_the_reference_values(emu_lib):
+    pc.check_calibration_kat(emu_lib)

@@ -30,3 +30,9 @@ def test_unstructured_mesh_with_permuted_numbering(gpu_lib, name):
     pc.check_assembly(gpu_lib, name, splitting=True, D_scale=(1.0, 0.5))
     pc.check_post_step(gpu_lib, name)
     pc.check_solvers(gpu_lib, name, pcs=(1,))
+
+
+def test_calibration_run_lands_on_the_reference_values(gpu_lib):
+    """known answer from the reference's own calibration run (tests/parity_checks.py:check_calibration_kat);
+    100 000 launches of the ODE kernel on one membrane point"""
+    pc.check_calibration_kat(gpu_lib)

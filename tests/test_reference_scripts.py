@@ -245,3 +245,33 @@ def test_run_emix_script_unchanged_on_its_own_mesh(ref_env):
     assert neuron[0] < -45 and neuron.max() > 40
     c = d["concentrations"][-1]
     assert np.isfinite(c).all() and c.min() > 3.0
+
+
+@pytest.mark.skipif(os.environ.get("KNP_SLOW_TESTS") != "1",
+                    reason="~45 s on the host emulation (100 000 steps, 11 table reads each): set KNP_SLOW_TESTS=1")
+def test_run_calibration_script_unchanged(ref_env, capsys, monkeypatch):
+    """run_calibration.py + mm_calibration.py: a free-standing MembraneModel (no Solver) on the 16
+    facets of a 2 x 2 unit square, 100 000 steps; matplotlib (absent here) is replaced by a stub that
+    swallows the plotting calls.  The printed steady state is what the reference hard-codes in
+    emix-simulations/mm_hh.py:11-14."""
+    for name in ("run_calibration.py", "mm_calibration.py"):
+        shutil.copy(os.path.join(EMIX, name), ref_env / name)
+    os.makedirs(ref_env / "matplotlib")
+    (ref_env / "matplotlib/__init__.py").write_text("")
+    (ref_env / "matplotlib/pyplot.py").write_text(
+        "class _Any:\n    def __call__(self, *a, **k): return _Any()\n    def __getattr__(self, n): return _Any()\n"
+        "def __getattr__(name): return _Any()\n")
+    monkeypatch.setenv("KNPEMIDG_VARIANT_DIR", str(ref_env / "variants"))
+    for mod in ("matplotlib", "matplotlib.pyplot", "mm_calibration"):
+        monkeypatch.delitem(sys.modules, mod, raising=False)
+    try:
+        g = runpy.run_path(str(ref_env / "run_calibration.py"), run_name="__main__")
+    finally:
+        for mod in ("matplotlib", "matplotlib.pyplot", "mm_calibration"):
+            sys.modules.pop(mod, None)
+    assert g["membrane"].nodes == 16
+    out = capsys.readouterr().out
+    got = {line.split("=")[0].strip(): float(line.split("=")[1]) for line in out.splitlines() if "_init =" in line}
+    for key, want in (("n_init", 0.18821645700362638), ("m_init", 0.016651023270342777),
+                      ("h_init", 0.8541791472445746), ("phi_M_n_init", -74.3848784437955)):
+        assert abs(got[key] / want - 1.0) < 1e-10, (key, got[key], want)
