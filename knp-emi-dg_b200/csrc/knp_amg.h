@@ -212,6 +212,8 @@ struct AmgValues {                 // numeric part, one per linear system
   std::vector<DevBuf<double>> dinv;  // l1-Jacobi diagonals
   DevBuf<double> dense;              // inverse of the last level
   DevBuf<double> binv;               // level-0 inverse diagonal blocks [nc][ND][ND]
+  DevBuf<float> a32, binv32;         // single-precision copies of the level-0 matrix ((ND+1) slots) and of
+                                     // binv, made at refresh, read by the level-0 sweeps (SolverOptions::pc_fp32)
   // work vectors (per system: independent systems are solved concurrently)
   std::vector<LevelVectors> vec;     // per level >= 1
   DevBuf<double> x0, r0, t0;         // level-0 work vectors

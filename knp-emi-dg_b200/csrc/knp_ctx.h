@@ -34,6 +34,7 @@ struct SolverOptions {
   // V(0,1) on the DG level inside GMRES: 13 % faster time step at equal iteration counts on the
   // bench workload (profiles/); KNP_KNP_PRESMOOTH=1 in the environment restores V(1,1)
   bool knp_presmooth0 = false;
+  bool pc_fp32 = false;         // KNP_AMG_FP32=1: level-0 sweeps of the preconditioner read fp32 copies of the matrix
   bool fuse_prolong = false;    // KNP_FUSE_PROLONG=1
   // initial guess of the EMI solve = 2 phi_n - phi_{n-1} instead of phi_n (the reference starts
   // from phi_n, solver.py:431 `ksp_initial_guess_nonzero`); same stopping test, fewer iterations.

@@ -10,19 +10,29 @@ namespace knp {
 
 // A scalar matrix in block-ELL form; `diag` may point somewhere else than slot 0 of
 // `off` (the EMI preconditioner matrix B shares A's off-diagonal blocks, solver.py:393-395).
-struct BellMat {
+// T = double everywhere except the optional single-precision COPY the preconditioner sweeps read
+// (SolverOptions::pc_fp32): values are widened on load, all arithmetic stays fp64.
+template <typename T>
+struct BellMatT {
   int64_t nc = 0;
-  const double* off = nullptr;   // (ND+1) slot arrays, slot 0 unused when diag != off
-  const double* diag = nullptr;  // [nc][ND][ND]
+  const T* off = nullptr;        // (ND+1) slot arrays, slot 0 unused when diag != off
+  const T* diag = nullptr;       // [nc][ND][ND]
   const int32_t* nbr = nullptr;  // [ND][nc], -1 = no coupling
+};
+using BellMat = BellMatT<double>;
+using BellMat32 = BellMatT<float>;
+
+struct DemoteKernel {  // out = (float) in
+  const double* in; float* out;
+  KNP_HD void operator()(int64_t i) const { out[i] = (float)in[i]; }
 };
 
 // y = A x (mode 0), y = b - A x (mode 1).  One thread per row; consecutive threads read
 // consecutive ND-double row segments of every slot array (fully coalesced), x is
 // gathered per neighbour cell (ND contiguous doubles, shared by the ND rows of a cell).
-template <int ND>
+template <int ND, typename T = double>
 struct BellSpmvKernel {
-  BellMat A;
+  BellMatT<T> A;
   const double* x; const double* b; double* y; int mode;
   KNP_HD void operator()(int64_t row) const {
     const int64_t cell = row / ND;
@@ -30,36 +40,36 @@ struct BellSpmvKernel {
     const int64_t bs = ND * ND;
     double acc = 0.0;
     {
-      const double* a = A.diag + cell * bs + i * ND;
+      const T* a = A.diag + cell * bs + i * ND;
       const double* xc = x + cell * ND;
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc += a[j] * xc[j];
+      for (int j = 0; j < ND; ++j) acc += (double)a[j] * xc[j];
     }
 #pragma unroll
     for (int f = 0; f < ND; ++f) {
       const int64_t c2 = A.nbr[f * A.nc + cell];
       if (c2 < 0) continue;
-      const double* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND;
+      const T* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND;
       const double* xc = x + c2 * ND;
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc += a[j] * xc[j];
+      for (int j = 0; j < ND; ++j) acc += (double)a[j] * xc[j];
     }
     y[row] = mode ? b[row] - acc : acc;
   }
 };
 
 // z = w * Dinv r (mode 0)   or   x += w * Dinv r (mode 1); Dinv = inverse diagonal blocks
-template <int ND>
+template <int ND, typename T = double>
 struct BlockDiagApplyKernel {
-  const double* dinv; const double* r; double* out; double w; int mode;
+  const T* dinv; const double* r; double* out; double w; int mode;
   KNP_HD void operator()(int64_t row) const {
     const int64_t cell = row / ND;
     const int i = (int)(row - cell * ND);
-    const double* a = dinv + cell * ND * ND + i * ND;
+    const T* a = dinv + cell * ND * ND + i * ND;
     const double* rc = r + cell * ND;
     double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < ND; ++j) acc += a[j] * rc[j];
+    for (int j = 0; j < ND; ++j) acc += (double)a[j] * rc[j];
     if (mode) out[row] += w * acc; else out[row] = w * acc;
   }
 };
@@ -69,9 +79,9 @@ struct BlockDiagApplyKernel {
 // between the ND lanes that own its rows with warp shuffles (ND = 4: groups of 4 lanes
 // never straddle a warp; ND = 3: each lane recomputes the cell's other rows, the loads
 // are warp broadcasts).
-template <int ND>
+template <int ND, typename T = double>
 struct BellJacobiKernel {
-  BellMat A; const double* dinv; const double* b; const double* xin; double* xout; double w;
+  BellMatT<T> A; const T* dinv; const double* b; const double* xin; double* xout; double w;
   // optional fused prolongation (post-smoothing of the V-cycle): the sweep runs on
   // x' = xin + P xc with (P xc)_d = xc[agg[d]] (unit aggregation transfer); xin == nullptr
   // means x' = P xc (no pre-smoothed iterate)
@@ -85,17 +95,17 @@ struct BellJacobiKernel {
     const int64_t bs = ND * ND;
     double acc = b[cell * ND + i];
     {
-      const double* a = A.diag + cell * bs + i * ND;
+      const T* a = A.diag + cell * bs + i * ND;
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc -= a[j] * xval(cell * ND + j);
+      for (int j = 0; j < ND; ++j) acc -= (double)a[j] * xval(cell * ND + j);
     }
 #pragma unroll
     for (int f = 0; f < ND; ++f) {
       const int64_t c2 = A.nbr[f * A.nc + cell];
       if (c2 < 0) continue;
-      const double* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND;
+      const T* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND;
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc -= a[j] * xval(c2 * ND + j);
+      for (int j = 0; j < ND; ++j) acc -= (double)a[j] * xval(c2 * ND + j);
     }
     return acc;
   }
@@ -115,10 +125,10 @@ struct BellJacobiKernel {
     {
       for (int j = 0; j < ND; ++j) r[j] = row_residual(cell, j);
     }
-    const double* di = dinv + cell * ND * ND + i * ND;
+    const T* di = dinv + cell * ND * ND + i * ND;
     double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < ND; ++j) acc += di[j] * r[j];
+    for (int j = 0; j < ND; ++j) acc += (double)di[j] * r[j];
     xout[row] = xval(row) + w * acc;
   }
 };

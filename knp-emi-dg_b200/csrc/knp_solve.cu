@@ -9,6 +9,7 @@
 #include "../../include/knpemi.h"
 #include "knp_ctx.h"
 #include <thread>
+#include <type_traits>
 
 using namespace knp;
 
@@ -43,24 +44,27 @@ static knp_stream_t cs(knp_ctx* c) { return ws(c).stream; }
 static void halo0(knp_ctx* c, const double* x) {
   if (c->comm.active()) c->comm.halo(cs(c), c->halo0, const_cast<double*>(x), ws(c).id);
 }
-template <int ND>
-static void bell_spmv(knp_ctx* c, const BellMat& A, const double* x, const double* b, double* y, int mode) {
-  BellSpmvKernel<ND> k{A, x, b, y, mode};
+template <int ND, typename T>
+static void bell_spmv_nd(knp_ctx* c, const BellMatT<T>& A, const double* x, const double* b, double* y, int mode) {
+  BellSpmvKernel<ND, T> k{A, x, b, y, mode};
   parallel_for(cs(c), c->n_own, k, 256);
 }
-static void bell_spmv(knp_ctx* c, const BellMat& A, const double* x, const double* b, double* y, int mode) {
+template <typename T>
+static void bell_spmv(knp_ctx* c, const BellMatT<T>& A, const double* x, const double* b, double* y, int mode) {
   halo0(c, x);
-  if (c->nd == 3) bell_spmv<3>(c, A, x, b, y, mode); else bell_spmv<4>(c, A, x, b, y, mode);
+  if (c->nd == 3) bell_spmv_nd<3, T>(c, A, x, b, y, mode); else bell_spmv_nd<4, T>(c, A, x, b, y, mode);
 }
-static void block_apply(knp_ctx* c, const double* dinv, const double* r, double* out, double w, int mode) {
-  if (c->nd == 3) { BlockDiagApplyKernel<3> k{dinv, r, out, w, mode}; parallel_for(cs(c), c->n_own, k); }
-  else { BlockDiagApplyKernel<4> k{dinv, r, out, w, mode}; parallel_for(cs(c), c->n_own, k); }
+template <typename T>
+static void block_apply(knp_ctx* c, const T* dinv, const double* r, double* out, double w, int mode) {
+  if (c->nd == 3) { BlockDiagApplyKernel<3, T> k{dinv, r, out, w, mode}; parallel_for(cs(c), c->n_own, k); }
+  else { BlockDiagApplyKernel<4, T> k{dinv, r, out, w, mode}; parallel_for(cs(c), c->n_own, k); }
 }
-static void bell_jacobi(knp_ctx* c, const BellMat& A, const double* dinv, const double* b,
+template <typename T>
+static void bell_jacobi(knp_ctx* c, const BellMatT<T>& A, const T* dinv, const double* b,
                         const double* xin, double* xout, double w) {
   halo0(c, xin);
-  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 192); }
-  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 256); }
+  if (c->nd == 3) { BellJacobiKernel<3, T> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 192); }
+  else { BellJacobiKernel<4, T> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 256); }
 }
 // post-smoothing sweep fused with the prolongation: out = x' + w Dinv (b - A x'), x' = xin + P xc
 // (xin may be nullptr).  The ghost entries of xin (if any) and of xc must be valid.
@@ -267,6 +271,9 @@ static void preload_solver_kernels_nd() {
   touch_kernel(pf_kernel<BellSpmvKernel<ND>>);
   touch_kernel(pf_kernel<BlockDiagApplyKernel<ND>>);
   touch_kernel(pf_kernel<BellJacobiKernel<ND>>);
+  touch_kernel(pf_kernel<BellSpmvKernel<ND, float>>);
+  touch_kernel(pf_kernel<BlockDiagApplyKernel<ND, float>>);
+  touch_kernel(pf_kernel<BellJacobiKernel<ND, float>>);
   touch_kernel(block_inverse_kernel<ND>);
 }
 static void preload_solver_kernels(knp_ctx* c) {
@@ -592,6 +599,14 @@ static double estimate_lambda_max(knp_ctx* c, AmgValues& V, const BellMat& A, co
 static void amg_refresh(knp_ctx* c, AmgValues& V, const BellMat& A0, const double* fine_values, const double* diag_blocks) {
   knp_stream_t s = cs(c);
   block_inverse(c, diag_blocks, V.binv.p);
+  if (c->opt.pc_fp32) {
+    // single-precision copies for the level-0 sweeps (they stay as they are until the next refresh)
+    const int64_t ss = c->slot_stride();
+    if (V.a32.n != (size_t)((c->nd + 1) * ss)) { V.a32.alloc((size_t)(c->nd + 1) * ss); V.binv32.alloc(ss); }
+    { DemoteKernel k{A0.diag, V.a32.p}; parallel_for(s, ss, k); }
+    { DemoteKernel k{A0.off + ss, V.a32.p + ss}; parallel_for(s, (int64_t)c->nd * ss, k); }
+    { DemoteKernel k{V.binv.p, V.binv32.p}; parallel_for(s, ss, k); }
+  }
   if (c->opt.omega > 0.0) V.omega = c->opt.omega;
   else if (V.omega <= 0.0 || ++V.age >= OMEGA_PERIOD) {
     V.omega = 4.0 / (3.0 * 1.05 * estimate_lambda_max(c, V, A0, V.binv.p));
@@ -759,12 +774,10 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
 // `presmooth0` = false drops the pre-smoothing sweep of the DG level (a V(0,1) cycle there:
 // the right-hand side is restricted directly, one matrix pass less per application).  The
 // resulting operator is not symmetric: fine for GMRES (KNP), not used with CG (EMI).
-static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const double* bj, const double* r, double* z,
-                         bool presmooth0 = true) {
-  if (c->opt.pc == 0 || !c->amg.ready) {
-    block_apply(c, bj, r, z, 1.0, 0);
-    return;
-  }
+// one V-cycle; T = the type the level-0 matrix A0 and its inverse diagonal blocks binv are stored in
+template <typename T>
+static void vcycle(knp_ctx* c, AmgValues& V, const BellMatT<T>& A0, const T* binv, const double* r, double* z,
+                   bool presmooth0) {
   AmgPlan& amg = c->amg;
   AmgLevelPlan& C = amg.lev[0];
   LevelVectors& Cv = V.vec[0];
@@ -773,23 +786,24 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
   // (measured on B200: the fused prolongation + sweep is ~2 % SLOWER than prolongation and sweep
   // as two launches - 40 extra gathers per row in a kernel that otherwise runs at 0.9 of the
   // HBM roofline - so it is opt-in)
-  const bool fused_post = c->opt.fuse_prolong && c->opt.nu_post == 1 && C.t_unit && c->opt.nu_pre == 1;
-  if (fused_post) {
-    const double* rr = r;
-    if (presmooth0) {
-      block_apply(c, V.binv.p, r, x, w, 0);
-      bell_spmv(c, A0, x, r, V.r0.p, 1);          // refreshes the ghost entries of x as well
-      rr = V.r0.p;
+  if constexpr (std::is_same<T, double>::value) {
+    if (c->opt.fuse_prolong && c->opt.nu_post == 1 && C.t_unit && c->opt.nu_pre == 1) {
+      const double* rr = r;
+      if (presmooth0) {
+        block_apply(c, binv, r, x, w, 0);
+        bell_spmv(c, A0, x, r, V.r0.p, 1);          // refreshes the ghost entries of x as well
+        rr = V.r0.p;
+      }
+      { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, rr, Cv.b.p, 0}; parallel_rows<8>(cs(c), C.n, k); }
+      coarse_cycle(c, V, 0, c->comm.active());        // ghost entries of C.x are read by the fused sweep
+      bell_jacobi_prolong(c, A0, binv, r, presmooth0 ? x : nullptr, C.pidx.p, Cv.x.p, z, w);
+      return;
     }
-    { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, rr, Cv.b.p, 0}; parallel_rows<8>(cs(c), C.n, k); }
-    coarse_cycle(c, V, 0, c->comm.active());        // ghost entries of C.x are read by the fused sweep
-    bell_jacobi_prolong(c, A0, V.binv.p, r, presmooth0 ? x : nullptr, C.pidx.p, Cv.x.p, z, w);
-    return;
   }
   const double* rr = r;
   if (presmooth0) {
-    block_apply(c, V.binv.p, r, x, w, 0);
-    for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, V.binv.p, r, x, t, w); std::swap(x, t); }
+    block_apply(c, binv, r, x, w, 0);
+    for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, binv, r, x, t, w); std::swap(x, t); }
     bell_spmv(c, A0, x, r, V.r0.p, 1);
     rr = V.r0.p;
   }
@@ -799,11 +813,26 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
   if (c->opt.nu_post == 0) { d2d(z, x, c->n * sizeof(double), cs(c)); return; }
   for (int it = 0; it < c->opt.nu_post; ++it) {
     double* out = (it + 1 == c->opt.nu_post) ? z : t;
-    bell_jacobi(c, A0, V.binv.p, r, x, out, w);
+    bell_jacobi(c, A0, binv, r, x, out, w);
     if (out != z) std::swap(x, t);
   }
   // keep the plan's buffers in their slots for the next call
   if (x != V.x0.p) std::swap(V.x0.p, V.t0.p);
+}
+
+static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const double* bj, const double* r, double* z,
+                         bool presmooth0 = true) {
+  if (c->opt.pc == 0 || !c->amg.ready) {
+    block_apply(c, bj, r, z, 1.0, 0);
+    return;
+  }
+  if (c->opt.pc_fp32 && V.a32.n) {
+    BellMat32 A32;
+    A32.nc = A0.nc; A32.nbr = A0.nbr; A32.off = V.a32.p; A32.diag = V.a32.p;
+    vcycle<float>(c, V, A32, V.binv32.p, r, z, presmooth0);
+  } else {
+    vcycle<double>(c, V, A0, V.binv.p, r, z, presmooth0);
+  }
 }
 
 // ---------------------------------------------------------------------------------

@@ -91,6 +91,14 @@ def test_solver_engineering_switches_do_not_change_the_solution(emu_lib):
         assert rel_err(c[k], ref_c[k]) < 1e-8
     # and they must not cost iterations on this case
     assert sum(st["emi_niter"]) <= sum(ref_st["emi_niter"]) + 6
+    # single-precision copies of the level-0 matrices inside the V-cycle (KNP_AMG_FP32=1; the Krylov
+    # operators and every vector stay fp64): same answer, same iteration counts
+    pm32, c32, st32 = _bundle_run(emu_lib, {"KNP_AMG_FP32": "1"})
+    assert rel_err(pm32, pm) < 1e-7
+    for k in range(3):
+        assert rel_err(c32[k], c[k]) < 1e-8
+    assert sum(st32["emi_niter"]) <= sum(st["emi_niter"]) + 2
+    assert sum(st32["knp_niter"]) <= sum(st["knp_niter"]) + 2
 
 
 def test_picard_variant(emu_lib):
