@@ -275,3 +275,37 @@ def test_run_calibration_script_unchanged(ref_env, capsys, monkeypatch):
     for key, want in (("n_init", 0.18821645700362638), ("m_init", 0.016651023270342777),
                       ("h_init", 0.8541791472445746), ("phi_M_n_init", -74.3848784437955)):
         assert abs(got[key] / want - 1.0) < 1e-10, (key, got[key], want)
+
+
+@pytest.mark.skipif(os.environ.get("KNP_SLOW_TESTS") != "1",
+                    reason="~40 s on the host emulation (48 000 tetrahedra + per-entity mesh script): set KNP_SLOW_TESTS=1")
+def test_run_check_calibration_script_unchanged(ref_env):
+    """run_check_calibration.py: the full KNP-EMI system started from the calibrated ODE steady state
+    (neuron mm_hh on tag 1, glia mm_glial on tag 2, no stimulus) must stay at rest - the reference's
+    own verification that the calibration is consistent with the PDE model.  The script imports its
+    mesh generator under a module name that does not exist in the checkout
+    (`make_mesh_3D_two_tags`, run_check_calibration.py:171; the file is make_mesh.py): the test
+    supplies make_mesh.py under that name, nothing else is touched."""
+    for name in ("run_check_calibration.py", "mm_hh.py", "mm_glial.py"):
+        shutil.copy(os.path.join(EMIX, name), ref_env / name)
+    shutil.copy(os.path.join(EMIX, "make_mesh.py"), ref_env / "make_mesh_3D_two_tags.py")
+    for mod in ("mm_hh", "mm_glial", "make_mesh_3D_two_tags"):
+        sys.modules.pop(mod, None)
+    try:
+        g = runpy.run_path(str(ref_env / "run_check_calibration.py"), run_name="__main__")
+    finally:
+        for mod in ("mm_hh", "mm_glial", "make_mesh_3D_two_tags"):
+            sys.modules.pop(mod, None)
+    S = g["S"]
+    assert S.engine.k == 10
+    assert (ref_env / "meshes/3D_two_tags/subdomains_0.pvd").exists()
+    d = np.load(ref_env / "results/data/calibration/results.npz", allow_pickle=True)
+    phi, sub = d["potential"], d["subdomains"]
+    mean = lambda k: np.array([p[sub == k].mean() for p in phi])
+    neuron, glia = mean(1) - mean(0), mean(2) - mean(0)
+    assert np.all(np.abs(neuron + 74.3848784437955) < 2e-3)          # mV; emix-simulations/mm_hh.py:14
+    assert np.all(np.abs(glia + 83.08511451850003) < 2e-3)           # emix-simulations/mm_glial.py:11
+    assert np.abs(neuron[-1] - neuron[0]) < 1e-4 and np.abs(glia[-1] - glia[0]) < 1e-4
+    c0, c1 = d["concentrations"][0], d["concentrations"][-1]
+    assert np.abs(c1 / c0 - 1.0).max() < 1e-4                          # concentrations at rest too
+    assert max(S.engine.stats["emi_niter"][1:]) <= 2                   # the previous potential already solves the system
