@@ -35,6 +35,11 @@ struct SolverOptions {
   // bench workload (profiles/); KNP_KNP_PRESMOOTH=1 in the environment restores V(1,1)
   bool knp_presmooth0 = false;
   bool pc_fp32 = false;         // KNP_AMG_FP32=1: level-0 sweeps of the preconditioner read fp32 copies of the matrix
+  // KNP_AMG_CHEBY=2: degree-2 Chebyshev (block-Jacobi preconditioned) instead of one damped block-Jacobi
+  // sweep before and after the coarse correction of the EMI V-cycle.  Halves the CG iteration count on
+  // irregular meshes (two-level experiment) at 2 more level-0 sweeps per cycle; no gain
+  // where the extrapolated initial guess already leaves 0-3 iterations (the bench workload)
+  int cheby = 1;
   bool fuse_prolong = false;    // KNP_FUSE_PROLONG=1
   // initial guess of the EMI solve = 2 phi_n - phi_{n-1} instead of phi_n (the reference starts
   // from phi_n, solver.py:431 `ksp_initial_guess_nonzero`); same stopping test, fewer iterations.

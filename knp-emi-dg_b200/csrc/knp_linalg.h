@@ -79,13 +79,16 @@ struct BlockDiagApplyKernel {
 // between the ND lanes that own its rows with warp shuffles (ND = 4: groups of 4 lanes
 // never straddle a warp; ND = 3: each lane recomputes the cell's other rows, the loads
 // are warp broadcasts).
-template <int ND, typename T = double>
+// MOM: second step of a degree-2 Chebyshev smoother, xout = xin + beta (xin - xprev) + w Dinv (b - A xin)
+// (xprev == nullptr: zero; xout may alias xprev - a thread touches only its own row of both).
+template <int ND, typename T = double, bool MOM = false>
 struct BellJacobiKernel {
   BellMatT<T> A; const T* dinv; const double* b; const double* xin; double* xout; double w;
   // optional fused prolongation (post-smoothing of the V-cycle): the sweep runs on
   // x' = xin + P xc with (P xc)_d = xc[agg[d]] (unit aggregation transfer); xin == nullptr
   // means x' = P xc (no pre-smoothed iterate)
   const int32_t* agg = nullptr; const double* xc = nullptr;
+  const double* xprev = nullptr; double beta = 0.0;   // MOM only
   KNP_HD double xval(int64_t d) const {
     double v = xin ? xin[d] : 0.0;
     if (agg) v += xc[agg[d]];
@@ -129,7 +132,12 @@ struct BellJacobiKernel {
     double acc = 0.0;
 #pragma unroll
     for (int j = 0; j < ND; ++j) acc += (double)di[j] * r[j];
-    xout[row] = xval(row) + w * acc;
+    if constexpr (MOM) {
+      const double xv = xval(row);
+      xout[row] = xv + beta * (xv - (xprev ? xprev[row] : 0.0)) + w * acc;
+    } else {
+      xout[row] = xval(row) + w * acc;
+    }
   }
 };
 

@@ -66,6 +66,19 @@ static void bell_jacobi(knp_ctx* c, const BellMatT<T>& A, const T* dinv, const d
   if (c->nd == 3) { BellJacobiKernel<3, T> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 192); }
   else { BellJacobiKernel<4, T> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 256); }
 }
+// second Chebyshev step: xout = xin + beta (xin - xprev) + w Dinv (b - A xin); xprev may be nullptr (zero)
+template <typename T>
+static void bell_jacobi_mom(knp_ctx* c, const BellMatT<T>& A, const T* dinv, const double* b, const double* xin,
+                            const double* xprev, double* xout, double w, double beta) {
+  halo0(c, xin);
+  if (c->nd == 3) {
+    BellJacobiKernel<3, T, true> k{A, dinv, b, xin, xout, w, nullptr, nullptr, xprev, beta};
+    parallel_for(cs(c), c->n_own, k, 192);
+  } else {
+    BellJacobiKernel<4, T, true> k{A, dinv, b, xin, xout, w, nullptr, nullptr, xprev, beta};
+    parallel_for(cs(c), c->n_own, k, 256);
+  }
+}
 // post-smoothing sweep fused with the prolongation: out = x' + w Dinv (b - A x'), x' = xin + P xc
 // (xin may be nullptr).  The ghost entries of xin (if any) and of xc must be valid.
 static void bell_jacobi_prolong(knp_ctx* c, const BellMat& A, const double* dinv, const double* b,
@@ -274,6 +287,8 @@ static void preload_solver_kernels_nd() {
   touch_kernel(pf_kernel<BellSpmvKernel<ND, float>>);
   touch_kernel(pf_kernel<BlockDiagApplyKernel<ND, float>>);
   touch_kernel(pf_kernel<BellJacobiKernel<ND, float>>);
+  touch_kernel(pf_kernel<BellJacobiKernel<ND, double, true>>);
+  touch_kernel(pf_kernel<BellJacobiKernel<ND, float, true>>);
   touch_kernel(block_inverse_kernel<ND>);
 }
 static void preload_solver_kernels(knp_ctx* c) {
@@ -777,12 +792,29 @@ static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
 // one V-cycle; T = the type the level-0 matrix A0 and its inverse diagonal blocks binv are stored in
 template <typename T>
 static void vcycle(knp_ctx* c, AmgValues& V, const BellMatT<T>& A0, const T* binv, const double* r, double* z,
-                   bool presmooth0) {
+                   bool presmooth0, int cheby) {
   AmgPlan& amg = c->amg;
   AmgLevelPlan& C = amg.lev[0];
   LevelVectors& Cv = V.vec[0];
   const double w = V.omega;
   double* x = V.x0.p; double* t = V.t0.p;
+  if (cheby == 2 && presmooth0) {
+    // degree-2 Chebyshev in Dinv A on [lmax / 4, lmax], lmax = 1.05 x the estimate behind V.omega; the
+    // same polynomial before and after the coarse correction keeps the cycle symmetric (CG)
+    const double lmax = 4.0 / (3.0 * w), lmin = 0.25 * lmax;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+    const double sigma = theta / delta, rho0 = 1.0 / sigma, rho1 = 1.0 / (2.0 * sigma - rho0);
+    const double w1 = 1.0 / theta, w2 = 2.0 * rho1 / delta, beta = rho1 * rho0;
+    block_apply(c, binv, r, t, w1, 0);                                   // x1 = w1 Dinv r         (x0 = 0)
+    bell_jacobi_mom(c, A0, binv, r, t, (const double*)nullptr, x, w2, beta);   // x2
+    bell_spmv(c, A0, x, r, V.r0.p, 1);
+    { TransferRowsKernel k{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, V.r0.p, Cv.b.p, 0}; parallel_rows<8>(cs(c), C.n, k); }
+    coarse_cycle(c, V, 0, false);
+    transfer(c, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, Cv.x.p, x, 1);
+    bell_jacobi(c, A0, binv, r, x, t, w1);                               // x1' from x0' = x
+    bell_jacobi_mom(c, A0, binv, r, t, x, z, w2, beta);                  // x2' -> z
+    return;
+  }
   // (measured on B200: the fused prolongation + sweep is ~2 % SLOWER than prolongation and sweep
   // as two launches - 40 extra gathers per row in a kernel that otherwise runs at 0.9 of the
   // HBM roofline - so it is opt-in)
@@ -822,6 +854,7 @@ static void vcycle(knp_ctx* c, AmgValues& V, const BellMatT<T>& A0, const T* bin
 
 static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const double* bj, const double* r, double* z,
                          bool presmooth0 = true) {
+  const int cheby = presmooth0 ? c->opt.cheby : 1;      // the symmetric (EMI) cycle only
   if (c->opt.pc == 0 || !c->amg.ready) {
     block_apply(c, bj, r, z, 1.0, 0);
     return;
@@ -829,9 +862,9 @@ static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const doub
   if (c->opt.pc_fp32 && V.a32.n) {
     BellMat32 A32;
     A32.nc = A0.nc; A32.nbr = A0.nbr; A32.off = V.a32.p; A32.diag = V.a32.p;
-    vcycle<float>(c, V, A32, V.binv32.p, r, z, presmooth0);
+    vcycle<float>(c, V, A32, V.binv32.p, r, z, presmooth0, cheby);
   } else {
-    vcycle<double>(c, V, A0, V.binv.p, r, z, presmooth0);
+    vcycle<double>(c, V, A0, V.binv.p, r, z, presmooth0, cheby);
   }
 }
 

@@ -94,6 +94,12 @@ def test_solver_engineering_switches_do_not_change_the_solution(emu_lib):
     # single-precision copies of the level-0 matrices inside the V-cycle (KNP_AMG_FP32=1; the Krylov
     # operators and every vector stay fp64): same answer, same iteration counts
     pm32, c32, st32 = _bundle_run(emu_lib, {"KNP_AMG_FP32": "1"})
+    # degree-2 Chebyshev smoothing in the EMI V-cycle (KNP_AMG_CHEBY=2), together with the fp32 copies
+    pmc, cc, stc = _bundle_run(emu_lib, {"KNP_AMG_CHEBY": "2", "KNP_AMG_FP32": "1"})
+    assert rel_err(pmc, pm) < 1e-7
+    for k in range(3):
+        assert rel_err(cc[k], c[k]) < 1e-8
+    assert sum(stc["emi_niter"]) <= sum(st["emi_niter"])
     assert rel_err(pm32, pm) < 1e-7
     for k in range(3):
         assert rel_err(c32[k], c[k]) < 1e-8
