@@ -37,6 +37,9 @@ def ref_env(tmp_path, monkeypatch, emu_lib):
     monkeypatch.chdir(tmp_path)
     monkeypatch.syspath_prepend(SHIMS)
     monkeypatch.syspath_prepend(str(tmp_path))
+    # run_MMS_time.py generates its mesh with os.system('python3 make_mesh_MMS.py ...'): the child needs the
+    # dolfin stand-in and the package on its path too
+    monkeypatch.setenv("PYTHONPATH", os.pathsep.join([SHIMS, PKG, os.environ.get("PYTHONPATH", "")]))
     if not hasattr(np, "float_"):                      # the reference predates numpy 2
         monkeypatch.setattr(np, "float_", np.float64, raising=False)
     from knpemidg import _lib
