@@ -15,6 +15,8 @@ and keeps the small amount of host state (step counter, times, statistics).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -128,6 +130,13 @@ class Engine:
         tau = 20.0 * self.d * degree                                   # solver.py:110-111
         ext = mesh.coords.max(axis=0) - mesh.coords.min(axis=0)
         Lp = float(ext.max())                                          # solver.py:383-391
+        # The EMI preconditioner matrix B = A + kappa/Lp^2 (u, v) (solver.py:393-395) over-weights the
+        # constants of compact intracellular regions when the box is much larger than the cells: on the
+        # reference's EMIx mesh the kappa/Lp^2 |cell| of a cell is ~70x its membrane coupling C_phi |membrane|,
+        # which leaves one outlying eigenvalue per cell in M^-1 A (a 16-iteration CG plateau).
+        # KNP_EMI_LP_SCALE=10 divides the shift by 100: 47 -> 14 CG iterations there, same solution (B
+        # only preconditions).  Default 1 = the reference's B.
+        Lp *= float(os.environ.get("KNP_EMI_LP_SCALE", "1"))
 
         def table(sub):
             return [float(sub[int(t)]) if int(t) in sub else 0.0 for t in self.tags]

@@ -131,7 +131,13 @@ def test_run_mms_space_script_unchanged(ref_env):
 def test_run_mms_time_script_unchanged(ref_env):
     """tests/run_MMS_time.py + tests/mms_time.py: first order in time.  Last verified in the build
     container: rates 0.88, 0.94, 0.975, 0.989, 0.995, 0.997 (concentrations) and
-    0.75, 0.91, 0.96, 0.98, 0.99, 0.996 (potential) for dt = 1e-2 / 2^i, i = 1..7."""
+    0.75, 0.91, 0.96, 0.98, 0.99, 0.996 (potential) for dt = 1e-2 / 2^i, i = 1..7.
+    The script expects the resolution-6 mesh that run_MMS_space.py leaves behind in the same directory
+    (its own fallback, os.system('python3 make_mesh_MMS.py 6') at run_MMS_time.py:35-37, passes an
+    argument the mesh script does not accept), so the mesh is generated here the way run_MMS_space.py:71-72
+    does it - with the reference's own make_mesh_MMS.main."""
+    import make_mesh_MMS
+    make_mesh_MMS.main(["-r", "6", "-d", str(ref_env / "meshes/MMS") + "/"])
     g = runpy.run_path(str(ref_env / "run_MMS_time.py"), run_name="__main__")
     for key in ("rates_ca", "rates_cb", "rates_cc", "rates_phi"):
         rates = np.array(g[key], dtype=float)

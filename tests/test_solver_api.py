@@ -50,8 +50,8 @@ def test_mms_time_rates_through_the_product_path(emu_lib):
     assert np.all(np.diff(rates, axis=0) > 0)          # approaching 1 from below
 
 
-def _bundle_run(lib, env, nsteps=6):
-    """a few steps of the small 3D bundle under the given library environment switches"""
+def _bundle_run(lib, env, nsteps=6, mesh_fn=None):
+    """a few steps of the small 3D bundle (or of mesh_fn()) under the given environment switches"""
     import os
     import bench
     from knpemidg.engine import Engine
@@ -60,7 +60,7 @@ def _bundle_run(lib, env, nsteps=6):
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
     try:
-        mesh, sub, surf = kmesh.bundle_3d_mesh(0)
+        mesh, sub, surf = mesh_fn() if mesh_fn else kmesh.bundle_3d_mesh(0)
         eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), lib=lib, **bench.PHYS)
         eng.set_concentrations_by_tag(bench.C_INIT)
         eng.add_membrane_model(1, mm_hh, bench.ION_NAMES, stimulus=bench.STIMULUS, stimulus_locator=bench.stim_locator)
@@ -105,6 +105,24 @@ def test_solver_engineering_switches_do_not_change_the_solution(emu_lib):
         assert rel_err(c32[k], c[k]) < 1e-8
     assert sum(st32["emi_niter"]) <= sum(st["emi_niter"]) + 2
     assert sum(st32["knp_niter"]) <= sum(st["knp_niter"]) + 2
+
+
+def test_smaller_preconditioner_shift_for_compact_cells(emu_lib):
+    """KNP_EMI_LP_SCALE: compact cells in a large box (the EMIx geometry) - the mass shift kappa/Lp^2 of
+    the reference's preconditioner matrix B outweighs the membrane coupling of each cell and costs CG
+    iterations; a 100x smaller shift gives the same solution in fewer iterations"""
+    from common import kmesh
+
+    def mesh_fn():
+        mesh, sub, surf = kmesh.emix_like_mesh(12, n_cells=6, length=4.0e-5)
+        sub.array()[sub.array() == 2] = 1            # one intracellular tag (bench.C_INIT / D_sub know 0 and 1)
+        return mesh, sub, surf
+    pm, c, st = _bundle_run(emu_lib, {"KNP_EXTRAPOLATE": "0"}, nsteps=3, mesh_fn=mesh_fn)
+    pm2, c2, st2 = _bundle_run(emu_lib, {"KNP_EXTRAPOLATE": "0", "KNP_EMI_LP_SCALE": "10"}, nsteps=3, mesh_fn=mesh_fn)
+    assert rel_err(pm2, pm) < 1e-7
+    for k in range(3):
+        assert rel_err(c2[k], c[k]) < 1e-8
+    assert sum(st2["emi_niter"]) < sum(st["emi_niter"]), (st["emi_niter"], st2["emi_niter"])
 
 
 def test_picard_variant(emu_lib):
