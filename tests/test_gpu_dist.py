@@ -13,7 +13,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world,case", [(2, "bundle_r0"), (2, "bundle_r0_quad")])
+@pytest.mark.parametrize("world,case", [(2, "bundle_r0"), (2, "bundle_r0_quad"), (2, "unstr3d")])
 def test_nccl_partitioned_run_matches_single_gpu(gpu_lib, tmp_path, world, case):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
