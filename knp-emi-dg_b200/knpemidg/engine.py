@@ -107,6 +107,7 @@ class Engine:
         facet_tags = np.asarray(facet_tags)
         self.tags = np.unique(cell_tags)
         self.nc_global = mesh.cells.shape[0]
+        self._global_cell_tags = cell_tags
         self.global_membrane_facets = np.flatnonzero(
             (mesh.facet_cells[:, 1] >= 0) & np.isin(facet_tags, [int(t) for t in membrane_tags]))
         if self.transport is not None:
@@ -135,8 +136,11 @@ class Engine:
         # reference's EMIx mesh the kappa/Lp^2 |cell| of a cell is ~70x its membrane coupling C_phi |membrane|,
         # which leaves one outlying eigenvalue per cell in M^-1 A (a 16-iteration CG plateau).
         # KNP_EMI_LP_SCALE=10 divides the shift by 100: 47 -> 14 CG iterations there, same solution (B
-        # only preconditions).  Default 1 = the reference's B.
-        Lp *= float(os.environ.get("KNP_EMI_LP_SCALE", "1"))
+        # only preconditions).  Default 1 = the reference's B; "auto" picks the scale from the geometry at
+        # initialize() (see _auto_lp_scale).
+        self._lp_mode = os.environ.get("KNP_EMI_LP_SCALE", "1")
+        if self._lp_mode != "auto":
+            Lp *= float(self._lp_mode)
 
         def table(sub):
             return [float(sub[int(t)]) if int(t) in sub else 0.0 for t in self.tags]
@@ -265,6 +269,11 @@ class Engine:
         """What the reference does before the loop: initial Nernst potentials
         (setup_varform_emi, solver.py:299) and the first assembly (setup_solver_*,
         :452-453, 710); here the first assembly also fixes the AMG plan."""
+        if self._lp_mode == "auto":
+            scale = self._auto_lp_scale()
+            if scale > 1.0:
+                self._params["Lp"] *= scale
+                self.ctx.set_params(splitting=self.splitting, **self._params)
         self.ctx.post_step(_lib.POST_NERNST)
         self.ctx.assemble_emi()
         if pc == 1:
@@ -272,6 +281,33 @@ class Engine:
             self.amg_ready = True
         self.ctx.solver_options(pc=pc)
         self._initialized = True
+
+    def _auto_lp_scale(self):
+        """KNP_EMI_LP_SCALE=auto: the factor on Lp that brings the mass shift kappa |region| / Lp^2 of the
+        preconditioner matrix B down to the membrane coupling C_phi |membrane| of every intracellular
+        region (1 where it already is below, e.g. the long thin axons of the bundle: B then is the
+        reference's).  Whole-mesh quantities from the initial state; setup-time host code."""
+        mesh, tags = self.global_mesh, self._global_cell_tags
+        vol = mesh.cell_volume()
+        X = mesh.coords[mesh.facet_verts[self.global_membrane_facets]]
+        if mesh.gdim == 3:
+            area = 0.5 * np.linalg.norm(np.cross(X[:, 1] - X[:, 0], X[:, 2] - X[:, 0]), axis=1)
+        else:
+            area = np.linalg.norm(X[:, 1] - X[:, 0], axis=1)
+        fc = mesh.facet_cells[self.global_membrane_facets]
+        side = np.maximum(tags[fc[:, 0]], tags[fc[:, 1]])                # the intracellular side
+        P = self._params
+        psi = P["F"] / (P["R"] * P["T"])
+        c = [self.concentration(k, gather=True).mean(axis=1) for k in range(self.N)]
+        worst = 0.0
+        for ti, t in enumerate(self.tags):
+            sel = side == t
+            if not sel.any():
+                continue
+            cells = tags == t
+            kappa = P["F"] * psi * sum(P["z"][k] ** 2 * P["D"][k][ti] * float(c[k][cells].mean()) for k in range(self.N))
+            worst = max(worst, kappa * vol[cells].sum() / (P["Lp"] ** 2 * P["C_phi"] * area[sel].sum()))
+        return float(np.sqrt(worst)) if worst > 1.0 else 1.0
 
     def ode_phase(self):
         for m in self.members:

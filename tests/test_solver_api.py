@@ -123,6 +123,14 @@ def test_smaller_preconditioner_shift_for_compact_cells(emu_lib):
     for k in range(3):
         assert rel_err(c2[k], c[k]) < 1e-8
     assert sum(st2["emi_niter"]) < sum(st["emi_niter"]), (st["emi_niter"], st2["emi_niter"])
+    # "auto": the scale that brings the shift of every region down to its membrane coupling ...
+    pm3, c3, st3 = _bundle_run(emu_lib, {"KNP_EXTRAPOLATE": "0", "KNP_EMI_LP_SCALE": "auto"}, nsteps=3, mesh_fn=mesh_fn)
+    assert rel_err(pm3, pm) < 1e-7
+    assert sum(st3["emi_niter"]) < sum(st["emi_niter"])
+    # ... and 1 (the reference's B, bit for bit the same run) for the long thin axons of the bench geometry
+    a = _bundle_run(emu_lib, {"KNP_EMI_LP_SCALE": "auto"}, nsteps=2)
+    b = _bundle_run(emu_lib, {}, nsteps=2)
+    assert np.array_equal(a[0], b[0]) and a[2] == b[2]
 
 
 def test_picard_variant(emu_lib):
