@@ -126,6 +126,34 @@ def build_engine(dims, device, transport=None, nblocks=1):
     return eng
 
 
+# BASELINE configs[4]: EMIx-style tissue block, ms / cm / mV units, calibrated initial state
+# (examples/emix-simulations/run_EMIx_simulation.py:56-147, 249); a second workload for A/B runs of the
+# solver switches on compact cells (`--emix M`), not the headline line
+EMIX_DT, EMIX_CM = 0.1, 2.0
+EMIX_PHYS = dict(F=96485e3, R=8.314e3, T=300e3, C_M=EMIX_CM, C_phi=EMIX_CM / EMIX_DT, dt=EMIX_DT, z=[1.0, -1.0, 1.0],
+                 D_sub=[{t: d for t in (0, 1, 2)} for d in (1.96e-8, 2.03e-8, 1.33e-8)],
+                 rho_sub={0: 0.0, 1: 0.0, 2: 0.0})
+_K = {0: 3.3236967382613933, 1: 102.75563828644862, 2: 124.15397583492471}       # ECS, glia, neuron
+_NA = {0: 100.71925900028181, 1: 12.39731187972181, 2: 12.838513108606818}
+EMIX_C_INIT = [_K, {t: _K[t] + _NA[t] for t in _K}, _NA]                           # K, Cl, Na
+
+
+def build_engine_emix(M, device, transport=None, lib=None):
+    from knpemidg import mesh as kmesh
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_glial_emix, mm_hh_emix
+    mesh, sub, surf = kmesh.emix_like_mesh(M, n_cells=100, length=1.0e-3)
+    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), device=device, transport=transport,
+                 lib=lib, **EMIX_PHYS)
+    eng.set_concentrations_by_tag(EMIX_C_INIT)
+    stim = {"stim_amplitude": 5.0}
+    locator = lambda x: x[0] < 3.0e-4                                              # noqa: E731
+    eng.add_membrane_model(1, mm_glial_emix, ION_NAMES, stimulus=stim, stimulus_locator=locator)
+    eng.add_membrane_model(2, mm_hh_emix, ION_NAMES, stimulus=stim, stimulus_locator=locator)
+    eng.initialize(pc=1)
+    return eng
+
+
 def cpu_reference_steps(nsteps, dims=SAMPLE_DIMS):
     """The CPU restatement (oracle/) stepping the same kind of workload on a bounded
     sample; returns (seconds per step, dofs of the sample, timers)."""
@@ -225,6 +253,9 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=("weak", "strong"))
     ap.add_argument("--dims", default=None, help="nx,ny,nz override (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--emix", type=int, default=0, metavar="M",
+                    help="second workload (BASELINE configs[4]): EMIx-like block of M^3 x 6 tets, ~100 cells; "
+                         "M = 66 gives 20.7 M DOFs.  For A/B runs of solver switches; fixed mesh (strong scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -269,7 +300,11 @@ def main():
 
     nblocks = world if args.scaling == "weak" else 1
     progress("building the engine")
-    eng = build_engine(dims, local_rank, transport, nblocks)
+    if args.emix:
+        args.scaling, args.no_cpu_baseline = "strong", True
+        eng = build_engine_emix(args.emix, local_rank, transport)
+    else:
+        eng = build_engine(dims, local_rank, transport, nblocks)
     progress("engine ready")
     ctx = eng.ctx
     dofs = eng.dofs()                                  # of the whole (partitioned) mesh
@@ -386,6 +421,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "DOF-steps/s", "h2d_bytes_per_step": bytes_dir,
                     "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps, "steps_per_s": e2e_steps / (ms_e2e * 1e-3)},
             "gpu_launches": launches, "comm": comm_info, "comm_latency": comm_us, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    if args.emix:
+        line["config"]["workload"] = (f"EMIx-like tissue block {args.emix}^3 x 6 tets, ~100 cells (BASELINE configs[4]), "
+                                      f"{eng.nc_global} cells, {dofs} DOFs, mm_hh + mm_glial membranes, dt=0.1 ms")
+        line["roofline"]["traffic"] = None          # the ncu capture behind TRAFFIC_SPMV is of the bundle workload
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -133,6 +133,23 @@ def test_smaller_preconditioner_shift_for_compact_cells(emu_lib):
     assert np.array_equal(a[0], b[0]) and a[2] == b[2]
 
 
+def test_bench_emix_workload_builder(emu_lib, monkeypatch):
+    """bench.py --emix M (BASELINE configs[4], the A/B workload for solver switches): glia stay at their
+    calibrated rest, stimulated neurons depolarise, and the geometry-aware shift saves CG iterations"""
+    import bench
+    its = {}
+    for mode in ("1", "auto"):
+        monkeypatch.setenv("KNP_EMI_LP_SCALE", mode)
+        eng = bench.build_engine_emix(12, 0, lib=emu_lib)
+        for _ in range(3):
+            eng.step()
+        its[mode] = sum(eng.stats["emi_niter"])
+        pm = eng.phi_M()
+        assert abs(pm.min() + 83.085) < 0.05 and pm.max() > -60.0            # mV
+        assert max(eng.stats["knp_niter"]) <= 8
+    assert its["auto"] < its["1"], its
+
+
 def test_picard_variant(emu_lib):
     """solve_for_time_step_picard (solver.py:850-927): converges in a few iterations at the
     reference's time step and stays close to the split step it refines"""
