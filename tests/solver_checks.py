@@ -144,3 +144,26 @@ def run_mms_time(lib, i, r=3, dt0=1.0e-2):
     errs = [mm.l2_error(P, uh[0].nodal(), "c", 0), mm.l2_error(P, uh[1].nodal(), "c", 1),
             mm.l2_error(P, uh[2].nodal(), "phi", mean_free=True)]
     return np.array(errs), S, L
+
+
+def run_emix_block(lib, M, nsteps, rtol_emi=1e-12, rtol_knp=1e-13):
+    """bench.py's second workload (BASELINE configs[4]: EMIx-like block, three cell tags, mm_glial on tag 1 and
+    mm_hh on tag 2, ms / cm / mV units, calibrated initial state, synaptic stimulus) through the engine
+    and through the oracle; returns (engine, oracle)"""
+    import bench
+    from knpemidg.models import mm_glial_emix, mm_hh_emix
+    eng = bench.build_engine_emix(M, 0, lib=lib)
+    eng.rtol_emi, eng.rtol_knp = rtol_emi, rtol_knp
+    mesh = eng.global_mesh
+    sub, surf = eng._global_cell_tags, None
+    mesh2, sub2, surf2 = kmesh.emix_like_mesh(M, n_cells=100, length=1.0e-3)          # same seeded generator
+    assert np.array_equal(mesh2.cells, mesh.cells) and np.array_equal(sub2.array(), sub)
+    P = forms.Problem(mesh2, sub2.array(), surf2.array(), membrane_tags=(1, 2), **bench.EMIX_PHYS)
+    c0 = np.stack([np.choose(sub2.array(), [ci[0], ci[1], ci[2]])[:, None] * np.ones((P.nc, P.nd))
+                   for ci in bench.EMIX_C_INIT])
+    O = stepper.OracleSolver(P, c0, models={1: mm_glial_emix, 2: mm_hh_emix}, stimulus={"stim_amplitude": 5.0},
+                             stimulus_locator=lambda x: x[0] < 3.0e-4, ion_names=["K", "Cl", "Na"])
+    for _ in range(nsteps):
+        eng.step()
+    O.run(nsteps)
+    return eng, O

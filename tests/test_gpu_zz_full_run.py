@@ -36,3 +36,14 @@ def test_calibration_run_lands_on_the_reference_values(gpu_lib):
     """known answer from the reference's own calibration run (tests/parity_checks.py:check_calibration_kat);
     100 000 launches of the ODE kernel on one membrane point"""
     pc.check_calibration_kat(gpu_lib)
+
+
+def test_emix_block_matches_oracle(gpu_lib):
+    """GPU twin of tests/test_solver_api.py::test_emix_block_matches_oracle (bench.py --emix workload at
+    test size: glial + neuronal membranes, ms/cm/mV units), four steps"""
+    eng, O = sc.run_emix_block(gpu_lib, 9, 4)
+    assert eng.phi_M().max() > -60.0
+    assert rel_err(eng.phi_M(), O.phi_M) < 1e-6
+    for k in range(2):
+        assert rel_err(eng.concentration(k), O.c[k]) < 1e-9
+    assert rel_err(eng.concentration(2), O.c_elim) < 1e-9

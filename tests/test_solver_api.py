@@ -150,6 +150,17 @@ def test_bench_emix_workload_builder(emu_lib, monkeypatch):
     assert its["auto"] < its["1"], its
 
 
+def test_emix_block_matches_oracle(emu_lib):
+    """three cell tags, glial + neuronal membrane models side by side, ms/cm/mV units, synaptic stimulus:
+    the engine against the oracle's time loop (north_star trace tolerance 1e-6)"""
+    eng, O = sc.run_emix_block(emu_lib, 9, 2)
+    assert eng.phi_M().max() > -60.0 and abs(eng.phi_M().min() + 83.085) < 0.01      # a neuron fires, glia rest
+    assert rel_err(eng.phi_M(), O.phi_M) < 1e-6
+    for k in range(2):
+        assert rel_err(eng.concentration(k), O.c[k]) < 1e-9
+    assert rel_err(eng.concentration(2), O.c_elim) < 1e-9
+
+
 def test_picard_variant(emu_lib):
     """solve_for_time_step_picard (solver.py:850-927): converges in a few iterations at the
     reference's time step and stays close to the split step it refines"""
