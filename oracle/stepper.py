@@ -64,8 +64,11 @@ class OracleSolver:
             for tag, module in models.items():
                 rows = np.flatnonzero(P.mem_tag == tag)
                 m = {"tag": tag, "module": module, "rows": rows,
-                     "states": np.array([module.init_state_values() for _ in rows]),
-                     "parameters": np.array([module.init_parameter_values() for _ in rows]),
+                     # (reshape: a tag without facets gives empty tables, not 1-D arrays)
+                     "states": np.array([module.init_state_values() for _ in rows]).reshape(
+                         len(rows), len(module.init_state_values())),
+                     "parameters": np.array([module.init_parameter_values() for _ in rows]).reshape(
+                         len(rows), len(module.init_parameter_values())),
                      "time": 0.0}
                 m["parameters"][:, module.parameter_indices("Cm")] = P.C_M      # solver.py:248
                 if stimulus_locator is None:

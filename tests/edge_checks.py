@@ -96,3 +96,15 @@ def check_nonconvergence_raises(lib):
     eng.ctx.assemble_knp()
     with pytest.raises(_lib.KnpError, match="did not converge"):
         eng.ctx.solve_knp(1e-15, 1e-300, 1)
+
+
+def check_model_without_facets(lib):
+    """a membrane model registered for a tag that no facet carries (an EMIx-like block in which only glia
+    were placed): empty ODE tables on both sides, the run goes on and agrees with the oracle"""
+    import solver_checks as sc
+    from common import rel_err
+    eng, O = sc.run_emix_block(lib, 8, 2)
+    tags = np.bincount(eng.mem["tag"], minlength=3)
+    assert tags[1] > 0 and tags[2] == 0
+    assert [m.rows.size for m in eng.members] == [int(tags[1]), 0]
+    assert rel_err(eng.phi_M(), O.phi_M) < 1e-6

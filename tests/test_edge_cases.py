@@ -16,3 +16,7 @@ def test_contract_violations_raise(emu_lib):
 
 def test_krylov_nonconvergence_raises(emu_lib):
     ec.check_nonconvergence_raises(emu_lib)
+
+
+def test_membrane_model_without_facets(emu_lib):
+    ec.check_model_without_facets(emu_lib)

@@ -4,6 +4,7 @@ test_traces_over_an_action_potential_match_oracle, and a 200-step run on the hos
 membrane potential - pass).  Runs last so that a surprise here cannot hide the rest of the GPU suite."""
 import pytest
 
+import edge_checks as ec
 import parity_checks as pc
 import solver_checks as sc
 from common import rel_err
@@ -47,3 +48,8 @@ def test_emix_block_matches_oracle(gpu_lib):
     for k in range(2):
         assert rel_err(eng.concentration(k), O.c[k]) < 1e-9
     assert rel_err(eng.concentration(2), O.c_elim) < 1e-9
+
+
+def test_membrane_model_without_facets(gpu_lib):
+    """GPU twin of tests/test_edge_cases.py::test_membrane_model_without_facets (empty ODE tables)"""
+    ec.check_model_without_facets(gpu_lib)
