@@ -170,3 +170,26 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=float)
     den = np.abs(b).max()
     return np.abs(a - b).max() / (den if den > 0 else 1.0)
+
+
+def entrywise_failures(a, b, rtol=1e-12, row_floor=1e-14):
+    """Entry-by-entry comparison (north_star: "entries must agree within 1e-12 relative"):
+    an entry fails when |a - b| > rtol |b| + row_floor max|row of b|.  The row-relative floor is
+    what round-off in the sum of a row's contributions allows for entries that cancel to (almost)
+    zero.  Returns (number of failing entries, worst |a - b| / bound)."""
+    import scipy.sparse as sp
+    if sp.issparse(a) or sp.issparse(b):
+        a, b = sp.csr_matrix(a), sp.csr_matrix(b)
+        d = (a - b).tocoo()
+        if d.nnz == 0:
+            return 0, 0.0
+        rowmax = np.asarray(abs(b).max(axis=1).todense()).ravel()
+        bv = np.abs(np.asarray(b[d.row, d.col]).ravel())
+        bound = rtol * bv + row_floor * rowmax[d.row]
+        ratio = np.abs(d.data) / np.maximum(bound, 1e-300)
+        return int((ratio > 1.0).sum()), float(ratio.max())
+    a = np.asarray(a, dtype=float).ravel()
+    b = np.asarray(b, dtype=float).ravel()
+    bound = rtol * np.abs(b) + row_floor * np.abs(b).max()
+    ratio = np.abs(a - b) / np.maximum(bound, 1e-300)
+    return int((ratio > 1.0).sum()), float(ratio.max()) if ratio.size else 0.0

@@ -1,0 +1,232 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ref_*.npz by EXECUTING the reference (adajel/KNP-EMI-DG, /root/reference,
+unmodified) on top of the numeric dolfin / petsc4py / numbalsoda stand-ins of oracle/refexec.
+
+    python tests/golden/make_reference_golden.py [outdir]          (this container only)
+
+Every fixture holds the mesh, the parameters and the seeded input fields of one case together
+with what the reference's own code produced from them:
+
+  ref_forms_<case>.npz   assemble(S.a_emi), assemble(S.L_emi), assemble(S.B_emi), assemble(S.A_knp),
+                         assemble(S.L_knp) after S.setup_varform_emi() / S.setup_varform_knp()
+                         (src/knpemidg/solver.py:270-403, 534-663) and the state after one
+                         S.solve_for_time_step() (solver.py:794-847: phi, c, phi_M, Nernst potentials,
+                         eliminated ion) - cases 2d (splitting), 2d_nosplit, 3d (three cell tags,
+                         two membrane tags, region-dependent D, rho != 0, a source term);
+  ref_run_2d.npz         S.solve_system_active() (solver.py:1014-1135) for 40 steps of the 2D neuron
+                         of examples/idealized-geometries/run_2D.py on its resolution-1 mesh (resolution 0 does not resolve the membrane) with the
+                         reference's mm_hh.py: membrane potential at every membrane facet and step,
+                         final fields.
+
+dof numbering of the stored tensors: DG1 dof = nd*cell + local vertex; the mixed KNP space
+stacks the ions (ion k at offset k*nd*ncells); facet quantities by facet index.
+"""
+import importlib.util
+import os
+import sys
+from collections import namedtuple
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refexec  # noqa: E402
+
+ref = refexec.install()
+import dolfin as df  # noqa: E402  (the stand-in)
+from knpemidg import Solver  # noqa: E402  (the reference)
+from knpemidg.utils import plus, minus, pcws_constant_project  # noqa: E402
+
+
+def load_by_path(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+kmesh = load_by_path("_kmesh_for_golden", os.path.join(ROOT, "knp-emi-dg_b200", "knpemidg", "mesh.py"))
+REF_EX = "/root/reference/examples"
+sys.path.insert(0, os.path.join(REF_EX, "idealized-geometries"))
+mm_hh = load_by_path("mm_hh", os.path.join(REF_EX, "idealized-geometries", "mm_hh.py"))
+mm_hh_no_stim = load_by_path("mm_hh_no_stim", os.path.join(REF_EX, "idealized-geometries", "mm_hh_no_stim.py"))
+
+
+class RefSolver(Solver):
+    """the sub-class of examples/idealized-geometries/run_2D.py:30-50"""
+
+    def __init__(self, params, ion_list, degree_emi=1, degree_knp=1, mms=None, sf=1):
+        Solver.__init__(self, params, ion_list, degree_emi=1, degree_knp=1, mms=None, sf=1)
+        self.trace = []
+
+    def update_ode(self, ode_model):
+        K_e = plus(self.c_prev_k.split()[0], self.n_g)
+        ode_model.set_parameter('K_e', pcws_constant_project(K_e, self.Q))
+        Na_i = minus(self.ion_list[-1]['c'], self.n_g)
+        ode_model.set_parameter('Na_i', pcws_constant_project(Na_i, self.Q))
+
+    def solve_for_time_step(self, k, t):
+        Solver.solve_for_time_step(self, k, t)
+        self.trace.append(self.phi_M_prev_PDE.vector().get_local().copy())
+
+
+Params = namedtuple('params', ('dt', 'n_steps_ODE', 'F', 'psi', 'phi_M_init', 'C_phi', 'C_M', 'R', 'temperature',
+                               'phi_M_init_type', 'rho_sub'))
+SolverParams = namedtuple('solver_params', ('direct_emi', 'direct_knp', 'resolution', 'rtol_emi', 'rtol_knp',
+                                            'atol_emi', 'atol_knp', 'threshold_emi', 'threshold_knp'))
+StimParams = namedtuple('membrane_params', ('g_syn_bar', 'stimulus', 'stimulus_locator'))
+
+PHYS = dict(dt=1.0e-4, C_M=0.02, T=300.0, F=96485.0, R=8.314)
+D_PHYS = {"K": 1.96e-9, "Cl": 2.03e-9, "Na": 1.33e-9}
+NA_I, NA_E, K_I, K_E = 12.838513108648856, 100.71925900027354, 124.15397583491901, 3.3236967382705265
+
+
+def build_solver(mesh, sub, surf, tags, ode_models, D_scale=None, rho=None, f_source=None):
+    """reference Solver set up as run_2D.py / run_3D.py do (ions K, Cl, Na; Na eliminated)"""
+    dt, C_M = PHYS["dt"], PHYS["C_M"]
+    rho_sub = {int(t): df.Constant((rho or {}).get(int(t), 0.0)) for t in tags}
+    params = Params(dt, 25, PHYS["F"], PHYS["F"] / (PHYS["R"] * PHYS["T"]), df.Constant(-0.0743860937), C_M / dt, C_M,
+                    PHYS["R"], PHYS["T"], 'constant', rho_sub)
+    ci = {"K": K_I, "Na": NA_I, "Cl": K_I + NA_I}
+    ce = {"K": K_E, "Na": NA_E, "Cl": K_E + NA_E}
+    ions = []
+    for name, z in (("K", 1.0), ("Cl", -1.0), ("Na", 1.0)):
+        scale = D_scale or {}
+        ions.append({'c_init_sub': {int(t): df.Constant(ce[name] if t == 0 else ci[name]) for t in tags},
+                     'c_init_sub_type': 'constant', 'bdry': None, 'z': z, 'name': name,
+                     'D_sub': {int(t): df.Constant(D_PHYS[name] * scale.get(int(t), 1.0)) for t in tags},
+                     'f_source': (f_source or {}).get(name, df.Constant(0))})
+    S = RefSolver(params, ions)
+    dmesh = df.Mesh(mesh)
+    S.setup_domain(dmesh, df.MeshFunction.from_array(dmesh, mesh.gdim, sub), df.MeshFunction.from_array(dmesh, mesh.gdim - 1, surf))
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    stim = StimParams(10, {'stim_amplitude': 10}, lambda x: x[0] < 20e-6)
+    S.setup_membrane_model(stim, ode_models)
+    return S, ions
+
+
+def coo(M):
+    A = M.A.tocoo()
+    A.sum_duplicates()
+    return A.row.astype(np.int32), A.col.astype(np.int32), A.data
+
+
+def forms_case(name, mesh, sub, surf, ode_models, splitting=True, D_scale=None, rho=None, f_src=None, seed=0):
+    mesh.init_topology()
+    tags = np.unique(sub)
+    fs = None
+    if f_src is not None:
+        fs = {"K": df.Constant(f_src[0]), "Cl": df.Constant(f_src[1])}
+    S, ions = build_solver(mesh, sub, surf, tags, ode_models, D_scale, rho, fs)
+    nc, nd = mesh.num_cells(), mesh.nd
+    n = nc * nd
+    rng = np.random.default_rng(seed)
+    ics = (sub != 0)[:, None]
+    base_i = [K_I, K_I + NA_I, NA_I]
+    base_e = [K_E, K_E + NA_E, NA_E]
+    c_all = np.stack([np.where(ics, base_i[k], base_e[k]) * (1.0 + 0.01 * rng.uniform(-1, 1, (nc, nd))) for k in range(3)])
+    c_n = c_all[:2] * (1.0 + 0.001 * rng.uniform(-1, 1, (2, nc, nd)))
+    phi = np.where(ics, -0.07, 0.0) * (1.0 + 0.01 * rng.uniform(-1, 1, (nc, nd)))
+    nf = mesh.facet_cells.shape[0]
+    phi_M = -0.07 * (1.0 + 0.01 * rng.uniform(-1, 1, nf))
+    I_ch = 1e-3 * rng.uniform(-1, 1, (3, nf))
+    # the seeded state goes into the reference's own Functions
+    S.c_prev_k.vector().set_local(c_all[:2].reshape(-1))
+    S.c_prev_n.vector().set_local(c_n.reshape(-1))
+    S.c.vector().set_local(c_all[:2].reshape(-1))
+    ions[-1]['c'].vector().set_local(c_all[2].reshape(-1))
+    S.phi.vector().set_local(phi.reshape(-1))
+    S.phi_M_prev_PDE.vector().set_local(phi_M)
+    for mm in S.mem_models:
+        for k, nm_ in enumerate(("K", "Cl", "Na")):
+            mm['I_ch_k'][nm_].vector().set_local(I_ch[k])
+    S.splitting_scheme = splitting
+    S.setup_varform_emi()
+    S.setup_varform_knp()
+    A, B, b = df.assemble(S.a_emi), df.assemble(S.B_emi), df.assemble(S.L_emi)
+    Ak, bk = df.assemble(S.A_knp), df.assemble(S.L_knp)
+    out = dict(coords=mesh.coords, cells=mesh.cells, cell_tag=sub.astype(np.int32), facet_tag=surf.astype(np.int32),
+               membrane_tags=np.array(sorted(ode_models), dtype=np.int32), splitting=np.array(int(splitting)),
+               F=PHYS["F"], R=PHYS["R"], T=PHYS["T"], C_M=PHYS["C_M"], dt=PHYS["dt"], z=np.array([1.0, -1.0, 1.0]),
+               tags=tags.astype(np.int32),
+               D=np.array([[D_PHYS[nm_] * (D_scale or {}).get(int(t), 1.0) for t in tags] for nm_ in ("K", "Cl", "Na")]),
+               rho=np.array([(rho or {}).get(int(t), 0.0) for t in tags]),
+               f_source=np.array(f_src if f_src is not None else [0.0, 0.0]),
+               c_all=c_all, c_n=c_n, phi=phi, phi_M=phi_M, I_ch=I_ch,
+               E0=np.stack([ion['E'].vector().get_local() for ion in ions]),   # Nernst potentials of the input state
+               n_g=S.n_g.vector().get_local().reshape(nf, mesh.gdim),
+               b_emi=b.get_local(), b_knp=bk.get_local())
+    for key, M in (("A_emi", A), ("B_emi", B), ("A_knp", Ak)):
+        r, c, v = coo(M)
+        out[key + "_row"], out[key + "_col"], out[key + "_val"] = r, c, v
+    # one PDE step of the reference (direct solves), solver.py:794-847
+    S.direct_emi = S.direct_knp = True
+    S.save_solver_stats = False
+    S.setup_solver_emi()
+    S.setup_solver_knp()
+    S.solve_for_time_step(0, df.Constant(0.0))
+    out.update(step_phi=S.phi.vector().get_local(), step_c=S.c.vector().get_local(),
+               step_phi_M=S.phi_M_prev_PDE.vector().get_local(),
+               step_E=np.stack([ion['E'].vector().get_local() for ion in ions]),
+               step_c_elim=ions[-1]['c'].vector().get_local())
+    return out
+
+
+def mesh_3d_two_cells():
+    """6 x 4 x 4 boxes (x6 tets), a 'glial' block (cell tag 1, membrane tag 1) and a 'neuronal' block
+    (cell tag 2, membrane tag 2) that do not touch; exterior facets 5; scaled to micrometres"""
+    m = kmesh.box_mesh((0.0, 0.0, 0.0), (6.0, 4.0, 4.0), 6, 4, 4)
+    m.init_topology()
+    mid = m.cell_midpoints()
+    sub = np.zeros(m.num_cells(), dtype=np.int64)
+    inside = lambda lo, hi: np.all((mid > lo) & (mid < hi), axis=1)   # noqa: E731
+    sub[inside(np.array([1.0, 1.0, 1.0]), np.array([2.0, 3.0, 3.0]))] = 1
+    sub[inside(np.array([3.0, 1.0, 1.0]), np.array([5.0, 3.0, 2.0]))] = 2
+    fc = m.facet_cells
+    interior = fc[:, 1] >= 0
+    t0 = sub[fc[:, 0]]
+    t1 = np.where(interior, sub[np.maximum(fc[:, 1], 0)], t0)
+    surf = np.zeros(fc.shape[0], dtype=np.int64)
+    surf[interior & (t0 != t1)] = np.maximum(t0, t1)[interior & (t0 != t1)]
+    surf[~interior] = 5
+    m2 = kmesh.SimplexMesh(m.coords * 1e-6, m.cells)
+    m2.init_topology()
+    return m2, sub, surf
+
+
+def run_case(nsteps=40):
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
+    S, ions = build_solver(mesh, sub, surf, np.unique(sub), {1: mm_hh})
+    sp = SolverParams(True, True, 0, 1e-5, 1e-7, 1e-40, 1e-40, None, None)
+    t = df.Constant(0.0)
+    S.solve_system_active(nsteps * PHYS["dt"], t, sp)
+    mem = np.flatnonzero(surf == 1)
+    return dict(nsteps=np.array(nsteps), mem_facets=mem.astype(np.int32), phi_M_trace=np.stack(S.trace)[:, mem],
+                final_phi=S.phi.vector().get_local(), final_c=S.c.vector().get_local(),
+                final_c_elim=ions[-1]['c'].vector().get_local(),
+                final_E=np.stack([ion['E'].vector().get_local()[mem] for ion in ions]),
+                final_states=S.mem_models[0]['ode'].states.copy(), t_end=np.array(float(t)))
+
+
+def main(outdir):
+    os.makedirs(outdir, exist_ok=True)
+    m2, s2, f2 = kmesh.neuron_2d_mesh(1)
+    s2, f2 = np.asarray(s2.array()), np.asarray(f2.array())
+    np.savez_compressed(os.path.join(outdir, "ref_forms_2d.npz"), **forms_case("2d", m2, s2, f2, {1: mm_hh}))
+    np.savez_compressed(os.path.join(outdir, "ref_forms_2d_nosplit.npz"),
+                        **forms_case("2d_nosplit", m2, s2, f2, {1: mm_hh}, splitting=False, seed=1))
+    m3, s3, f3 = mesh_3d_two_cells()
+    np.savez_compressed(os.path.join(outdir, "ref_forms_3d.npz"),
+                        **forms_case("3d", m3, s3, f3, {1: mm_hh_no_stim, 2: mm_hh}, D_scale={1: 0.5, 2: 0.7},
+                                     rho={0: 0.0, 1: 3.0, 2: -2.0}, f_src=[250.0, -125.0], seed=2))
+    np.savez_compressed(os.path.join(outdir, "ref_run_2d.npz"), **run_case())
+    print("wrote", sorted(os.listdir(outdir)))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else HERE)

@@ -1,0 +1,220 @@
+"""Checks against the REFERENCE-EXECUTED golden fixtures tests/golden/ref_*.npz.
+
+The fixtures are produced by tests/golden/make_reference_golden.py, which runs the reference's
+own unmodified form code, step updates and time loop (/root/reference/src/knpemidg) on the numeric
+dolfin stand-in of oracle/refexec.  Three things are compared with them, all on the stored inputs:
+the oracle restatement (oracle/forms.py, oracle/stepper.py), the host-emulation build and the CUDA
+library (through the C ABI).
+
+Tolerance for assembled tensors: ENTRYWISE, |a - b| <= 1e-12 |b| + 1e-14 max|row| (common.py).
+"""
+import os
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from common import _lib, entrywise_failures, rel_err  # noqa: F401
+from knpemidg import mesh as kmesh
+from oracle import forms
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FORM_CASES = ("2d", "2d_nosplit", "3d")
+
+
+class Golden:
+    def __init__(self, name):
+        self.g = g = np.load(os.path.join(GOLDEN, f"ref_forms_{name}.npz"))
+        self.mesh = kmesh.SimplexMesh(g["coords"], g["cells"])
+        self.mesh.init_topology()
+        self.tags = g["tags"]
+        self.splitting = bool(g["splitting"])
+        self.mtags = tuple(int(t) for t in g["membrane_tags"])
+        D_sub = [{int(t): g["D"][k][i] for i, t in enumerate(self.tags)} for k in range(3)]
+        rho_sub = {int(t): g["rho"][i] for i, t in enumerate(self.tags)}
+        self.P = forms.Problem(self.mesh, g["cell_tag"], g["facet_tag"], F=float(g["F"]), R=float(g["R"]),
+                               T=float(g["T"]), C_M=float(g["C_M"]), C_phi=float(g["C_M"]) / float(g["dt"]),
+                               dt=float(g["dt"]), z=g["z"], D_sub=D_sub, rho_sub=rho_sub, membrane_tags=self.mtags)
+        P = self.P
+        self.n = P.ndof
+        mf = P.mem_facets
+        self.phi_M, self.I_ch = g["phi_M"][mf], g["I_ch"][:, mf]
+        self.f_source = [float(v) for v in g["f_source"]]
+
+    def ref_matrix(self, key, block=None):
+        g, n = self.g, self.n
+        N = n if key != "A_knp" else 2 * n
+        M = sp.coo_matrix((g[key + "_val"], (g[key + "_row"], g[key + "_col"])), shape=(N, N)).tocsr()
+        if block is not None:
+            M = M[block * n:(block + 1) * n, block * n:(block + 1) * n]
+        return M
+
+    def loads(self):
+        """f_source v dx(0) of the solved ions as nodal load vectors (solver.py:599)"""
+        P = self.P
+        out = []
+        for f in self.f_source:
+            load = np.zeros((P.nc, P.nd))
+            ecs = P.cell_tag == 0
+            load[ecs] = (f * P.vol[ecs] / (P.d + 1))[:, None]
+            out.append(load)
+        return out
+
+    def context(self, lib):
+        g, P = self.g, self.P
+        ctx = _lib.Context(0, lib)
+        region = np.searchsorted(self.tags, g["cell_tag"]).astype(np.int32)
+        ctx.set_mesh(self.mesh.coords, self.mesh.cells, region, self.mesh.facet_cells, g["facet_tag"], self.mtags)
+        ctx.set_params(F=P.F, R=P.R, T=P.T, C_M=P.C_M, C_phi=P.C_phi, dt=P.dt, tau_emi=P.tau, tau_knp=P.tau,
+                       Lp=P.Lp, z=list(g["z"]), D=g["D"], rho=list(g["rho"]), splitting=self.splitting)
+        for k in range(3):
+            ctx.set_field(_lib.F_C, k, g["c_all"][k])
+            ctx.set_field(_lib.F_ICH, k, self.I_ch[k])
+        for k in range(2):
+            ctx.set_field(_lib.F_CN, k, g["c_n"][k])
+            if self.f_source[k] != 0.0:
+                ctx.set_field(_lib.F_LOAD_KNP, k, self.loads()[k])
+        ctx.set_field(_lib.F_PHI, 0, g["phi"])
+        ctx.set_field(_lib.F_PHIM, 0, self.phi_M)
+        return ctx
+
+
+def _assert_entrywise(what, a, b, rtol=1e-12):
+    # right-hand sides: the ions' contributions to one entry cancel to ~1e-2 of their size (electroneutral
+    # state), so the round-off floor of a vector entry is 1e-13 of the largest entry, not 1e-14
+    floor = 1e-14 if sp.issparse(b) else 1e-13
+    nfail, worst = entrywise_failures(a, b, rtol=rtol, row_floor=floor)
+    assert nfail == 0, f"{what}: {nfail} entries off, worst {worst:.2f} x the bound"
+
+
+def check_oracle_forms(name):
+    """oracle/forms.py against what the reference's own form code assembled"""
+    G = Golden(name)
+    g, P, n = G.g, G.P, G.n
+    A, B, b = forms.assemble_emi(P, g["c_all"], G.phi_M, G.I_ch, splitting=G.splitting)
+    _assert_entrywise("A_emi", A, G.ref_matrix("A_emi"))
+    _assert_entrywise("B_emi", B, G.ref_matrix("B_emi"))
+    _assert_entrywise("b_emi", b, g["b_emi"])
+    Ak, bk = forms.assemble_knp(P, g["c_all"], g["c_n"], g["phi"], G.phi_M, G.I_ch, splitting=G.splitting,
+                                f_source=G.f_source)
+    full = G.ref_matrix("A_knp")
+    assert abs(full[:n, n:]).sum() == 0.0 and abs(full[n:, :n]).sum() == 0.0    # the ions are uncoupled
+    for k in range(2):
+        _assert_entrywise(f"A_knp[{k}]", Ak[k], G.ref_matrix("A_knp", k))
+        _assert_entrywise(f"b_knp[{k}]", bk[k], g["b_knp"][k * n:(k + 1) * n], rtol=1e-11)
+    mf = P.mem_facets
+    for k in range(3):
+        assert rel_err(forms.nernst(P, g["c_all"][k], P.z[k]), g["E0"][k][mf]) < 1e-13
+    # orientation: n_g points from the lower to the higher cell tag (utils.py:80)
+    ng = g["n_g"][mf]
+    toward_i = P.X[P.mem_cell_i].mean(axis=1) - P.X[P.mem_cell_e].mean(axis=1)
+    assert np.all(np.einsum("fk,fk->f", ng, toward_i) > 0)
+    # one PDE step (solver.py:794-847)
+    x = _solve_singular(G.ref_matrix("A_emi"), g["b_emi"])
+    assert _rel_mod_const(g["step_phi"], x) < 1e-9
+    phi1 = g["step_phi"].reshape(P.nc, P.nd)
+    assert rel_err(forms.membrane_potential(P, phi1), g["step_phi_M"][mf]) < 1e-12
+    c1 = g["step_c"].reshape(2, P.nc, P.nd)
+    ce = forms.eliminated_concentration(P, c1)
+    assert rel_err(ce.ravel(), g["step_c_elim"]) < 1e-13
+    for k in range(3):
+        ck = c1[k] if k < 2 else ce
+        assert rel_err(forms.nernst(P, ck, P.z[k]), g["step_E"][k][mf]) < 1e-12
+    return G
+
+
+def _solve_singular(A, b):
+    n = A.shape[0]
+    one = sp.csc_matrix(np.ones((n, 1)))
+    K = sp.bmat([[A.tocsc(), one], [one.T, None]], format="csc")
+    return spla.spsolve(K, np.concatenate([b - b.mean(), [0.0]]))[:n]
+
+
+def _rel_mod_const(a, b):
+    a = a - a.mean()
+    b = b - b.mean()
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def check_library_forms(lib, name):
+    """the library (emulation or CUDA build, through the C ABI) against the reference-executed tensors"""
+    G = Golden(name)
+    g, P, n = G.g, G.P, G.n
+    ctx = G.context(lib)
+    mf = P.mem_facets
+    ctx.post_step(_lib.POST_NERNST)
+    for k in range(3):
+        assert rel_err(ctx.get_field(_lib.F_NERNST, k), g["E0"][k][mf]) < 1e-12
+    ctx.assemble_emi()
+    _assert_entrywise("A_emi", ctx.matrix(0), G.ref_matrix("A_emi"))
+    _assert_entrywise("B_emi", ctx.matrix(1), G.ref_matrix("B_emi"))
+    _assert_entrywise("b_emi", ctx.get_field(_lib.F_RHS_EMI), g["b_emi"])
+    ctx.assemble_knp()
+    for k in range(2):
+        _assert_entrywise(f"A_knp[{k}]", ctx.matrix(2 + k), G.ref_matrix("A_knp", k))
+        _assert_entrywise(f"b_knp[{k}]", ctx.get_field(_lib.F_RHS_KNP, k), g["b_knp"][k * n:(k + 1) * n], rtol=1e-11)
+    # one PDE step with tight Krylov tolerances against the reference's direct solves
+    ctx.amg_setup()
+    ctx.solver_options(pc=1)
+    ctx.solve_emi(rtol=1e-12, atol=1e-40, maxit=2000)
+    assert _rel_mod_const(ctx.get_field(_lib.F_PHI), g["step_phi"]) < 1e-8
+    ctx.assemble_knp()
+    ctx.solve_knp(rtol=1e-13, atol=1e-40, maxit=2000)
+    for k in range(2):
+        assert rel_err(ctx.get_field(_lib.F_C, k), g["step_c"][k * n:(k + 1) * n]) < 1e-9
+    ctx.post_step(_lib.POST_ALL)
+    assert rel_err(ctx.get_field(_lib.F_PHIM), g["step_phi_M"][mf]) < 1e-8
+    assert rel_err(ctx.get_field(_lib.F_C, 2), g["step_c_elim"]) < 1e-9
+    for k in range(3):
+        assert rel_err(ctx.get_field(_lib.F_NERNST, k), g["step_E"][k][mf]) < 1e-8
+    return ctx
+
+
+# ---- the reference's time loop (ref_run_2d.npz) -------------------------------------------------
+RUN_PHYS = dict(F=96485.0, R=8.314, T=300.0, C_M=0.02, C_phi=0.02 / 1.0e-4, dt=1.0e-4, z=[1.0, -1.0, 1.0],
+                D_sub=[{0: 1.96e-9, 1: 1.96e-9}, {0: 2.03e-9, 1: 2.03e-9}, {0: 1.33e-9, 1: 1.33e-9}],
+                rho_sub={0: 0.0, 1: 0.0})
+NA_I, NA_E, K_I, K_E = 12.838513108648856, 100.71925900027354, 124.15397583491901, 3.3236967382705265
+RUN_C_INIT = [{1: K_I, 0: K_E}, {1: NA_I + K_I, 0: NA_E + K_E}, {1: NA_I, 0: NA_E}]
+
+
+def run_golden():
+    return np.load(os.path.join(GOLDEN, "ref_run_2d.npz"))
+
+
+def trace_deviation(trace, ref):
+    """max over steps and facets of |phi_M - ref| relative to the range of the reference trace"""
+    return float(np.abs(trace - ref).max() / (ref.max() - ref.min()))
+
+
+def oracle_run(convention, nsteps):
+    from knpemidg.models import mm_hh
+    from oracle import stepper
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    P = forms.Problem(mesh, sub.array(), surf.array(), membrane_tags=(1,), **RUN_PHYS)
+    c0 = np.stack([np.where((sub.array() == 1)[:, None], ci[1], ci[0]) * np.ones((P.nc, P.nd)) for ci in RUN_C_INIT])
+    O = stepper.OracleSolver(P, c0, models={1: mm_hh}, stimulus={"stim_amplitude": 10.0},
+                             stimulus_locator=lambda x: x[0] < 20e-6, ion_names=["K", "Cl", "Na"], direct=True,
+                             current_convention=convention)
+    tr = []
+    for _ in range(nsteps):
+        O.step()
+        tr.append(O.phi_M.copy())
+    return np.stack(tr), O
+
+
+def library_run(lib, nsteps, rtol_emi=1e-5, rtol_knp=1e-7):
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_hh
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1,), lib=lib, **RUN_PHYS)
+    eng.set_concentrations_by_tag(RUN_C_INIT)
+    eng.add_membrane_model(1, mm_hh, ["K", "Cl", "Na"], stimulus={"stim_amplitude": 10.0},
+                           stimulus_locator=lambda x: x[0] < 20e-6)
+    eng.rtol_emi, eng.rtol_knp = rtol_emi, rtol_knp
+    eng.initialize(pc=1)
+    tr = []
+    for _ in range(nsteps):
+        eng.step()
+        tr.append(eng.phi_M().copy())
+    return np.stack(tr), eng

@@ -1,0 +1,25 @@
+"""CUDA library (C ABI) against the reference-EXECUTED golden fixtures (tests/golden/ref_*.npz):
+assembled tensors entry by entry at 1e-12, one PDE step, and the 40-step membrane-potential
+traces of the reference's own time loop at 1e-6."""
+import numpy as np
+import pytest
+
+import golden_checks as gc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", gc.FORM_CASES)
+def test_cuda_forms_match_the_reference(gpu_lib, name):
+    assert gpu_lib.is_cuda()
+    ctx = gc.check_library_forms(gpu_lib, name)
+    assert ctx.launch_count() > 0
+
+
+def test_cuda_run_matches_the_reference(gpu_lib):
+    g = gc.run_golden()
+    ref, n = g["phi_M_trace"], int(g["nsteps"])
+    tr, eng = gc.library_run(gpu_lib, n, 1e-10, 1e-11)
+    assert gc.trace_deviation(tr, ref) < 1e-6
+    cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
+    assert gc.rel_err(cfin, g["final_c"]) < 1e-7
