@@ -23,7 +23,7 @@ import numpy as np
 
 __all__ = [
     "SimplexMesh", "MeshFunction", "rectangle_mesh", "box_mesh", "mms_mesh",
-    "neuron_2d_mesh", "bundle_3d_mesh", "emix_like_mesh",
+    "neuron_2d_mesh", "bundle_3d_mesh", "emix_like_mesh", "astro_like_mesh",
 ]
 
 
@@ -379,4 +379,40 @@ def emix_like_mesh(M, n_cells=100, seed=1234, length=1.0e-3):
     surf.array()[~interior] = 5
     mesh.scale(length)
     mesh.n_ics_cells = len(boxes)
+    return mesh, sub, surf
+
+
+def astro_like_mesh(M, length=5.0e-4):
+    """Synthetic stand-in for the mesh of examples/local-astrocyte-depolarization/run_tortuosity.py
+    (BASELINE configs[3]; the emimesh data set behind meshes/synapse.yml is not in the checkout):
+    BoxMesh M^3 x 6 tets (M >= 8) with two neuronal cuboids (cell tag 1; membrane facet tags 1 and 3)
+    and one glial cuboid (cell tag 2; membrane tag 2) - the tag layout the script's
+    `ode_models = {1: mm_hh, 2: mm_glial, 3: mm_hh}` and `rho_sub = {0, 1, 2}` expect
+    (run_tortuosity.py:107, 298).  Exterior facets 5.  `mesh.source_box` = (lo, hi), the ECS slab
+    between the first neuron and the glial cell where the K+/Na+ source of run_tortuosity.py:180-200
+    acts.  Coordinates in cm (the script's units), edge `length`."""
+    assert M >= 8
+    mesh = box_mesh((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), M, M, M)
+    mesh.init_topology()
+    occ = np.zeros((M, M, M), dtype=np.int32)      # [ix, iy, iz] -> membrane tag of the enclosing cuboid
+    boxes = [((M // 8, M // 4, M // 4), (3 * M // 8, 3 * M // 4, M // 2), 1),
+             ((M // 2, M // 4, M // 4), (7 * M // 8, M // 2, 3 * M // 4), 2),
+             ((M // 8, M // 4, 5 * M // 8), (3 * M // 8, 3 * M // 4, 7 * M // 8), 3)]
+    for lo, hi, tag in boxes:
+        occ[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = tag
+    mem_of_box = occ.transpose(2, 1, 0).ravel()      # box index = iz*M*M + iy*M + ix
+    mem_of_cell = np.repeat(mem_of_box, 6)
+    sub = MeshFunction(mesh, 3, 0)
+    surf = MeshFunction(mesh, 2, 0)
+    sub.array()[:] = np.where(mem_of_cell == 2, 2, np.where(mem_of_cell > 0, 1, 0))
+    fc = mesh.facet_cells
+    interior = fc[:, 1] >= 0
+    m0 = mem_of_cell[fc[:, 0]]
+    m1 = np.where(interior, mem_of_cell[np.maximum(fc[:, 1], 0)], m0)
+    memb = interior & (m0 != m1)
+    surf.array()[memb] = np.maximum(m0, m1)[memb]
+    surf.array()[~interior] = 5
+    mesh.scale(length)
+    h = length / M
+    mesh.source_box = (np.array([3 * M // 8, M // 4, M // 4]) * h, np.array([M // 2, 3 * M // 4, 3 * M // 4]) * h)
     return mesh, sub, surf

@@ -29,6 +29,10 @@ def available():
 
 def install():
     from . import fake_dolfin, fake_petsc, fake_numbalsoda
+    import numpy as np
+    for old, new in (("float_", np.float64), ("Inf", np.inf)):     # NumPy 1.x names the reference still uses
+        if not hasattr(np, old):
+            setattr(np, old, new)
     if "knpemidg" in sys.modules and not sys.modules["knpemidg"].__file__.startswith(REFERENCE_SRC):
         raise RuntimeError("the product's knpemidg is already imported in this process")
     sys.modules["dolfin"] = fake_dolfin

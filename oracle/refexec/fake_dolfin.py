@@ -199,12 +199,22 @@ class CompiledExpression:
         self.subdomains = kw["subdomains"]
 
 
-class Expression:
+class Expression(U.Expr):
     """A python callable f(x[npts, d]) -> values stands in for the C++ string expressions of the
-    run scripts; `degree` as in dolfin (the expression is interpolated, here into P1)."""
+    run scripts (e.g. the source window of run_tortuosity.py:180-200, which reads the time from a
+    Constant it captured).  In a form it is evaluated at the quadrature points and counts with its
+    declared `degree` in the degree estimate; dolfin would first interpolate it into P_degree on
+    every cell, which is the same thing for data that is polynomial (here: constant) per cell."""
 
     def __init__(self, fn, degree=1, **kw):
-        self.fn, self.degree = fn, degree
+        self.fn, self._degree = fn, degree
+
+    def degree(self):
+        return self._degree
+
+    def eval(self, ctx, side):
+        x = ctx.x.reshape(-1, ctx.x.shape[-1])
+        return np.asarray(self.fn(x), dtype=float).reshape(ctx.E, ctx.Q)[:, :, None, None, None]
 
 
 def interpolate(f, V):

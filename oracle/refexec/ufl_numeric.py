@@ -102,6 +102,7 @@ class Ctx:
             else:
                 self.cells = {None: c0}
         self._lam = {}
+        self.memo = {}
 
     def cell(self, side):
         if side not in self.cells:
@@ -134,6 +135,22 @@ def as_expr(v):
 
 class Expr:
     ufl_shape = ()
+
+    def __init_subclass__(cls, **kw):
+        """every node's eval is memoised per (context, side): the reference's integrands reuse the same
+        sub-expressions (kappa, alpha_sum, the traces of c) dozens of times"""
+        super().__init_subclass__(**kw)
+        raw = cls.__dict__.get("eval")
+        if raw is None:
+            return
+
+        def eval(self, ctx, side, _raw=raw):
+            key = (id(self), side)
+            hit = ctx.memo.get(key)
+            if hit is None:
+                hit = ctx.memo[key] = _raw(self, ctx, side)
+            return hit
+        cls.eval = eval
 
     # -- algebra --
     def __add__(self, o):

@@ -2,7 +2,7 @@
 """Generate tests/golden/ref_*.npz by EXECUTING the reference (adajel/KNP-EMI-DG, /root/reference,
 unmodified) on top of the numeric dolfin / petsc4py / numbalsoda stand-ins of oracle/refexec.
 
-    python tests/golden/make_reference_golden.py [outdir]          (this container only)
+    python tests/golden/make_reference_golden.py [outdir] [--only=name,name]      (this container only)
 
 Every fixture holds the mesh, the parameters and the seeded input fields of one case together
 with what the reference's own code produced from them:
@@ -16,7 +16,11 @@ with what the reference's own code produced from them:
   ref_run_2d.npz         S.solve_system_active() (solver.py:1014-1135) for 40 steps of the 2D neuron
                          of examples/idealized-geometries/run_2D.py on its resolution-1 mesh (resolution 0 does not resolve the membrane) with the
                          reference's mm_hh.py: membrane potential at every membrane facet and step,
-                         final fields.
+                         final fields;
+  ref_run_astro.npz      S.solve_system_active() for 16 steps of the problem of
+                         examples/local-astrocyte-depolarization/run_tortuosity.py (BASELINE configs[3]: three
+                         membrane tags, neuronal + glial models, rho != 0, tortuosity, the time-windowed K+/Na+
+                         source) on the synthetic mesh knpemidg.mesh.astro_like_mesh(8).
 
 dof numbering of the stored tensors: DG1 dof = nd*cell + local vertex; the mixed KNP space
 stacks the ions (ion k at offset k*nd*ncells); facet quantities by facet index.
@@ -213,20 +217,91 @@ def run_case(nsteps=40):
                 final_states=S.mem_models[0]['ode'].states.copy(), t_end=np.array(float(t)))
 
 
-def main(outdir):
+# ---- BASELINE configs[3]: examples/local-astrocyte-depolarization/run_tortuosity.py ------------------------
+ASTRO = dict(dt=0.1, C_M=1.0, T=307e3, F=96500e3, R=8.315e3, g_syn=26.0, t_syn=1.2, lambda_i=3.2 * 4, lambda_e=1.6 * 4,
+             D={"K": 1.96e-8, "Na": 1.33e-8, "Cl": 2.03e-8},
+             c={"K": (3.092970607490389, 124.13988964240784, 99.3100014897692),       # ECS, neuron, glia
+                "Na": (144.60625137617149, 12.850454639128186, 15.775818906083778),
+                "Cl": (133.62525154406637, 5.0, 5.203660274163705)})
+
+
+class RefSolverAstro(RefSolver):
+    """run_tortuosity.py:30-51: Na_i is the trace of the SECOND solved ion"""
+
+    def update_ode(self, ode_model):
+        K_e = plus(self.c_prev_k.split()[0], self.n_g)
+        ode_model.set_parameter('K_e', pcws_constant_project(K_e, self.Q))
+        Na_i = minus(self.c_prev_k.split()[1], self.n_g)
+        ode_model.set_parameter('Na_i', pcws_constant_project(Na_i, self.Q))
+
+
+def run_astro_case(nsteps=16, M=8):
+    """the problem definition of run_tortuosity.py:81-298 (ions K, Na, Cl with Cl eliminated, rho != 0,
+    tortuosity-scaled D, the K+/Na+ source window, membrane models {1: mm_hh, 2: mm_glial, 3: mm_hh},
+    stimulus 0 everywhere) on the synthetic mesh knpemidg.mesh.astro_like_mesh(M)"""
+    adir = os.path.join(REF_EX, "local-astrocyte-depolarization")
+    a_hh = load_by_path("astro_mm_hh", os.path.join(adir, "mm_hh.py"))
+    a_glial = load_by_path("astro_mm_glial", os.path.join(adir, "mm_glial.py"))
+    mesh, sub, surf = kmesh.astro_like_mesh(M)
+    sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
+    A = ASTRO
+    c = A["c"]
+    rho = {t: -(c["Na"][t] + c["K"][t] - c["Cl"][t]) for t in range(3)}
+    rho_sub = {t: df.Constant(rho[t]) for t in range(3)}
+    params = namedtuple('params', ('dt', 'n_steps_ODE', 'F', 'psi', 'C_phi', 'C_M', 'R', 'temperature',
+                                   'phi_M_init_type', 'rho_sub'))(
+        A["dt"], 25, A["F"], A["F"] / (A["R"] * A["T"]), A["C_M"] / A["dt"], A["C_M"], A["R"], A["T"], 'constant', rho_sub)
+    t = df.Constant(0.0)
+    lo, hi = mesh.source_box
+
+    def window(sign):
+        def f(x):
+            inside = np.all((x >= lo[None, :]) & (x <= hi[None, :]), axis=1)
+            return sign * A["g_syn"] * inside * (0.2 <= float(t)) * (float(t) <= A["t_syn"])
+        return df.Expression(f, degree=4)
+
+    lam = {0: A["lambda_e"], 1: A["lambda_i"], 2: A["lambda_i"]}
+    src = {"K": window(1.0), "Na": window(-1.0), "Cl": df.Constant(0)}
+    ions = [{'c_init_sub': {tg: df.Constant(c[nm_][tg]) for tg in range(3)}, 'c_init_sub_type': 'constant', 'bdry': None,
+             'z': z, 'name': nm_, 'D_sub': {tg: df.Constant(A["D"][nm_] / lam[tg] ** 2) for tg in range(3)},
+             'f_source': src[nm_]} for nm_, z in (("K", 1.0), ("Na", 1.0), ("Cl", -1.0))]
+    S = RefSolverAstro(params, ions)
+    dmesh = df.Mesh(mesh)
+    S.setup_domain(dmesh, df.MeshFunction.from_array(dmesh, 3, sub), df.MeshFunction.from_array(dmesh, 2, surf))
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    S.setup_membrane_model(StimParams(0, {'stim_amplitude': 0}, lambda x: True), {1: a_hh, 2: a_glial, 3: a_hh})
+    S.solve_system_active(nsteps * A["dt"], t, SolverParams(True, True, 0, 1e-5, 1e-7, 1e-40, 1e-40, 0.9, 0.75))
+    mem = np.flatnonzero(np.isin(surf, (1, 2, 3)))
+    return dict(nsteps=np.array(nsteps), M=np.array(M), mem_facets=mem.astype(np.int32), mem_tag=surf[mem].astype(np.int32),
+                phi_M_trace=np.stack(S.trace)[:, mem], final_phi=S.phi.vector().get_local(),
+                final_c=S.c.vector().get_local(), final_c_elim=ions[-1]['c'].vector().get_local(),
+                final_E=np.stack([ion['E'].vector().get_local()[mem] for ion in ions]), t_end=np.array(float(t)))
+
+
+def main(outdir, only=None):
     os.makedirs(outdir, exist_ok=True)
+
+    def want(name):
+        return only is None or name in only
+
+    def save(name, maker):
+        if want(name):
+            np.savez_compressed(os.path.join(outdir, name + ".npz"), **maker())
+
     m2, s2, f2 = kmesh.neuron_2d_mesh(1)
     s2, f2 = np.asarray(s2.array()), np.asarray(f2.array())
-    np.savez_compressed(os.path.join(outdir, "ref_forms_2d.npz"), **forms_case("2d", m2, s2, f2, {1: mm_hh}))
-    np.savez_compressed(os.path.join(outdir, "ref_forms_2d_nosplit.npz"),
-                        **forms_case("2d_nosplit", m2, s2, f2, {1: mm_hh}, splitting=False, seed=1))
+    save("ref_forms_2d", lambda: forms_case("2d", m2, s2, f2, {1: mm_hh}))
+    save("ref_forms_2d_nosplit", lambda: forms_case("2d_nosplit", m2, s2, f2, {1: mm_hh}, splitting=False, seed=1))
     m3, s3, f3 = mesh_3d_two_cells()
-    np.savez_compressed(os.path.join(outdir, "ref_forms_3d.npz"),
-                        **forms_case("3d", m3, s3, f3, {1: mm_hh_no_stim, 2: mm_hh}, D_scale={1: 0.5, 2: 0.7},
-                                     rho={0: 0.0, 1: 3.0, 2: -2.0}, f_src=[250.0, -125.0], seed=2))
-    np.savez_compressed(os.path.join(outdir, "ref_run_2d.npz"), **run_case())
-    print("wrote", sorted(os.listdir(outdir)))
+    save("ref_forms_3d", lambda: forms_case("3d", m3, s3, f3, {1: mm_hh_no_stim, 2: mm_hh}, D_scale={1: 0.5, 2: 0.7},
+                                            rho={0: 0.0, 1: 3.0, 2: -2.0}, f_src=[250.0, -125.0], seed=2))
+    save("ref_run_2d", run_case)
+    save("ref_run_astro", run_astro_case)          # ~2.5 min (4 224 LSODA calls through scipy)
+    print("wrote", sorted(f for f in os.listdir(outdir) if f.endswith(".npz")))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else HERE)
+    args = [a for a in sys.argv[1:] if not a.startswith("--only=")]
+    only = [a[len("--only="):].split(",") for a in sys.argv[1:] if a.startswith("--only=")]
+    main(args[0] if args else HERE, only[0] if only else None)

@@ -218,3 +218,74 @@ def library_run(lib, nsteps, rtol_emi=1e-5, rtol_knp=1e-7):
         eng.step()
         tr.append(eng.phi_M().copy())
     return np.stack(tr), eng
+
+
+# ---- BASELINE configs[3]: run_tortuosity.py on knpemidg.mesh.astro_like_mesh (ref_run_astro.npz) ---------
+ASTRO = dict(dt=0.1, C_M=1.0, T=307e3, F=96500e3, R=8.315e3, g_syn=26.0, t_syn=1.2, lambda_i=3.2 * 4, lambda_e=1.6 * 4)
+ASTRO_D = [1.96e-8, 1.33e-8, 2.03e-8]                                                # K, Na, Cl (cm^2/ms)
+ASTRO_C = [(3.092970607490389, 124.13988964240784, 99.3100014897692),               # K: ECS, neuron, glia
+           (144.60625137617149, 12.850454639128186, 15.775818906083778),             # Na
+           (133.62525154406637, 5.0, 5.203660274163705)]                             # Cl (eliminated)
+ASTRO_NAMES = ["K", "Na", "Cl"]
+ASTRO_LINKS = (("K_e", 0, "plus"), ("Na_i", 1, "minus"))                             # run_tortuosity.py:38-49
+
+
+def astro_golden():
+    return np.load(os.path.join(GOLDEN, "ref_run_astro.npz"))
+
+
+def astro_problem_args():
+    A = ASTRO
+    lam = [A["lambda_e"], A["lambda_i"], A["lambda_i"]]
+    D_sub = [{t: D / lam[t] ** 2 for t in range(3)} for D in ASTRO_D]
+    rho_sub = {t: -(ASTRO_C[1][t] + ASTRO_C[0][t] - ASTRO_C[2][t]) for t in range(3)}
+    return dict(F=A["F"], R=A["R"], T=A["T"], C_M=A["C_M"], C_phi=A["C_M"] / A["dt"], dt=A["dt"], z=[1.0, 1.0, -1.0],
+                D_sub=D_sub, rho_sub=rho_sub)
+
+
+def astro_source(mesh, sign):
+    lo, hi = mesh.source_box
+
+    def f(x, t):
+        x = np.asarray(x)
+        inside = np.all((x >= lo) & (x <= hi), axis=-1)
+        return sign * ASTRO["g_syn"] * inside * (0.2 <= t) * (t <= ASTRO["t_syn"])
+    return f
+
+
+def oracle_run_astro(nsteps, M):
+    from knpemidg.models import mm_glial_astro, mm_hh_astro
+    from oracle import stepper
+    mesh, sub, surf = kmesh.astro_like_mesh(M)
+    P = forms.Problem(mesh, sub.array(), surf.array(), membrane_tags=(1, 2, 3), **astro_problem_args())
+    tag = sub.array()
+    c0 = np.stack([np.choose(tag, ci)[:, None] * np.ones((P.nc, P.nd)) for ci in ASTRO_C])
+    O = stepper.OracleSolver(P, c0, models={1: mm_hh_astro, 2: mm_glial_astro, 3: mm_hh_astro},
+                             stimulus={"stim_amplitude": 0.0}, stimulus_locator=lambda x: True, ion_names=ASTRO_NAMES,
+                             direct=True, f_source=[astro_source(mesh, 1.0), astro_source(mesh, -1.0)],
+                             ode_links=list(ASTRO_LINKS), current_convention="last_call")
+    tr = []
+    for _ in range(nsteps):
+        O.step()
+        tr.append(O.phi_M.copy())
+    return np.stack(tr), O
+
+
+def library_run_astro(lib, nsteps, M, rtol_emi=1e-5, rtol_knp=1e-7):
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_glial_astro, mm_hh_astro
+    mesh, sub, surf = kmesh.astro_like_mesh(M)
+    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2, 3), lib=lib, **astro_problem_args())
+    eng.set_concentrations_by_tag([{t: ci[t] for t in range(3)} for ci in ASTRO_C])
+    for tag_, mod in ((1, mm_hh_astro), (2, mm_glial_astro), (3, mm_hh_astro)):
+        eng.add_membrane_model(tag_, mod, ASTRO_NAMES, stimulus={"stim_amplitude": 0.0}, links=ASTRO_LINKS)
+    eng.rtol_emi, eng.rtol_knp = rtol_emi, rtol_knp
+    src = [astro_source(mesh, 1.0), astro_source(mesh, -1.0)]
+    eng.initialize(pc=1)
+    tr = []
+    for _ in range(nsteps):
+        for k in range(2):                              # sources at the OLD time (t.assign comes last, solver.py:845)
+            eng.set_source(k, lambda x, f=src[k], t=eng.t: float(f(x, t)))
+        eng.step()
+        tr.append(eng.phi_M().copy())
+    return np.stack(tr), eng

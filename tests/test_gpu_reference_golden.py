@@ -23,3 +23,14 @@ def test_cuda_run_matches_the_reference(gpu_lib):
     assert gc.trace_deviation(tr, ref) < 1e-6
     cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
     assert gc.rel_err(cfin, g["final_c"]) < 1e-7
+
+
+def test_cuda_astro_run_matches_the_reference(gpu_lib):
+    """BASELINE configs[3] through the CUDA path: rho != 0, three membrane tags, glial + neuronal
+    membranes, tortuosity, the time-windowed source - against the reference's own loop"""
+    g = gc.astro_golden()
+    tr, eng = gc.library_run_astro(gpu_lib, int(g["nsteps"]), int(g["M"]), 1e-10, 1e-11)
+    assert gc.trace_deviation(tr, g["phi_M_trace"]) < 1e-6
+    cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
+    assert gc.rel_err(cfin, g["final_c"]) < 1e-7
+    assert gc.rel_err(eng.concentration(2).reshape(-1), g["final_c_elim"]) < 1e-7

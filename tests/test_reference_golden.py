@@ -15,11 +15,16 @@ from oracle import refexec
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d"
+
+
 @pytest.mark.skipif(not refexec.available(), reason="/root/reference is not present (GPU box)")
-def test_fixtures_regenerate_from_the_reference(tmp_path):
+@pytest.mark.parametrize("only", [FAST, pytest.param("ref_run_astro", marks=pytest.mark.skipif(
+    os.environ.get("KNP_SLOW_TESTS") != "1", reason="2.5 min; set KNP_SLOW_TESTS=1"))])
+def test_fixtures_regenerate_from_the_reference(tmp_path, only):
     """the committed fixtures are what the reference produces here, today"""
-    subprocess.run([sys.executable, os.path.join(gc.GOLDEN, "make_reference_golden.py"), str(tmp_path)],
-                   check=True, stdout=subprocess.DEVNULL, timeout=900)
+    subprocess.run([sys.executable, os.path.join(gc.GOLDEN, "make_reference_golden.py"), str(tmp_path), "--only=" + only],
+                   check=True, stdout=subprocess.DEVNULL, timeout=1800)
     for name in sorted(os.listdir(tmp_path)):
         new, old = np.load(tmp_path / name), np.load(os.path.join(gc.GOLDEN, name))
         assert sorted(new.files) == sorted(old.files), name
@@ -101,3 +106,23 @@ def test_emulation_run_matches_the_reference(emu_lib):
     # at the reference's own tolerances (CG 1e-5, GMRES 1e-7) the traces agree to what those allow
     tr2, _ = gc.library_run(emu_lib, n)
     assert gc.trace_deviation(tr2, ref) < 1e-3
+
+
+@pytest.mark.skipif(os.environ.get("KNP_SLOW_TESTS") != "1", reason="1.5 min (scipy LSODA in Python); set KNP_SLOW_TESTS=1")
+def test_oracle_astro_run_matches_the_reference():
+    """BASELINE configs[3] (run_tortuosity.py: three membrane tags, glial + neuronal models, rho != 0,
+    tortuosity, the time-windowed K+/Na+ source) - the reference's own loop against the oracle loop"""
+    g = gc.astro_golden()
+    tr, O = gc.oracle_run_astro(int(g["nsteps"]), int(g["M"]))
+    assert gc.trace_deviation(tr, g["phi_M_trace"]) < 1e-6
+    assert gc.rel_err(O.c.reshape(-1), g["final_c"]) < 1e-7
+    assert gc.rel_err(O.c_elim.reshape(-1), g["final_c_elim"]) < 1e-7
+
+
+def test_emulation_astro_run_matches_the_reference(emu_lib):
+    g = gc.astro_golden()
+    tr, eng = gc.library_run_astro(emu_lib, int(g["nsteps"]), int(g["M"]), 1e-10, 1e-11)
+    assert gc.trace_deviation(tr, g["phi_M_trace"]) < 1e-6
+    cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
+    assert gc.rel_err(cfin, g["final_c"]) < 1e-7
+    assert gc.rel_err(eng.concentration(2).reshape(-1), g["final_c_elim"]) < 1e-7
