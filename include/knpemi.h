@@ -109,7 +109,9 @@ int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, int* niter,
 
 /* ---- post-step updates: replaces solver.py:809-842 (c_prev <- c, phi_M
  * facet mean of phi_i - phi_e, Nernst potentials, eliminated ion) and the
- * pcws_constant_project calls (utils.py:100-124). */
+ * pcws_constant_project calls (utils.py:100-124).  KNP_POST_ALL is the update at the end of a regular
+ * time step and includes c_prev_n <- c (solver.py:810): a c_prev_n written separately through
+ * KNP_F_CN is dropped by it. */
 enum { KNP_POST_ELIMINATED = 1, KNP_POST_PHIM = 2, KNP_POST_NERNST = 4, KNP_POST_ALL = 7 };
 int knp_post_step(knp_ctx* ctx, int what);
 /* facet mean of the one-sided trace of a field on the membrane rows;

@@ -322,7 +322,10 @@ static double* field_ptr(knp_ctx* c, int which, int idx, int64_t& count, bool fo
     case KNP_F_C: need(idx >= 0 && idx < N, "C"); count = c->n; return c->c[idx].p;
     case KNP_F_CN:
       need(idx >= 0 && idx < N - 1, "CN"); count = c->n;
-      if (for_write && !c->cn_separate[idx]) { c->cn_own[idx].alloc(c->n); c->cn_separate[idx] = true; }
+      if (for_write && !c->cn_separate[idx]) {
+        if (c->cn_own[idx].n != (size_t)c->n) c->cn_own[idx].alloc(c->n);
+        c->cn_separate[idx] = true;
+      }
       return const_cast<double*>(c->cn(idx));
     case KNP_F_PHI: count = c->n; return c->phi.p;
     case KNP_F_PHIM: count = c->nm; return c->phiM.p;
@@ -554,6 +557,11 @@ int knp_post_step(knp_ctx* ctx, int what) {
   if (!ctx->params_set) fail("knp_post_step: parameters not set");
   PhaseTimer t(ctx, T_POST);
   if (ctx->d == 2) post_step_t<2>(ctx, what); else post_step_t<3>(ctx, what);
+  // KNP_POST_ALL is the update at the end of a regular time step, which includes
+  // c_prev_n.assign(c) (solver.py:809-810): a c_prev_n that was written separately through
+  // KNP_F_CN (Picard iteration, tests) is dropped, KNP_F_CN reads c again.
+  if ((what & KNP_POST_ALL) == KNP_POST_ALL)
+    for (int k = 0; k < MAX_IONS; ++k) ctx->cn_separate[k] = false;
   KNP_CATCH
 }
 

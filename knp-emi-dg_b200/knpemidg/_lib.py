@@ -338,18 +338,36 @@ class Context:
         rows = _i32(rows)
         states = _f64(states)
         params = _f64(params)
+        ns, npar = self._model_dims(model_id)
+        if states.size != rows.size * ns or params.size != rows.size * npar:
+            raise KnpError(f"membrane_register: model {model_id} needs states [{rows.size}, {ns}] and parameters "
+                           f"[{rows.size}, {npar}], got {states.shape} and {params.shape}")
         h = C.c_int()
         self._call("knp_membrane_register", model_id, rows.size, _p(rows, _ip), _p(states, _dp),
                    _p(params, _dp), C.byref(h))
+        self._mem_shapes = getattr(self, "_mem_shapes", {})
+        self._mem_shapes[h.value] = {"states": rows.size * ns, "params": rows.size * npar}
         return h.value
+
+    def _model_dims(self, model_id):
+        for _, (mid, ns, npar) in self.lib.models().items():
+            if mid == model_id:
+                return ns, npar
+        raise KnpError(f"unknown membrane model id {model_id}")
 
     def membrane_get(self, handle, what, shape):
         out = np.empty(shape)
+        want = getattr(self, "_mem_shapes", {}).get(handle, {}).get(what)
+        if want is not None and out.size != want:
+            raise KnpError(f"membrane_get({what}): shape {shape} for a table of {want} values")
         self._call("knp_membrane_%s_get" % what, handle, _p(out, _dp))
         return out
 
     def membrane_set(self, handle, what, values):
         v = _f64(values)
+        want = getattr(self, "_mem_shapes", {}).get(handle, {}).get(what)
+        if want is not None and v.size != want:
+            raise KnpError(f"membrane_set({what}): {v.size} values for a table of {want}")
         self._call("knp_membrane_%s_set" % what, handle, _p(v, _dp))
 
     def membrane_link(self, handle, col, kind, which, idx=0, side=0):

@@ -225,19 +225,26 @@ class Engine:
         """setup_membrane_model for one tag (solver.py:228-267).  `links`: the
         update_ode hook as data: (parameter name, ion index, side)."""
         lib = self.ctx.lib
-        name = module.__name__.split(".")[-1]
         models = lib.models()
-        if name not in models:
-            try:
-                name = self.resolve_model(module)
-            except (_lib.KnpError, AttributeError):
-                raise _lib.KnpError(f"membrane model '{name}' is not compiled into libknpemi.so "
-                                    f"(available: {sorted(models)})") from None
+        # The compiled model is found by WHAT the module computes (table sizes, defaults, right-hand
+        # side on probe inputs), never by its bare name: the reference ships different modules that
+        # are all called mm_hh (examples/idealized-geometries, emix-simulations,
+        # local-astrocyte-depolarization).
+        try:
+            name = self.resolve_model(module)
+        except AttributeError:
+            raise _lib.KnpError(f"membrane model '{module.__name__}' does not follow the mm_*.py protocol "
+                                "(init_state_values, init_parameter_values, state_indices, parameter_indices)") from None
         mid, ns, npar = models[name]
         rows = np.flatnonzero(self.mem["tag"] == tag).astype(np.int32)   # ascending facet index
         m = MembraneHandle(self, tag, module, rows, mid, ns, npar)
-        states = np.tile(np.asarray(module.init_state_values(), dtype=float), (len(rows), 1))
-        params = np.tile(np.asarray(module.init_parameter_values(), dtype=float), (len(rows), 1))
+        s0 = np.asarray(module.init_state_values(), dtype=float)
+        p0 = np.asarray(module.init_parameter_values(), dtype=float)
+        if s0.size != ns or p0.size != npar:
+            raise _lib.KnpError(f"membrane model '{module.__name__}': tables of {s0.size} states / {p0.size} parameters, "
+                                f"the compiled model '{name}' has {ns} / {npar}")
+        states = np.tile(s0, (len(rows), 1))
+        params = np.tile(p0, (len(rows), 1))
         params[:, module.parameter_indices("Cm")] = self.C_M              # solver.py:248
         m.handle = self.ctx.membrane_register(mid, rows, states, params)
         ich = [module.parameter_indices("I_ch_" + nme) for nme in ion_names]

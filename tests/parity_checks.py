@@ -2,8 +2,9 @@
 function takes the loaded library, builds a seeded case, runs the hot path
 through the C ABI and compares with the oracle (oracle/).
 
-Tolerances: assembled matrix / right-hand-side entries 1e-12 relative to the
-largest entry of the object (north_star: "within 1e-12 relative (fp64)");
+Tolerances: assembled matrix entries ENTRY BY ENTRY, |a - b| <= 1e-12 |b| + 1e-14 max|row|
+(north_star: "within 1e-12 relative (fp64)"; the row-relative floor is the round-off of the
+sum of contributions that cancel), right-hand sides 1e-12 |b| + 1e-13 max|b|;
 linear solutions against a sparse direct solve at the level the KSP tolerance
 allows; ODE states against a 1e-10 LSODA solve at 1e-6 (north_star trace
 tolerance).
@@ -13,11 +14,17 @@ import importlib
 import numpy as np
 import scipy.sparse.linalg as spla
 
-from common import Case, rel_err, _lib
+from common import Case, rel_err, entrywise_failures, _lib
 from oracle import forms, ode as oracle_ode
 from oracle.stepper import solve_singular_direct
 
 TOL_ASM = 1e-12
+
+
+def assert_entrywise(what, a, b, rtol=TOL_ASM):
+    import scipy.sparse as sp
+    nfail, worst = entrywise_failures(a, b, rtol=rtol, row_floor=1e-14 if sp.issparse(b) else 1e-13)
+    assert nfail == 0, f"{what}: {nfail} entries outside the entrywise bound, worst {worst:.2f} x"
 
 
 def check_assembly(lib, name, splitting=True, D_scale=(1.0, 1.0), seed=0):
@@ -29,6 +36,9 @@ def check_assembly(lib, name, splitting=True, D_scale=(1.0, 1.0), seed=0):
     assert rel_err(Ag, A) < TOL_ASM
     assert rel_err(Bg, B) < TOL_ASM
     assert rel_err(ctx.get_field(_lib.F_RHS_EMI), b) < TOL_ASM
+    assert_entrywise("A_emi", Ag, A)
+    assert_entrywise("B_emi", Bg, B)
+    assert_entrywise("b_emi", ctx.get_field(_lib.F_RHS_EMI), b)
     # structure: symmetric, constants in the null space (solver.py:465-466)
     assert abs(Ag - Ag.T).max() < 1e-12 * abs(Ag).max()
     assert np.abs(Ag @ np.ones(P.ndof)).max() < 1e-10 * abs(Ag).max()
@@ -41,6 +51,8 @@ def check_assembly(lib, name, splitting=True, D_scale=(1.0, 1.0), seed=0):
         assert rel_err(ctx.matrix(2 + k), As[k]) < TOL_ASM
         bg = ctx.get_field(_lib.F_RHS_KNP, k)
         assert rel_err(bg, bs[k]) < TOL_ASM
+        assert_entrywise(f"A_knp[{k}]", ctx.matrix(2 + k), As[k])
+        assert_entrywise(f"b_knp[{k}]", bg, bs[k], rtol=1e-11)
         mem = bs[k] - bs0[k]
         assert np.abs((bg - bs0[k]) - mem).max() < max(1e-8 * np.abs(mem).max(), 1e-13 * np.abs(bs[k]).max())
     # SpMV kernel against the exported matrix

@@ -167,3 +167,143 @@ def run_emix_block(lib, M, nsteps, rtol_emi=1e-12, rtol_knp=1e-13):
         eng.step()
     O.run(nsteps)
     return eng, O
+
+
+def check_picard(lib):
+    """solve_for_time_step_picard (solver.py:850-927): converges in a few iterations at the
+    reference's time step and stays close to the split step it refines"""
+    import bench
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_hh
+    from common import kmesh
+
+    def make():
+        mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+        eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1,), lib=lib, **bench.PHYS)
+        eng.set_concentrations_by_tag(bench.C_INIT)
+        eng.add_membrane_model(1, mm_hh, bench.ION_NAMES, stimulus=bench.STIMULUS, stimulus_locator=bench.stim_locator)
+        eng.rtol_emi, eng.rtol_knp = 1e-10, 1e-11
+        eng.initialize(pc=1)
+        return eng
+    a, b = make(), make()
+    for _ in range(3):
+        a.step()
+        b.ode_phase()
+        it = b.pde_phase_picard()
+        b.k += 1
+        assert 1 <= it <= 6
+    assert rel_err(b.phi_M(), a.phi_M()) < 1e-3
+    for k in range(3):
+        assert rel_err(b.concentration(k), a.concentration(k)) < 1e-4
+    # the fixed point: one more Picard sweep from the converged state changes nothing above tol
+    assert b.picard_iterations <= 3
+
+
+def _neuron_engine(lib, resolution=1, tight=True):
+    import bench
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_hh
+    from common import kmesh
+    mesh, sub, surf = kmesh.neuron_2d_mesh(resolution)
+    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1,), lib=lib, **bench.PHYS)
+    eng.set_concentrations_by_tag(bench.C_INIT)
+    eng.add_membrane_model(1, mm_hh, bench.ION_NAMES, stimulus=bench.STIMULUS, stimulus_locator=bench.stim_locator)
+    if tight:
+        eng.rtol_emi, eng.rtol_knp = 1e-10, 1e-11
+    eng.initialize(pc=1)
+    return eng
+
+
+def check_picard_then_regular(lib):
+    """a Picard step writes c_prev_n separately (KNP_F_CN); the regular steps after it must again
+    take the time derivative against the concentrations of the step before (c_prev_n.assign(c),
+    solver.py:810) - not against the ones the Picard step left behind"""
+    from knpemidg import _lib
+    a, b = _neuron_engine(lib), _neuron_engine(lib)
+    for eng in (a, b):
+        eng.step()
+    # b: one Picard step; a: the same state transplanted into it afterwards
+    b.ode_phase()
+    b.pde_phase_picard()
+    b.k += 1
+    a.ode_phase()
+    a.pde_phase_picard()
+    a.k += 1
+    fresh = _neuron_engine(lib)                          # never touched KNP_F_CN
+    for k in range(3):
+        fresh.ctx.set_field(_lib.F_C, k, a.ctx.get_field(_lib.F_C, k))
+    fresh.ctx.set_field(_lib.F_PHI, 0, a.ctx.get_field(_lib.F_PHI))
+    fresh.ctx.set_field(_lib.F_PHIM, 0, a.ctx.get_field(_lib.F_PHIM))
+    for k in range(3):
+        fresh.ctx.set_field(_lib.F_ICH, k, a.ctx.get_field(_lib.F_ICH, k))
+    fresh.ctx.post_step(_lib.POST_NERNST)
+    for _ in range(2):                                   # regular PDE steps (no ODE: same currents on both sides)
+        b.pde_phase()
+        fresh.pde_phase()
+        for k in range(2):
+            assert np.array_equal(b.ctx.get_field(_lib.F_CN, k), b.ctx.get_field(_lib.F_C, k))
+    for k in range(3):
+        assert rel_err(b.concentration(k), fresh.concentration(k)) < 1e-9
+    assert rel_err(b.phi_M(), fresh.phi_M()) < 1e-7
+
+
+def check_membrane_shape_validation(lib):
+    """tables whose shape does not match the compiled model are refused before any pointer is taken;
+    a module is matched to a compiled model by what it computes, not by its name"""
+    import types
+    import pytest
+    from knpemidg import _lib
+    from knpemidg.models import mm_hh, mm_leak
+    eng = _neuron_engine(lib, resolution=0, tight=False)
+    mid, ns, npar = lib.models()["mm_hh"]
+    rows = np.arange(4, dtype=np.int32)
+    with pytest.raises(_lib.KnpError):
+        eng.ctx.membrane_register(mid, rows, np.zeros((4, ns + 1)), np.zeros((4, npar)))
+    with pytest.raises(_lib.KnpError):
+        eng.ctx.membrane_register(mid, rows, np.zeros((4, ns)), np.zeros((3, npar)))
+    h = eng.members[0].handle
+    with pytest.raises(_lib.KnpError):
+        eng.ctx.membrane_set(h, "params", np.zeros(5))
+    # a module CALLED mm_hh that is in fact the leak model resolves to the compiled leak model
+    fake = types.ModuleType("mm_hh")
+    for name in ("init_state_values", "init_parameter_values", "state_indices", "parameter_indices", "rhs_numba"):
+        setattr(fake, name, getattr(mm_leak, name))
+    assert eng.resolve_model(fake) == "mm_leak"
+    assert eng.resolve_model(mm_hh) == "mm_hh"
+
+
+def check_solver_emi(lib):
+    """SolverEMI (solver_emi.py): the run-script flow with the EMI sub-problem only - the
+    membrane fires, the concentrations never move"""
+    from collections import namedtuple
+    from knpemidg import SolverEMI
+    from knpemidg.frontend import Constant
+    from knpemidg.models import mm_hh
+    from common import kmesh
+
+    class EMI2D(SolverEMI):
+        def update_ode(self, ode_model):
+            Solver2D.update_ode(self, ode_model)
+
+    params = namedtuple("params", "dt n_steps_ODE F psi phi_M_init C_phi C_M R temperature phi_M_init_type "
+                                  "rho_sub")(DT, 25, F, F / (R * T), Constant(-0.0743), C_M / DT,
+                                             C_M, R, T, "constant", {0: Constant(0), 1: Constant(0)})
+    ion_list = [_ion("K", 1.0, 1.96e-9, K_I, K_E), _ion("Cl", -1.0, 2.03e-9, NA_I + K_I, NA_E + K_E),
+                _ion("Na", 1.0, 1.33e-9, NA_I, NA_E)]
+    stim = namedtuple("membrane_params", "g_syn_bar stimulus stimulus_locator")(
+        10.0, {"stim_amplitude": 10.0}, lambda x: x[0] < 20e-6)
+    sp = SolverParams(False, False, 0, 1e-5, 1e-7, 1e-40, 1e-40, None, None)
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    S = EMI2D(params, ion_list, lib=lib)
+    S.setup_domain(mesh, sub, surf)
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    S.setup_membrane_model(stim, {1: mm_hh})
+    c0 = [S.c.split()[k].nodal().copy() for k in range(2)]
+    t = Constant(0.0)
+    S.solve_system_active(30 * DT, t, sp)
+    pm = S.phi_M_prev_PDE.vector().get_local()
+    assert pm.max() > 0.0                                         # the spike (peak at step ~29 in the full model)
+    for k in range(2):
+        assert np.array_equal(S.c.split()[k].nodal(), c0[k])
+    assert all(n == 0 for n in S.engine.stats["knp_niter"]) and abs(float(t) - 30 * DT) < 1e-15

@@ -63,3 +63,21 @@ def test_rest_state_is_preserved_at_scale(gpu_lib):
     z = bench.PHYS["z"]
     total = sum(z[k] * eng.concentration(k) for k in range(3))
     assert np.abs(total).max() < 1e-9 * np.abs(c0[1]).max()
+
+
+def test_picard_variant(gpu_lib):
+    """solve_for_time_step_picard (solver.py:850-927) on the CUDA path"""
+    sc.check_picard(gpu_lib)
+
+
+def test_picard_then_regular_steps_use_the_current_c_prev_n(gpu_lib):
+    sc.check_picard_then_regular(gpu_lib)
+
+
+def test_solver_emi_keeps_concentrations_frozen(gpu_lib):
+    """SolverEMI (solver_emi.py:52-822) on the CUDA path"""
+    sc.check_solver_emi(gpu_lib)
+
+
+def test_membrane_table_shapes_are_validated(gpu_lib):
+    sc.check_membrane_shape_validation(gpu_lib)

@@ -162,33 +162,15 @@ def test_emix_block_matches_oracle(emu_lib):
 
 
 def test_picard_variant(emu_lib):
-    """solve_for_time_step_picard (solver.py:850-927): converges in a few iterations at the
-    reference's time step and stays close to the split step it refines"""
-    import bench
-    from knpemidg.engine import Engine
-    from knpemidg.models import mm_hh
-    from common import kmesh
+    sc.check_picard(emu_lib)
 
-    def make():
-        mesh, sub, surf = kmesh.neuron_2d_mesh(1)
-        eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1,), lib=emu_lib, **bench.PHYS)
-        eng.set_concentrations_by_tag(bench.C_INIT)
-        eng.add_membrane_model(1, mm_hh, bench.ION_NAMES, stimulus=bench.STIMULUS, stimulus_locator=bench.stim_locator)
-        eng.rtol_emi, eng.rtol_knp = 1e-10, 1e-11
-        eng.initialize(pc=1)
-        return eng
-    a, b = make(), make()
-    for _ in range(3):
-        a.step()
-        b.ode_phase()
-        it = b.pde_phase_picard()
-        b.k += 1
-        assert 1 <= it <= 6
-    assert rel_err(b.phi_M(), a.phi_M()) < 1e-3
-    for k in range(3):
-        assert rel_err(b.concentration(k), a.concentration(k)) < 1e-4
-    # the fixed point: one more Picard sweep from the converged state changes nothing above tol
-    assert b.picard_iterations <= 3
+
+def test_picard_then_regular_steps_use_the_current_c_prev_n(emu_lib):
+    sc.check_picard_then_regular(emu_lib)
+
+
+def test_membrane_table_shapes_are_validated(emu_lib):
+    sc.check_membrane_shape_validation(emu_lib)
 
 
 def test_traces_over_an_action_potential_match_oracle(emu_lib):
@@ -205,37 +187,4 @@ def test_traces_over_an_action_potential_match_oracle(emu_lib):
 
 
 def test_solver_emi_keeps_concentrations_frozen(emu_lib):
-    """SolverEMI (solver_emi.py): the run-script flow with the EMI sub-problem only - the
-    membrane fires, the concentrations never move"""
-    from collections import namedtuple
-    from knpemidg import SolverEMI
-    from knpemidg.frontend import Constant
-    from knpemidg.models import mm_hh
-    from common import kmesh
-
-    class EMI2D(SolverEMI):
-        def update_ode(self, ode_model):
-            sc.Solver2D.update_ode(self, ode_model)
-
-    params = namedtuple("params", "dt n_steps_ODE F psi phi_M_init C_phi C_M R temperature phi_M_init_type "
-                                  "rho_sub")(sc.DT, 25, sc.F, sc.F / (sc.R * sc.T), Constant(-0.0743), sc.C_M / sc.DT,
-                                             sc.C_M, sc.R, sc.T, "constant", {0: Constant(0), 1: Constant(0)})
-    ion_list = [sc._ion("K", 1.0, 1.96e-9, sc.K_I, sc.K_E), sc._ion("Cl", -1.0, 2.03e-9, sc.NA_I + sc.K_I, sc.NA_E + sc.K_E),
-                sc._ion("Na", 1.0, 1.33e-9, sc.NA_I, sc.NA_E)]
-    stim = namedtuple("membrane_params", "g_syn_bar stimulus stimulus_locator")(
-        10.0, {"stim_amplitude": 10.0}, lambda x: x[0] < 20e-6)
-    sp = sc.SolverParams(False, False, 0, 1e-5, 1e-7, 1e-40, 1e-40, None, None)
-    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
-    S = EMI2D(params, ion_list, lib=emu_lib)
-    S.setup_domain(mesh, sub, surf)
-    S.setup_parameters()
-    S.setup_FEM_spaces()
-    S.setup_membrane_model(stim, {1: mm_hh})
-    c0 = [S.c.split()[k].nodal().copy() for k in range(2)]
-    t = Constant(0.0)
-    S.solve_system_active(30 * sc.DT, t, sp)
-    pm = S.phi_M_prev_PDE.vector().get_local()
-    assert pm.max() > 0.0                                         # the spike (peak at step ~29 in the full model)
-    for k in range(2):
-        assert np.array_equal(S.c.split()[k].nodal(), c0[k])
-    assert all(n == 0 for n in S.engine.stats["knp_niter"]) and abs(float(t) - 30 * sc.DT) < 1e-15
+    sc.check_solver_emi(emu_lib)
