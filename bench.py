@@ -1,24 +1,29 @@
 #!/usr/bin/env python
-"""bench.py - KNP-EMI DOF-steps/s (and time-steps/s) on the 3D axon-bundle workload
-(BASELINE.json configs[2]).
+"""bench.py - KNP-EMI DOF-steps/s (and time-steps/s) on the EMIx-style tissue block
+(BASELINE.json configs[4], the workload north_star sets its targets on).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling weak|strong]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload emix|bundle|astro] [--size M] [--scaling strong|weak]
 
 One "step" = one full time step of the reference's loop (solver.py:1072-1127): membrane
 ODE step -> EMI assembly + CG/AMG solve -> KNP assembly + GMRES/AMG solves -> post-step.
-Workload: 32 x 0.9 x 0.9 um box with four axons (make_mesh_3D.py:81-111) at 96 x 27 x 27 x 6
-tetrahedra = 419,904 cells, 5.04 M DOFs (3 fields x 4 dofs x cells), Hodgkin-Huxley membranes
-with the synaptic stimulus of run_3D.py, dt = 0.1 ms, CG rtol 1e-5, GMRES(30) rtol 1e-7.
 
-N > 1 (one process per GPU, torchrun): the mesh is partitioned by cell, one part per GPU,
-DG halos over NCCL send/recv and Krylov dots over NCCL allreduce inside libknpemi.so.
-Weak scaling (default): N copies of the four-axon block side by side (32 x 0.9 N x 0.9 um,
-96 x 27 N x 27 x 6 tetrahedra, 4 N axons), so every GPU holds the N = 1 workload (5.04 M DOFs); `--scaling strong` keeps the N = 1 mesh.
+Default workload (`emix`, M = 66): a 10 um block of 66^3 x 6 = 1,724,976 tetrahedra with ~100
+compact cells (alternately glial, `mm_glial`, and neuronal, `mm_hh`; ms/cm/mV units, calibrated
+initial state, run_EMIx_simulation.py:56-147, 249): 20.7 M DOFs, dt = 0.1 ms, CG rtol 1e-5,
+GMRES(30) rtol 1e-7.  N > 1 (one process per GPU, torchrun): the SAME mesh partitioned by cell
+(strong scaling), DG halos and Krylov dots over NVLink peer memory / NCCL inside libknpemi.so.
+Other workloads: `bundle` = BASELINE configs[2] (96x27x27x6 tets, 5.04 M DOFs, HH membranes; weak
+scaling = N four-axon blocks side by side), `astro` = configs[3] (three membrane tags, glial +
+neuronal models, rho != 0, tortuosity, time-windowed source; run_tortuosity.py).
 
 Prints ONE JSON line (rank 0).  `value` = DOF-steps/s = (DOFs of the whole mesh) x steps /
 time with everything resident in HBM (`steps_per_s` beside it); `e2e` = the same loop
 driven with HOST buffers through the C ABI (state uploaded from pinned memory before and
-downloaded after every step).
+downloaded after every step).  `cpu_baseline` / `--impl reference`: the reference itself
+(dolfin + PETSc + numbalsoda) cannot be installed here; the CPU arm is the C++/OpenMP port of
+this library's own kernels (oracle/_port, `g++ -DKNP_EMU -fopenmp`) stepping the SAME workload
+on all host cores.
 """
 import argparse
 import json
@@ -40,8 +45,9 @@ if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("KNP_CONCURRENT
 
 import numpy as np  # noqa: E402
 
-WORKLOAD_DIMS = (96, 27, 27)
-SAMPLE_DIMS = (32, 9, 9)          # CPU arms: bundle r=0 (make_mesh_3D.py resolution 0)
+WORKLOAD_DIMS = (96, 27, 27)      # bundle
+EMIX_M = 66                       # emix: 66^3 x 6 tets = 20.7 M DOFs (north_star: >= 20 M)
+ASTRO_M = 48                      # astro: 48^3 x 6 tets = 7.96 M DOFs
 DT, C_M = 1.0e-4, 0.02
 PHYS = dict(F=96485.0, R=8.314, T=300.0, C_M=C_M, C_phi=C_M / DT, dt=DT, z=[1.0, -1.0, 1.0],
             D_sub=[{0: 1.96e-9, 1: 1.96e-9}, {0: 2.03e-9, 1: 2.03e-9}, {0: 1.33e-9, 1: 1.33e-9}],
@@ -50,9 +56,10 @@ NA_I, NA_E, K_I, K_E = 12.838513108648856, 100.71925900027354, 124.1539758349190
 C_INIT = [{1: K_I, 0: K_E}, {1: NA_I + K_I, 0: NA_E + K_E}, {1: NA_I, 0: NA_E}]   # K, Cl, Na (run_3D.py)
 ION_NAMES = ["K", "Cl", "Na"]
 STIMULUS = {"stim_amplitude": 10.0}
-# dram__bytes_read.sum + dram__bytes_write.sum of one BellSpmvKernel<4> launch on the N = 1 workload, from
-# the `ncu --set full` capture summarised in profiles/kernels_r01_solver.md
-TRAFFIC_SPMV = 3.119e8     # 299.4 MB read + 12.5 MB written (profiles/kernels_r01_solver.md, launch #1)
+# dram__bytes_read.sum + dram__bytes_write.sum of one BellSpmvKernel<4> launch on the N = 1 workloads, from
+# the `ncu --set full` captures summarised in profiles/ (None: not captured for that workload)
+TRAFFIC_SPMV = {"bundle": 3.119e8,    # 299.4 MB read + 12.5 MB written (profiles/kernels_r01_solver.md, launch #1)
+                "emix": None, "astro": None}
 
 
 def stim_locator(x):
@@ -112,13 +119,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_engine(dims, device, transport=None, nblocks=1):
+def build_engine(dims, device, transport=None, nblocks=1, lib=None):
     from knpemidg import mesh as kmesh
     from knpemidg.engine import Engine
     from knpemidg.models import mm_hh, mm_hh_no_stim
     mesh, sub, surf = kmesh.bundle_3d_mesh(dims=dims, nblocks=nblocks)
     eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), device=device, transport=transport,
-                 **PHYS)
+                 lib=lib, **PHYS)
     eng.set_concentrations_by_tag(C_INIT)
     eng.add_membrane_model(1, mm_hh, ION_NAMES, stimulus=STIMULUS, stimulus_locator=stim_locator)
     eng.add_membrane_model(2, mm_hh_no_stim, ION_NAMES, stimulus=STIMULUS, stimulus_locator=stim_locator)
@@ -127,8 +134,7 @@ def build_engine(dims, device, transport=None, nblocks=1):
 
 
 # BASELINE configs[4]: EMIx-style tissue block, ms / cm / mV units, calibrated initial state
-# (examples/emix-simulations/run_EMIx_simulation.py:56-147, 249); a second workload for A/B runs of the
-# solver switches on compact cells (`--emix M`), not the headline line
+# (examples/emix-simulations/run_EMIx_simulation.py:56-147, 249)
 EMIX_DT, EMIX_CM = 0.1, 2.0
 EMIX_PHYS = dict(F=96485e3, R=8.314e3, T=300e3, C_M=EMIX_CM, C_phi=EMIX_CM / EMIX_DT, dt=EMIX_DT, z=[1.0, -1.0, 1.0],
                  D_sub=[{t: d for t in (0, 1, 2)} for d in (1.96e-8, 2.03e-8, 1.33e-8)],
@@ -154,60 +160,72 @@ def build_engine_emix(M, device, transport=None, lib=None):
     return eng
 
 
-def cpu_reference_steps(nsteps, dims=SAMPLE_DIMS):
-    """The CPU restatement (oracle/) stepping the same kind of workload on a bounded
-    sample; returns (seconds per step, dofs of the sample, timers)."""
+# BASELINE configs[3]: examples/local-astrocyte-depolarization/run_tortuosity.py:81-298 on the synthetic
+# mesh knpemidg.mesh.astro_like_mesh (ions K, Na, Cl with Cl eliminated; rho != 0; tortuosity)
+ASTRO = dict(dt=0.1, C_M=1.0, T=307e3, F=96500e3, R=8.315e3, g_syn=26.0, t_syn=1.2, lambda_i=3.2 * 4, lambda_e=1.6 * 4)
+ASTRO_D = [1.96e-8, 1.33e-8, 2.03e-8]
+ASTRO_C = [(3.092970607490389, 124.13988964240784, 99.3100014897692),
+           (144.60625137617149, 12.850454639128186, 15.775818906083778),
+           (133.62525154406637, 5.0, 5.203660274163705)]
+
+
+def build_engine_astro(M, device, transport=None, lib=None):
     from knpemidg import mesh as kmesh
-    from knpemidg.models import mm_hh, mm_hh_no_stim
-    from oracle import forms, stepper
-    mesh, sub, surf = kmesh.bundle_3d_mesh(dims=dims)
-    P = forms.Problem(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), **PHYS)
-    c0 = np.stack([np.where((sub.array() == 1)[:, None], ci[1], ci[0]) * np.ones((P.nc, P.nd)) for ci in C_INIT])
-    O = stepper.OracleSolver(P, c0, models={1: mm_hh, 2: mm_hh_no_stim}, stimulus=STIMULUS,
-                             stimulus_locator=stim_locator, ion_names=ION_NAMES, direct=False)
-    O.step()                                   # warm-up (numpy/scipy first-call costs, AMG plan)
-    t0 = time.perf_counter()
-    for _ in range(nsteps):
-        O.step()
-    dt = (time.perf_counter() - t0) / nsteps
-    return dt, 3 * P.ndof, {"emi_niter": O.niter["emi"][-1:], "knp_niter": O.niter["knp"][-2:]}
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_glial_astro, mm_hh_astro
+    A = ASTRO
+    lam = [A["lambda_e"], A["lambda_i"], A["lambda_i"]]
+    mesh, sub, surf = kmesh.astro_like_mesh(M)
+    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2, 3), device=device, transport=transport, lib=lib,
+                 F=A["F"], R=A["R"], T=A["T"], C_M=A["C_M"], C_phi=A["C_M"] / A["dt"], dt=A["dt"], z=[1.0, 1.0, -1.0],
+                 D_sub=[{t: D / lam[t] ** 2 for t in range(3)} for D in ASTRO_D],
+                 rho_sub={t: -(ASTRO_C[1][t] + ASTRO_C[0][t] - ASTRO_C[2][t]) for t in range(3)})
+    eng.set_concentrations_by_tag([{t: ci[t] for t in range(3)} for ci in ASTRO_C])
+    names = ["K", "Na", "Cl"]
+    links = (("K_e", 0, "plus"), ("Na_i", 1, "minus"))                              # run_tortuosity.py:38-49
+    for tag, mod in ((1, mm_hh_astro), (2, mm_glial_astro), (3, mm_hh_astro)):
+        eng.add_membrane_model(tag, mod, names, stimulus={"stim_amplitude": 0.0}, links=links)
+    # the K+/Na+ source of run_tortuosity.py:180-200 inside its time window (constant on the source box)
+    lo, hi = mesh.source_box
+    mid = eng.mesh.coords[eng.mesh.cells].mean(axis=1)
+    inside = np.all((mid >= lo) & (mid <= hi), axis=1) & (eng.cell_tags == 0)
+    vol = eng.mesh.cell_volume()
+    for k, sign in ((0, 1.0), (1, -1.0)):
+        load = np.zeros((eng.nc, eng.nd))
+        load[inside] = (sign * A["g_syn"] * vol[inside] / 4.0)[:, None]
+        eng.ctx.set_field(_lib_mod().F_LOAD_KNP, k, load)
+    eng.initialize(pc=1)
+    return eng
 
 
-def workload_dofs(dims, nblocks=1):
-    return 3 * 4 * 6 * dims[0] * dims[1] * dims[2] * nblocks
+def _lib_mod():
+    from knpemidg import _lib
+    return _lib
 
 
-def _cpu_worker(nsteps, q):
-    try:
-        try:                                    # one thread per copy: the copies fill the cores
-            from threadpoolctl import threadpool_limits
-            threadpool_limits(1)
-        except Exception:
-            pass
-        q.put(cpu_reference_steps(nsteps))
-    except Exception as e:  # pragma: no cover
-        q.put(e)
+def make_engine(args, device, transport=None, lib=None, nblocks=1):
+    if args.workload == "emix":
+        return build_engine_emix(args.size or EMIX_M, device, transport, lib)
+    if args.workload == "astro":
+        return build_engine_astro(args.size or ASTRO_M, device, transport, lib)
+    dims = tuple(int(v) for v in args.dims.split(",")) if args.dims else WORKLOAD_DIMS
+    return build_engine(dims, device, transport, nblocks, lib)
 
 
-def cpu_reference_parallel(nsteps, nproc):
-    """`nproc` independent copies of the CPU restatement stepping the sample at the same time
-    (what `mpirun -n nproc` of the reference could reach at best: perfect scaling, no
-    communication).  Returns aggregate DOF-steps/s, seconds per step of the slowest copy, dofs."""
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_cpu_worker, args=(nsteps, q)) for _ in range(nproc)]
-    for p in procs:
-        p.start()
-    res = [q.get() for _ in procs]
-    for p in procs:
-        p.join()
-    for r in res:
-        if isinstance(r, Exception):
-            raise r
-    sec = max(r[0] for r in res)
-    dofs = res[0][1]
-    return nproc * dofs / sec, sec, dofs, res[0][2]
+def workload_name(args, eng, nblocks=1):
+    dofs = eng.dofs()
+    if args.workload == "emix":
+        M = args.size or EMIX_M
+        return (f"EMIx-like tissue block {M}^3 x 6 tets, ~100 cells, mm_hh + mm_glial membranes, calibrated initial "
+                f"state, dt=0.1 ms (BASELINE configs[4]), {eng.nc_global} cells, {dofs} DOFs")
+    if args.workload == "astro":
+        M = args.size or ASTRO_M
+        return (f"astrocyte depolarisation block {M}^3 x 6 tets, 2 neurons + 1 glial cell, 3 membrane tags, rho != 0, "
+                f"tortuosity, K+/Na+ source on, dt=0.1 ms (BASELINE configs[3]), {eng.nc_global} cells, {dofs} DOFs")
+    dims = tuple(int(v) for v in args.dims.split(",")) if args.dims else WORKLOAD_DIMS
+    return (f"3D axon bundle {dims[0]}x{dims[1] * nblocks}x{dims[2]}x6 tets (BASELINE configs[2]"
+            + (f", {nblocks} four-axon blocks side by side" if nblocks > 1 else "") + "), "
+            f"{eng.nc_global} cells, {dofs} DOFs, HH membranes, dt=1e-4 s")
 
 
 def host_cores():
@@ -217,53 +235,106 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def omp_port_path():
+    return os.path.join(ROOT, "oracle", "_port", "libknpemi_omp.so")
+
+
 def run_reference(args, rank):
-    """The reference's own path is dolfin + PETSc + numbalsoda, none of which exists in this
-    image: the reference arm times the CPU restatement (oracle/) of the same
-    time step on the host cores, one copy per core."""
+    """CPU arm.  The reference's own path is dolfin + PETSc + numbalsoda, none of which exists in
+    this image: what is timed is the C++/OpenMP port of this library's kernels and host
+    logic (oracle/_port/libknpemi_omp.so: same sources, g++ -DKNP_EMU -fopenmp) stepping the SAME
+    workload - same mesh, membranes, tolerances - on all host cores."""
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    cores = max(1, min(host_cores(), 32))
-    value, sec, dofs, info = cpu_reference_parallel(steps, cores)
-    sample = (f"{cores} independent copies (one per host core) of the oracle/ restatement on the bundle "
-              f"{SAMPLE_DIMS[0]}x{SAMPLE_DIMS[1]}x{SAMPLE_DIMS[2]}x6 tets ({dofs} DOFs each), {steps} steps of "
-              f"{sec:.2f} s after 1 warm-up step; DOF-steps/s summed over the copies")
-    full = workload_dofs(WORKLOAD_DIMS)
+    cores = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OMP_PROC_BIND", "false")
+    path = omp_port_path()
+    if not os.path.exists(path):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("knp_build", os.path.join(ROOT, "knp-emi-dg_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build_omp()
+    from knpemidg import _lib
+    lib = _lib.Lib(path)
+    assert not lib.is_cuda()
+    steps = max(1, min(args.steps, 20))          # bounded: ~3-6 s per step of the 20.7 M-DOF workload
+    warmup = max(1, min(args.warmup, 3))
+    t0 = time.perf_counter()
+    eng = make_engine(args, 0, None, lib=lib)
+    setup_s = time.perf_counter() - t0
+    for _ in range(warmup):
+        eng.step()
+    eng.ctx.timers(reset=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.step()
+    sec = (time.perf_counter() - t0) / steps
+    phase = eng.ctx.timers()
+    dofs = eng.dofs()
+    value = dofs / sec
+    sample = (f"C++/OpenMP port of the library's kernels (oracle/_port, g++ -O3 -fopenmp), the full workload, {steps} steps of "
+              f"{sec:.2f} s after {warmup} warm-up step(s), {cores} threads; setup {setup_s:.1f} s not counted")
     line = {"impl": "reference", "metric": "dof_steps_per_s", "value": value, "unit": "DOF-steps/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": 1e3 * full / value,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "3D axon bundle 96x27x27x6 tets, 5.04M DOFs, HH membranes (BASELINE configs[2])",
-                       "note": "dolfin+PETSc+numbalsoda cannot be installed here; CPU restatement (oracle/) on "
-                               "numpy/scipy on a bounded sample; ms_per_step = the full workload at this rate"},
-            "steps_per_s": value / full,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sec,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, eng),
+                       "note": "dolfin+PETSc+numbalsoda cannot be installed here; the CPU arm is the C++/OpenMP port "
+                               "of this library's kernels on the same workload, all host cores"},
+            "steps_per_s": 1.0 / sec,
+            "seconds_per_step": {k: v / steps for k, v in phase.items()},
+            "iterations": {"emi": eng.stats["emi_niter"][-steps:], "knp": eng.stats["knp_niter"][-steps:]},
             "cpu_baseline": {"value": value, "unit": "DOF-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "DOF-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "detail": info}
+            "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """the CPU arm on 2 steps of the same workload, in a process of its own (its OpenMP runtime and
+    ~10 GB of host matrices stay out of the GPU process)"""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--workload", args.workload, "--scaling", args.scaling]
+    if args.size:
+        cmd += ["--size", str(args.size)]
+    if args.dims:
+        cmd += ["--dims", args.dims]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"]
+    except Exception as e:  # the baseline is a reported number, not a reason to lose the GPU line
+        return {"value": None, "unit": "DOF-steps/s", "cores": host_cores(), "kind": "port", "sample": f"failed: {e}"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--scaling", default="weak", choices=("weak", "strong"))
-    ap.add_argument("--dims", default=None, help="nx,ny,nz override (debug)")
+    ap.add_argument("--workload", default="emix", choices=("emix", "bundle", "astro"))
+    ap.add_argument("--size", type=int, default=0, metavar="M", help="emix / astro: M^3 x 6 tetrahedra (default 66 / 48)")
+    ap.add_argument("--scaling", default=None, choices=("weak", "strong"),
+                    help="default strong (the same mesh on every N); weak is available for the bundle")
+    ap.add_argument("--dims", default=None, help="bundle: nx,ny,nz override")
+    ap.add_argument("--emix", type=int, default=0, metavar="M", help="same as --workload emix --size M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--emix", type=int, default=0, metavar="M",
-                    help="second workload (BASELINE configs[4]): EMIx-like block of M^3 x 6 tets, ~100 cells; "
-                         "M = 66 gives 20.7 M DOFs.  For A/B runs of solver switches; fixed mesh (strong scaling)")
     args = ap.parse_args()
+    if args.emix:
+        args.workload, args.size = "emix", args.emix
+    if args.scaling is None:
+        args.scaling = "strong"
+    if args.scaling == "weak" and args.workload != "bundle":
+        ap.error("weak scaling is defined for the bundle workload only")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    dims = tuple(int(v) for v in args.dims.split(",")) if args.dims else WORKLOAD_DIMS
     warmup = max(args.warmup, 3)
 
     import torch
@@ -300,11 +371,7 @@ def main():
 
     nblocks = world if args.scaling == "weak" else 1
     progress("building the engine")
-    if args.emix:
-        args.scaling, args.no_cpu_baseline = "strong", True
-        eng = build_engine_emix(args.emix, local_rank, transport)
-    else:
-        eng = build_engine(dims, local_rank, transport, nblocks)
+    eng = make_engine(args, local_rank, transport, nblocks=nblocks)
     progress("engine ready")
     ctx = eng.ctx
     dofs = eng.dofs()                                  # of the whole (partitioned) mesh
@@ -386,7 +453,8 @@ def main():
             comm_us[name] = {"us": kms * 1e3, "bytes": kbytes}
     dom = kern["bell_spmv"]
     roofline = {"bound": "hbm", "kernel": "knp::BellSpmvKernel<4> (block-ELL fp64 SpMV)",
-                "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"], "traffic": TRAFFIC_SPMV,
+                "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": TRAFFIC_SPMV.get(args.workload) if (world == 1 and not args.size and not args.dims) else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
                 "ms_per_launch": dom["ms"], "other_kernels": kern}
     launches = int(sum_over_ranks(float(launches)))
@@ -399,18 +467,13 @@ def main():
         return
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        sec, sdofs, info = cpu_reference_steps(2)
-        cpu = {"value": sdofs / sec, "unit": "DOF-steps/s", "cores": 1, "kind": "port",
-               "sample": f"oracle/ restatement (numpy/scipy, one core), bundle {SAMPLE_DIMS} x6 tets ({sdofs} DOFs), "
-                         f"2 steps of {sec:.2f} s after 1 warm-up step",
-               "steps_per_s_on_workload": sdofs / sec / dofs}
+        progress("CPU baseline (C++/OpenMP port, same workload, 2 steps)")
+        cpu = cpu_baseline_subprocess(args)
     line = {"metric": "dof_steps_per_s", "value": value, "unit": "DOF-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D axon bundle {dims[0]}x{dims[1] * nblocks}x{dims[2]}x6 tets (BASELINE configs[2]"
-                                   + (f", {nblocks} four-axon blocks side by side" if nblocks > 1 else "") + "), "
-                                   f"{eng.nc_global} cells, {dofs} DOFs, HH membranes, dt=1e-4 s",
-                       "parallelism": (f"cell partition, {world} parts (recursive bisection), NCCL halo + allreduce"
+            "config": {"workload": workload_name(args, eng, nblocks),
+                       "parallelism": (f"cell partition, {world} parts (recursive bisection), peer-memory / NCCL halo + allreduce"
                                        if world > 1 else "single"),
                        "l2_policy": "inputs larger than L2 (matrices 3 x %.0f MB per GPU)" % (ctx.nnz * 8 / 1e6),
                        "solver": "CG rtol 1e-5 / GMRES(30) rtol 1e-7 (min 5 its), aggregation AMG: plan built once, values "
@@ -421,10 +484,6 @@ def main():
             "e2e": {"value": e2e_value, "unit": "DOF-steps/s", "h2d_bytes_per_step": bytes_dir,
                     "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps, "steps_per_s": e2e_steps / (ms_e2e * 1e-3)},
             "gpu_launches": launches, "comm": comm_info, "comm_latency": comm_us, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
-    if args.emix:
-        line["config"]["workload"] = (f"EMIx-like tissue block {args.emix}^3 x 6 tets, ~100 cells (BASELINE configs[4]), "
-                                      f"{eng.nc_global} cells, {dofs} DOFs, mm_hh + mm_glial membranes, dt=0.1 ms")
-        line["roofline"]["traffic"] = None          # the ncu capture behind TRAFFIC_SPMV is of the bundle workload
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -87,6 +87,24 @@ def build_emu(force=False):
     return out
 
 
+def build_omp(force=False):
+    """C++/OpenMP port of the same sources (-DKNP_EMU -fopenmp -O3): the CPU baseline that bench.py
+    times on the GPU box's host cores (`cpu_baseline`, `--impl reference`).  Lives under oracle/
+    because it is measurement infrastructure, never loaded by the package."""
+    gen = generate_models()
+    outdir = os.path.join(ROOT, "oracle", "_port")
+    os.makedirs(outdir, exist_ok=True)
+    out = os.path.join(outdir, "libknpemi_omp.so")
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [gen, os.path.join(ROOT, "include", "knpemi.h")]
+    if not force and not _stale(out, deps):
+        return out
+    cmd = ["g++", "-std=c++17", "-O3", "-fopenmp", "-DKNP_EMU", "-fPIC", "-pthread", "-shared", "-o", out]
+    for f in SOURCES:
+        cmd += ["-x", "c++", os.path.join(CSRC, f)]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build_variant(user_modules, emu=False, cache_dir=None):
     """A copy of the library that carries, besides the bundled membrane models, the given
     user ODE modules (anything that follows the reference's mm_*.py protocol: the Python source
@@ -135,7 +153,9 @@ def build_variant(user_modules, emu=False, cache_dir=None):
 
 
 if __name__ == "__main__":
-    if "--emu" in sys.argv:
+    if "--omp" in sys.argv:
+        print(build_omp(force="--force" in sys.argv))
+    elif "--emu" in sys.argv:
         print(build_emu(force="--force" in sys.argv))
     else:
         print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -161,8 +161,13 @@ inline std::atomic<long long>& launch_counter() {
 // One-thread-per-index kernels are functor structs with `void operator()(int64_t) const`;
 // the functor type names the kernel in profiles (knp::pf_kernel<knp::EmiCellKernel<3>>).
 #ifdef KNP_EMU
+// (-fopenmp: the C++/OpenMP port that bench.py times as the CPU baseline; the test-suite's
+// emulation library is built without it and stays serial and bit-reproducible)
 template <class F>
 inline void parallel_for(knp_stream_t, int64_t n, const F& f, int = 256) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) if (n > 2048)
+#endif
   for (int64_t i = 0; i < n; ++i) f(i);
 }
 #else

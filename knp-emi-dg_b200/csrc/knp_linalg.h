@@ -227,6 +227,9 @@ inline void parallel_rows(knp_stream_t s, int64_t nrows, const F& f) {
   if (nrows <= 0) return;
 #ifdef KNP_EMU
   (void)s;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) if (nrows > 2048)
+#endif
   for (int64_t r = 0; r < nrows; ++r) f.finish(r, f.partial(r, 0, 1));
 #else
   const int64_t threads = nrows * LANES;
@@ -567,6 +570,9 @@ inline void multi_dot_device(knp_stream_t s, int64_t n, int64_t stride, int k, c
     (void)s; (void)partial;
     for (int i = 0; i < kk; ++i) {
       double acc = 0.0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : acc) if (n > 2048)
+#endif
       for (int64_t e = 0; e < n; ++e) acc += Vb[(int64_t)i * stride + e] * w[e];
       out[base + i] = acc;
     }
@@ -589,6 +595,9 @@ inline void pair_dot_device(knp_stream_t s, int64_t n, int k, const DotPairs& P,
   (void)s; (void)partial;
   for (int i = 0; i < k; ++i) {
     double acc = 0.0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : acc) if (n > 2048)
+#endif
     for (int64_t e = 0; e < n; ++e) acc += P.a[i][e] * P.b[i][e];
     out[i] = acc;
   }

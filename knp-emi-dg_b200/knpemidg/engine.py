@@ -138,7 +138,7 @@ class Engine:
         # KNP_EMI_LP_SCALE=10 divides the shift by 100: 47 -> 14 CG iterations there, same solution (B
         # only preconditions).  Default 1 = the reference's B; "auto" picks the scale from the geometry at
         # initialize() (see _auto_lp_scale).
-        self._lp_mode = os.environ.get("KNP_EMI_LP_SCALE", "1")
+        self._lp_mode = os.environ.get("KNP_EMI_LP_SCALE", "auto")
         if self._lp_mode != "auto":
             Lp *= float(self._lp_mode)
 
@@ -233,8 +233,9 @@ class Engine:
         try:
             name = self.resolve_model(module)
         except AttributeError:
-            raise _lib.KnpError(f"membrane model '{module.__name__}' does not follow the mm_*.py protocol "
-                                "(init_state_values, init_parameter_values, state_indices, parameter_indices)") from None
+            raise _lib.KnpError(f"membrane model '{module.__name__}' is not compiled into libknpemi.so and does not follow "
+                                "the mm_*.py protocol (init_state_values, init_parameter_values, state_indices, "
+                                f"parameter_indices); available: {sorted(models)}") from None
         mid, ns, npar = models[name]
         rows = np.flatnonzero(self.mem["tag"] == tag).astype(np.int32)   # ascending facet index
         m = MembraneHandle(self, tag, module, rows, mid, ns, npar)

@@ -1,8 +1,9 @@
-"""Short driver for ncu captures: builds the bench workload (bench.py, 3D axon bundle),
-steps it once and launches each hot kernel a few times (knp_bench_kernel).
+"""Short driver for ncu captures: builds a bench workload (bench.py), steps it once and launches each
+hot kernel a few times (knp_bench_kernel).
 
-    python profiles/prof_kernels.py [nx,ny,nz] [reps]
+    python profiles/prof_kernels.py [emix|bundle|astro] [size] [reps]
 """
+import argparse
 import os
 import sys
 
@@ -10,9 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-dims = tuple(int(v) for v in sys.argv[1].split(",")) if len(sys.argv) > 1 else bench.WORKLOAD_DIMS
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-eng = bench.build_engine(dims, 0)
+workload = sys.argv[1] if len(sys.argv) > 1 else "emix"
+size = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+args = argparse.Namespace(workload=workload, size=size, dims=None)
+eng = bench.make_engine(args, 0)
 eng.step()
 for kid, name in ((0, "bell_spmv"), (3, "bell_block_jacobi"), (1, "emi_assembly"), (2, "knp_assembly")):
     ms, nbytes = eng.ctx.bench_kernel(kid, reps)

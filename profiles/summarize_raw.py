@@ -9,7 +9,7 @@ import io
 import re
 import sys
 
-KERNELS = r"(BellSpmvKernel<\d>|BellJacobiKernel<\d>|emi_assemble_kernel|knp_assemble_kernel|EmiPrepassKernel|GradKernel|coarse_tail_kernel|p2p_halo_kernel)"
+KERNELS = r"(BellSpmvKernel<[^>]*>|BellJacobiKernel<[^>]*>|emi_assemble_kernel|knp_assemble_kernel|EmiPrepassKernel|GradKernel|coarse_tail_kernel|p2p_halo_kernel)"
 
 
 def main(path):
