@@ -38,11 +38,6 @@ for p in (ROOT, os.path.join(ROOT, "knp-emi-dg_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-# spin-waiting exchange kernels and lazily loaded CUDA modules do not mix (csrc/knp_solve.cu,
-# preload_solver_kernels): ask for eager loading before anything initialises CUDA
-if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("KNP_CONCURRENT_IONS") == "1":
-    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")   # (the opt-in cross-rank concurrency)
-
 import numpy as np  # noqa: E402
 
 WORKLOAD_DIMS = (96, 27, 27)      # bundle

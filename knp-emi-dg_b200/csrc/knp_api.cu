@@ -63,8 +63,7 @@ int knp_ctx_create(int device, knp_ctx** out) {
   KNP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 #endif
   { const char* e = getenv("KNP_KNP_PRESMOOTH"); c->opt.knp_presmooth0 = (e && e[0] == '1'); }
-  { const char* e = getenv("KNP_FUSE_PROLONG"); c->opt.fuse_prolong = (e && e[0] == '1'); }
-  { const char* e = getenv("KNP_AMG_FP32"); c->opt.pc_fp32 = (e && e[0] == '1'); }
+  { const char* e = getenv("KNP_AMG_FP32"); c->opt.pc_fp32 = !(e && e[0] == '0'); }
   { const char* e = getenv("KNP_AMG_CHEBY"); c->opt.cheby = (e && e[0] == '2') ? 2 : 1; }
   { const char* e = getenv("KNP_EXTRAPOLATE"); c->opt.extrapolate_phi = !(e && e[0] == '0'); }
   { const char* e = getenv("KNP_AMG_REFRESH_PERIOD"); c->opt.refresh_period = e ? std::max(1, atoi(e)) : 4; }

@@ -36,6 +36,7 @@ constexpr int P2P_MAX_WS = 7;       // independent exchange channels (one per co
 // peer-memory state of one halo plan on one channel (filled by Comm::register_plan)
 struct P2PChannel {
   bool ready = false;
+  int cap = 0;                                       // vectors per exchange the staging buffers hold
   unsigned long long seq = 0;                        // exchanges done on this channel
   size_t local_flag_off[P2P_MAX_NB] = {0}, local_data_off[P2P_MAX_NB] = {0};    // in my arena
   size_t remote_flag_off[P2P_MAX_NB] = {0}, remote_data_off[P2P_MAX_NB] = {0};  // in the neighbour's arena
@@ -112,8 +113,8 @@ typedef unsigned long long p2p_u64;
 constexpr long long P2P_SPIN_LIMIT = 40000000000LL;   // clock64 ticks (~20 s): a dead peer must not hang the GPU
 
 struct P2PHaloArgs {
-  int nn;
-  double* x; const int32_t* send_idx; int64_t n_own;
+  int nn, nvec;                           // neighbours; vectors exchanged at once (a batch of linear systems)
+  double* x[MAX_BATCH]; const int32_t* send_idx; int64_t n_own;
   int64_t send_off[P2P_MAX_NB + 1], recv_off[P2P_MAX_NB + 1];
   double* remote_data[P2P_MAX_NB];        // neighbour's staging buffer for my entries (this parity)
   p2p_u64* remote_flag[P2P_MAX_NB];
@@ -133,7 +134,9 @@ static __global__ void __launch_bounds__(256) p2p_halo_kernel(const P2PHaloArgs 
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < ns; k += (int64_t)gridDim.x * blockDim.x) {
     int i = 0;
     while (k >= a.send_off[i + 1]) ++i;
-    a.remote_data[i][k - a.send_off[i]] = a.x[a.send_idx[k]];
+    const int64_t nsi = a.send_off[i + 1] - a.send_off[i];
+    const int32_t src = a.send_idx[k];
+    for (int v = 0; v < a.nvec; ++v) a.remote_data[i][v * nsi + (k - a.send_off[i])] = a.x[v][src];
   }
   __threadfence_system();
   __syncthreads();
@@ -153,9 +156,12 @@ static __global__ void __launch_bounds__(256) p2p_halo_kernel(const P2PHaloArgs 
     }
     __syncthreads();
     const int64_t nr = a.recv_off[i + 1] - a.recv_off[i];
-    double* dst = a.x + a.n_own + a.recv_off[i];
-    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nr; k += (int64_t)gridDim.x * blockDim.x)
-      dst[k] = __ldcv(a.local_data[i] + k);
+    for (int v = 0; v < a.nvec; ++v) {
+      double* dst = a.x[v] + a.n_own + a.recv_off[i];
+      const double* src = a.local_data[i] + v * nr;
+      for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nr; k += (int64_t)gridDim.x * blockDim.x)
+        dst[k] = __ldcv(src + k);
+    }
   }
 }
 
@@ -225,6 +231,7 @@ struct Comm {
   knp_allreduce_fn rfn = nullptr;
   void* user = nullptr;
   std::atomic<int64_t> n_halo{0}, n_allreduce{0};
+  int batch_cap = 1;                         // vectors per exchange the peer-memory staging is sized for
 #ifndef KNP_EMU
   ncclComm_t nccl = nullptr;
   P2P p2p;
@@ -297,16 +304,19 @@ struct Comm {
 
   // staging buffers and flags of one halo plan on one channel; the partners learn where to
   // write through one small NCCL exchange (collective among the plan's partners; main thread)
-  void register_plan(knp_stream_t s, HaloPlan& H, int w) {
+  void register_plan(knp_stream_t s, HaloPlan& H, int w, int cap = 0) {
     P2P& P = p2p;
     P2PChannel& C = H.ch[w];
+    if (cap < batch_cap) cap = batch_cap;
+    if (cap < 1) cap = 1;
+    C.cap = cap;
     const std::vector<int32_t>& R = partners(H);
     const int nn = (int)R.size();
     std::vector<double> mine(2 * (size_t)nn + 2, 0.0), theirs(2 * (size_t)nn + 2, 0.0);
     for (int i = 0; i < nn; ++i) {
       const int64_t nr = H.recv_off[i + 1] - H.recv_off[i];
       C.local_flag_off[i] = P.alloc(2 * sizeof(p2p_u64));
-      C.local_data_off[i] = P.alloc(2 * (size_t)nr * sizeof(double));
+      C.local_data_off[i] = P.alloc(2 * (size_t)nr * cap * sizeof(double));
       mine[2 * i] = (double)C.local_flag_off[i]; mine[2 * i + 1] = (double)C.local_data_off[i];
     }
     C.counter_off = P.alloc(sizeof(unsigned int));
@@ -353,23 +363,31 @@ struct Comm {
   }
 
   // ghost entries of x (x + H.n_own ...) <- the owners' values
-  void halo(knp_stream_t s, HaloPlan& H, double* x, int w = 0) {
+  void halo(knp_stream_t s, HaloPlan& H, double* x, int w = 0) { halo_batch(s, H, 1, &x, w); }
+
+  // the same for `nvec` vectors at once (the solved ions' systems share mesh, partition and halo
+  // plan): ONE peer-memory kernel / one flag round trip for all of them
+  void halo_batch(knp_stream_t s, HaloPlan& H, int nvec, double* const* xs, int w = 0) {
     if (!active()) return;
     require_transport();
+    if (nvec < 1 || nvec > MAX_BATCH) fail("halo_batch: bad vector count");
     ++n_halo;
     const std::vector<int32_t>& nbr = partners(H);   // (shadows the DG neighbour list on purpose)
     const int nn = (int)nbr.size();
 #ifndef KNP_EMU
     if (p2p.on && nn <= P2P_MAX_NB && w < P2P_MAX_WS) {
       if (nn == 0) return;
-      if (!H.ch[w].ready) {
+      if (!H.ch[w].ready || H.ch[w].cap < nvec) {
+        // (first use, or more vectors than the staging holds: collective among the partners, every
+        // rank gets here in the same call)
         if (in_worker()) fail("halo plan was not prepared for concurrent use");
-        register_plan(s, H, w);
+        register_plan(s, H, w, nvec);
       }
       P2P& P = p2p;
       P2PChannel& C = H.ch[w];
       P2PHaloArgs a;
-      a.nn = nn; a.x = x; a.send_idx = H.send_idx.p; a.n_own = H.n_own;
+      a.nn = nn; a.nvec = nvec; a.send_idx = H.send_idx.p; a.n_own = H.n_own;
+      for (int v = 0; v < nvec; ++v) a.x[v] = xs[v];
       const p2p_u64 seq = ++C.seq;
       const size_t par = (size_t)(seq & 1);
       int64_t most = 1;
@@ -377,16 +395,16 @@ struct Comm {
       for (int i = 0; i < nn; ++i) {
         const int64_t ns = H.send_off[i + 1] - H.send_off[i], nr = H.recv_off[i + 1] - H.recv_off[i];
         char* pb = P.peer[nbr[i]];
-        a.remote_data[i] = reinterpret_cast<double*>(pb + C.remote_data_off[i]) + par * (size_t)ns;
+        a.remote_data[i] = reinterpret_cast<double*>(pb + C.remote_data_off[i]) + par * (size_t)ns * C.cap;
         a.remote_flag[i] = reinterpret_cast<p2p_u64*>(pb + C.remote_flag_off[i]) + par;
-        a.local_data[i] = reinterpret_cast<const double*>(P.arena + C.local_data_off[i]) + par * (size_t)nr;
+        a.local_data[i] = reinterpret_cast<const double*>(P.arena + C.local_data_off[i]) + par * (size_t)nr * C.cap;
         a.local_flag[i] = reinterpret_cast<volatile p2p_u64*>(P.arena + C.local_flag_off[i]) + par;
         most = ns > most ? ns : most; most = nr > most ? nr : most;
       }
       a.seq = seq;
       a.counter = reinterpret_cast<unsigned int*>(P.arena + C.counter_off);
       a.err = reinterpret_cast<int*>(P.arena + P2P::ERR_OFF);
-      int64_t grid = (most + 255) / 256;
+      int64_t grid = (most + 255) / 256;   // (one block per 256 entries; every thread moves nvec values)
       if (grid < 1) grid = 1;
       if (grid > 32) grid = 32;
       ++launch_counter(); ++n_p2p;
@@ -398,23 +416,27 @@ struct Comm {
 #ifndef KNP_EMU
     if (in_worker()) fail("NCCL exchange requested from a worker thread");
 #endif
-    if (H.nsend() > 0) {
-      PackKernel k{H.send_idx.p, x, H.sendbuf.p};
-      parallel_for(s, H.nsend(), k);
-    }
+    // fallback transports: one vector after the other (the send buffer is reused in stream order)
+    for (int v = 0; v < nvec; ++v) {
+      double* x = xs[v];
+      if (H.nsend() > 0) {
+        PackKernel k{H.send_idx.p, x, H.sendbuf.p};
+        parallel_for(s, H.nsend(), k);
+      }
 #ifdef KNP_EMU
-    if (xfn(user, nn, nbr.data(), H.sendbuf.p, H.send_off.data(), x + H.n_own, H.recv_off.data()))
-      fail("halo exchange callback failed");
+      if (xfn(user, nn, nbr.data(), H.sendbuf.p, H.send_off.data(), x + H.n_own, H.recv_off.data()))
+        fail("halo exchange callback failed");
 #else
-    NcclApi& N = nccl_api();
-    N.check(N.GroupStart(), "ncclGroupStart");
-    for (int i = 0; i < nn; ++i) {
-      const int64_t ns = H.send_off[i + 1] - H.send_off[i], nr = H.recv_off[i + 1] - H.recv_off[i];
-      if (ns > 0) N.check(N.Send(H.sendbuf.p + H.send_off[i], (size_t)ns, ncclDouble, nbr[i], nccl, s), "ncclSend");
-      if (nr > 0) N.check(N.Recv(x + H.n_own + H.recv_off[i], (size_t)nr, ncclDouble, nbr[i], nccl, s), "ncclRecv");
-    }
-    N.check(N.GroupEnd(), "ncclGroupEnd");
+      NcclApi& N = nccl_api();
+      N.check(N.GroupStart(), "ncclGroupStart");
+      for (int i = 0; i < nn; ++i) {
+        const int64_t ns = H.send_off[i + 1] - H.send_off[i], nr = H.recv_off[i + 1] - H.recv_off[i];
+        if (ns > 0) N.check(N.Send(H.sendbuf.p + H.send_off[i], (size_t)ns, ncclDouble, nbr[i], nccl, s), "ncclSend");
+        if (nr > 0) N.check(N.Recv(x + H.n_own + H.recv_off[i], (size_t)nr, ncclDouble, nbr[i], nccl, s), "ncclRecv");
+      }
+      N.check(N.GroupEnd(), "ncclGroupEnd");
 #endif
+    }
   }
 
   // in-place all-gather: rank r's `count` doubles sit at buf + r*count on entry (own segment)

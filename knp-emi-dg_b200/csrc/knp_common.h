@@ -186,4 +186,35 @@ inline void parallel_for(knp_stream_t s, int64_t n, const F& f, int block = 256)
 }
 #endif
 
+// ---- batched launch ---------------------------------------------------------
+// The same one-thread-per-index functor for up to MAX_BATCH independent data sets (the solved
+// ions' linear systems: same mesh, same sparsity, different matrices and vectors) in ONE launch:
+// blockIdx.y selects the functor.  Halves (N_ions = 2) the launch count and the latency-bound
+// tails of the KNP solve, which treats the ions as one block-diagonal system like the
+// reference's mixed space (solver.py:168-169).
+constexpr int MAX_BATCH = 6;
+template <class F>
+struct BatchOf { F f[MAX_BATCH]; };
+#ifdef KNP_EMU
+template <class F>
+inline void parallel_for_batch(knp_stream_t s, int64_t n, int nb, const BatchOf<F>& b, int block = 256) {
+  for (int k = 0; k < nb; ++k) parallel_for(s, n, b.f[k], block);
+}
+#else
+template <class F>
+__global__ void pf_batch_kernel(int64_t n, const BatchOf<F> b) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) b.f[blockIdx.y](i);
+}
+template <class F>
+inline void parallel_for_batch(knp_stream_t s, int64_t n, int nb, const BatchOf<F>& b, int block = 256) {
+  if (n <= 0 || nb <= 0) return;
+  if (nb == 1) { parallel_for(s, n, b.f[0], block); return; }
+  const int64_t grid = (n + block - 1) / block;
+  ++launch_counter();
+  pf_batch_kernel<F><<<dim3((unsigned)grid, (unsigned)nb), block, 0, s>>>(n, b);
+  KNP_CUDA(cudaGetLastError());
+}
+#endif
+
 }  // namespace knp

@@ -222,6 +222,35 @@ __global__ void __launch_bounds__(256) subwarp_kernel(int64_t nrows, const F f) 
   if (ok && lane == 0) f.finish(row, acc);
 }
 #endif
+#ifndef KNP_EMU
+template <int LANES, class F>
+__global__ void __launch_bounds__(256) subwarp_batch_kernel(int64_t nrows, const BatchOf<F> b) {
+  const F& f = b.f[blockIdx.y];
+  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t row = gt / LANES;
+  const int lane = (int)(gt % LANES);
+  const bool ok = row < nrows;
+  double acc = ok ? f.partial(row, lane, LANES) : 0.0;
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LANES);
+  if (ok && lane == 0) f.finish(row, acc);
+}
+#endif
+template <int LANES, class F>
+inline void parallel_rows(knp_stream_t s, int64_t nrows, const F& f);
+template <int LANES, class F>
+inline void parallel_rows_batch(knp_stream_t s, int64_t nrows, int nb, const BatchOf<F>& b) {
+  if (nrows <= 0 || nb <= 0) return;
+#ifdef KNP_EMU
+  for (int k = 0; k < nb; ++k) parallel_rows<LANES>(s, nrows, b.f[k]);
+#else
+  if (nb == 1) { parallel_rows<LANES>(s, nrows, b.f[0]); return; }
+  const int64_t threads = nrows * LANES;
+  ++launch_counter();
+  subwarp_batch_kernel<LANES, F><<<dim3((unsigned)((threads + 255) / 256), (unsigned)nb), 256, 0, s>>>(nrows, b);
+  KNP_CUDA(cudaGetLastError());
+#endif
+}
 template <int LANES, class F>
 inline void parallel_rows(knp_stream_t s, int64_t nrows, const F& f) {
   if (nrows <= 0) return;
@@ -322,13 +351,15 @@ struct TailArgs {
 }  // namespace knp
 #include <cooperative_groups.h>
 namespace knp {
+struct TailBatch { TailArgs s[MAX_BATCH]; };
 static __global__ void __cluster_dims__(TAIL_CTAS, 1, 1) __launch_bounds__(TAIL_THREADS)
-coarse_tail_kernel(const TailArgs a) {
+coarse_tail_kernel(const TailBatch batch) {
   namespace cg = cooperative_groups;
-  cg::cluster_group grid = cg::this_cluster();   // the whole grid is one cluster
+  cg::cluster_group grid = cg::this_cluster();   // one cluster per linear system of the batch
   constexpr int LANES = 8;
-  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const TailArgs& a = batch.s[blockIdx.x / TAIL_CTAS];
+  const int64_t gt = (blockIdx.x % TAIL_CTAS) * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)TAIL_CTAS * blockDim.x;
   const int lane = (int)(gt % LANES);
   const int64_t nsub = nthreads / LANES;       // rows processed per pass
   const int64_t sub = gt / LANES;
@@ -473,21 +504,25 @@ struct CombineKernel {
 constexpr int DOT_MAX = 8;
 constexpr int RED_BLOCKS = 592;   // 4 x 148 SMs
 constexpr int RED_THREADS = 256;
+// (the sums run over the `nb` data sets of a batch: the ions' systems are ONE block system)
+struct DotBatch { int nb; const double* V[MAX_BATCH]; const double* w[MAX_BATCH]; };
 
 #ifndef KNP_EMU
 template <int K>
-__global__ void __launch_bounds__(RED_THREADS) multi_dot_partial(int64_t n, int64_t stride,
-                                                                 const double* __restrict__ V,
-                                                                 const double* __restrict__ w,
+__global__ void __launch_bounds__(RED_THREADS) multi_dot_partial(int64_t n, int64_t stride, const DotBatch B,
                                                                  double* __restrict__ partial) {
   double acc[K];
 #pragma unroll
   for (int i = 0; i < K; ++i) acc[i] = 0.0;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    const double we = w[e];
+  for (int s = 0; s < B.nb; ++s) {
+    const double* __restrict__ V = B.V[s];
+    const double* __restrict__ w = B.w[s];
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+         e += (int64_t)gridDim.x * blockDim.x) {
+      const double we = w[e];
 #pragma unroll
-    for (int i = 0; i < K; ++i) acc[i] += V[(int64_t)i * stride + e] * we;
+      for (int i = 0; i < K; ++i) acc[i] += V[(int64_t)i * stride + e] * we;
+    }
   }
   __shared__ double sm[K][RED_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -561,24 +596,29 @@ __global__ void __launch_bounds__(RED_THREADS) pair_dot_partial(int64_t n, const
 
 // device-side dots over the first n entries of k vectors `stride` apart; `out` (device,
 // >= k doubles) receives the results, `partial` is a scratch buffer of DOT_MAX*RED_BLOCKS doubles.
-inline void multi_dot_device(knp_stream_t s, int64_t n, int64_t stride, int k, const double* V, const double* w,
-                             double* partial, double* out) {
+inline void multi_dot_batch(knp_stream_t s, int64_t n, int64_t stride, int k, const DotBatch& B0,
+                            double* partial, double* out) {
   for (int base = 0; base < k; base += DOT_MAX) {
     const int kk = (k - base < DOT_MAX) ? k - base : DOT_MAX;
-    const double* Vb = V + (int64_t)base * stride;
+    DotBatch B = B0;
+    for (int b = 0; b < B.nb; ++b) B.V[b] = B0.V[b] + (int64_t)base * stride;
 #ifdef KNP_EMU
     (void)s; (void)partial;
     for (int i = 0; i < kk; ++i) {
       double acc = 0.0;
+      for (int b = 0; b < B.nb; ++b) {
+        const double* Vb = B.V[b];
+        const double* w = B.w[b];
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static) reduction(+ : acc) if (n > 2048)
 #endif
-      for (int64_t e = 0; e < n; ++e) acc += Vb[(int64_t)i * stride + e] * w[e];
+        for (int64_t e = 0; e < n; ++e) acc += Vb[(int64_t)i * stride + e] * w[e];
+      }
       out[base + i] = acc;
     }
 #else
     switch (kk) {
-#define KNP_CASE(K) case K: multi_dot_partial<K><<<RED_BLOCKS, RED_THREADS, 0, s>>>(n, stride, Vb, w, partial); break;
+#define KNP_CASE(K) case K: multi_dot_partial<K><<<RED_BLOCKS, RED_THREADS, 0, s>>>(n, stride, B, partial); break;
       KNP_CASE(1) KNP_CASE(2) KNP_CASE(3) KNP_CASE(4) KNP_CASE(5) KNP_CASE(6) KNP_CASE(7) KNP_CASE(8)
 #undef KNP_CASE
     }
@@ -588,6 +628,12 @@ inline void multi_dot_device(knp_stream_t s, int64_t n, int64_t stride, int k, c
     KNP_CUDA(cudaGetLastError());
 #endif
   }
+}
+inline void multi_dot_device(knp_stream_t s, int64_t n, int64_t stride, int k, const double* V, const double* w,
+                             double* partial, double* out) {
+  DotBatch B;
+  B.nb = 1; B.V[0] = V; B.w[0] = w;
+  multi_dot_batch(s, n, stride, k, B, partial, out);
 }
 
 inline void pair_dot_device(knp_stream_t s, int64_t n, int k, const DotPairs& P, double* partial, double* out) {

@@ -8,7 +8,6 @@
 // ||M^-1 r|| <= max(rtol * ||M^-1 b||, atol), nonzero initial guess.
 #include "../../include/knpemi.h"
 #include "knp_ctx.h"
-#include <thread>
 #include <type_traits>
 
 using namespace knp;
@@ -29,62 +28,83 @@ static double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// ---- per-solve workspace -----------------------------------------------------------------
-// Every helper below issues on the stream of the CURRENT workspace and uses its scratch
-// buffers: the context's main workspace by default, a per-ion workspace inside the worker
-// threads that solve the independent KNP systems concurrently.
-static thread_local KrylovWs* tl_ws = nullptr;
-static KrylovWs& ws(knp_ctx* c) { return tl_ws ? *tl_ws : c->kr0; }
-static knp_stream_t cs(knp_ctx* c) { return ws(c).stream; }
+// ---- batches of linear systems --------------------------------------------------------------
+// Every operator below acts on a BATCH of nb independent linear systems that share the mesh, the
+// sparsity pattern and the AMG plan but have their own matrix values and vectors: nb = 1 for the
+// EMI system; nb = N_ions for the KNP solve, where the reference's mixed-space system
+// (solver.py:168-169, 684-701) is block diagonal - the ions are uncoupled in the form
+// (solver.py:550-594) - and is solved as ONE system: one Krylov space, one residual norm, one
+// Hessenberg matrix, and every kernel launched once for all ions (blockIdx.y = ion).
+struct Sys {
+  AmgValues* V;          // numeric hierarchy and work vectors of this system
+  BellMat A;             // level-0 matrix the preconditioner is built from (EMI: B_emi)
+  const double* bj;      // inverse diagonal blocks (pc == 0: element block-Jacobi only)
+};
+struct Batch { int nb; Sys s[MAX_BATCH]; };
+struct Vecs { double* p[MAX_BATCH]; };
+static Vecs vecs1(const double* x) { Vecs v{}; v.p[0] = const_cast<double*>(x); return v; }
+static Vecs offset(const Vecs& v, int nb, int64_t off) {
+  Vecs o{};
+  for (int b = 0; b < nb; ++b) o.p[b] = v.p[b] ? v.p[b] + off : nullptr;
+  return o;
+}
+template <class Fn>
+static void by_nd(knp_ctx* c, Fn&& fn) {
+  if (c->nd == 3) fn(std::integral_constant<int, 3>{}); else fn(std::integral_constant<int, 4>{});
+}
+
+static KrylovWs& ws(knp_ctx* c) { return c->kr0; }
+static knp_stream_t cs(knp_ctx* c) { return c->stream; }
 
 // ---- small helpers ---------------------------------------------------------------------
 // Multi-GPU: every kernel below runs over the OWNED rows (the first n_own entries of a
 // vector); the operators that read a vector through the matrix first refresh its ghost
-// entries from their owners (knp_comm.h).
-static void halo0(knp_ctx* c, const double* x) {
-  if (c->comm.active()) c->comm.halo(cs(c), c->halo0, const_cast<double*>(x), ws(c).id);
+// entries from their owners (knp_comm.h) - one exchange for the whole batch.
+static void halo_of(knp_ctx* c, HaloPlan& H, int nb, const Vecs& x) {
+  if (c->comm.active()) c->comm.halo_batch(cs(c), H, nb, x.p);
 }
-template <int ND, typename T>
-static void bell_spmv_nd(knp_ctx* c, const BellMatT<T>& A, const double* x, const double* b, double* y, int mode) {
-  BellSpmvKernel<ND, T> k{A, x, b, y, mode};
-  parallel_for(cs(c), c->n_own, k, 256);
+static void halo0(knp_ctx* c, int nb, const Vecs& x) { halo_of(c, c->halo0, nb, x); }
+static void halo0(knp_ctx* c, const double* x) { halo0(c, 1, vecs1(x)); }
+
+template <typename T>
+static void bell_spmv(knp_ctx* c, int nb, const BellMatT<T>* A, const Vecs& x, const Vecs& b, const Vecs& y, int mode) {
+  halo0(c, nb, x);
+  by_nd(c, [&](auto nd) {
+    constexpr int ND = decltype(nd)::value;
+    BatchOf<BellSpmvKernel<ND, T>> k{};
+    for (int s = 0; s < nb; ++s) k.f[s] = BellSpmvKernel<ND, T>{A[s], x.p[s], b.p[s], y.p[s], mode};
+    parallel_for_batch(cs(c), c->n_own, nb, k, 256);
+  });
+}
+static void bell_spmv(knp_ctx* c, const BellMat& A, const double* x, const double* b, double* y, int mode) {
+  bell_spmv<double>(c, 1, &A, vecs1(x), vecs1(b), vecs1(y), mode);
 }
 template <typename T>
-static void bell_spmv(knp_ctx* c, const BellMatT<T>& A, const double* x, const double* b, double* y, int mode) {
-  halo0(c, x);
-  if (c->nd == 3) bell_spmv_nd<3, T>(c, A, x, b, y, mode); else bell_spmv_nd<4, T>(c, A, x, b, y, mode);
+static void block_apply(knp_ctx* c, int nb, const T* const* dinv, const Vecs& r, const Vecs& out, const double* w, int mode) {
+  by_nd(c, [&](auto nd) {
+    constexpr int ND = decltype(nd)::value;
+    BatchOf<BlockDiagApplyKernel<ND, T>> k{};
+    for (int s = 0; s < nb; ++s) k.f[s] = BlockDiagApplyKernel<ND, T>{dinv[s], r.p[s], out.p[s], w[s], mode};
+    parallel_for_batch(cs(c), c->n_own, nb, k);
+  });
 }
-template <typename T>
-static void block_apply(knp_ctx* c, const T* dinv, const double* r, double* out, double w, int mode) {
-  if (c->nd == 3) { BlockDiagApplyKernel<3, T> k{dinv, r, out, w, mode}; parallel_for(cs(c), c->n_own, k); }
-  else { BlockDiagApplyKernel<4, T> k{dinv, r, out, w, mode}; parallel_for(cs(c), c->n_own, k); }
+static void block_apply(knp_ctx* c, const double* dinv, const double* r, double* out, double w, int mode) {
+  block_apply<double>(c, 1, &dinv, vecs1(r), vecs1(out), &w, mode);
 }
-template <typename T>
-static void bell_jacobi(knp_ctx* c, const BellMatT<T>& A, const T* dinv, const double* b,
-                        const double* xin, double* xout, double w) {
-  halo0(c, xin);
-  if (c->nd == 3) { BellJacobiKernel<3, T> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 192); }
-  else { BellJacobiKernel<4, T> k{A, dinv, b, xin, xout, w}; parallel_for(cs(c), c->n_own, k, 256); }
-}
-// second Chebyshev step: xout = xin + beta (xin - xprev) + w Dinv (b - A xin); xprev may be nullptr (zero)
-template <typename T>
-static void bell_jacobi_mom(knp_ctx* c, const BellMatT<T>& A, const T* dinv, const double* b, const double* xin,
-                            const double* xprev, double* xout, double w, double beta) {
-  halo0(c, xin);
-  if (c->nd == 3) {
-    BellJacobiKernel<3, T, true> k{A, dinv, b, xin, xout, w, nullptr, nullptr, xprev, beta};
-    parallel_for(cs(c), c->n_own, k, 192);
-  } else {
-    BellJacobiKernel<4, T, true> k{A, dinv, b, xin, xout, w, nullptr, nullptr, xprev, beta};
-    parallel_for(cs(c), c->n_own, k, 256);
-  }
-}
-// post-smoothing sweep fused with the prolongation: out = x' + w Dinv (b - A x'), x' = xin + P xc
-// (xin may be nullptr).  The ghost entries of xin (if any) and of xc must be valid.
-static void bell_jacobi_prolong(knp_ctx* c, const BellMat& A, const double* dinv, const double* b,
-                                const double* xin, const int32_t* agg, const double* xc, double* xout, double w) {
-  if (c->nd == 3) { BellJacobiKernel<3> k{A, dinv, b, xin, xout, w, agg, xc}; parallel_for(cs(c), c->n_own, k, 192); }
-  else { BellJacobiKernel<4> k{A, dinv, b, xin, xout, w, agg, xc}; parallel_for(cs(c), c->n_own, k, 256); }
+// xout = xin + w Dinv (b - A xin); MOM: second Chebyshev step, + beta (xin - xprev), xprev may hold nullptr (zero)
+template <typename T, bool MOM = false>
+static void bell_jacobi(knp_ctx* c, int nb, const BellMatT<T>* A, const T* const* dinv, const Vecs& b,
+                        const Vecs& xin, const Vecs& xout, const double* w, const Vecs* xprev = nullptr, double beta = 0.0) {
+  halo0(c, nb, xin);
+  by_nd(c, [&](auto nd) {
+    constexpr int ND = decltype(nd)::value;
+    BatchOf<BellJacobiKernel<ND, T, MOM>> k{};
+    for (int s = 0; s < nb; ++s) {
+      k.f[s] = BellJacobiKernel<ND, T, MOM>{A[s], dinv[s], b.p[s], xin.p[s], xout.p[s], w[s]};
+      if (MOM) { k.f[s].xprev = xprev ? xprev->p[s] : nullptr; k.f[s].beta = beta; }
+    }
+    parallel_for_batch(cs(c), c->n_own, nb, k, ND == 3 ? 192 : 256);
+  });
 }
 static void block_inverse(knp_ctx* c, const double* blocks, double* inv) {
 #ifdef KNP_EMU
@@ -99,10 +119,14 @@ static void block_inverse(knp_ctx* c, const double* blocks, double* inv) {
 #endif
 }
 
-// host-visible dot products over all ranks (one sync each)
-static void dots_host(knp_ctx* c, int k, const double* V, const double* w, double* out_host) {
-  multi_dot_device(cs(c), c->n_own, c->n, k, V, w, ws(c).partial.p, ws(c).scal.p);
-  c->comm.allreduce(cs(c), ws(c).scal.p, k, ws(c).id);
+// host-visible dot products over all ranks and over the systems of a batch (one sync each):
+// out[i] = sum_s V_s[i] . w_s
+static void dots_host(knp_ctx* c, int k, int nb, const Vecs& V, const Vecs& w, double* out_host) {
+  DotBatch B;
+  B.nb = nb;
+  for (int s = 0; s < nb; ++s) { B.V[s] = V.p[s]; B.w[s] = w.p[s]; }
+  multi_dot_batch(cs(c), c->n_own, c->n, k, B, ws(c).partial.p, ws(c).scal.p);
+  c->comm.allreduce(cs(c), ws(c).scal.p, k);
   d2h(out_host, ws(c).scal.p, k * sizeof(double), cs(c));
 }
 // sum over ranks of a few host numbers (setup-time decisions must agree on every rank)
@@ -113,11 +137,12 @@ static void global_sum(knp_ctx* c, double* v, int k) {
   c->comm.allreduce(cs(c), dev, k);
   d2h(v, dev, k * sizeof(double), cs(c));
 }
-static double dot_host(knp_ctx* c, const double* x, const double* y) {
+static double dot_host(knp_ctx* c, int nb, const Vecs& x, const Vecs& y) {
   double v;
-  dots_host(c, 1, x, y, &v);
+  dots_host(c, 1, nb, x, y, &v);
   return v;
 }
+static double dot_host(knp_ctx* c, const double* x, const double* y) { return dot_host(c, 1, vecs1(x), vecs1(y)); }
 
 // ---------------------------------------------------------------------------------
 // AMG setup (host plan) -----------------------------------------------------------
@@ -266,64 +291,6 @@ static int64_t double_coarsening_rows() {
   const char* e = getenv("KNP_AMG_DOUBLE");
   return e ? atoll(e) : 0;
 }
-
-#ifndef KNP_EMU
-// CUDA loads kernels lazily (CUDA_MODULE_LOADING=LAZY is the default since 12.2): the first
-// launch of a kernel may have to wait until the kernels that are running have finished.  A
-// worker thread that launches a not-yet-loaded kernel while the OTHER worker's exchange kernel
-// is spinning on a neighbour rank - which may be stuck the same way - is a cross-rank deadlock.
-// Every kernel the concurrent solves can launch is therefore loaded up front
-// (cudaFuncGetAttributes loads the function).
-template <class K>
-static void touch_kernel(K kernel) {
-  cudaFuncAttributes a;
-  if (cudaFuncGetAttributes(&a, (const void*)kernel) != cudaSuccess) cudaGetLastError();   // best effort
-}
-template <int ND>
-static void preload_solver_kernels_nd() {
-  touch_kernel(pf_kernel<BellSpmvKernel<ND>>);
-  touch_kernel(pf_kernel<BlockDiagApplyKernel<ND>>);
-  touch_kernel(pf_kernel<BellJacobiKernel<ND>>);
-  touch_kernel(pf_kernel<BellSpmvKernel<ND, float>>);
-  touch_kernel(pf_kernel<BlockDiagApplyKernel<ND, float>>);
-  touch_kernel(pf_kernel<BellJacobiKernel<ND, float>>);
-  touch_kernel(pf_kernel<BellJacobiKernel<ND, double, true>>);
-  touch_kernel(pf_kernel<BellJacobiKernel<ND, float, true>>);
-  touch_kernel(block_inverse_kernel<ND>);
-}
-static void preload_solver_kernels(knp_ctx* c) {
-  if (c->nd == 3) preload_solver_kernels_nd<3>(); else preload_solver_kernels_nd<4>();
-  touch_kernel(pf_kernel<TransferKernel>);
-  touch_kernel(pf_kernel<GalerkinKernel>);
-  touch_kernel(pf_kernel<CsrL1DiagKernel>);
-  touch_kernel(pf_kernel<CsrToDenseKernel>);
-  touch_kernel(pf_kernel<CsrSpmvKernel>);
-  touch_kernel(pf_kernel<CsrJacobiKernel>);
-  touch_kernel(pf_kernel<DiagScaleKernel>);
-  touch_kernel(pf_kernel<DenseMatvecKernel>);
-  touch_kernel(pf_kernel<ScatterOffsetKernel>);
-  touch_kernel(pf_kernel<GatherMapKernel>);
-  touch_kernel(pf_kernel<ScaleKernel>);
-  touch_kernel(pf_kernel<CombineKernel>);
-  touch_kernel(pf_kernel<GsNormalizeKernel>);
-  touch_kernel(pf_kernel<AddConstKernel>);
-  touch_kernel(pf_kernel<PackKernel>);
-  touch_kernel(subwarp_kernel<8, CoarseResidualKernel>);
-  touch_kernel(subwarp_kernel<8, TransferRowsKernel>);
-  touch_kernel(subwarp_kernel<8, CoarseUpKernel>);
-  touch_kernel(coarse_tail_kernel);
-  touch_kernel(dense_inverse_smem_kernel);
-  touch_kernel(dense_inverse_kernel);
-  touch_kernel(multi_dot_final);
-  touch_kernel(multi_dot_partial<1>); touch_kernel(multi_dot_partial<2>); touch_kernel(multi_dot_partial<3>);
-  touch_kernel(multi_dot_partial<4>); touch_kernel(multi_dot_partial<5>); touch_kernel(multi_dot_partial<6>);
-  touch_kernel(multi_dot_partial<7>); touch_kernel(multi_dot_partial<8>);
-  touch_kernel(pair_dot_partial<1>); touch_kernel(pair_dot_partial<2>);
-  touch_kernel(pair_dot_partial<3>); touch_kernel(pair_dot_partial<4>);
-  touch_kernel(p2p_halo_kernel);
-  touch_kernel(p2p_allreduce_kernel);
-}
-#endif
 
 // rows (over all ranks) below which the rest of the hierarchy is replicated; 0 disables
 static int64_t replicate_threshold() {
@@ -538,16 +505,13 @@ extern "C" int knp_amg_setup(knp_ctx* ctx, double theta, int max_levels, int coa
 #endif
 #ifndef KNP_EMU
   if (ctx->comm.active() && ctx->comm.p2p.on) {
-    // every exchange channel a concurrently running solve may use is registered now, on the
-    // main thread (registration talks NCCL; the worker threads must not)
-    const int nws = ctx->P.N;   // main + one per solved ion
+    // staging buffers sized for one exchange of all solved ions' vectors at once
+    ctx->comm.batch_cap = ctx->P.N - 1 > 1 ? ctx->P.N - 1 : 1;
+    const int nws = 1;
     ctx->comm.prepare_plan(ctx->stream, ctx->halo0, nws);
     for (size_t l = 0; l < amg.lev.size() && l < amg.rep_from; ++l) ctx->comm.prepare_plan(ctx->stream, amg.lev[l].halo, nws);
     if (amg.rep_from != (size_t)-1) ctx->comm.prepare_plan(ctx->stream, amg.rep_plan, nws);
   }
-#endif
-#ifndef KNP_EMU
-  preload_solver_kernels(ctx);
 #endif
   alloc_values(ctx, ctx->amg_emi);
   for (int k = 0; k < ctx->P.N - 1; ++k) alloc_values(ctx, ctx->amg_knp[k]);
@@ -674,198 +638,242 @@ static void note_solve(AmgValues& V, bool refreshed, int iters) {
 // ---------------------------------------------------------------------------------
 // cycle
 // ---------------------------------------------------------------------------------
-static void transfer(knp_ctx* c, int64_t nrows, const int32_t* ptr, const int32_t* idx, const double* w,
-                     const double* x, double* y, int add) {
-  TransferKernel k{nrows, ptr, idx, w, x, y, add};
-  parallel_for(cs(c), nrows, k);
+static void transfer(knp_ctx* c, int nb, int64_t nrows, const int32_t* ptr, const int32_t* idx, const double* w,
+                     const Vecs& x, const Vecs& y, int add) {
+  BatchOf<TransferKernel> k{};
+  for (int s = 0; s < nb; ++s) k.f[s] = TransferKernel{nrows, ptr, idx, w, x.p[s], y.p[s], add};
+  parallel_for_batch(cs(c), nrows, nb, k);
+}
+static void restrict_rows(knp_ctx* c, int nb, const AmgLevelPlan& C, const Vecs& x, const Vecs& y) {
+  BatchOf<TransferRowsKernel> k{};
+  for (int s = 0; s < nb; ++s) k.f[s] = TransferRowsKernel{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, x.p[s], y.p[s], 0};
+  parallel_rows_batch<8>(cs(c), C.n, nb, k);
 }
 
-// solve level l (>= 1, index into lev = l-1) approximately: L.x <- cycle(L.b)
-// On return the ghost entries of L.x are valid when ghost_x is set (the parent's fused
-// prolongation+smoothing sweep reads them).
-static void coarse_cycle(knp_ctx* c, AmgValues& V, size_t li, bool ghost_x) {
+// per-system vectors of one level
+enum LevelVec { LV_B, LV_X, LV_R, LV_T };
+static Vecs level_vecs(const Batch& B, size_t li, LevelVec which) {
+  Vecs v{};
+  for (int s = 0; s < B.nb; ++s) {
+    LevelVectors& L = B.s[s].V->vec[li];
+    v.p[s] = which == LV_B ? L.b.p : which == LV_X ? L.x.p : which == LV_R ? L.r.p : L.t.p;
+  }
+  return v;
+}
+static void swap_xt(const Batch& B, size_t li) {
+  for (int s = 0; s < B.nb; ++s) std::swap(B.s[s].V->vec[li].x.p, B.s[s].V->vec[li].t.p);
+}
+
+// solve level l (>= 1, index into lev = l-1) approximately for every system of the batch:
+// L.x <- cycle(L.b).  On return the ghost entries of L.x are valid when ghost_x is set.
+static void coarse_cycle(knp_ctx* c, const Batch& B, size_t li, bool ghost_x) {
   knp_stream_t s = cs(c);
+  const int nb = B.nb;
   AmgLevelPlan& L = c->amg.lev[li];
-  LevelVectors& Lv = V.vec[li];
   Comm& comm = c->comm;
-  const int wid = ws(c).id;
   const bool dist = comm.active() && li < c->amg.rep_from;   // this level's vectors have ghosts
+  const Vecs Lb = level_vecs(B, li, LV_B), Lx = level_vecs(B, li, LV_X), Lr = level_vecs(B, li, LV_R), Lt = level_vecs(B, li, LV_T);
 #ifndef KNP_EMU
   if (li == c->amg.tail_from && c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1) {
     AmgPlan& amg = c->amg;
-    TailArgs a;
-    a.nlev = (int)(amg.lev.size() - li);
-    for (int k = 0; k < a.nlev; ++k) {
-      AmgLevelPlan& T = amg.lev[li + k];
-      TailLevel& t = a.L[k];
-      t.n = T.n; t.ptr = T.ptr.p; t.col = T.col.p; t.val = V.val[li + k].p; t.dinv = V.dinv[li + k].p;
-      t.b = V.vec[li + k].b.p; t.x = V.vec[li + k].x.p; t.r = V.vec[li + k].r.p;
-      t.rptr = T.rptr.p; t.ridx = T.ridx.p; t.agg = T.pidx.p;
+    TailBatch tb;
+    for (int q = 0; q < nb; ++q) {
+      AmgValues& V = *B.s[q].V;
+      TailArgs& a = tb.s[q];
+      a.nlev = (int)(amg.lev.size() - li);
+      for (int k = 0; k < a.nlev; ++k) {
+        AmgLevelPlan& T = amg.lev[li + k];
+        TailLevel& t = a.L[k];
+        t.n = T.n; t.ptr = T.ptr.p; t.col = T.col.p; t.val = V.val[li + k].p; t.dinv = V.dinv[li + k].p;
+        t.b = V.vec[li + k].b.p; t.x = V.vec[li + k].x.p; t.r = V.vec[li + k].r.p;
+        t.rptr = T.rptr.p; t.ridx = T.ridx.p; t.agg = T.pidx.p;
+      }
+      a.denseT = V.dense.p;
     }
-    a.denseT = V.dense.p;
     ++launch_counter();
-    coarse_tail_kernel<<<TAIL_CTAS, TAIL_THREADS, 0, s>>>(a);
+    coarse_tail_kernel<<<TAIL_CTAS * nb, TAIL_THREADS, 0, s>>>(tb);
     KNP_CUDA(cudaGetLastError());
     return;
   }
 #endif
   if (li + 1 == c->amg.rep_from) {
-    // hand over to the replicated rest of the hierarchy: all-gather the right-hand side, run
+    // hand over to the replicated rest of the hierarchy: all-gather the right-hand sides, run
     // the remaining cycle redundantly, pick this rank's owned and ghost unknowns
     AmgPlan& amg = c->amg;
     AmgLevelPlan& T0 = amg.lev[li + 1];
-    LevelVectors& T0v = V.vec[li + 1];
-    d2d(V.rep_b.p + (int64_t)comm.rank * amg.rep_bstride, Lv.b.p, L.n * sizeof(double), s);
+    Vecs rep{};
+    for (int q = 0; q < nb; ++q) {
+      rep.p[q] = B.s[q].V->rep_b.p;
+      d2d(rep.p[q] + (int64_t)comm.rank * amg.rep_bstride, Lb.p[q], L.n * sizeof(double), s);
+    }
 #ifndef KNP_EMU
-    if (comm.p2p.on && comm.world <= P2P_MAX_NB) comm.halo(s, amg.rep_plan, V.rep_b.p, wid);
+    if (comm.p2p.on && comm.world <= P2P_MAX_NB) comm.halo_batch(s, amg.rep_plan, nb, rep.p);
     else
 #endif
-      comm.allgather(s, V.rep_b.p, amg.rep_bstride);
-    { GatherMapKernel k{V.rep_b.p, amg.rep_bmap.p, T0v.b.p}; parallel_for(s, T0.n, k); }
-    coarse_cycle(c, V, li + 1, false);
-    { GatherMapKernel k{T0v.x.p, amg.rep_xmap.p, Lv.x.p}; parallel_for(s, L.nloc, k); }
+      for (int q = 0; q < nb; ++q) comm.allgather(s, rep.p[q], amg.rep_bstride);
+    const Vecs T0b = level_vecs(B, li + 1, LV_B);
+    { BatchOf<GatherMapKernel> k{}; for (int q = 0; q < nb; ++q) k.f[q] = GatherMapKernel{rep.p[q], amg.rep_bmap.p, T0b.p[q]};
+      parallel_for_batch(s, T0.n, nb, k); }
+    coarse_cycle(c, B, li + 1, false);
+    const Vecs T0x = level_vecs(B, li + 1, LV_X);
+    { BatchOf<GatherMapKernel> k{}; for (int q = 0; q < nb; ++q) k.f[q] = GatherMapKernel{T0x.p[q], amg.rep_xmap.p, Lx.p[q]};
+      parallel_for_batch(s, L.nloc, nb, k); }
     return;
   }
   if (li + 1 == c->amg.lev.size()) {
     if (!dist) {
-      DenseMatvecKernel k{L.n, V.dense.p, Lv.b.p, Lv.x.p};
-      parallel_for(s, L.n, k, 64);
+      BatchOf<DenseMatvecKernel> k{};
+      for (int q = 0; q < nb; ++q) k.f[q] = DenseMatvecKernel{L.n, B.s[q].V->dense.p, Lb.p[q], Lx.p[q]};
+      parallel_for_batch(s, L.n, nb, k, 64);
       return;
     }
     // the global right-hand side is summed over ranks, every rank applies the replicated
-    // inverse and picks its owned and ghost unknowns
+    // inverse and picks its owned and ghost unknowns (small meshes only: one system after the other)
     AmgPlan& amg = c->amg;
     const int64_t m = amg.m_dense;
-    dev_zero(V.dense_b.p, (size_t)m * sizeof(double), s);
-    { ScatterOffsetKernel k{Lv.b.p, V.dense_b.p, amg.dense_off}; parallel_for(s, L.n, k); }
-    comm.allreduce(s, V.dense_b.p, m, wid);
-    { DenseMatvecKernel k{m, V.dense.p, V.dense_b.p, V.dense_x.p}; parallel_for(s, m, k, 64); }
-    { GatherMapKernel k{V.dense_x.p, amg.dense_map.p, Lv.x.p}; parallel_for(s, L.nloc, k); }
+    for (int q = 0; q < nb; ++q) {
+      AmgValues& V = *B.s[q].V;
+      dev_zero(V.dense_b.p, (size_t)m * sizeof(double), s);
+      { ScatterOffsetKernel k{Lb.p[q], V.dense_b.p, amg.dense_off}; parallel_for(s, L.n, k); }
+      comm.allreduce(s, V.dense_b.p, m);
+      { DenseMatvecKernel k{m, V.dense.p, V.dense_b.p, V.dense_x.p}; parallel_for(s, m, k, 64); }
+      { GatherMapKernel k{V.dense_x.p, amg.dense_map.p, Lx.p[q]}; parallel_for(s, L.nloc, k); }
+    }
     return;
   }
-  CsrMat A = csr_of(L, V, li);
   AmgLevelPlan& C = c->amg.lev[li + 1];
-  LevelVectors& Cv = V.vec[li + 1];
+  const Vecs Cb = level_vecs(B, li + 1, LV_B);
+  auto mat = [&](int q) { return csr_of(L, *B.s[q].V, li); };
+  auto dinv = [&](int q) { return B.s[q].V->dinv[li].p; };
   if (c->opt.nu_pre == 1 && c->opt.nu_post == 1 && c->opt.gamma == 1 && C.t_unit) {
     // fused V(1,1) path: two kernels down (smooth+residual, restrict), one up (prolong+smooth)
-    if (dist) comm.halo(s, L.halo, Lv.b.p, wid);
-    { CoarseResidualKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, Lv.r.p}; parallel_rows<8>(s, L.n, k); }
+    if (dist) halo_of(c, L.halo, nb, Lb);
+    { BatchOf<CoarseResidualKernel> k{}; for (int q = 0; q < nb; ++q) k.f[q] = CoarseResidualKernel{mat(q), dinv(q), Lb.p[q], Lx.p[q], Lr.p[q]};
+      parallel_rows_batch<8>(s, L.n, nb, k); }
     if (L.halo.n_ghost > 0) {   // x = dinv b on the ghost unknowns too (read by the sweep up)
-      DiagScaleKernel k{V.dinv[li].p + L.n, Lv.b.p + L.n, Lv.x.p + L.n, 1.0};
-      parallel_for(s, L.halo.n_ghost, k);
+      BatchOf<DiagScaleKernel> k{};
+      for (int q = 0; q < nb; ++q) k.f[q] = DiagScaleKernel{dinv(q) + L.n, Lb.p[q] + L.n, Lx.p[q] + L.n, 1.0};
+      parallel_for_batch(s, L.halo.n_ghost, nb, k);
     }
-    { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, Lv.r.p, Cv.b.p, 0}; parallel_rows<8>(s, C.n, k); }
-    coarse_cycle(c, V, li + 1, true);
-    { CoarseUpKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, C.pidx.p, Cv.x.p, Lv.t.p}; parallel_rows<8>(s, L.n, k); }
-    std::swap(Lv.x.p, Lv.t.p);
-    if (ghost_x && dist) comm.halo(s, L.halo, Lv.x.p, wid);
+    restrict_rows(c, nb, C, Lr, Cb);
+    coarse_cycle(c, B, li + 1, true);
+    const Vecs Cx = level_vecs(B, li + 1, LV_X);
+    { BatchOf<CoarseUpKernel> k{}; for (int q = 0; q < nb; ++q) k.f[q] = CoarseUpKernel{mat(q), dinv(q), Lb.p[q], Lx.p[q], C.pidx.p, Cx.p[q], Lt.p[q]};
+      parallel_rows_batch<8>(s, L.n, nb, k); }
+    swap_xt(B, li);
+    if (ghost_x && dist) halo_of(c, L.halo, nb, level_vecs(B, li, LV_X));
     return;
   }
-  // pre-smoothing from a zero guess
-  { DiagScaleKernel k{V.dinv[li].p, Lv.b.p, Lv.x.p, 1.0}; parallel_for(s, L.n, k); }
-  for (int it = 1; it < c->opt.nu_pre; ++it) {
-    if (dist) comm.halo(s, L.halo, Lv.x.p, wid);
-    CsrJacobiKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, Lv.t.p, 1.0};
-    parallel_for(s, L.n, k);
-    std::swap(Lv.x.p, Lv.t.p);
-  }
+  // general path (other cycle parameters): sweep by sweep
+  auto jacobi = [&]() {
+    const Vecs x = level_vecs(B, li, LV_X), t = level_vecs(B, li, LV_T);
+    if (dist) halo_of(c, L.halo, nb, x);
+    BatchOf<CsrJacobiKernel> k{};
+    for (int q = 0; q < nb; ++q) k.f[q] = CsrJacobiKernel{mat(q), dinv(q), Lb.p[q], x.p[q], t.p[q], 1.0};
+    parallel_for_batch(s, L.n, nb, k);
+    swap_xt(B, li);
+  };
+  { BatchOf<DiagScaleKernel> k{}; for (int q = 0; q < nb; ++q) k.f[q] = DiagScaleKernel{dinv(q), Lb.p[q], Lx.p[q], 1.0};
+    parallel_for_batch(s, L.n, nb, k); }                      // pre-smoothing from a zero guess
+  for (int it = 1; it < c->opt.nu_pre; ++it) jacobi();
   for (int g = 0; g < c->opt.gamma; ++g) {
-    if (dist) comm.halo(s, L.halo, Lv.x.p, wid);
-    { CsrSpmvKernel k{A, Lv.x.p, Lv.b.p, Lv.r.p, 1}; parallel_for(s, L.n, k); }
-    transfer(c, C.n, C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, Lv.r.p, Cv.b.p, 0);
-    coarse_cycle(c, V, li + 1, false);
-    transfer(c, L.n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, Cv.x.p, Lv.x.p, 1);
+    const Vecs x = level_vecs(B, li, LV_X);
+    if (dist) halo_of(c, L.halo, nb, x);
+    { BatchOf<CsrSpmvKernel> k{}; for (int q = 0; q < nb; ++q) k.f[q] = CsrSpmvKernel{mat(q), x.p[q], Lb.p[q], Lr.p[q], 1};
+      parallel_for_batch(s, L.n, nb, k); }
+    transfer(c, nb, C.n, C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, Lr, Cb, 0);
+    coarse_cycle(c, B, li + 1, false);
+    transfer(c, nb, L.n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, level_vecs(B, li + 1, LV_X), x, 1);
   }
-  for (int it = 0; it < c->opt.nu_post; ++it) {
-    if (dist) comm.halo(s, L.halo, Lv.x.p, wid);
-    CsrJacobiKernel k{A, V.dinv[li].p, Lv.b.p, Lv.x.p, Lv.t.p, 1.0};
-    parallel_for(s, L.n, k);
-    std::swap(Lv.x.p, Lv.t.p);
-  }
-  if (ghost_x && dist) comm.halo(s, L.halo, Lv.x.p, wid);
+  for (int it = 0; it < c->opt.nu_post; ++it) jacobi();
+  if (ghost_x && dist) halo_of(c, L.halo, nb, level_vecs(B, li, LV_X));
 }
 
-// z = M^-1 r
+// z = M^-1 r for every system of the batch: one V-cycle.
 // `presmooth0` = false drops the pre-smoothing sweep of the DG level (a V(0,1) cycle there:
 // the right-hand side is restricted directly, one matrix pass less per application).  The
 // resulting operator is not symmetric: fine for GMRES (KNP), not used with CG (EMI).
-// one V-cycle; T = the type the level-0 matrix A0 and its inverse diagonal blocks binv are stored in
+// T = the type the level-0 matrices A0 and their inverse diagonal blocks binv are stored in.
 template <typename T>
-static void vcycle(knp_ctx* c, AmgValues& V, const BellMatT<T>& A0, const T* binv, const double* r, double* z,
+static void vcycle(knp_ctx* c, const Batch& B, const BellMatT<T>* A0, const T* const* binv, const Vecs& r, const Vecs& z,
                    bool presmooth0, int cheby) {
   AmgPlan& amg = c->amg;
+  const int nb = B.nb;
   AmgLevelPlan& C = amg.lev[0];
-  LevelVectors& Cv = V.vec[0];
-  const double w = V.omega;
-  double* x = V.x0.p; double* t = V.t0.p;
+  const Vecs Cb = level_vecs(B, 0, LV_B);
+  double w[MAX_BATCH];
+  Vecs x{}, t{}, r0{};
+  for (int q = 0; q < nb; ++q) { AmgValues& V = *B.s[q].V; w[q] = V.omega; x.p[q] = V.x0.p; t.p[q] = V.t0.p; r0.p[q] = V.r0.p; }
   if (cheby == 2 && presmooth0) {
     // degree-2 Chebyshev in Dinv A on [lmax / 4, lmax], lmax = 1.05 x the estimate behind V.omega; the
     // same polynomial before and after the coarse correction keeps the cycle symmetric (CG)
-    const double lmax = 4.0 / (3.0 * w), lmin = 0.25 * lmax;
-    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
-    const double sigma = theta / delta, rho0 = 1.0 / sigma, rho1 = 1.0 / (2.0 * sigma - rho0);
-    const double w1 = 1.0 / theta, w2 = 2.0 * rho1 / delta, beta = rho1 * rho0;
-    block_apply(c, binv, r, t, w1, 0);                                   // x1 = w1 Dinv r         (x0 = 0)
-    bell_jacobi_mom(c, A0, binv, r, t, (const double*)nullptr, x, w2, beta);   // x2
-    bell_spmv(c, A0, x, r, V.r0.p, 1);
-    { TransferRowsKernel k{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, V.r0.p, Cv.b.p, 0}; parallel_rows<8>(cs(c), C.n, k); }
-    coarse_cycle(c, V, 0, false);
-    transfer(c, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, Cv.x.p, x, 1);
-    bell_jacobi(c, A0, binv, r, x, t, w1);                               // x1' from x0' = x
-    bell_jacobi_mom(c, A0, binv, r, t, x, z, w2, beta);                  // x2' -> z
+    double w1[MAX_BATCH], w2[MAX_BATCH], beta = 0.0;
+    for (int q = 0; q < nb; ++q) {
+      const double lmax = 4.0 / (3.0 * w[q]), lmin = 0.25 * lmax;
+      const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin);
+      const double sigma = theta / delta, rho0 = 1.0 / sigma, rho1 = 1.0 / (2.0 * sigma - rho0);
+      w1[q] = 1.0 / theta; w2[q] = 2.0 * rho1 / delta; beta = rho1 * rho0;     // (beta depends on the ratio only)
+    }
+    block_apply<T>(c, nb, binv, r, t, w1, 0);                               // x1 = w1 Dinv r         (x0 = 0)
+    bell_jacobi<T, true>(c, nb, A0, binv, r, t, x, w2, nullptr, beta);       // x2
+    bell_spmv<T>(c, nb, A0, x, r, r0, 1);
+    restrict_rows(c, nb, C, r0, Cb);
+    coarse_cycle(c, B, 0, false);
+    transfer(c, nb, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, level_vecs(B, 0, LV_X), x, 1);
+    bell_jacobi<T>(c, nb, A0, binv, r, x, t, w1);                            // x1' from x0' = x
+    bell_jacobi<T, true>(c, nb, A0, binv, r, t, z, w2, &x, beta);            // x2' -> z
     return;
   }
-  // (measured on B200: the fused prolongation + sweep is ~2 % SLOWER than prolongation and sweep
-  // as two launches - 40 extra gathers per row in a kernel that otherwise runs at 0.9 of the
-  // HBM roofline - so it is opt-in)
-  if constexpr (std::is_same<T, double>::value) {
-    if (c->opt.fuse_prolong && c->opt.nu_post == 1 && C.t_unit && c->opt.nu_pre == 1) {
-      const double* rr = r;
-      if (presmooth0) {
-        block_apply(c, binv, r, x, w, 0);
-        bell_spmv(c, A0, x, r, V.r0.p, 1);          // refreshes the ghost entries of x as well
-        rr = V.r0.p;
-      }
-      { TransferRowsKernel k{C.rptr.p, C.ridx.p, nullptr, rr, Cv.b.p, 0}; parallel_rows<8>(cs(c), C.n, k); }
-      coarse_cycle(c, V, 0, c->comm.active());        // ghost entries of C.x are read by the fused sweep
-      bell_jacobi_prolong(c, A0, binv, r, presmooth0 ? x : nullptr, C.pidx.p, Cv.x.p, z, w);
-      return;
-    }
-  }
-  const double* rr = r;
+  Vecs rr = r;
   if (presmooth0) {
-    block_apply(c, binv, r, x, w, 0);
-    for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi(c, A0, binv, r, x, t, w); std::swap(x, t); }
-    bell_spmv(c, A0, x, r, V.r0.p, 1);
-    rr = V.r0.p;
+    block_apply<T>(c, nb, binv, r, x, w, 0);
+    for (int it = 1; it < c->opt.nu_pre; ++it) { bell_jacobi<T>(c, nb, A0, binv, r, x, t, w); std::swap(x, t); }
+    bell_spmv<T>(c, nb, A0, x, r, r0, 1);
+    rr = r0;
   }
-  { TransferRowsKernel k{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, rr, Cv.b.p, 0}; parallel_rows<8>(cs(c), C.n, k); }
-  coarse_cycle(c, V, 0, false);
-  transfer(c, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, Cv.x.p, x, presmooth0 ? 1 : 0);
-  if (c->opt.nu_post == 0) { d2d(z, x, c->n * sizeof(double), cs(c)); return; }
+  restrict_rows(c, nb, C, rr, Cb);
+  coarse_cycle(c, B, 0, false);
+  transfer(c, nb, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, level_vecs(B, 0, LV_X), x, presmooth0 ? 1 : 0);
+  if (c->opt.nu_post == 0) {
+    for (int q = 0; q < nb; ++q) d2d(z.p[q], x.p[q], c->n * sizeof(double), cs(c));
+    return;
+  }
   for (int it = 0; it < c->opt.nu_post; ++it) {
-    double* out = (it + 1 == c->opt.nu_post) ? z : t;
-    bell_jacobi(c, A0, binv, r, x, out, w);
-    if (out != z) std::swap(x, t);
+    const Vecs& out = (it + 1 == c->opt.nu_post) ? z : t;
+    bell_jacobi<T>(c, nb, A0, binv, r, x, out, w);
+    if (it + 1 != c->opt.nu_post) std::swap(x, t);
   }
-  // keep the plan's buffers in their slots for the next call
-  if (x != V.x0.p) std::swap(V.x0.p, V.t0.p);
 }
 
-static void precondition(knp_ctx* c, AmgValues& V, const BellMat& A0, const double* bj, const double* r, double* z,
-                         bool presmooth0 = true) {
+static void precondition(knp_ctx* c, const Batch& B, const Vecs& r, const Vecs& z, bool presmooth0 = true) {
   const int cheby = presmooth0 ? c->opt.cheby : 1;      // the symmetric (EMI) cycle only
+  const int nb = B.nb;
   if (c->opt.pc == 0 || !c->amg.ready) {
-    block_apply(c, bj, r, z, 1.0, 0);
+    const double* bj[MAX_BATCH]; double one[MAX_BATCH];
+    for (int q = 0; q < nb; ++q) { bj[q] = B.s[q].bj; one[q] = 1.0; }
+    block_apply<double>(c, nb, bj, r, z, one, 0);
     return;
   }
-  if (c->opt.pc_fp32 && V.a32.n) {
-    BellMat32 A32;
-    A32.nc = A0.nc; A32.nbr = A0.nbr; A32.off = V.a32.p; A32.diag = V.a32.p;
-    vcycle<float>(c, V, A32, V.binv32.p, r, z, presmooth0, cheby);
+  bool fp32 = c->opt.pc_fp32;
+  for (int q = 0; q < nb; ++q) fp32 = fp32 && B.s[q].V->a32.n;
+  if (fp32) {
+    BellMat32 A32[MAX_BATCH]; const float* binv[MAX_BATCH];
+    for (int q = 0; q < nb; ++q) {
+      AmgValues& V = *B.s[q].V;
+      A32[q].nc = B.s[q].A.nc; A32[q].nbr = B.s[q].A.nbr; A32[q].off = V.a32.p; A32[q].diag = V.a32.p;
+      binv[q] = V.binv32.p;
+    }
+    vcycle<float>(c, B, A32, binv, r, z, presmooth0, cheby);
   } else {
-    vcycle<double>(c, V, A0, V.binv.p, r, z, presmooth0, cheby);
+    BellMat A0[MAX_BATCH]; const double* binv[MAX_BATCH];
+    for (int q = 0; q < nb; ++q) { A0[q] = B.s[q].A; binv[q] = B.s[q].V->binv.p; }
+    vcycle<double>(c, B, A0, binv, r, z, presmooth0, cheby);
   }
+}
+static Batch batch1(AmgValues& V, const BellMat& A, const double* bj) {
+  Batch B{};
+  B.nb = 1; B.s[0] = Sys{&V, A, bj};
+  return B;
 }
 
 // ---------------------------------------------------------------------------------
@@ -880,23 +888,29 @@ static void remove_mean(knp_ctx* c, double* v) {
   parallel_for(cs(c), c->n_own, k);
 }
 
-static void ensure_krylov(knp_ctx* c) {
+// Krylov vectors: the main workspace serves the EMI solve and system 0 of the KNP batch, the
+// further systems of the batch have their own vectors in kr_ion[1..]
+static void ensure_vectors(knp_ctx* c, KrylovWs& K, bool basis) {
+  const size_t n = c->n;
+  if (K.r.n != 2 * n) { K.r.alloc(2 * n); K.p.alloc(n); K.q.alloc(n); K.w.alloc(n); }
+  const size_t need = (size_t)(c->opt.restart + 1) * n;
+  if (basis && K.V.n < need) K.V.alloc(need);
+}
+static void ensure_krylov(knp_ctx* c, int nsys = 1) {
   const size_t n = c->n;
   KrylovWs& K = ws(c);
   if (K.scal.n == 0) { K.scal.alloc(1024); K.partial.alloc((size_t)DOT_MAX * RED_BLOCKS); }
-  if (K.r.n != 2 * n) { K.r.alloc(2 * n); K.p.alloc(n); K.q.alloc(n); K.w.alloc(n); }
+  ensure_vectors(c, K, true);
+  for (int q = 1; q < nsys; ++q) ensure_vectors(c, c->kr_ion[q], true);
   if (c->kr_ones.n != n) {
     c->kr_ones.alloc(n);
     std::vector<double> one(n, 1.0);
     h2d(c->kr_ones.p, one.data(), n * sizeof(double), cs(c));
   }
-  const size_t need = (size_t)(c->opt.restart + 1) * n;
-  if (K.V.n < need) K.V.alloc(need);
-  if (tl_ws == nullptr) {     // (worker threads find it set by the main thread)
-    double ng = (double)c->n_own;
-    global_sum(c, &ng, 1);
-    c->n_global = ng;
-  }
+  c->comm.batch_cap = c->P.N - 1 > 1 ? c->P.N - 1 : 1;
+  double ng = (double)c->n_own;
+  global_sum(c, &ng, 1);
+  c->n_global = ng;
 }
 
 extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, int* niter, double* resid) {
@@ -917,6 +931,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
   }
   double* x = c->phi.p; double* r = ws(c).r.p; double* z = ws(c).r.p + n; double* p = ws(c).p.p; double* q = ws(c).q.p;
   const double* b = c->rhs_emi.p;
+  const Batch PB = batch1(c->amg_emi, B, c->bj_emi.p);          // the preconditioner is built from B_emi
   if (c->opt.extrapolate_phi) {
     if (c->phi_old.n != (size_t)n) { c->phi_old.alloc(n); c->phi_old_valid = false; }
     // the first stored field is an initial condition, not a solution: extrapolate only once two
@@ -947,13 +962,13 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
     zz_out = fmax(d[1] - Ng * mu_out * mu_out, 0.0);
   };
   // reference norm ||M^-1 b||
-  precondition(c, c->amg_emi, B, c->bj_emi.p, b, z);
+  precondition(c, PB, vecs1(b), vecs1(z));
   remove_mean(c, z);
   const double bnorm = sqrt(dot_host(c, z, z));
   const double tol = fmax(rtol * bnorm, atol);
   bell_spmv(c, A, x, b, r, 1);
   remove_mean(c, r);
-  precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
+  precondition(c, PB, vecs1(r), vecs1(z));
   double rz, zz, mu;
   fused_dots(rz, zz, mu);
   double zn = sqrt(zz);
@@ -981,7 +996,7 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
       }
       const double alpha = rz / pq;
       { Axpy2ProjKernel k{alpha, p, q, x, r, (sum_r - alpha * sum_q) / Ng}; parallel_for(s, no, k); }
-      precondition(c, c->amg_emi, B, c->bj_emi.p, r, z);
+      precondition(c, PB, vecs1(r), vecs1(z));
       double rz_new;
       fused_dots(rz_new, zz, mu);
       zn = sqrt(zz);
@@ -1012,84 +1027,107 @@ extern "C" int knp_solve_emi(knp_ctx* ctx, double rtol, double atol, int maxit, 
 // ---------------------------------------------------------------------------------
 // GMRES (KNP), one ion at a time
 // ---------------------------------------------------------------------------------
-// preconditioner of ion's system after a re-assembly (the reference rebuilds BoomerAMG at
-// every setOperators, solver.py:767)
-static void knp_refresh(knp_ctx* c, int ion) {
-  AmgValues& V = c->amg_knp[ion];
-  V.refreshed_now = refresh_due(c, V);
-  if (!V.refreshed_now) return;
-  BellMat A = bell_of(c, 2 + ion);
-  if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, V, A, c->A_knp[ion].p, c->A_knp[ion].p);
-  else { if (c->bj_knp[ion].n != (size_t)c->slot_stride()) c->bj_knp[ion].alloc(c->slot_stride()); block_inverse(c, c->A_knp[ion].p, c->bj_knp[ion].p); }
+// preconditioners of the ions' systems after a re-assembly (the reference rebuilds BoomerAMG at
+// every setOperators, solver.py:767); the lagged-refresh bookkeeping of the block system is kept
+// in the first ion's AmgValues
+static bool knp_refresh(knp_ctx* c, int nion) {
+  AmgValues& V0 = c->amg_knp[0];
+  const bool due = refresh_due(c, V0);
+  if (!due) return false;
+  for (int ion = 0; ion < nion; ++ion) {
+    BellMat A = bell_of(c, 2 + ion);
+    if (c->opt.pc == 1 && c->amg.ready) amg_refresh(c, c->amg_knp[ion], A, c->A_knp[ion].p, c->A_knp[ion].p);
+    else { if (c->bj_knp[ion].n != (size_t)c->slot_stride()) c->bj_knp[ion].alloc(c->slot_stride()); block_inverse(c, c->A_knp[ion].p, c->bj_knp[ion].p); }
+  }
+  return true;
 }
 
-static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, double* resid_out, bool refresh = true) {
+// Left-preconditioned restarted GMRES on the block-diagonal system of all solved ions (the
+// reference's mixed-space system, solver.py:684-701, 767-771): vectors are nb blocks, inner products
+// sum over the blocks, convergence is tested on the norm of the whole preconditioned residual.
+static int gmres_block(knp_ctx* c, int nb, double rtol, double atol, int maxit, double* resid_out) {
   knp_stream_t s = cs(c);
   const int64_t n = c->n, no = c->n_own;   // stride of the Krylov basis / owned rows
   const int m = c->opt.restart;
-  BellMat A = bell_of(c, 2 + ion);
-  AmgValues& Vv = c->amg_knp[ion];
-  if (refresh) knp_refresh(c, ion);
-  const double* bj = c->bj_knp[ion].p;
-  double* x = c->c[ion].p;
-  const double* b = c->rhs_knp[ion].p;
-  double* V = ws(c).V.p; double* w = ws(c).w.p; double* r = ws(c).r.p;
+  const bool refreshed = knp_refresh(c, nb);
+  Batch B{};
+  B.nb = nb;
+  BellMat A[MAX_BATCH];
+  Vecs x{}, b{}, V{}, w{}, r{};
+  for (int q = 0; q < nb; ++q) {
+    A[q] = bell_of(c, 2 + q);
+    B.s[q] = Sys{&c->amg_knp[q], A[q], c->bj_knp[q].p};
+    KrylovWs& K = q == 0 ? c->kr0 : c->kr_ion[q];
+    x.p[q] = c->c[q].p; b.p[q] = c->rhs_knp[q].p;
+    V.p[q] = K.V.p; w.p[q] = K.w.p; r.p[q] = K.r.p;
+  }
+  const Vecs none{};
   double* hdev = ws(c).scal.p + 512;  // device copy of the current Hessenberg column / y
   const bool pre0 = c->opt.knp_presmooth0;
-  precondition(c, Vv, A, bj, b, w, pre0);
-  const double bnorm = sqrt(dot_host(c, w, w));
+  precondition(c, B, b, w, pre0);
+  const double bnorm = sqrt(dot_host(c, nb, w, w));
   const double tol = fmax(rtol * bnorm, atol);
-  std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), g(m + 1), y(m), hcol(m + 2);
+  std::vector<double> H((size_t)(m + 1) * m), cs_(m), sn(m), g(m + 1), y(m), hcol(m + 2);
   int it = 0;
   double res = 0.0;
   while (true) {
-    bell_spmv(c, A, x, b, r, 1);
-    precondition(c, Vv, A, bj, r, V, pre0);        // V0 = M^-1 (b - A x)
-    const double beta = sqrt(dot_host(c, V, V));
+    bell_spmv<double>(c, nb, A, x, b, r, 1);
+    precondition(c, B, r, V, pre0);        // V0 = M^-1 (b - A x)
+    const double beta = sqrt(dot_host(c, nb, V, V));
     res = beta;
     if ((beta <= tol && it >= c->opt.knp_min_it) || it >= maxit || beta == 0.0) break;
-    { ScaleKernel k{1.0 / beta, V, V}; parallel_for(s, no, k); }
+    { BatchOf<ScaleKernel> k{}; for (int q = 0; q < nb; ++q) k.f[q] = ScaleKernel{1.0 / beta, V.p[q], V.p[q]};
+      parallel_for_batch(s, no, nb, k); }
     std::fill(g.begin(), g.end(), 0.0);
     g[0] = beta;
     int j = 0;
     bool done = false;
     for (; j < m && it < maxit; ++j) {
-      double* vj = V + (int64_t)j * n;
-      double* vn = V + (int64_t)(j + 1) * n;
-      bell_spmv(c, A, vj, nullptr, r, 0);
-      precondition(c, Vv, A, bj, r, vn, pre0);     // w = M^-1 A v_j, built in the next basis slot
+      const Vecs vj = offset(V, nb, (int64_t)j * n), vn = offset(V, nb, (int64_t)(j + 1) * n);
+      bell_spmv<double>(c, nb, A, vj, none, r, 0);
+      precondition(c, B, r, vn, pre0);     // w = M^-1 A v_j, built in the next basis slot
       // classical Gram-Schmidt with ONE reduction per step: h = V^T w and |w|^2 in the same
       // pass (w is basis slot j+1), the new norm from Pythagoras, update + normalisation fused;
       // h stays on the device for the update, the host reads it once for the Givens rotations
-      multi_dot_device(s, no, n, j + 2, V, vn, ws(c).partial.p, hdev);
-      c->comm.allreduce(s, hdev, j + 2, ws(c).id);
+      {
+        DotBatch D;
+        D.nb = nb;
+        for (int q = 0; q < nb; ++q) { D.V[q] = V.p[q]; D.w[q] = vn.p[q]; }
+        multi_dot_batch(s, no, n, j + 2, D, ws(c).partial.p, hdev);
+      }
+      c->comm.allreduce(s, hdev, j + 2);
       // the Pythagorean norm carries a relative error of about eps |w|^2 / hn^2: keep it below
       // the requested tolerance, otherwise fall back to the explicit norm
       const double cancel_tol = fmax(1e-6, 100.0 * 2.2e-16 / fmax(rtol, 1e-16));
-      { GsNormalizeKernel k{n, j + 1, V, hdev, vn, cancel_tol}; parallel_for(s, no, k); }
+      { BatchOf<GsNormalizeKernel> k{}; for (int q = 0; q < nb; ++q) k.f[q] = GsNormalizeKernel{n, j + 1, V.p[q], hdev, vn.p[q], cancel_tol};
+        parallel_for_batch(s, no, nb, k); }
       d2h(hcol.data(), hdev, (j + 2) * sizeof(double), s);
       double hsum = 0.0;
       for (int i = 0; i <= j; ++i) hsum += hcol[i] * hcol[i];
       double hn2 = hcol[j + 1] - hsum;
       if (!(hn2 >= cancel_tol * hcol[j + 1] && hn2 > 0.0)) {
         // too much cancellation (w almost in span V): explicit norm of the updated vector
-        hn2 = dot_host(c, vn, vn);
-        if (hn2 > 0.0) { ScaleKernel k{1.0 / sqrt(hn2), vn, vn}; parallel_for(s, no, k); }
+        hn2 = dot_host(c, nb, vn, vn);
+        if (hn2 > 0.0) {
+          BatchOf<ScaleKernel> k{};
+          for (int q = 0; q < nb; ++q) k.f[q] = ScaleKernel{1.0 / sqrt(hn2), vn.p[q], vn.p[q]};
+          parallel_for_batch(s, no, nb, k);
+        }
       }
       const double hn = hn2 > 0.0 ? sqrt(hn2) : 0.0;
       for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hcol[i];
       H[(size_t)(j + 1) * m + j] = hn;
       for (int i = 0; i < j; ++i) {                // apply previous rotations
         const double a = H[(size_t)i * m + j], bq = H[(size_t)(i + 1) * m + j];
-        H[(size_t)i * m + j] = cs[i] * a + sn[i] * bq;
-        H[(size_t)(i + 1) * m + j] = -sn[i] * a + cs[i] * bq;
+        H[(size_t)i * m + j] = cs_[i] * a + sn[i] * bq;
+        H[(size_t)(i + 1) * m + j] = -sn[i] * a + cs_[i] * bq;
       }
       const double a = H[(size_t)j * m + j], bq = H[(size_t)(j + 1) * m + j];
       const double den = hypot(a, bq);
-      cs[j] = den > 0 ? a / den : 1.0; sn[j] = den > 0 ? bq / den : 0.0;
+      cs_[j] = den > 0 ? a / den : 1.0; sn[j] = den > 0 ? bq / den : 0.0;
       H[(size_t)j * m + j] = den; H[(size_t)(j + 1) * m + j] = 0.0;
       g[j + 1] = -sn[j] * g[j];
-      g[j] = cs[j] * g[j];
+      g[j] = cs_[j] * g[j];
       ++it;
       res = fabs(g[j + 1]);
       if ((res <= tol && it >= c->opt.knp_min_it) || hn == 0.0) { ++j; done = true; break; }
@@ -1103,8 +1141,9 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
     }
     if (k > 0) {
       h2d(hdev, y.data(), k * sizeof(double), s);
-      CombineKernel ck{n, k, V, hdev, x};
-      parallel_for(s, no, ck);
+      BatchOf<CombineKernel> ck{};
+      for (int q = 0; q < nb; ++q) ck.f[q] = CombineKernel{n, k, V.p[q], hdev, x.p[q]};
+      parallel_for_batch(s, no, nb, ck);
     }
     if (done || it >= maxit) {
       if (!done) { *resid_out = res; return -it; }
@@ -1112,7 +1151,7 @@ static int gmres_one(knp_ctx* c, int ion, double rtol, double atol, int maxit, d
     }
   }
   *resid_out = res;
-  note_solve(Vv, Vv.refreshed_now, it);
+  note_solve(c->amg_knp[0], refreshed, it);
   return it;
 }
 
@@ -1121,99 +1160,24 @@ extern "C" int knp_solve_knp(knp_ctx* ctx, double rtol, double atol, int maxit, 
   if (!ctx->knp_assembled) fail("knp_solve_knp: assemble first");
   stream_sync(ctx->stream);
   const double t0 = now_s();
-  ensure_krylov(ctx);
-  int worst = 0;
-  double rmax = 0.0;
   const int nion = ctx->P.N - 1;
-  bool concurrent = false;
-#ifndef KNP_EMU
+  if (nion > MAX_BATCH) fail("knp_solve_knp: too many ions");
+  ensure_krylov(ctx, nion);
+  double res = 0.0;
+  const int it = gmres_block(ctx, nion, rtol, atol, maxit, &res);
+  if (it < 0) fail("knp_solve_knp: GMRES did not converge in " + std::to_string(maxit) +
+                   " iterations (ksp_error_if_not_converged, solver.py:428)");
   {
-    // The ions' systems are independent (solver.py:550-594).  On one GPU they are solved
-    // CONCURRENTLY: one host thread and one stream per ion, so the latency-bound parts of one
-    // solve (small AMG levels, host round trips of the Krylov scalars) overlap the
-    // bandwidth-bound kernels of the other.  (Multi-GPU runs keep them in sequence: the
-    // exchange kernels of a plan must be issued in the same order on every rank.)
-    // Multi-GPU: every worker talks to its peers on its own exchange channel (peer-memory
-    // kernels only - NCCL calls must come from one thread in one order); the preconditioner
-    // refresh, which all-gathers matrix values with NCCL, is done up front on the main thread.
-    // KNP_CONCURRENT_IONS: unset = concurrent on a single GPU only; 0 = never; 1 = also across
-    // ranks.  The multi-rank mode is still OPT-IN: it measured -16 % at N=2, but 4 of 10 runs at
-    // N=2 ended in an exchange time-out once the per-solve preconditioner refresh (whose NCCL
-    // all-gather had kept the ranks in step) became lagged.  Suspected cause: lazy kernel loading
-    // (preload_solver_kernels above); 2 of 2 runs were clean with the preload + eager loading,
-    // not yet enough to flip the default.
-    const char* e = getenv("KNP_CONCURRENT_IONS");
-    const bool dist = ctx->comm.active();
-    const bool dist_ok = !dist || (e && e[0] == '1' && ctx->comm.p2p.on && ctx->comm.world <= P2P_MAX_NB &&
-                                   nion + 1 <= P2P_MAX_WS && ctx->opt.pc == 1 && ctx->amg.ready &&
-                                   (ctx->amg.rep_from != (size_t)-1 || ctx->amg.m_dense <= P2P_AR_MAX));
-    concurrent = nion > 1 && dist_ok && !(e && e[0] == '0');
-  }
-  if (concurrent) {
-    // Streams and workspace buffers are created HERE, on the main thread, while this device is
-    // idle: cudaMalloc / cudaFree / stream creation may synchronise the whole device, and a
-    // device-wide wait issued while a peer-memory exchange kernel of the other worker is spinning
-    // on a neighbour rank (whose matching kernel may sit behind ITS allocation) can deadlock
-    // across ranks.
-    for (int ion = 0; ion < nion; ++ion) {
-      KrylovWs& K = ctx->kr_ion[ion];
-      K.id = 1 + ion;
-      if (!K.own_stream) { KNP_CUDA(cudaStreamCreateWithFlags(&K.stream, cudaStreamNonBlocking)); K.own_stream = true; }
-      tl_ws = &K;
-      ensure_krylov(ctx);
-      tl_ws = nullptr;
-    }
-    const bool refresh_in_worker = !ctx->comm.active();
-    if (!refresh_in_worker)
-      for (int ion = 0; ion < nion; ++ion) knp_refresh(ctx, ion);
-    cudaEvent_t ready;
-    KNP_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    KNP_CUDA(cudaEventRecord(ready, ctx->stream));
-    std::vector<std::thread> th;
-    std::vector<int> its(nion, 0);
-    std::vector<double> ress(nion, 0.0);
-    std::vector<std::string> errs(nion);
-    for (int ion = 0; ion < nion; ++ion) {
-      KrylovWs& K = ctx->kr_ion[ion];
-      KNP_CUDA(cudaStreamWaitEvent(K.stream, ready, 0));
-      th.emplace_back([ctx, ion, rtol, atol, maxit, refresh_in_worker, &its, &ress, &errs, &K]() {
-        try {
-          KNP_CUDA(cudaSetDevice(ctx->device));
-          tl_ws = &K;
-          Comm::in_worker() = true;
-          its[ion] = gmres_one(ctx, ion, rtol, atol, maxit, &ress[ion], refresh_in_worker);
-          if (its[ion] >= 0) halo0(ctx, ctx->c[ion].p);   // ghost cells of the new concentration
-          stream_sync(K.stream);
-        } catch (const std::exception& ex) { errs[ion] = ex.what(); }
-        catch (...) { errs[ion] = "unknown error"; }
-        Comm::in_worker() = false;
-        tl_ws = nullptr;
-      });
-    }
-    for (auto& t : th) t.join();
-    cudaEventDestroy(ready);
-    for (int ion = 0; ion < nion; ++ion) {
-      if (!errs[ion].empty()) fail(errs[ion]);
-      if (its[ion] < 0) fail("knp_solve_knp: GMRES did not converge for ion " + std::to_string(ion));
-      worst = its[ion] > worst ? its[ion] : worst;
-      rmax = ress[ion] > rmax ? ress[ion] : rmax;
-    }
-  }
-#endif
-  for (int ion = 0; ion < nion && !concurrent; ++ion) {
-    double res = 0.0;
-    const int it = gmres_one(ctx, ion, rtol, atol, maxit, &res);
-    if (it < 0) fail("knp_solve_knp: GMRES did not converge for ion " + std::to_string(ion));
-    halo0(ctx, ctx->c[ion].p);   // post-step and the next assembly read c on the ghost cells
-    worst = it > worst ? it : worst;
-    rmax = res > rmax ? res : rmax;
+    Vecs x{};
+    for (int q = 0; q < nion; ++q) x.p[q] = ctx->c[q].p;
+    halo0(ctx, nion, x);   // post-step and the next assembly read c on the ghost cells
   }
   stream_sync(ctx->stream);
 #ifndef KNP_EMU
   ctx->comm.check_p2p(ctx->stream);
 #endif
-  if (niter) *niter = worst;
-  if (resid) *resid = rmax;
+  if (niter) *niter = it;
+  if (resid) *resid = res;
   ctx->timers[T_KNP_SOLVE] += now_s() - t0;
   KNP_CATCH
 }

@@ -14,11 +14,6 @@ import json
 import os
 import sys
 
-# spin-waiting exchange kernels and lazily loaded CUDA modules do not mix (csrc/knp_solve.cu,
-# preload_solver_kernels): ask for eager loading before anything initialises CUDA
-if os.environ.get("KNP_CONCURRENT_IONS") == "1":
-    os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
-
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
