@@ -54,7 +54,8 @@ STIMULUS = {"stim_amplitude": 10.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of one BellSpmvKernel<4> launch on the N = 1 workloads, from
 # the `ncu --set full` captures summarised in profiles/ (None: not captured for that workload)
 TRAFFIC_SPMV = {"bundle": 3.119e8,    # 299.4 MB read + 12.5 MB written (profiles/kernels_r01_solver.md, launch #1)
-                "emix": None, "astro": None}
+                "emix": 1.2352e9,     # 1181.3 MB read + 53.9 MB written (profiles/kernels_r02_emix.md, launch #0)
+                "astro": None}
 
 
 def stim_locator(x):
