@@ -307,3 +307,145 @@ class File(Group):
                 yield offs, size, mask, child
             else:
                 yield from self._chunks(child, rank)
+
+
+# ---------------------------------------------------------------------------------------------
+# writer
+# ---------------------------------------------------------------------------------------------
+class Writer:
+    """Minimal HDF5 WRITER for the field time series of `Solver.save_h5` (reference layout
+    src/knpemidg/solver.py:1214-1242: /mesh, /subdomains, /surfaces, /concentrations/vector_i,
+    /elim_concentration/vector_i, /potential/vector_i).  Classic layout only: superblock v0, groups as
+    symbol tables (one v1 B-tree node + one symbol node + local heap per group; the group K values
+    in the superblock are raised so that a single symbol node holds every link), version-1 object
+    headers, contiguous little-endian int32/int64/float64 datasets.  Dataset bytes are appended to the
+    file as they are written (nothing but the directory is kept in memory); the directory and the
+    superblock are written by close().  Validated by reading back through `File` above - there is no
+    libhdf5 in this image to cross-check with."""
+
+    def __init__(self, path):
+        self._fh = open(path, "wb")
+        self._fh.write(b"\0" * 2048)                 # superblock goes here at close()
+        self._pos = 2048
+        self._root = {}                              # name -> dict (group) | (addr, shape, dtype)
+        self._closed = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+        return False
+
+    def _append(self, raw):
+        pad = (-self._pos) % 8
+        if pad:
+            self._fh.write(b"\0" * pad)
+            self._pos += pad
+        addr = self._pos
+        self._fh.write(raw)
+        self._pos += len(raw)
+        return addr
+
+    def write(self, name, array):
+        """dataset `name` ('/group/sub/data') <- array (int32, int64 or float64; others are converted)"""
+        a = np.asarray(array)
+        if a.dtype.kind == "f":
+            a = a.astype("<f8", copy=False)
+        elif a.dtype.kind in "iub":
+            a = a.astype("<i8" if a.dtype.itemsize > 4 else "<i4", copy=False)
+        else:
+            raise H5Error(f"{name}: cannot write dtype {a.dtype}")
+        a = np.ascontiguousarray(a)
+        parts = [p for p in name.split("/") if p]
+        node = self._root
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+            if not isinstance(node, dict):
+                raise H5Error(f"{name}: {p} is a dataset")
+        if parts[-1] in node:
+            raise H5Error(f"{name}: already written")
+        addr = self._append(a.tobytes()) if a.size else UNDEF
+        node[parts[-1]] = (addr, a.shape, a.dtype)
+
+    # ---- directory --------------------------------------------------------------------------
+    @staticmethod
+    def _msg(mtype, body):
+        body = body + b"\0" * ((-len(body)) % 8)
+        return struct.pack("<HHB3x", mtype, len(body), 0) + body
+
+    def _object_header(self, msgs):
+        data = b"".join(msgs)
+        return struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(data)) + data
+
+    def _dataset(self, addr, shape, dtype):
+        rank = len(shape)
+        space = struct.pack("<BBB5x", 1, rank, 0) + b"".join(struct.pack("<Q", int(s)) for s in shape)
+        if dtype.kind == "f":
+            dt = struct.pack("<BBBBI", 0x11, 0x20, 63, 0, 8) + struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023)
+        else:
+            dt = struct.pack("<BBBBI", 0x10, 0x08, 0, 0, dtype.itemsize) + struct.pack("<HH", 0, 8 * dtype.itemsize)
+        fill = struct.pack("<BBBB", 2, 2, 0, 0)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize if rank else dtype.itemsize
+        layout = struct.pack("<BBQQ", 3, 1, addr, nbytes)
+        return self._append(self._object_header([self._msg(0x01, space), self._msg(0x03, dt), self._msg(0x05, fill),
+                                                 self._msg(0x08, layout)]))
+
+    def _group(self, links, leaf_k, internal_k):
+        """links: {name: (object header address, is_group, btree, heap)}; returns (ohdr, btree, heap)"""
+        names = sorted(links, key=lambda s: s.encode())
+        heap_data = bytearray(8)                     # offset 0: the empty string
+        offs = {}
+        for nme in names:
+            offs[nme] = len(heap_data)
+            raw = nme.encode() + b"\0"
+            heap_data += raw + b"\0" * ((-len(raw)) % 8)
+        free_off = len(heap_data)
+        heap_data += struct.pack("<QQ", 1, 16)       # one free block at the end (next = 1: none; size 16)
+        data_addr = self._append(bytes(heap_data))
+        heap = self._append(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), free_off, data_addr))
+        snod = bytearray(b"SNOD" + struct.pack("<BBH", 1, 0, len(names)))
+        for nme in names:
+            ohdr, is_group, bt, hp = links[nme]
+            snod += struct.pack("<QQII", offs[nme], ohdr, 1 if is_group else 0, 0)
+            snod += struct.pack("<QQ", bt, hp) if is_group else b"\0" * 16
+        snod += b"\0" * (8 + 2 * leaf_k * 40 - len(snod))
+        snod_addr = self._append(bytes(snod))
+        tree = bytearray(b"TREE" + struct.pack("<BBHQQ", 0, 0, 1 if names else 0, UNDEF, UNDEF))
+        if names:
+            tree += struct.pack("<QQQ", 0, snod_addr, offs[names[-1]])
+        tree += b"\0" * (24 + (2 * internal_k + 1) * 8 + 2 * internal_k * 8 - len(tree))
+        btree = self._append(bytes(tree))
+        ohdr = self._append(self._object_header([self._msg(0x11, struct.pack("<QQ", btree, heap))]))
+        return ohdr, btree, heap
+
+    def close(self):
+        if self._closed:
+            return
+        self._closed = True
+
+        def widest(node):
+            return max([len(node)] + [widest(v) for v in node.values() if isinstance(v, dict)])
+        leaf_k = max(4, (widest(self._root) + 1) // 2)
+        if leaf_k > 32767:
+            raise H5Error("too many links in one group for this writer")
+        internal_k = 16
+
+        def emit(node):
+            links = {}
+            for nme, v in node.items():
+                if isinstance(v, dict):
+                    ohdr, bt, hp = emit(v)
+                    links[nme] = (ohdr, True, bt, hp)
+                else:
+                    links[nme] = (self._dataset(*v), False, 0, 0)
+            return self._group(links, leaf_k, internal_k)
+        ohdr, btree, heap = emit(self._root)
+        eof = self._pos
+        sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBB", 0, 0, 0, 0, 0, 8, 8, 0)
+        sb += struct.pack("<HHI", leaf_k, internal_k, 0)
+        sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
+        sb += struct.pack("<QQII", 0, ohdr, 1, 0) + struct.pack("<QQ", btree, heap)
+        self._fh.seek(0)
+        self._fh.write(sb)
+        self._fh.close()

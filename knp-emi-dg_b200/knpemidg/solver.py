@@ -331,17 +331,45 @@ class Solver:
             f.close()
 
     def init_h5_savefile(self, filename):
+        """HDF5 time series in the reference's layout (solver.py:1214-1227): /mesh, /subdomains,
+        /surfaces, then /concentrations/vector_i, /elim_concentration/vector_i, /potential/vector_i
+        for i = 0 (the state before the first step), 1, 2, ... - written incrementally through
+        knpemidg.h5lite.Writer (no libhdf5 in this image).  dolfin's per-function dof-map datasets
+        (cell_dofs, x_cell_dofs, cells) are written next to the vectors: dof = nd*cell + local
+        vertex, the mixed concentration space stacks the ions."""
+        from . import h5lite
         os.makedirs(os.path.dirname(filename) or ".", exist_ok=True)
-        self._series = {"concentrations": [], "elim_concentration": [], "potential": []}
-        self._series_file = os.path.splitext(filename)[0] + ".npz"
+        eng = self.engine
+        mesh = self.mesh
+        w = self._h5 = h5lite.Writer(filename)
+        self.h5_idx = 0
+        nc, nd = mesh.cells.shape
+        w.write("/mesh/coordinates", mesh.coords)
+        w.write("/mesh/topology", mesh.cells.astype(np.int64))
+        w.write("/mesh/cell_indices", np.arange(nc, dtype=np.int64))
+        for name, tags, dim in (("subdomains", self._cell_tags, mesh.gdim), ("surfaces", self._facet_tags, mesh.gdim - 1)):
+            w.write(f"/{name}/coordinates", mesh.coords)
+            w.write(f"/{name}/topology", (mesh.cells if dim == mesh.gdim else mesh.facet_verts).astype(np.int64))
+            w.write(f"/{name}/values", np.asarray(tags).astype(np.int64))
+        cells = np.arange(nc, dtype=np.int64)
+        scalar = (nd * cells[:, None] + np.arange(nd)[None, :])
+        for group, ncomp in (("concentrations", self.N_ions), ("elim_concentration", 1), ("potential", 1)):
+            dofs = np.concatenate([k * nc * nd + scalar for k in range(ncomp)], axis=1)
+            w.write(f"/{group}/cell_dofs", dofs.reshape(-1))
+            w.write(f"/{group}/x_cell_dofs", np.arange(nc + 1, dtype=np.int64) * (nd * ncomp))
+            w.write(f"/{group}/cells", cells)
+        self._write_h5_fields()
+
+    def _write_h5_fields(self):
+        eng, w, i = self.engine, self._h5, self.h5_idx
+        w.write(f"/concentrations/vector_{i}",
+                np.concatenate([eng.concentration(k, gather=True).reshape(-1) for k in range(self.N_ions)]))
+        w.write(f"/elim_concentration/vector_{i}", eng.concentration(eng.N - 1, gather=True).reshape(-1))
+        w.write(f"/potential/vector_{i}", eng.phi(gather=True).reshape(-1))
 
     def save_h5(self):
-        eng = self.engine
-        self._series["concentrations"].append(np.stack([eng.concentration(k) for k in range(self.N_ions)]))
-        self._series["elim_concentration"].append(eng.concentration(eng.N - 1))
-        self._series["potential"].append(eng.phi())
+        self.h5_idx += 1
+        self._write_h5_fields()
 
     def close_h5(self):
-        np.savez_compressed(self._series_file, mesh_coords=self.mesh.coords, mesh_cells=self.mesh.cells,
-                            subdomains=self._cell_tags, surfaces=self._facet_tags,
-                            **{k: np.array(v) for k, v in self._series.items()})
+        self._h5.close()

@@ -193,3 +193,20 @@ def entrywise_failures(a, b, rtol=1e-12, row_floor=1e-14):
     bound = rtol * np.abs(b) + row_floor * np.abs(b).max()
     ratio = np.abs(a - b) / np.maximum(bound, 1e-300)
     return int((ratio > 1.0).sum()), float(ratio.max()) if ratio.size else 0.0
+
+
+def load_h5_series(path):
+    """results.h5 written by Solver.save_h5 (reference layout, solver.py:1214-1242) -> dict with
+    'potential' [nsteps+1, nc, nd], 'concentrations' [nsteps+1, N_ions, nc, nd], 'elim_concentration',
+    'subdomains' [nc], 'surfaces' [nf], 'coordinates', 'topology' (vector_0 = state before the first step)"""
+    from knpemidg import h5lite
+    f = h5lite.File(str(path))
+    cells = f["/mesh/topology"].read()
+    nc, nd = cells.shape
+    out = {"coordinates": f["/mesh/coordinates"].read(), "topology": cells,
+           "subdomains": f["/subdomains/values"].read(), "surfaces": f["/surfaces/values"].read()}
+    n = len([k for k in f["/potential"].keys() if k.startswith("vector_")])
+    out["potential"] = np.stack([f[f"/potential/vector_{i}"].read().reshape(nc, nd) for i in range(n)])
+    out["elim_concentration"] = np.stack([f[f"/elim_concentration/vector_{i}"].read().reshape(nc, nd) for i in range(n)])
+    out["concentrations"] = np.stack([f[f"/concentrations/vector_{i}"].read().reshape(-1, nc, nd) for i in range(n)])
+    return out

@@ -20,7 +20,7 @@ import sys
 import numpy as np
 import pytest
 
-from common import PKG, kmesh
+from common import PKG, kmesh, load_h5_series
 
 REF = "/root/reference/examples/idealized-geometries"
 SHIMS = os.path.join(PKG, "shims")
@@ -63,8 +63,8 @@ def test_run_2d_script_unchanged(ref_env):
     out = ref_env / "results/data/2D"
     stats = sorted(os.listdir(out / "solver"))
     assert stats == sorted(f"{a}_{b}_2.txt" for a in ("emi", "knp") for b in ("assem", "solve", "niter"))
-    d = np.load(out / "results.npz", allow_pickle=True)
-    phi, sub = d["potential"], d["subdomains"]
+    d = load_h5_series(out / "results.h5")
+    phi, sub = d["potential"][1:], d["subdomains"]      # (vector_0 = the initial state)
     assert phi.shape[0] == 200
     ics = sub == 1
     trace = np.array([p[ics].mean() - p[~ics].mean() for p in phi])          # ~ membrane potential
@@ -87,8 +87,8 @@ def test_run_3d_script_unchanged(ref_env):
     g = runpy.run_path(str(ref_env / "run_3D.py"), run_name="__main__")
     S = g["S"]
     assert S.engine.k == 200
-    d = np.load(ref_env / "results/data/3D/results.npz", allow_pickle=True)
-    phi, sub = d["potential"], d["subdomains"]
+    d = load_h5_series(ref_env / "results/data/3D/results.h5")
+    phi, sub = d["potential"][1:], d["subdomains"]
     ics = sub == 1
     trace = np.array([p[ics].mean() - p[~ics].mean() for p in phi])
     assert -0.050 < trace.max() < -0.035 and 8 < int(np.argmax(trace)) < 30
@@ -246,8 +246,8 @@ def test_run_emix_script_unchanged_on_its_own_mesh(ref_env):
     S = g["S"]
     assert S.engine.k == 10
     assert max(S.engine.stats["emi_niter"]) < 80 and max(S.engine.stats["knp_niter"]) < 15
-    d = np.load(ref_env / "results/data/EMIx/results.npz", allow_pickle=True)
-    phi, sub = d["potential"], d["subdomains"]
+    d = load_h5_series(ref_env / "results/data/EMIx/results.h5")
+    phi, sub = d["potential"][1:], d["subdomains"]
     mean = lambda k: np.array([p[sub == k].mean() for p in phi])
     glia, neuron = mean(1) - mean(0), mean(2) - mean(0)
     assert np.all(np.abs(glia + 83.2) < 1.5)                                  # mV
@@ -308,13 +308,13 @@ def test_run_check_calibration_script_unchanged(ref_env):
     S = g["S"]
     assert S.engine.k == 10
     assert (ref_env / "meshes/3D_two_tags/subdomains_0.pvd").exists()
-    d = np.load(ref_env / "results/data/calibration/results.npz", allow_pickle=True)
-    phi, sub = d["potential"], d["subdomains"]
+    d = load_h5_series(ref_env / "results/data/calibration/results.h5")
+    phi, sub = d["potential"][1:], d["subdomains"]
     mean = lambda k: np.array([p[sub == k].mean() for p in phi])
     neuron, glia = mean(1) - mean(0), mean(2) - mean(0)
     assert np.all(np.abs(neuron + 74.3848784437955) < 2e-3)          # mV; emix-simulations/mm_hh.py:14
     assert np.all(np.abs(glia + 83.08511451850003) < 2e-3)           # emix-simulations/mm_glial.py:11
     assert np.abs(neuron[-1] - neuron[0]) < 1e-4 and np.abs(glia[-1] - glia[0]) < 1e-4
-    c0, c1 = d["concentrations"][0], d["concentrations"][-1]
+    c0, c1 = d["concentrations"][1], d["concentrations"][-1]
     assert np.abs(c1 / c0 - 1.0).max() < 1e-4                          # concentrations at rest too
     assert max(S.engine.stats["emi_niter"][1:]) <= 2                   # the previous potential already solves the system

@@ -27,7 +27,14 @@ def test_run_2d_flow_matches_oracle(emu_lib, tmp_path):
     # statistics files keep the reference's format (solver.py:1146-1198)
     txt = open(os.path.join(out, "solver", "emi_niter_0.txt")).read().splitlines()
     assert txt[0].startswith("num cells:") and txt[1].startswith("dofs:") and len(txt) == 2 + 4
-    assert os.path.exists(os.path.join(out, "results.npz"))
+    # field time series: HDF5 in the reference's layout (solver.py:1214-1242), vector_0 = the initial state
+    from common import load_h5_series
+    d = load_h5_series(os.path.join(out, "results.h5"))
+    assert d["potential"].shape[0] == 5 and d["concentrations"].shape[:2] == (5, 2)
+    assert np.array_equal(d["potential"][-1].ravel(), S.phi.nodal().ravel())
+    assert np.array_equal(d["concentrations"][-1][1].ravel(), S.c.split()[1].nodal().ravel())
+    assert np.array_equal(d["elim_concentration"][-1].ravel(), S.ion_list[-1]["c"].nodal().ravel())
+    assert np.array_equal(d["subdomains"], np.asarray(S._cell_tags)) and np.all(d["potential"][0] == 0.0)
 
 
 def test_reference_tolerances_give_traces_within_solver_tolerance(emu_lib):
