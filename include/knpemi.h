@@ -145,9 +145,11 @@ int knp_membrane_outputs(knp_ctx* ctx, int handle, int v_col, int n_ion, const i
 int knp_membrane_stimulus(knp_ctx* ctx, int handle, const uint8_t* mask, int ncols,
                           const int32_t* cols, const double* values);
 /* one step_lsoda: gather (set_v: also states[:,V] <- phi_M, solver.py:1094),
- * integrate t0 -> t0+dt with relative tolerance rtol, scatter. */
+ * integrate t0 -> t0+dt with relative tolerance rtol, scatter.  Explicit Dormand-Prince 5(4); facets
+ * whose step turns out stability-limited (stiff models: LSODA would switch to BDF, membrane.py:108-112)
+ * finish the interval with an L-stable Rosenbrock pair. */
 int knp_ode_step(knp_ctx* ctx, int handle, double t0, double dt, double rtol, double atol,
-                 int set_v, int64_t* stats /* [2]: max steps, total rhs evals; may be NULL */);
+                 int set_v, int64_t* stats /* [3]: max steps, total rhs evals, facets on the stiff path; may be NULL */);
 
 /* ---- multi-GPU: cell-partitioned mesh, one context (= one process, one GPU) per part.
  * Replaces what the reference gets from dolfin's distributed mesh + PETSc's MPI

@@ -87,6 +87,9 @@ int knp_ctx_destroy(knp_ctx* ctx) {
   knp_stream_t s = ctx->stream;
 #ifndef KNP_EMU
   for (auto& k : ctx->kr_ion) if (k.own_stream) { cudaStreamSynchronize(k.stream); cudaStreamDestroy(k.stream); }
+  if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+  if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+  if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
 #endif
   delete ctx;
 #ifndef KNP_EMU
@@ -724,8 +727,12 @@ int knp_ode_step(knp_ctx* ctx, int h, double t0, double dt, double rtol, double 
   if (!done) fail("model not compiled in");
   int64_t hs[4];
   d2h(hs, ctx->ode_stats.p, sizeof hs, ctx->stream);
-  if (stats) { stats[0] = hs[0]; stats[1] = hs[1]; }
-  if (hs[2] != 0) fail("knp_ode_step: the integrator failed on " + std::to_string(hs[2]) + " membrane facets");
+  if (stats) { stats[0] = hs[0]; stats[1] = hs[1]; stats[2] = hs[3]; }
+  if (hs[2] != 0)
+    fail("knp_ode_step: model '" + std::string(knp_model_names[m.model_id]) + "' (membrane handle " + std::to_string(h) +
+         "): the integrator failed on " + std::to_string(hs[2]) + " of " + std::to_string(m.nrows) +
+         " facets in [" + std::to_string(t0) + ", " + std::to_string(t0 + dt) + "] (step size underflow, NaN or step limit; " +
+         std::to_string(hs[3]) + " facets were on the stiff path)");
   KNP_CATCH
 }
 
@@ -778,6 +785,14 @@ int knp_dist_set(knp_ctx* ctx, int rank, int world, int64_t nc_owned, int nneigh
     for (int f = 0; f < nd; ++f) nblocks += c->h_nbr[(size_t)f * c->nc + cell] >= 0;
   }
   c->nnz_export = nblocks * nd * nd;
+  // leading owned cells without a ghost neighbour (their rows do not wait for the halo)
+  c->nc_int = 0;
+  for (int64_t cell = 0; cell < nc_owned; ++cell) {
+    bool interior = true;
+    for (int f = 0; f < nd; ++f) interior = interior && c->h_nbr[(size_t)f * c->nc + cell] < nc_owned;
+    if (!interior) break;
+    c->nc_int = cell + 1;
+  }
   {
     std::vector<int32_t> mc;
     for (int32_t v : c->h_mem_ci) if (v < nc_owned) mc.push_back(v);
@@ -822,6 +837,17 @@ int knp_dist_init_nccl(knp_ctx* ctx, const char uid[128]) {
   memcpy(&id, uid, 128);
   N.check(N.CommInitRank(&ctx->comm.nccl, ctx->comm.world, id, ctx->comm.rank), "ncclCommInitRank");
   ctx->comm.setup_p2p(ctx->stream);   // peer-memory kernels where CUDA IPC works, NCCL otherwise
+  // overlap of the level-0 halo with the interior rows (KNP_OVERLAP=0 disables): a second stream for the
+  // exchange kernel, two events to fork from and join the main stream
+  {
+    const char* e = getenv("KNP_OVERLAP");
+    ctx->overlap = ctx->comm.p2p.on && !(e && e[0] == '0');
+    if (ctx->overlap && !ctx->comm_stream) {
+      KNP_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+      KNP_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
+      KNP_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+    }
+  }
 #endif
   KNP_CATCH
 }

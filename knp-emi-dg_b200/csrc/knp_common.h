@@ -200,11 +200,30 @@ template <class F>
 inline void parallel_for_batch(knp_stream_t s, int64_t n, int nb, const BatchOf<F>& b, int block = 256) {
   for (int k = 0; k < nb; ++k) parallel_for(s, n, b.f[k], block);
 }
+template <class F>
+inline void parallel_for_batch_range(knp_stream_t, int64_t lo, int64_t hi, int nb, const BatchOf<F>& b, int = 256) {
+  for (int k = 0; k < nb; ++k)
+    for (int64_t i = lo; i < hi; ++i) b.f[k](i);
+}
 #else
 template <class F>
 __global__ void pf_batch_kernel(int64_t n, const BatchOf<F> b) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) b.f[blockIdx.y](i);
+}
+// indices lo .. hi-1 only (lo a multiple of the block size's lane grouping: callers pass multiples of ND)
+template <class F>
+__global__ void pf_batch_range_kernel(int64_t lo, int64_t hi, const BatchOf<F> b) {
+  int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < hi) b.f[blockIdx.y](i);
+}
+template <class F>
+inline void parallel_for_batch_range(knp_stream_t s, int64_t lo, int64_t hi, int nb, const BatchOf<F>& b, int block = 256) {
+  if (hi <= lo || nb <= 0) return;
+  const int64_t grid = (hi - lo + block - 1) / block;
+  ++launch_counter();
+  pf_batch_range_kernel<F><<<dim3((unsigned)grid, (unsigned)nb), block, 0, s>>>(lo, hi, b);
+  KNP_CUDA(cudaGetLastError());
 }
 template <class F>
 inline void parallel_for_batch(knp_stream_t s, int64_t n, int nb, const BatchOf<F>& b, int block = 256) {

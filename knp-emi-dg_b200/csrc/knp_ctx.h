@@ -82,6 +82,12 @@ struct knp_ctx {
   // multi-GPU: nc/n count the LOCAL cells/dofs (owned + ghost, the stride and size of every
   // per-cell array and vector); rows are assembled, solved and reduced over the owned ones
   int64_t nc_own = 0, n_own = 0;
+  // owned cells 0 .. nc_int-1 have no ghost neighbour (knpemidg/partition.py numbers them first): their
+  // rows of the level-0 operators run WHILE the halo of the input vector is in flight on comm_stream,
+  // the remaining owned rows after it has landed (PETSc overlaps the VecScatter of MatMult the same way)
+  int64_t nc_int = 0;
+  bool overlap = false;
+  knp_stream_t comm_stream = 0;
   double n_global = 0.0;        // owned dofs summed over all ranks
   knp::Comm comm;
   knp::HaloPlan halo0;          // level-0 (DG dof) halo
@@ -122,6 +128,7 @@ struct knp_ctx {
   double timers[knp::T_COUNT] = {0};
 #ifndef KNP_EMU
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;   // main -> comm stream / comm -> main stream
 #endif
   double host_t0 = 0.0;
 

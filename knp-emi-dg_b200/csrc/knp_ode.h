@@ -10,6 +10,11 @@
 // automatic initial step, last step clipped to land exactly on t0+dt.  The membrane
 // models of the reference are non-stiff at the PDE step sizes used (dt = 0.1 ms vs. gate
 // time constants >= 0.1 ms), so LSODA itself stays in its Adams mode there.
+// Stiff problems (LSODA would switch to BDF, membrane.py:108-112): when the explicit pair has
+// spent STIFF_SWITCH steps inside one interval its step is stability-, not accuracy-limited; the
+// rest of the interval is integrated by an L-stable linearly implicit Rosenbrock pair (Shampine &
+// Reichelt's ode23s: order 2 with a 3rd-order error estimate, finite-difference Jacobian, one
+// LU factorisation per step) under the same error norm and tolerances.
 //
 // Channel currents: the model right-hand side stores I_ch_* into the parameter row as a
 // side effect (e.g. examples/idealized-geometries/mm_hh.py:154-159).  After the last
@@ -40,6 +45,95 @@ struct OdeLink {
   int side;           // kind 1: 0 plus/ECS, 1 minus/ICS
   const double* src;
 };
+
+constexpr int STIFF_SWITCH = 4000;   // explicit steps inside one interval before the implicit pair takes over
+
+// Linearly implicit Rosenbrock pair (ode23s) from t to t1, in place.  Kept out of line: its
+// Jacobian and LU factors live in local memory and must not enlarge the frame of the common path.
+template <class M>
+#if defined(__CUDACC__) && !defined(KNP_EMU)
+__device__ __noinline__
+#else
+inline
+#endif
+void ros23s(double t, double t1, double* y, double* p, double rtol, double atol, int& nsteps, int& nfev, int& ok) {
+  constexpr int NS = M::NS;
+  const double tiny = 1e-300;
+  const double d = 1.0 / (2.0 + 1.4142135623730951), e32 = 6.0 + 1.4142135623730951;
+  const double span = t1 - t;
+  double J[NS][NS], W[NS][NS], F0[NS], F1[NS], F2[NS], T[NS], k1[NS], k2[NS], k3[NS], yt[NS];
+  int piv[NS];
+  auto solve = [&](double* b) {            // W x = b with the stored LU factors (partial pivoting)
+    for (int i = 0; i < NS; ++i) { const double tmp = b[i]; b[i] = b[piv[i]]; b[piv[i]] = tmp;
+      for (int j = 0; j < i; ++j) b[i] -= W[i][j] * b[j]; }
+    for (int i = NS - 1; i >= 0; --i) { for (int j = i + 1; j < NS; ++j) b[i] -= W[i][j] * b[j]; b[i] /= W[i][i]; }
+  };
+  double h = fmin(span, fmax(1e-6 * span, 1e-3 * span));
+  const int max_steps = 400000;
+  while (t < t1) {
+    if (nsteps >= max_steps) { ok = 0; return; }
+    M::rhs(t, y, F0, p); nfev++;
+    // finite-difference Jacobian and time derivative
+    for (int j = 0; j < NS; ++j) {
+      const double yj = y[j];
+      const double dy = 1.4901161193847656e-08 * fmax(fabs(yj), 1e-6);
+      y[j] = yj + dy;
+      M::rhs(t, y, F1, p); nfev++;
+      y[j] = yj;
+      for (int i = 0; i < NS; ++i) J[i][j] = (F1[i] - F0[i]) / dy;
+    }
+    {
+      const double dtt = 1.4901161193847656e-08 * fmax(fabs(t), span);
+      M::rhs(t + dtt, y, F1, p); nfev++;
+      for (int i = 0; i < NS; ++i) T[i] = (F1[i] - F0[i]) / dtt;
+    }
+    for (;;) {   // retry with a smaller step until accepted
+      bool final_step = false;
+      if (t + h >= t1 || t1 - (t + h) < 1e-12 * span) { h = t1 - t; final_step = true; }
+      for (int i = 0; i < NS; ++i)
+        for (int j = 0; j < NS; ++j) W[i][j] = ((i == j) ? 1.0 : 0.0) - h * d * J[i][j];
+      bool singular = false;
+      for (int c = 0; c < NS; ++c) {          // LU with partial pivoting, row swaps recorded in piv
+        int r = c;
+        for (int i = c + 1; i < NS; ++i) if (fabs(W[i][c]) > fabs(W[r][c])) r = i;
+        piv[c] = r;
+        if (r != c) for (int j = 0; j < NS; ++j) { const double tmp = W[c][j]; W[c][j] = W[r][j]; W[r][j] = tmp; }
+        if (W[c][c] == 0.0) { singular = true; break; }
+        for (int i = c + 1; i < NS; ++i) {
+          W[i][c] /= W[c][c];
+          for (int j = c + 1; j < NS; ++j) W[i][j] -= W[i][c] * W[c][j];
+        }
+      }
+      double err = 2.0;
+      if (!singular) {
+        for (int i = 0; i < NS; ++i) k1[i] = F0[i] + h * d * T[i];
+        solve(k1);
+        for (int i = 0; i < NS; ++i) yt[i] = y[i] + 0.5 * h * k1[i];
+        M::rhs(t + 0.5 * h, yt, F1, p); nfev++;
+        for (int i = 0; i < NS; ++i) k2[i] = F1[i] - k1[i];
+        solve(k2);
+        for (int i = 0; i < NS; ++i) { k2[i] += k1[i]; yt[i] = y[i] + h * k2[i]; }
+        M::rhs(t + h, yt, F2, p); nfev++;
+        for (int i = 0; i < NS; ++i) k3[i] = F2[i] - e32 * (k2[i] - F1[i]) - 2.0 * (k1[i] - F0[i]) + h * d * T[i];
+        solve(k3);
+        err = 0.0;
+        for (int i = 0; i < NS; ++i) {
+          const double sc = fmax(atol + rtol * fmax(fabs(y[i]), fabs(yt[i])), tiny);
+          err = fmax(err, fabs(h / 6.0 * (k1[i] - 2.0 * k2[i] + k3[i])) / sc);
+        }
+      }
+      nsteps++;
+      if (err <= 1.0) {
+        t = final_step ? t1 : t + h;
+        for (int i = 0; i < NS; ++i) y[i] = yt[i];
+        h *= (err < 1e-9) ? 5.0 : fmin(5.0, 0.8 * pow(err, -1.0 / 3.0));
+        break;
+      }
+      if (!(err == err) || h < 1e-14 * span || nsteps >= max_steps) { ok = 0; return; }
+      h *= fmax(0.2, 0.8 * pow(err, -1.0 / 3.0));
+    }
+  }
+}
 
 template <class M>
 KNP_HD void dopri5(double t0, double t1, double* y, double* p, double rtol, double atol,
@@ -89,6 +183,11 @@ KNP_HD void dopri5(double t0, double t1, double* y, double* p, double rtol, doub
   bool last_rejected = false;
   while (t < t1) {
     if (nsteps >= max_steps) { ok = 0; break; }
+    if (nsteps >= STIFF_SWITCH) {          // stability-limited: hand the rest of the interval to the implicit pair
+      ros23s<M>(t, t1, y, p, rtol, atol, nsteps, nfev, ok);
+      if (ok) ok = 2;                      // (statistics: this facet needed the stiff path)
+      break;
+    }
     bool final_step = false;
     if (t + h >= t1 || t1 - (t + h) < 1e-12 * span) { h = t1 - t; final_step = true; }
     for (int i = 0; i < NS; ++i) yt[i] = y[i] + h * a21 * k1[i];
@@ -158,7 +257,7 @@ struct OdeStepKernel {
   const uint8_t* stim_mask; int nstim; int stim_cols[MAX_STIM]; double stim_vals[MAX_STIM];
   const int32_t* mem_ci; const int32_t* mem_fi; const int32_t* nbr; const int32_t* finfo;
   double t0, dt, rtol, atol;
-  int64_t* stats;               // [0] max steps, [1] total rhs evaluations, [2] failures
+  int64_t* stats;               // [0] max steps, [1] total rhs evaluations, [2] failures, [3] facets that took the stiff path
 
   KNP_HD void operator()(int64_t row) const {
     constexpr int NS = M::NS, NP = M::NP;
@@ -199,6 +298,7 @@ struct OdeStepKernel {
       stat_max(stats + 0, nsteps);
       stat_add(stats + 1, nfev);
       if (!ok) stat_add(stats + 2, 1);
+      if (ok == 2) stat_add(stats + 3, 1);
     }
   }
 };

@@ -66,14 +66,57 @@ static void halo_of(knp_ctx* c, HaloPlan& H, int nb, const Vecs& x) {
 static void halo0(knp_ctx* c, int nb, const Vecs& x) { halo_of(c, c->halo0, nb, x); }
 static void halo0(knp_ctx* c, const double* x) { halo0(c, 1, vecs1(x)); }
 
+// Overlap of the level-0 halo with interior-row work: the exchange kernel is issued on the
+// context's second stream once everything queued so far on the main stream (the producer of x) is
+// done; the main stream meanwhile runs the rows of the interior cells (no ghost columns) and joins
+// the exchange before the rows next to the partition boundary.
+static bool overlap_split(knp_ctx* c) {
+#ifdef KNP_EMU
+  (void)c;
+  return false;
+#else
+  return c->overlap && c->comm.active() && c->nc_int * 4 >= c->nc_own;   // worth it: >= 25 % interior cells
+#endif
+}
+static void halo0_fork(knp_ctx* c, int nb, const Vecs& x) {
+#ifndef KNP_EMU
+  KNP_CUDA(cudaEventRecord(c->ev_ready, c->stream));
+  KNP_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0));
+  c->comm.halo_batch(c->comm_stream, c->halo0, nb, x.p);
+  KNP_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
+#else
+  (void)c; (void)nb; (void)x;
+#endif
+}
+static void halo0_join(knp_ctx* c) {
+#ifndef KNP_EMU
+  KNP_CUDA(cudaStreamWaitEvent(c->stream, c->ev_halo, 0));
+#else
+  (void)c;
+#endif
+}
+// launch a batch of level-0 row functors that read x through the matrix: with the exchange of x overlapped
+template <class F>
+static void rows_with_halo(knp_ctx* c, int nb, const Vecs& x, const BatchOf<F>& k, int nd, int block) {
+  if (!overlap_split(c)) {
+    halo0(c, nb, x);
+    parallel_for_batch(cs(c), c->n_own, nb, k, block);
+    return;
+  }
+  const int64_t ni = c->nc_int * nd;
+  halo0_fork(c, nb, x);
+  parallel_for_batch_range(cs(c), 0, ni, nb, k, block);          // interior cells: no ghost columns
+  halo0_join(c);
+  parallel_for_batch_range(cs(c), ni, c->n_own, nb, k, block);   // cells next to the partition boundary
+}
+
 template <typename T>
 static void bell_spmv(knp_ctx* c, int nb, const BellMatT<T>* A, const Vecs& x, const Vecs& b, const Vecs& y, int mode) {
-  halo0(c, nb, x);
   by_nd(c, [&](auto nd) {
     constexpr int ND = decltype(nd)::value;
     BatchOf<BellSpmvKernel<ND, T>> k{};
     for (int s = 0; s < nb; ++s) k.f[s] = BellSpmvKernel<ND, T>{A[s], x.p[s], b.p[s], y.p[s], mode};
-    parallel_for_batch(cs(c), c->n_own, nb, k, 256);
+    rows_with_halo(c, nb, x, k, ND, 256);
   });
 }
 static void bell_spmv(knp_ctx* c, const BellMat& A, const double* x, const double* b, double* y, int mode) {
@@ -95,7 +138,6 @@ static void block_apply(knp_ctx* c, const double* dinv, const double* r, double*
 template <typename T, bool MOM = false>
 static void bell_jacobi(knp_ctx* c, int nb, const BellMatT<T>* A, const T* const* dinv, const Vecs& b,
                         const Vecs& xin, const Vecs& xout, const double* w, const Vecs* xprev = nullptr, double beta = 0.0) {
-  halo0(c, nb, xin);
   by_nd(c, [&](auto nd) {
     constexpr int ND = decltype(nd)::value;
     BatchOf<BellJacobiKernel<ND, T, MOM>> k{};
@@ -103,7 +145,7 @@ static void bell_jacobi(knp_ctx* c, int nb, const BellMatT<T>* A, const T* const
       k.f[s] = BellJacobiKernel<ND, T, MOM>{A[s], dinv[s], b.p[s], xin.p[s], xout.p[s], w[s]};
       if (MOM) { k.f[s].xprev = xprev ? xprev->p[s] : nullptr; k.f[s].beta = beta; }
     }
-    parallel_for_batch(cs(c), c->n_own, nb, k, ND == 3 ? 192 : 256);
+    rows_with_halo(c, nb, xin, k, ND, ND == 3 ? 192 : 256);
   });
 }
 static void block_inverse(knp_ctx* c, const double* blocks, double* inv) {

@@ -385,8 +385,9 @@ class Context:
                    _p(cols, _ip), _p(values, _dp))
 
     def ode_step(self, handle, t0, dt, rtol=1e-8, atol=0.0, set_v=True):
-        stats = np.zeros(2, dtype=np.int64)
+        stats = np.zeros(3, dtype=np.int64)
         self._call("knp_ode_step", handle, t0, dt, rtol, atol, int(bool(set_v)), _p(stats, _lp))
+        self.ode_stiff_facets = int(stats[2])          # facets that finished the interval on the implicit pair
         return int(stats[0]), int(stats[1])
 
     def timers(self, reset=False):

@@ -165,6 +165,11 @@ class LocalPart:
         self.neigh = np.unique(gowner).astype(np.int32)
         self.recv_ptr = np.searchsorted(gowner, np.append(self.neigh, self.world + 1)).astype(np.int64)
         self.recv_ptr[-1] = ghosts.size
+        # owned cells: interior ones first, the ones that touch another part last - the library runs the
+        # rows of the interior cells while the halo of a vector is still in flight (csrc/knp_solve.cu)
+        bnd = np.unique(np.concatenate([a[(pa == rank) & (pb != rank)], b[(pb == rank) & (pa != rank)]]))
+        owned = np.concatenate([np.setdiff1d(owned, bnd, assume_unique=True), bnd])
+        self.nc_interior = int(owned.size - bnd.size)
         self.nc_owned = int(owned.size)
         self.l2g = np.concatenate([owned, ghosts]).astype(np.int64)
         g2l = -np.ones(nc + 1, dtype=np.int64)            # index -1 (no cell) maps to -1

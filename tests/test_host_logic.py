@@ -16,3 +16,23 @@ def test_h5lite_rejects_what_it_does_not_read(tmp_path):
     p.write_bytes(b"\x89HDF\r\n\x1a\n" + bytes([2]) + bytes(100))
     with pytest.raises(h5lite.H5Error, match="superblock version 2"):
         h5lite.File(str(p))
+
+
+def test_local_part_numbers_interior_cells_first():
+    """the library overlaps the halo of a vector with the rows of the cells that have no ghost
+    neighbour: the partitioner numbers those first (knpemidg/partition.py:LocalPart)"""
+    import numpy as np
+    from knpemidg import mesh as kmesh, partition
+    mesh, sub, surf = kmesh.bundle_3d_mesh(dims=(8, 9, 9))
+    part = partition.partition_cells(mesh, 4)
+    for rank in range(4):
+        L = partition.LocalPart(mesh, sub.array(), surf.array(), part, rank)
+        fc = L.mesh.facet_cells
+        both = fc[:, 1] >= 0
+        touches_ghost = np.zeros(L.l2g.size, dtype=bool)
+        ghost = np.arange(L.l2g.size) >= L.nc_owned
+        touches_ghost[fc[both, 0]] |= ghost[fc[both, 1]]
+        touches_ghost[fc[both, 1]] |= ghost[fc[both, 0]]
+        assert 0 < L.nc_interior < L.nc_owned
+        assert not touches_ghost[:L.nc_interior].any() and touches_ghost[L.nc_interior:L.nc_owned].all()
+        assert np.all(np.diff(L.l2g[:L.nc_interior]) > 0)          # both groups keep ascending global order
