@@ -31,8 +31,8 @@ def test_local_part_numbers_interior_cells_first():
         both = fc[:, 1] >= 0
         touches_ghost = np.zeros(L.l2g.size, dtype=bool)
         ghost = np.arange(L.l2g.size) >= L.nc_owned
-        touches_ghost[fc[both, 0]] |= ghost[fc[both, 1]]
-        touches_ghost[fc[both, 1]] |= ghost[fc[both, 0]]
+        np.logical_or.at(touches_ghost, fc[both, 0], ghost[fc[both, 1]])
+        np.logical_or.at(touches_ghost, fc[both, 1], ghost[fc[both, 0]])
         assert 0 < L.nc_interior < L.nc_owned
         assert not touches_ghost[:L.nc_interior].any() and touches_ghost[L.nc_interior:L.nc_owned].all()
         assert np.all(np.diff(L.l2g[:L.nc_interior]) > 0)          # both groups keep ascending global order
