@@ -17,11 +17,12 @@ Reference lines restated here:
   post-step updates            src/knpemidg/solver.py:809-842
   n_g / plus / minus / facet-mean projection   src/knpemidg/utils.py:61-124
 
-parity unpinned: dolfin/FFC are not in /root/reference and cannot be installed
-here, and the reference holds no golden matrices.  What pins this file is
-(i) the MMS convergence study of tests/run_MMS_space.py reproduced in
-tests/test_oracle_mms.py (rate ~2), (ii) symmetry / constant null space of the
-EMI operator, (iii) the rest-state known answer.
+PINNED by the reference itself: oracle/refexec executes the reference's own, unmodified
+form code (solver.py:270-403, 534-663) on a numeric dolfin stand-in, and every entry
+assembled here agrees with what those forms assembled (tests/golden/ref_forms_*.npz,
+tests/test_reference_golden.py: 1e-12 |entry| + 1e-14 max|row|, 0 entries fail).
+Further pins: the MMS convergence study of tests/run_MMS_space.py (rate ~2), symmetry /
+constant null space of the EMI operator, the rest-state known answer.
 
 Conventions: a DG-P1 field is an array [nc, nd] of nodal values at the cell's
 vertices; global dof = nd*cell + local vertex.

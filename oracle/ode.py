@@ -8,9 +8,10 @@ parameter row as a side effect (e.g. examples/idealized-geometries/mm_hh.py:154-
 
 Third-party dependency: numbalsoda (unpinned, pyproject.toml:14) - a C++ port
 of ODEPACK LSODA - is absent from /root/reference and from this image; scipy's
-`LSODA` (the Fortran ODEPACK original) stands in.  parity unpinned: the
-reference has no ODE-step test; pins are the rest-state known answer
- and agreement with a 1e-12-tolerance solve.
+`LSODA` (the Fortran ODEPACK original) stands in.  Pins: the reference's own
+membrane.py stepping its own mm_hh.py / mm_glial.py through this same integrator inside
+the reference-executed runs (tests/golden/ref_run_*.npz), the calibration known answer the
+reference hard-codes (examples/emix-simulations/mm_hh.py:11-14), the rest state.
 
 Two conventions for the currents handed to the PDEs are provided
 (SURVEY.md Appendix E): 'last_call' (reference behaviour: whatever the last

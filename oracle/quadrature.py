@@ -13,9 +13,9 @@ for which the rules FFC/FIAT select by default are tabulated here:
 interval: Gauss-Legendre ceil((deg+1)/2) points; triangle degree 4: 6-point
 Dunavant rule; triangle degree 5: 7-point (Radon) rule.
 
-parity unpinned: FFC/FIAT are not vendored in /root/reference, no golden
-vectors exist there; rules are checked for monomial exactness in
-tests/test_oracle_quadrature.py.
+FFC/FIAT are not vendored in /root/reference (unpinned dependency, environment.yml:5); the
+rules are checked for monomial exactness in tests/test_oracle.py.  Which rule is used where
+follows UFL's degree estimation as restated in oracle/refexec/ufl_numeric.py.
 """
 import numpy as np
 from math import factorial

@@ -9,7 +9,8 @@ with scipy sparse direct solves (the reference's MMS tests use MUMPS LU,
 tests/run_MMS_space.py:202, 208) or scipy Krylov solvers with the reference's
 tolerances (solver.py:425-444, 684-701).
 
-parity unpinned (see oracle/forms.py header).
+Pinned by the reference's own loop executed on oracle/refexec: 40 steps of the 2D neuron and 16 steps
+of the astrocyte problem (tests/golden/ref_run_*.npz), membrane-potential traces within 1e-6.
 """
 import numpy as np
 import scipy.sparse as sp
