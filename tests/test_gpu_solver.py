@@ -18,6 +18,15 @@ def test_run_2d_flow_matches_oracle(gpu_lib, tmp_path):
     assert rel_err(S.ion_list[-1]["c"].nodal(), O.c_elim) < 1e-6
 
 
+def test_run_2d_flow_at_the_reference_resolution(gpu_lib):
+    """run_2D.py:58 runs resolution 2 (3 968 cells, 248 ODE points): 10 steps against the oracle loop"""
+    S, O = sc.run_2d_neuron(gpu_lib, 10, rtol_emi=1e-12, rtol_knp=1e-13, resolution=2)
+    assert S.mem_models[0]["ode"].nodes == 248
+    assert rel_err(S.phi_M_prev_PDE.vector().get_local(), O.phi_M) < 1e-6
+    for k in range(2):
+        assert rel_err(S.c.split()[k].nodal(), O.c[k]) < 1e-8
+
+
 def test_reference_tolerances(gpu_lib):
     S, O = sc.run_2d_neuron(gpu_lib, 3)
     assert rel_err(S.phi_M_prev_PDE.vector().get_local(), O.phi_M) < 5e-4
