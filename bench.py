@@ -8,10 +8,10 @@
 One "step" = one full time step of the reference's loop (solver.py:1072-1127): membrane
 ODE step -> EMI assembly + CG/AMG solve -> KNP assembly + GMRES/AMG solves -> post-step.
 
-Default workload (`emix`, M = 66): a 10 um block of 66^3 x 6 = 1,724,976 tetrahedra with ~100
+Default workload (`emix`, M = 104): a 10 um block of 104^3 x 6 = 6,749,184 tetrahedra with ~100
 compact cells (alternately glial, `mm_glial`, and neuronal, `mm_hh`; ms/cm/mV units, calibrated
-initial state, run_EMIx_simulation.py:56-147, 249): 20.7 M DOFs, dt = 0.1 ms, CG rtol 1e-5,
-GMRES(30) rtol 1e-7.  N > 1 (one process per GPU, torchrun): the SAME mesh partitioned by cell
+initial state, run_EMIx_simulation.py:56-147, 249): 81.0 M DOFs (north_star: "at least 20 M";
+`--size 66` is the 20.7 M-DOF block), dt = 0.1 ms, CG rtol 1e-5, GMRES(30) rtol 1e-7.  N > 1 (one process per GPU, torchrun): the SAME mesh partitioned by cell
 (strong scaling), DG halos and Krylov dots over NVLink peer memory / NCCL inside libknpemi.so.
 Other workloads: `bundle` = BASELINE configs[2] (96x27x27x6 tets, 5.04 M DOFs, HH membranes; weak
 scaling = N four-axon blocks side by side), `astro` = configs[3] (three membrane tags, glial +
@@ -41,7 +41,7 @@ for p in (ROOT, os.path.join(ROOT, "knp-emi-dg_b200")):
 import numpy as np  # noqa: E402
 
 WORKLOAD_DIMS = (96, 27, 27)      # bundle
-EMIX_M = 66                       # emix: 66^3 x 6 tets = 20.7 M DOFs (north_star: >= 20 M)
+EMIX_M = 104                      # emix: 104^3 x 6 tets = 6.75 M cells = 81.0 M DOFs (north_star: >= 20 M; 66 -> 20.7 M)
 ASTRO_M = 48                      # astro: 48^3 x 6 tets = 7.96 M DOFs
 DT, C_M = 1.0e-4, 0.02
 PHYS = dict(F=96485.0, R=8.314, T=300.0, C_M=C_M, C_phi=C_M / DT, dt=DT, z=[1.0, -1.0, 1.0],
@@ -53,9 +53,9 @@ ION_NAMES = ["K", "Cl", "Na"]
 STIMULUS = {"stim_amplitude": 10.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of one BellSpmvKernel<4> launch on the N = 1 workloads, from
 # the `ncu --set full` captures summarised in profiles/ (None: not captured for that workload)
-TRAFFIC_SPMV = {"bundle": 3.119e8,    # 299.4 MB read + 12.5 MB written (profiles/kernels_r01_solver.md, launch #1)
-                "emix": 1.2352e9,     # 1181.3 MB read + 53.9 MB written (profiles/kernels_r02_emix.md, launch #0)
-                "astro": None}
+TRAFFIC_SPMV = {("bundle", 0): 3.119e8,   # 299.4 MB read + 12.5 MB written (profiles/kernels_r01_solver.md, launch #1)
+                ("emix", 66): 1.2352e9,   # 1181.3 MB read + 53.9 MB written (profiles/kernels_r02_emix.md, launch #0)
+                }
 
 
 def stim_locator(x):
@@ -255,7 +255,7 @@ def run_reference(args, rank):
     from knpemidg import _lib
     lib = _lib.Lib(path)
     assert not lib.is_cuda()
-    steps = max(1, min(args.steps, 20))          # bounded: ~3-6 s per step of the 20.7 M-DOF workload
+    steps = max(1, min(args.steps, 20))          # bounded: ~3 s per step of the 81 M-DOF workload on 16 cores
     warmup = max(1, min(args.warmup, 3))
     t0 = time.perf_counter()
     eng = make_engine(args, 0, None, lib=lib)
@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="emix", choices=("emix", "bundle", "astro"))
-    ap.add_argument("--size", type=int, default=0, metavar="M", help="emix / astro: M^3 x 6 tetrahedra (default 66 / 48)")
+    ap.add_argument("--size", type=int, default=0, metavar="M", help="emix / astro: M^3 x 6 tetrahedra (default 104 / 48)")
     ap.add_argument("--scaling", default=None, choices=("weak", "strong"),
                     help="default strong (the same mesh on every N); weak is available for the bundle")
     ap.add_argument("--dims", default=None, help="bundle: nx,ny,nz override")
@@ -450,7 +450,8 @@ def main():
     dom = kern["bell_spmv"]
     roofline = {"bound": "hbm", "kernel": "knp::BellSpmvKernel<4> (block-ELL fp64 SpMV)",
                 "achieved": dom["gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": TRAFFIC_SPMV.get(args.workload) if (world == 1 and not args.size and not args.dims) else None,
+                "traffic": TRAFFIC_SPMV.get((args.workload, (args.size or EMIX_M) if args.workload == "emix" else args.size))
+                if (world == 1 and not args.dims) else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
                 "ms_per_launch": dom["ms"], "other_kernels": kern}
     launches = int(sum_over_ranks(float(launches)))

@@ -372,11 +372,6 @@ int knp_field_get(knp_ctx* ctx, int which, int idx, double* dst, int64_t count) 
 // assembly
 // ---------------------------------------------------------------------------------
 #ifndef KNP_EMU
-static int asm_cell_variant() {   // KNP_ASM_CELL=<block size>: one thread per CELL (the emulation's driver) instead of per (cell, facet)
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("KNP_ASM_CELL"); v = e ? atoi(e) : 0; }
-  return v;
-}
 static int asm_min_blocks() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("KNP_ASM_MINB"); v = e ? atoi(e) : 4; }
@@ -403,7 +398,6 @@ static void assemble_emi_t(knp_ctx* c) {
 #ifdef KNP_EMU
   parallel_for(s, c->nc_own, EmiCellKernel<D>{k}, 128);
 #else
-  if (asm_cell_variant()) { parallel_for(s, c->nc_own, EmiCellKernel<D>{k}, asm_cell_variant()); return; }
   ++launch_counter();
   {
     const unsigned grid = (unsigned)((c->nc_own + ASM_CPB - 1) / ASM_CPB);
@@ -437,8 +431,6 @@ static void assemble_knp_t(knp_ctx* c) {
 #ifdef KNP_EMU
     parallel_for(s, c->nc_own, KnpCellKernel<D>{k}, 128);
 #else
-    if (asm_cell_variant()) parallel_for(s, c->nc_own, KnpCellKernel<D>{k}, asm_cell_variant());
-    else {
     ++launch_counter();
     {
       const unsigned grid = (unsigned)((c->nc_own + ASM_CPB - 1) / ASM_CPB);
@@ -449,7 +441,6 @@ static void assemble_knp_t(knp_ctx* c) {
       }
     }
     KNP_CUDA(cudaGetLastError());
-    }
 #endif
   }
   if (c->nmc > 0) {

@@ -196,6 +196,11 @@ static HostCsr level0_csr(knp_ctx* c) {
   const int64_t nc = c->nc, bs = c->bs(), ss = c->slot_stride();
   HostCsr A;
   A.n = c->n_own;
+  // the host-side plan addresses matrix entries with 32-bit offsets: refuse meshes beyond that range
+  // (~26 M cells per rank in 3D) instead of overflowing silently; partition the mesh over more GPUs
+  if ((int64_t)(nd + 2) * ss > 2147483647LL || c->nnz_export > 2147483647LL)
+    fail("knp_amg_setup: " + std::to_string(c->nc) + " cells on one rank exceed the 32-bit entry offsets of the AMG plan; "
+         "use more ranks");
   A.ptr.assign(A.n + 1, 0);
   A.col.reserve((size_t)c->nnz_export); A.pos.reserve((size_t)c->nnz_export);
   for (int64_t cell = 0; cell < c->nc_own; ++cell)

@@ -57,7 +57,7 @@ def test_properties_at_bench_size(gpu_lib):
 
 
 def test_properties_at_headline_size(gpu_lib):
-    """BASELINE configs[4] at bench.py's headline size (EMIx-like block, 1 724 976 cells, 20.7 M DOFs):
+    """BASELINE configs[4] at bench.py's headline size (EMIx-like block, 6 749 184 cells, 81 M DOFs):
     A_emi symmetric with the constants in its null space, the SpMV linear, glia at rest and the
     stimulated neurons depolarising, mass of every ion conserved up to the membrane exchange,
     electroneutrality of the eliminated ion, Krylov iteration counts in the expected range."""
