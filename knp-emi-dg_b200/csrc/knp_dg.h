@@ -236,12 +236,16 @@ struct RegBlocks {
   KNP_HD void setO(int i, int j, double v) const { O[i][j] = v; }
   KNP_HD void addD(int i, int j, double v) const { dg[i][j] += v; }
 };
+// The facet routines touch every entry they write exactly once (all ND x ND entries on a tag-0
+// facet, the entries off row / column F on a membrane facet, none otherwise), so the diagonal
+// contribution is STORED, not accumulated, and the staging rows need zeroing only for facets that
+// are not tag-0 facets (the caller does that): no read-modify-write, no blanket zero fill.
 template <int ND>
-struct SmemBlocks {   // O, D: rows of ND*ND (+pad) doubles, zeroed by the caller; w: facet info word
+struct SmemBlocks {   // O, D: rows of ND*ND (+pad) doubles; w: facet info word
   double* O; double* D; int w;
   KNP_HD void zeroO() const {}
   KNP_HD void setO(int i, int j, double v) const { O[i * ND + fi_perm(w, j)] = v; }
-  KNP_HD void addD(int i, int j, double v) const { D[i * ND + j] += v; }
+  KNP_HD void addD(int i, int j, double v) const { D[i * ND + j] = v; }
 };
 
 // facet F of `cell`.  Outputs are in the cell's OWN vertex numbering: O[i][j] couples my
@@ -453,9 +457,12 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) emi_assemble_kernel(con
     // straight into this thread's staging rows
     double* myO = sO[f][cl];
     double* myD = sD[f][cl];
-    #pragma unroll
-    for (int k = 0; k < BS; ++k) { myO[k] = 0.0; myD[k] = 0.0; }
-    const SmemBlocks<ND> blk{myO, myD, a.finfo[f * nc + cell]};
+    const int wf = a.finfo[f * nc + cell];
+    if (fi_kind(wf) != FK_SIP) {
+      #pragma unroll
+      for (int k = 0; k < BS; ++k) { myO[k] = 0.0; myD[k] = 0.0; }
+    }
+    const SmemBlocks<ND> blk{myO, myD, wf};
     double bdrow[ND], row[ND], ri;
     switch (f) {
       case 0: emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, blk, r);
@@ -475,6 +482,41 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) emi_assemble_kernel(con
   }
   __syncthreads();
   const int64_t ncell_blk = (a.nw - cell0 < ASM_CPB) ? (a.nw - cell0) : ASM_CPB;
+  if (ncell_blk == ASM_CPB) {
+    // full block (all but the last one): every trip count and every shared-memory address is a
+    // compile-time function of the thread index - element e = t + k NT of a slot belongs to cell
+    // e / BS = t / BS + k NT / BS and entry e % BS = t % BS
+    constexpr int STEP = NT / BS;                       // cells advanced per pass (NT is a multiple of BS for ND = 4)
+    static_assert(ND != 4 || NT % BS == 0, "store path assumes NT % BS == 0 in 3D");
+    if constexpr (NT % BS == 0) {
+      const int c0 = t / BS, kk = t % BS;
+      #pragma unroll
+      for (int s = 0; s < ND; ++s) {
+        double* dst = a.A + (int64_t)(1 + s) * nc * BS + cell0 * BS + t;
+        #pragma unroll
+        for (int k = 0; k < ASM_CPB * BS / NT; ++k) dst[k * NT] = sO[s][c0 + k * STEP][kk];
+      }
+      double* dA = a.Adiag + cell0 * BS + t;
+      double* dB = a.A + cell0 * BS + t;
+      #pragma unroll
+      for (int k = 0; k < ASM_CPB * BS / NT; ++k) {
+        const int c = c0 + k * STEP;
+        double v = 0.0;
+        #pragma unroll
+        for (int s = 0; s < ND; ++s) v += sD[s][c][kk];
+        dA[k * NT] = v;
+        dB[k * NT] = v + sB[c][kk];
+      }
+      {   // rhs: ASM_CPB * ND = NT entries, one per thread
+        const int c = t / ND, i = t % ND;
+        double v = 0.0;
+        #pragma unroll
+        for (int s = 0; s < ND; ++s) v += sR[s][c][i];
+        a.rhs[cell0 * ND + t] = v + (a.load ? a.load[cell0 * ND + t] : 0.0);
+      }
+      return;
+    }
+  }
   const int nval = (int)ncell_blk * BS;
   // off-diagonal slots
   #pragma unroll
@@ -810,8 +852,10 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) knp_assemble_kernel(con
       double row[ND], ri;
       double* myO = sO[f][cl];
       double* myD = sD[f][cl];
+      if (G.kind != FK_SIP) {
 #pragma unroll
-      for (int k = 0; k < BS; ++k) { myO[k] = 0.0; myD[k] = 0.0; }
+        for (int k = 0; k < BS; ++k) { myO[k] = 0.0; myD[k] = 0.0; }
+      }
       const SmemBlocks<ND> blk{myO, myD, G.w};
       switch (f) {
         case 0: knp_facet_ion<D, 0>(a.P, ion, G, Dme, blk);
@@ -829,6 +873,31 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) knp_assemble_kernel(con
     }
     __syncthreads();
     double* Aion = a.A[ion];
+    bool stored = false;
+    if constexpr (NT % BS == 0) {
+      if (ncell_blk == ASM_CPB) {        // full block: compile-time trip counts and staging addresses (see emi_assemble_kernel)
+        constexpr int STEP = NT / BS;
+        const int c0 = t / BS, kk = t % BS;
+#pragma unroll
+        for (int s = 0; s < ND; ++s) {
+          double* dst = Aion + (int64_t)(1 + s) * nc * BS + cell0 * BS + t;
+#pragma unroll
+          for (int k = 0; k < ASM_CPB * BS / NT; ++k) dst[k * NT] = sO[s][c0 + k * STEP][kk];
+        }
+        double* dA = Aion + cell0 * BS + t;
+#pragma unroll
+        for (int k = 0; k < ASM_CPB * BS / NT; ++k) {
+          const int c = c0 + k * STEP;
+          double v = 0.0;
+#pragma unroll
+          for (int s = 0; s < ND; ++s) v += sD[s][c][kk];
+          dA[k * NT] = v;
+        }
+        a.rhs[ion][cell0 * ND + t] = sR[t / ND][t % ND] + (a.load[ion] ? a.load[ion][cell0 * ND + t] : 0.0);
+        stored = true;
+      }
+    }
+    if (!stored) {
     for (int s = 0; s < ND; ++s) {
       double* dst = Aion + (int64_t)(1 + s) * nc * BS + cell0 * BS;
       for (int e = t; e < nval; e += NT) dst[e] = sO[s][e / BS][e % BS];
@@ -847,6 +916,7 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) knp_assemble_kernel(con
       double* dr = a.rhs[ion] + cell0 * ND;
       const double* ld = a.load[ion] ? a.load[ion] + cell0 * ND : nullptr;
       for (int e = t; e < nrow; e += NT) dr[e] = sR[e / ND][e % ND] + (ld ? ld[e] : 0.0);
+    }
     }
     __syncthreads();
   }
