@@ -27,6 +27,35 @@ struct DemoteKernel {  // out = (float) in
   KNP_HD void operator()(int64_t i) const { out[i] = (float)in[i]; }
 };
 
+// ND consecutive matrix entries (one row of an ND x ND block) / ND consecutive vector entries (one
+// cell) as doubles.  ND = 4 on the device: ONE 16-byte load for a float row, two for a double row or
+// a cell of x (rows are 16 / 32 bytes and aligned; cudaMalloc'ed arrays are 256-byte aligned) - the
+// fp32 preconditioner sweeps were issue-limited with scalar 4-byte loads (0.82 of the HBM peak).
+template <int ND>
+KNP_HD void load_row(const double* a, double (&out)[ND]) {
+#if defined(__CUDA_ARCH__)
+  if (ND == 4) {
+    const double2 u = reinterpret_cast<const double2*>(a)[0], v = reinterpret_cast<const double2*>(a)[1];
+    out[0] = u.x; out[1] = u.y; out[2] = v.x; out[ND - 1] = v.y;
+    return;
+  }
+#endif
+#pragma unroll
+  for (int j = 0; j < ND; ++j) out[j] = a[j];
+}
+template <int ND>
+KNP_HD void load_row(const float* a, double (&out)[ND]) {
+#if defined(__CUDA_ARCH__)
+  if (ND == 4) {
+    const float4 u = *reinterpret_cast<const float4*>(a);
+    out[0] = (double)u.x; out[1] = (double)u.y; out[2] = (double)u.z; out[ND - 1] = (double)u.w;
+    return;
+  }
+#endif
+#pragma unroll
+  for (int j = 0; j < ND; ++j) out[j] = (double)a[j];
+}
+
 // y = A x (mode 0), y = b - A x (mode 1).  One thread per row; consecutive threads read
 // consecutive ND-double row segments of every slot array (fully coalesced), x is
 // gathered per neighbour cell (ND contiguous doubles, shared by the ND rows of a cell).
@@ -39,20 +68,21 @@ struct BellSpmvKernel {
     const int i = (int)(row - cell * ND);
     const int64_t bs = ND * ND;
     double acc = 0.0;
+    double av[ND], xv[ND];
     {
-      const T* a = A.diag + cell * bs + i * ND;
-      const double* xc = x + cell * ND;
+      load_row<ND>(A.diag + cell * bs + i * ND, av);
+      load_row<ND>(x + cell * ND, xv);
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc += (double)a[j] * xc[j];
+      for (int j = 0; j < ND; ++j) acc += av[j] * xv[j];
     }
 #pragma unroll
     for (int f = 0; f < ND; ++f) {
       const int64_t c2 = A.nbr[f * A.nc + cell];
       if (c2 < 0) continue;
-      const T* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND;
-      const double* xc = x + c2 * ND;
+      load_row<ND>(A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND, av);
+      load_row<ND>(x + c2 * ND, xv);
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc += (double)a[j] * xc[j];
+      for (int j = 0; j < ND; ++j) acc += av[j] * xv[j];
     }
     y[row] = mode ? b[row] - acc : acc;
   }
@@ -65,11 +95,12 @@ struct BlockDiagApplyKernel {
   KNP_HD void operator()(int64_t row) const {
     const int64_t cell = row / ND;
     const int i = (int)(row - cell * ND);
-    const T* a = dinv + cell * ND * ND + i * ND;
-    const double* rc = r + cell * ND;
+    double av[ND], rv[ND];
+    load_row<ND>(dinv + cell * ND * ND + i * ND, av);
+    load_row<ND>(r + cell * ND, rv);
     double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < ND; ++j) acc += (double)a[j] * rc[j];
+    for (int j = 0; j < ND; ++j) acc += av[j] * rv[j];
     if (mode) out[row] += w * acc; else out[row] = w * acc;
   }
 };
@@ -84,31 +115,26 @@ struct BlockDiagApplyKernel {
 template <int ND, typename T = double, bool MOM = false>
 struct BellJacobiKernel {
   BellMatT<T> A; const T* dinv; const double* b; const double* xin; double* xout; double w;
-  // optional fused prolongation (post-smoothing of the V-cycle): the sweep runs on
-  // x' = xin + P xc with (P xc)_d = xc[agg[d]] (unit aggregation transfer); xin == nullptr
-  // means x' = P xc (no pre-smoothed iterate)
-  const int32_t* agg = nullptr; const double* xc = nullptr;
   const double* xprev = nullptr; double beta = 0.0;   // MOM only
-  KNP_HD double xval(int64_t d) const {
-    double v = xin ? xin[d] : 0.0;
-    if (agg) v += xc[agg[d]];
-    return v;
-  }
+  KNP_HD void cell_values(int64_t cell, double (&xv)[ND]) const { load_row<ND>(xin + cell * ND, xv); }
   KNP_HD double row_residual(int64_t cell, int i) const {
     const int64_t bs = ND * ND;
     double acc = b[cell * ND + i];
+    double av[ND], xv[ND];
     {
-      const T* a = A.diag + cell * bs + i * ND;
+      load_row<ND>(A.diag + cell * bs + i * ND, av);
+      cell_values(cell, xv);
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc -= (double)a[j] * xval(cell * ND + j);
+      for (int j = 0; j < ND; ++j) acc -= av[j] * xv[j];
     }
 #pragma unroll
     for (int f = 0; f < ND; ++f) {
       const int64_t c2 = A.nbr[f * A.nc + cell];
       if (c2 < 0) continue;
-      const T* a = A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND;
+      load_row<ND>(A.off + (int64_t)(1 + f) * A.nc * bs + cell * bs + i * ND, av);
+      cell_values(c2, xv);
 #pragma unroll
-      for (int j = 0; j < ND; ++j) acc -= (double)a[j] * xval(c2 * ND + j);
+      for (int j = 0; j < ND; ++j) acc -= av[j] * xv[j];
     }
     return acc;
   }
@@ -128,15 +154,16 @@ struct BellJacobiKernel {
     {
       for (int j = 0; j < ND; ++j) r[j] = row_residual(cell, j);
     }
-    const T* di = dinv + cell * ND * ND + i * ND;
+    double dv[ND];
+    load_row<ND>(dinv + cell * ND * ND + i * ND, dv);
     double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < ND; ++j) acc += (double)di[j] * r[j];
+    for (int j = 0; j < ND; ++j) acc += dv[j] * r[j];
     if constexpr (MOM) {
-      const double xv = xval(row);
+      const double xv = xin[row];
       xout[row] = xv + beta * (xv - (xprev ? xprev[row] : 0.0)) + w * acc;
     } else {
-      xout[row] = xval(row) + w * acc;
+      xout[row] = xin[row] + w * acc;
     }
   }
 };
@@ -190,6 +217,16 @@ struct TransferKernel {
     if (w) for (int32_t k = ptr[row]; k < ptr[row + 1]; ++k) acc += w[k] * x[idx[k]];
     else   for (int32_t k = ptr[row]; k < ptr[row + 1]; ++k) acc += x[idx[k]];
     if (add) y[row] += acc; else y[row] = acc;
+  }
+};
+
+// prolongation of a pure aggregation (one unit entry per fine row: (P xc)_i = xc[agg_i]): no row
+// pointers to read, y (=|+=) xc[agg]
+struct ProlongUnitKernel {
+  const int32_t* agg; const double* xc; double* y; int add;
+  KNP_HD void operator()(int64_t row) const {
+    const double v = xc[agg[row]];
+    if (add) y[row] += v; else y[row] = v;
   }
 };
 

@@ -691,6 +691,13 @@ static void transfer(knp_ctx* c, int nb, int64_t nrows, const int32_t* ptr, cons
   for (int s = 0; s < nb; ++s) k.f[s] = TransferKernel{nrows, ptr, idx, w, x.p[s], y.p[s], add};
   parallel_for_batch(cs(c), nrows, nb, k);
 }
+// y (=|+=) P xc for the transfer between a level and the coarser level C
+static void prolong(knp_ctx* c, int nb, int64_t nrows, const AmgLevelPlan& C, const Vecs& xc, const Vecs& y, int add) {
+  if (!C.t_unit) { transfer(c, nb, nrows, C.pptr.p, C.pidx.p, C.pw.p, xc, y, add); return; }
+  BatchOf<ProlongUnitKernel> k{};
+  for (int s = 0; s < nb; ++s) k.f[s] = ProlongUnitKernel{C.pidx.p, xc.p[s], y.p[s], add};
+  parallel_for_batch(cs(c), nrows, nb, k);
+}
 static void restrict_rows(knp_ctx* c, int nb, const AmgLevelPlan& C, const Vecs& x, const Vecs& y) {
   BatchOf<TransferRowsKernel> k{};
   for (int s = 0; s < nb; ++s) k.f[s] = TransferRowsKernel{C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, x.p[s], y.p[s], 0};
@@ -830,7 +837,7 @@ static void coarse_cycle(knp_ctx* c, const Batch& B, size_t li, bool ghost_x) {
       parallel_for_batch(s, L.n, nb, k); }
     transfer(c, nb, C.n, C.rptr.p, C.ridx.p, C.t_unit ? nullptr : C.rw.p, Lr, Cb, 0);
     coarse_cycle(c, B, li + 1, false);
-    transfer(c, nb, L.n, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, level_vecs(B, li + 1, LV_X), x, 1);
+    prolong(c, nb, L.n, C, level_vecs(B, li + 1, LV_X), x, 1);
   }
   for (int it = 0; it < c->opt.nu_post; ++it) jacobi();
   if (ghost_x && dist) halo_of(c, L.halo, nb, level_vecs(B, li, LV_X));
@@ -866,7 +873,7 @@ static void vcycle(knp_ctx* c, const Batch& B, const BellMatT<T>* A0, const T* c
     bell_spmv<T>(c, nb, A0, x, r, r0, 1);
     restrict_rows(c, nb, C, r0, Cb);
     coarse_cycle(c, B, 0, false);
-    transfer(c, nb, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, level_vecs(B, 0, LV_X), x, 1);
+    prolong(c, nb, c->n_own, C, level_vecs(B, 0, LV_X), x, 1);
     bell_jacobi<T>(c, nb, A0, binv, r, x, t, w1);                            // x1' from x0' = x
     bell_jacobi<T, true>(c, nb, A0, binv, r, t, z, w2, &x, beta);            // x2' -> z
     return;
@@ -880,7 +887,7 @@ static void vcycle(knp_ctx* c, const Batch& B, const BellMatT<T>* A0, const T* c
   }
   restrict_rows(c, nb, C, rr, Cb);
   coarse_cycle(c, B, 0, false);
-  transfer(c, nb, c->n_own, C.pptr.p, C.pidx.p, C.t_unit ? nullptr : C.pw.p, level_vecs(B, 0, LV_X), x, presmooth0 ? 1 : 0);
+  prolong(c, nb, c->n_own, C, level_vecs(B, 0, LV_X), x, presmooth0 ? 1 : 0);
   if (c->opt.nu_post == 0) {
     for (int q = 0; q < nb; ++q) d2d(z.p[q], x.p[q], c->n * sizeof(double), cs(c));
     return;
