@@ -55,6 +55,7 @@ STIMULUS = {"stim_amplitude": 10.0}
 # the `ncu --set full` captures summarised in profiles/ (None: not captured for that workload)
 TRAFFIC_SPMV = {("bundle", 0): 3.119e8,   # 299.4 MB read + 12.5 MB written (profiles/kernels_r01_solver.md, launch #1)
                 ("emix", 66): 1.2352e9,   # 1181.3 MB read + 53.9 MB written (profiles/kernels_r02_emix.md, launch #0)
+                ("emix", 104): 4.8861e9,  # 4669.9 MB read + 216.2 MB written (profiles/kernels_r02_emix104.md, launch #0)
                 }
 
 
