@@ -137,7 +137,7 @@ def build_variant(user_modules, emu=False, cache_dir=None):
     with open(header, "w") as f:
         f.write(text)
     define = f'-DKNP_MODELS_HEADER="{header}"'
-    tmp = out + ".tmp"
+    tmp = out + f".tmp{os.getpid()}"     # per process: several ranks may build the same variant at once
     if emu:
         cmd = ["g++", "-std=c++17", "-O2", "-DKNP_EMU", define, "-fPIC", "-pthread", "-shared", "-o", tmp]
         for f in SOURCES:

@@ -37,6 +37,27 @@ def _table_engine(ode, n, lib=None):
     return eng
 
 
+class _LazyTable:
+    """what step_lsoda returns: the state table, downloaded from the device only if it is looked at"""
+
+    def __init__(self, model):
+        self._model = model
+
+    def __array__(self, dtype=None, copy=None):
+        a = self._model.states
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, key):
+        return self._model.states[key]
+
+    def __len__(self):
+        return self._model.nodes
+
+    @property
+    def shape(self):
+        return (self._model.nodes, len(self._model.ode.init_state_values()))
+
+
 class MembraneModel:
     def __init__(self, ode, facet_f, tag, V):
         """facets with facet_f == tag are governed by `ode`; V is the solver's Q space
@@ -192,4 +213,4 @@ class MembraneModel:
                      self._set_v)
         self._set_v = False
         self.time = self.time + dt
-        return self.states
+        return _LazyTable(self)         # (the reference returns self.states; nobody in its loop reads it)

@@ -36,3 +36,31 @@ def test_local_part_numbers_interior_cells_first():
         assert 0 < L.nc_interior < L.nc_owned
         assert not touches_ghost[:L.nc_interior].any() and touches_ghost[L.nc_interior:L.nc_owned].all()
         assert np.all(np.diff(L.l2g[:L.nc_interior]) > 0)          # both groups keep ascending global order
+
+
+def test_h5lite_writer_round_trip(tmp_path):
+    """knpemidg.h5lite.Writer (the results.h5 of Solver.save_h5): nested groups, more links in a group
+    than a default symbol node holds, int32 / int64 / float64 and empty datasets, read back by the reader"""
+    import numpy as np
+    from knpemidg import h5lite
+    rng = np.random.default_rng(0)
+    data = {"/mesh/coordinates": rng.random((11, 3)), "/mesh/topology": rng.integers(0, 11, (7, 4)).astype(np.int64),
+            "/subdomains/values": np.arange(7, dtype=np.int32), "/empty": np.zeros((0, 3)),
+            "/a/b/c/deep": np.array([1.5, -2.5])}
+    for i in range(70):
+        data[f"/potential/vector_{i}"] = rng.random(28)
+    path = str(tmp_path / "t.h5")
+    with h5lite.Writer(path) as w:
+        for k, v in data.items():
+            w.write(k, v)
+        with pytest.raises(h5lite.H5Error, match="already written"):
+            w.write("/mesh/topology", np.zeros(3))
+    f = h5lite.File(path)
+    assert f.keys() == ["a", "empty", "mesh", "potential", "subdomains"]
+    assert len(f["/potential"].keys()) == 70
+    for k, v in data.items():
+        got = f[k].read()
+        assert got.dtype == v.dtype and got.shape == v.shape and np.array_equal(got, v), k
+    raw = open(path, "rb").read()
+    assert raw[:8] == bytes([0x89, 0x48, 0x44, 0x46, 0x0D, 0x0A, 0x1A, 0x0A])       # signature
+    assert int.from_bytes(raw[40:48], "little") == len(raw)                          # end-of-file address of the superblock
