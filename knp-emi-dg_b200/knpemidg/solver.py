@@ -8,9 +8,11 @@ What differs, deliberately:
     (or dolfin objects, adapted once through knpemidg.dolfin_adapter when dolfin exists);
   * fields are device handles (knpemidg.frontend), not dolfin Functions;
   * linear algebra, assembly and the ODE step run in libknpemi.so; the PETSc option
-    `threshold_*` (BoomerAMG strong threshold) has no counterpart and is ignored;
-  * `save_fields` writes a .npz time series (h5py/dolfin HDF5 are not available here) with
-    the reference's group names as keys; solver statistics keep the reference's text format.
+    `threshold_*` (BoomerAMG's classical strength threshold, run_3D.py:174) has no counterpart in
+    the aggregation hierarchy used here (fixed strength parameter 0.08): a value other than None
+    is reported once on stderr and otherwise ignored - it only ever affected iteration counts;
+  * `save_fields` writes results.h5 in the reference's HDF5 layout (solver.py:1214-1242) through
+    knpemidg.h5lite (no libhdf5 here); solver statistics keep the reference's text format.
 """
 from __future__ import annotations
 
@@ -180,6 +182,11 @@ class Solver:
         self.rtol_knp = 1e-13 if self.direct_knp else solver_params.rtol_knp
         self.atol_knp = 1e-300 if self.direct_knp else solver_params.atol_knp
         self.splitting_scheme = splitting
+        for name in ("threshold_emi", "threshold_knp"):
+            if getattr(solver_params, name, None) is not None and not getattr(Solver, "_threshold_noted", False):
+                print(f"knpemidg (B200): solver_params.{name} = {getattr(solver_params, name)} is a BoomerAMG option; the "
+                      "aggregation AMG of libknpemi.so has no such parameter, it is ignored", file=sys.stderr)
+                Solver._threshold_noted = True
         self._ensure_engine((1, 2, 3, 4) if self.mms is not None else (), splitting)
         eng = self.engine
         eng.rtol_emi, eng.atol_emi = self.rtol_emi, self.atol_emi
