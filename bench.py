@@ -479,7 +479,7 @@ def main():
                                        if world > 1 else "single"),
                        "l2_policy": "inputs larger than L2 (matrices 3 x %.0f MB per GPU)" % (ctx.nnz * 8 / 1e6),
                        "solver": "CG rtol 1e-5 / GMRES(30) rtol 1e-7 (min 5 its), aggregation AMG: plan built once, values "
-                                 "refreshed every %s solves or when iterations grow" % os.environ.get("KNP_AMG_REFRESH_PERIOD", "4")},
+                                 "refreshed every %s solves or when iterations grow" % os.environ.get("KNP_AMG_REFRESH_PERIOD", "8")},
             "steps_per_s": steps_per_s,
             "seconds_per_step": {k: v / args.steps for k, v in phase.items()},
             "iterations": {"emi": eng.stats["emi_niter"][-args.steps:], "knp": eng.stats["knp_niter"][-args.steps:]},

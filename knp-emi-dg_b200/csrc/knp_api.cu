@@ -66,7 +66,7 @@ int knp_ctx_create(int device, knp_ctx** out) {
   { const char* e = getenv("KNP_AMG_FP32"); c->opt.pc_fp32 = !(e && e[0] == '0'); }
   { const char* e = getenv("KNP_AMG_CHEBY"); c->opt.cheby = (e && e[0] == '2') ? 2 : 1; }
   { const char* e = getenv("KNP_EXTRAPOLATE"); c->opt.extrapolate_phi = !(e && e[0] == '0'); }
-  { const char* e = getenv("KNP_AMG_REFRESH_PERIOD"); c->opt.refresh_period = e ? std::max(1, atoi(e)) : 4; }
+  { const char* e = getenv("KNP_AMG_REFRESH_PERIOD"); c->opt.refresh_period = e ? std::max(1, atoi(e)) : 8; }
   c->kr0.stream = c->stream;
   c->kr0.scal.alloc(1024);
   c->kr0.partial.alloc((size_t)DOT_MAX * RED_BLOCKS);

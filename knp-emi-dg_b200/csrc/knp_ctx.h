@@ -53,10 +53,10 @@ struct SolverOptions {
   // smoother diagonals, block inverses, dense inverse) are recomputed only every P-th solve of a
   // system, or earlier when the Krylov iteration count has grown by more than 50 % (+2) since
   // the last refresh; the Krylov solve itself still runs on the freshly assembled operator to
-  // the reference's tolerance.  Default 4 (measured: -9.5 % step time at unchanged iteration
-  // counts on the bench workload); KNP_AMG_REFRESH_PERIOD=1 in the environment restores the
-  // refresh at every solve.
-  int refresh_period = 4;
+  // the reference's tolerance.  Default 8 (measured on B200, 81 M DOFs, unchanged iteration
+  // counts: period 4 56.2 ms/step, 8 54.6, 16 53.5; round 1 measured -9.5 % for 1 -> 4);
+  // KNP_AMG_REFRESH_PERIOD=1 in the environment restores the refresh at every solve.
+  int refresh_period = 8;
 };
 
 enum { T_EMI_ASM = 0, T_EMI_SOLVE, T_KNP_ASM, T_KNP_SOLVE, T_ODE, T_POST, T_COUNT };

@@ -91,7 +91,7 @@ def test_solver_engineering_switches_do_not_change_the_solution(emu_lib):
     Krylov tolerance (the switches are read when a context is created)"""
     ref_pm, ref_c, ref_st = _bundle_run(emu_lib, {"KNP_AMG_REFRESH_PERIOD": "1", "KNP_EXTRAPOLATE": "0",
                                                   "KNP_KNP_PRESMOOTH": "1"})
-    pm, c, st = _bundle_run(emu_lib, {"KNP_AMG_REFRESH_PERIOD": "4", "KNP_EXTRAPOLATE": "1",
+    pm, c, st = _bundle_run(emu_lib, {"KNP_AMG_REFRESH_PERIOD": "8", "KNP_EXTRAPOLATE": "1",
                                       "KNP_KNP_PRESMOOTH": "0"})
     assert rel_err(pm, ref_pm) < 1e-7
     for k in range(3):
