@@ -843,7 +843,11 @@ int knp_dist_init_nccl(knp_ctx* ctx, const char uid[128]) {
     const char* e = getenv("KNP_OVERLAP");
     ctx->overlap = ctx->comm.p2p.on && !(e && e[0] == '0');
     if (ctx->overlap && !ctx->comm_stream) {
-      KNP_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+      // highest priority: the few blocks of the exchange kernel must not queue behind the thousands of
+      // blocks of the interior-row kernel that runs beside it
+      int prio_lo = 0, prio_hi = 0;
+      KNP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      KNP_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
       KNP_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
       KNP_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
     }
