@@ -17,6 +17,8 @@ with what the reference's own code produced from them:
                          of examples/idealized-geometries/run_2D.py on its resolution-1 mesh (resolution 0 does not resolve the membrane) with the
                          reference's mm_hh.py: membrane potential at every membrane facet and step,
                          final fields;
+  ref_run_2d_picard.npz  the same problem, 12 steps, with the reference's Picard variant solve_for_time_step_picard
+                         (solver.py:850-927) in place of the split PDE step;
   ref_run_astro.npz      S.solve_system_active() for 16 steps of the problem of
                          examples/local-astrocyte-depolarization/run_tortuosity.py (BASELINE configs[3]: three
                          membrane tags, neuronal + glial models, rho != 0, tortuosity, the time-windowed K+/Na+
@@ -88,7 +90,7 @@ D_PHYS = {"K": 1.96e-9, "Cl": 2.03e-9, "Na": 1.33e-9}
 NA_I, NA_E, K_I, K_E = 12.838513108648856, 100.71925900027354, 124.15397583491901, 3.3236967382705265
 
 
-def build_solver(mesh, sub, surf, tags, ode_models, D_scale=None, rho=None, f_source=None):
+def build_solver(mesh, sub, surf, tags, ode_models, D_scale=None, rho=None, f_source=None, cls=None):
     """reference Solver set up as run_2D.py / run_3D.py do (ions K, Cl, Na; Na eliminated)"""
     dt, C_M = PHYS["dt"], PHYS["C_M"]
     rho_sub = {int(t): df.Constant((rho or {}).get(int(t), 0.0)) for t in tags}
@@ -103,7 +105,7 @@ def build_solver(mesh, sub, surf, tags, ode_models, D_scale=None, rho=None, f_so
                      'c_init_sub_type': 'constant', 'bdry': None, 'z': z, 'name': name,
                      'D_sub': {int(t): df.Constant(D_PHYS[name] * scale.get(int(t), 1.0)) for t in tags},
                      'f_source': (f_source or {}).get(name, df.Constant(0))})
-    S = RefSolver(params, ions)
+    S = (cls or RefSolver)(params, ions)
     dmesh = df.Mesh(mesh)
     S.setup_domain(dmesh, df.MeshFunction.from_array(dmesh, mesh.gdim, sub), df.MeshFunction.from_array(dmesh, mesh.gdim - 1, surf))
     S.setup_parameters()
@@ -202,10 +204,19 @@ def mesh_3d_two_cells():
     return m2, sub, surf
 
 
-def run_case(nsteps=40):
+class RefSolverPicard(RefSolver):
+    """the Picard variant the reference keeps beside the split step (solver.py:850-927; its call is commented
+    out at :1123): every PDE step of the loop goes through solve_for_time_step_picard"""
+
+    def solve_for_time_step(self, k, t):
+        Solver.solve_for_time_step_picard(self, k, t)
+        self.trace.append(self.phi_M_prev_PDE.vector().get_local().copy())
+
+
+def run_case(nsteps=40, picard=False):
     mesh, sub, surf = kmesh.neuron_2d_mesh(1)
     sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
-    S, ions = build_solver(mesh, sub, surf, np.unique(sub), {1: mm_hh})
+    S, ions = build_solver(mesh, sub, surf, np.unique(sub), {1: mm_hh}, cls=RefSolverPicard if picard else RefSolver)
     sp = SolverParams(True, True, 0, 1e-5, 1e-7, 1e-40, 1e-40, None, None)
     t = df.Constant(0.0)
     S.solve_system_active(nsteps * PHYS["dt"], t, sp)
@@ -297,6 +308,7 @@ def main(outdir, only=None):
     save("ref_forms_3d", lambda: forms_case("3d", m3, s3, f3, {1: mm_hh_no_stim, 2: mm_hh}, D_scale={1: 0.5, 2: 0.7},
                                             rho={0: 0.0, 1: 3.0, 2: -2.0}, f_src=[250.0, -125.0], seed=2))
     save("ref_run_2d", run_case)
+    save("ref_run_2d_picard", lambda: run_case(nsteps=12, picard=True))
     save("ref_run_astro", run_astro_case)          # ~2.5 min (4 224 LSODA calls through scipy)
     print("wrote", sorted(f for f in os.listdir(outdir) if f.endswith(".npz")))
 

@@ -203,6 +203,27 @@ def oracle_run(convention, nsteps):
     return np.stack(tr), O
 
 
+def library_run_picard(lib, nsteps, rtol_emi=1e-10, rtol_knp=1e-11):
+    """the run of library_run with Engine.pde_phase_picard (solve_for_time_step_picard, solver.py:850-927)
+    as the PDE step; returns the traces and the Picard iteration counts"""
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_hh
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1,), lib=lib, **RUN_PHYS)
+    eng.set_concentrations_by_tag(RUN_C_INIT)
+    eng.add_membrane_model(1, mm_hh, ["K", "Cl", "Na"], stimulus={"stim_amplitude": 10.0},
+                           stimulus_locator=lambda x: x[0] < 20e-6)
+    eng.rtol_emi, eng.rtol_knp = rtol_emi, rtol_knp
+    eng.initialize(pc=1)
+    tr, its = [], []
+    for _ in range(nsteps):
+        eng.ode_phase()
+        its.append(eng.pde_phase_picard())
+        eng.k += 1
+        tr.append(eng.phi_M().copy())
+    return np.stack(tr), its, eng
+
+
 def library_run(lib, nsteps, rtol_emi=1e-5, rtol_knp=1e-7):
     from knpemidg.engine import Engine
     from knpemidg.models import mm_hh

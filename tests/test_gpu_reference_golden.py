@@ -1,6 +1,8 @@
 """CUDA library (C ABI) against the reference-EXECUTED golden fixtures (tests/golden/ref_*.npz):
 assembled tensors entry by entry at 1e-12, one PDE step, and the 40-step membrane-potential
 traces of the reference's own time loop at 1e-6."""
+import os
+
 import numpy as np
 import pytest
 
@@ -34,3 +36,13 @@ def test_cuda_astro_run_matches_the_reference(gpu_lib):
     cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
     assert gc.rel_err(cfin, g["final_c"]) < 1e-7
     assert gc.rel_err(eng.concentration(2).reshape(-1), g["final_c_elim"]) < 1e-7
+
+
+def test_cuda_picard_run_matches_the_reference(gpu_lib):
+    """the Picard variant (solver.py:850-927) on the CUDA path against the reference's own Picard loop"""
+    g = np.load(os.path.join(gc.GOLDEN, "ref_run_2d_picard.npz"))
+    tr, its, eng = gc.library_run_picard(gpu_lib, int(g["nsteps"]))
+    assert max(its) <= 4
+    assert gc.trace_deviation(tr, g["phi_M_trace"]) < 1e-6
+    cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
+    assert gc.rel_err(cfin, g["final_c"]) < 1e-7

@@ -15,7 +15,7 @@ from oracle import refexec
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d"
+FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d,ref_run_2d_picard"
 
 
 @pytest.mark.skipif(not refexec.available(), reason="/root/reference is not present (GPU box)")
@@ -122,6 +122,18 @@ def test_oracle_astro_run_matches_the_reference():
 def test_emulation_astro_run_matches_the_reference(emu_lib):
     g = gc.astro_golden()
     tr, eng = gc.library_run_astro(emu_lib, int(g["nsteps"]), int(g["M"]), 1e-10, 1e-11)
+    assert gc.trace_deviation(tr, g["phi_M_trace"]) < 1e-6
+    cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
+    assert gc.rel_err(cfin, g["final_c"]) < 1e-7
+    assert gc.rel_err(eng.concentration(2).reshape(-1), g["final_c_elim"]) < 1e-7
+
+
+def test_emulation_picard_run_matches_the_reference(emu_lib):
+    """Engine.pde_phase_picard against the reference's own solve_for_time_step_picard (solver.py:850-927,
+    executed on oracle/refexec): 12 steps, membrane-potential traces and final concentrations"""
+    g = np.load(os.path.join(gc.GOLDEN, "ref_run_2d_picard.npz"))
+    tr, its, eng = gc.library_run_picard(emu_lib, int(g["nsteps"]))
+    assert max(its) <= 4
     assert gc.trace_deviation(tr, g["phi_M_trace"]) < 1e-6
     cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
     assert gc.rel_err(cfin, g["final_c"]) < 1e-7
