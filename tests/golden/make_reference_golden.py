@@ -19,6 +19,7 @@ with what the reference's own code produced from them:
                          final fields;
   ref_run_2d_picard.npz  the same problem, 12 steps, with the reference's Picard variant solve_for_time_step_picard
                          (solver.py:850-927) in place of the split PDE step;
+  ref_run_2d_emi.npz     the same problem, 25 steps, with the reference's EMI-only SolverEMI (solver_emi.py:52-822);
   ref_run_astro.npz      S.solve_system_active() for 16 steps of the problem of
                          examples/local-astrocyte-depolarization/run_tortuosity.py (BASELINE configs[3]: three
                          membrane tags, neuronal + glial models, rho != 0, tortuosity, the time-windowed K+/Na+
@@ -42,7 +43,7 @@ from oracle import refexec  # noqa: E402
 
 ref = refexec.install()
 import dolfin as df  # noqa: E402  (the stand-in)
-from knpemidg import Solver  # noqa: E402  (the reference)
+from knpemidg import Solver, SolverEMI  # noqa: E402  (the reference)
 from knpemidg.utils import plus, minus, pcws_constant_project  # noqa: E402
 
 
@@ -213,6 +214,29 @@ class RefSolverPicard(RefSolver):
         self.trace.append(self.phi_M_prev_PDE.vector().get_local().copy())
 
 
+class RefSolverEMI(SolverEMI):
+    """the reference's EMI-only solver (src/knpemidg/solver_emi.py:52-822), concentrations frozen"""
+
+    def __init__(self, params, ion_list, degree_emi=1, degree_knp=1, mms=None, sf=1):
+        SolverEMI.__init__(self, params, ion_list)
+        self.trace = []
+
+    def solve_for_time_step(self, k, t):
+        SolverEMI.solve_for_time_step(self, k, t)
+        self.trace.append(self.phi_M_prev_PDE.vector().get_local().copy())
+
+
+def run_emi_case(nsteps=25):
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
+    S, ions = build_solver(mesh, sub, surf, np.unique(sub), {1: mm_hh}, cls=RefSolverEMI)
+    t = df.Constant(0.0)
+    S.solve_system_active(nsteps * PHYS["dt"], t, SolverParams(True, True, 0, 1e-5, 1e-7, 1e-40, 1e-40, None, None))
+    mem = np.flatnonzero(surf == 1)
+    return dict(nsteps=np.array(nsteps), mem_facets=mem.astype(np.int32), phi_M_trace=np.stack(S.trace)[:, mem],
+                final_phi=S.phi.vector().get_local(), t_end=np.array(float(t)))
+
+
 def run_case(nsteps=40, picard=False):
     mesh, sub, surf = kmesh.neuron_2d_mesh(1)
     sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
@@ -309,6 +333,7 @@ def main(outdir, only=None):
                                             rho={0: 0.0, 1: 3.0, 2: -2.0}, f_src=[250.0, -125.0], seed=2))
     save("ref_run_2d", run_case)
     save("ref_run_2d_picard", lambda: run_case(nsteps=12, picard=True))
+    save("ref_run_2d_emi", run_emi_case)
     save("ref_run_astro", run_astro_case)          # ~2.5 min (4 224 LSODA calls through scipy)
     print("wrote", sorted(f for f in os.listdir(outdir) if f.endswith(".npz")))
 

@@ -307,3 +307,42 @@ def check_solver_emi(lib):
     for k in range(2):
         assert np.array_equal(S.c.split()[k].nodal(), c0[k])
     assert all(n == 0 for n in S.engine.stats["knp_niter"]) and abs(float(t) - 30 * DT) < 1e-15
+
+
+def check_solver_emi_against_reference(lib, rtol=1e-6):
+    """the run-script flow of SolverEMI, 25 steps of the 2D neuron, against tests/golden/ref_run_2d_emi.npz:
+    membrane-potential traces of the reference's own solver_emi.py (direct solves there, tight CG here)"""
+    import os
+    from knpemidg import SolverEMI
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_run_2d_emi.npz"))
+    trace = []
+
+    class EMI2D(SolverEMI):
+        def update_ode(self, ode_model):
+            Solver2D.update_ode(self, ode_model)
+
+        def solve_for_time_step(self, k, t):
+            SolverEMI.solve_for_time_step(self, k, t)
+            trace.append(self.phi_M_prev_PDE.vector().get_local().copy())
+
+    params = namedtuple("params", "dt n_steps_ODE F psi phi_M_init C_phi C_M R temperature phi_M_init_type "
+                                  "rho_sub")(DT, 25, F, F / (R * T), Constant(-0.0743), C_M / DT, C_M, R, T, "constant",
+                                             {0: Constant(0), 1: Constant(0)})
+    ion_list = [_ion("K", 1.0, 1.96e-9, K_I, K_E), _ion("Cl", -1.0, 2.03e-9, NA_I + K_I, NA_E + K_E),
+                _ion("Na", 1.0, 1.33e-9, NA_I, NA_E)]
+    stim = namedtuple("membrane_params", "g_syn_bar stimulus stimulus_locator")(
+        10.0, {"stim_amplitude": 10.0}, lambda x: x[0] < 20e-6)
+    sp = SolverParams(True, True, 0, 1e-5, 1e-7, 1e-40, 1e-40, None, None)     # "direct": iterate to ~1e-11
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    S = EMI2D(params, ion_list, lib=lib)
+    S.setup_domain(mesh, sub, surf)
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    S.setup_membrane_model(stim, {1: mm_hh})
+    t = Constant(0.0)
+    n = int(g["nsteps"])
+    S.solve_system_active(n * DT, t, sp)
+    ref = g["phi_M_trace"]
+    got = np.stack(trace)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() / (ref.max() - ref.min()) < rtol

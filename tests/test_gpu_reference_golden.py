@@ -46,3 +46,9 @@ def test_cuda_picard_run_matches_the_reference(gpu_lib):
     assert gc.trace_deviation(tr, g["phi_M_trace"]) < 1e-6
     cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
     assert gc.rel_err(cfin, g["final_c"]) < 1e-7
+
+
+def test_cuda_solver_emi_matches_the_reference(gpu_lib):
+    """SolverEMI on the CUDA path against the reference's own solver_emi.py (executed on oracle/refexec)"""
+    import solver_checks as sc
+    sc.check_solver_emi_against_reference(gpu_lib)

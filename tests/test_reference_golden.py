@@ -15,7 +15,7 @@ from oracle import refexec
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d,ref_run_2d_picard"
+FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d,ref_run_2d_picard,ref_run_2d_emi"
 
 
 @pytest.mark.skipif(not refexec.available(), reason="/root/reference is not present (GPU box)")
@@ -138,3 +138,9 @@ def test_emulation_picard_run_matches_the_reference(emu_lib):
     cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
     assert gc.rel_err(cfin, g["final_c"]) < 1e-7
     assert gc.rel_err(eng.concentration(2).reshape(-1), g["final_c_elim"]) < 1e-7
+
+
+def test_emulation_solver_emi_matches_the_reference(emu_lib):
+    """knpemidg.SolverEMI (run-script flow) against the reference's own solver_emi.py executed on oracle/refexec"""
+    import solver_checks as sc
+    sc.check_solver_emi_against_reference(emu_lib)
