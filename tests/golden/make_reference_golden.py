@@ -20,6 +20,7 @@ with what the reference's own code produced from them:
   ref_run_2d_picard.npz  the same problem, 12 steps, with the reference's Picard variant solve_for_time_step_picard
                          (solver.py:850-927) in place of the split PDE step;
   ref_run_2d_emi.npz     the same problem, 25 steps, with the reference's EMI-only SolverEMI (solver_emi.py:52-822);
+  ref_run_2d_passive.npz S.solve_system_passive() (solver.py:930-1011: PDE steps only, non-splitting forms), 10 steps;
   ref_run_astro.npz      S.solve_system_active() for 16 steps of the problem of
                          examples/local-astrocyte-depolarization/run_tortuosity.py (BASELINE configs[3]: three
                          membrane tags, neuronal + glial models, rho != 0, tortuosity, the time-windowed K+/Na+
@@ -237,6 +238,24 @@ def run_emi_case(nsteps=25):
                 final_phi=S.phi.vector().get_local(), t_end=np.array(float(t)))
 
 
+def run_passive_case(nsteps=10):
+    """solve_system_passive (solver.py:930-1011): PDE steps only, the non-splitting Robin forms (:337, 621-622),
+    membrane currents as the ODE tables hold them initially; perturbed initial membrane potential so that
+    something relaxes"""
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
+    S, ions = build_solver(mesh, sub, surf, np.unique(sub), {1: mm_hh})
+    nf = mesh.facet_cells.shape[0]
+    phi_M0 = -0.07 * (1.0 + 0.05 * np.sin(np.arange(nf)))
+    S.phi_M_prev_PDE.vector().set_local(phi_M0)
+    t = df.Constant(0.0)
+    uh, c_elim = S.solve_system_passive(nsteps * PHYS["dt"], t, SolverParams(True, True, 0, 1e-5, 1e-7, 1e-40, 1e-40, None, None), None)
+    mem = np.flatnonzero(surf == 1)
+    return dict(nsteps=np.array(nsteps), mem_facets=mem.astype(np.int32), phi_M0=phi_M0[mem],
+                phi_M_trace=np.stack(S.trace)[:, mem], final_phi=uh[-1].vector().get_local(),
+                final_c=S.c.vector().get_local(), final_c_elim=c_elim.vector().get_local())
+
+
 def run_case(nsteps=40, picard=False):
     mesh, sub, surf = kmesh.neuron_2d_mesh(1)
     sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
@@ -334,6 +353,7 @@ def main(outdir, only=None):
     save("ref_run_2d", run_case)
     save("ref_run_2d_picard", lambda: run_case(nsteps=12, picard=True))
     save("ref_run_2d_emi", run_emi_case)
+    save("ref_run_2d_passive", run_passive_case)
     save("ref_run_astro", run_astro_case)          # ~2.5 min (4 224 LSODA calls through scipy)
     print("wrote", sorted(f for f in os.listdir(outdir) if f.endswith(".npz")))
 

@@ -346,3 +346,44 @@ def check_solver_emi_against_reference(lib, rtol=1e-6):
     got = np.stack(trace)
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() / (ref.max() - ref.min()) < rtol
+
+
+def check_passive_run_against_reference(lib, rtol=1e-6):
+    """Solver.solve_system_passive (PDE steps only, non-splitting Robin forms) against the reference's own
+    solve_system_passive executed on oracle/refexec (tests/golden/ref_run_2d_passive.npz): 10 steps from a
+    perturbed membrane potential"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_run_2d_passive.npz"))
+    trace = []
+
+    class Passive2D(Solver2D):
+        def solve_for_time_step(self, k, t):
+            Solver2D.solve_for_time_step(self, k, t)
+            trace.append(self.phi_M_prev_PDE.vector().get_local().copy())
+
+    params = namedtuple("params", "dt n_steps_ODE F psi phi_M_init C_phi C_M R temperature phi_M_init_type "
+                                  "rho_sub")(DT, 25, F, F / (R * T), Constant(-0.0743), C_M / DT, C_M, R, T, "constant",
+                                             {0: Constant(0), 1: Constant(0)})
+    ion_list = [_ion("K", 1.0, 1.96e-9, K_I, K_E), _ion("Cl", -1.0, 2.03e-9, NA_I + K_I, NA_E + K_E),
+                _ion("Na", 1.0, 1.33e-9, NA_I, NA_E)]
+    stim = namedtuple("membrane_params", "g_syn_bar stimulus stimulus_locator")(
+        10.0, {"stim_amplitude": 10.0}, lambda x: x[0] < 20e-6)
+    sp = SolverParams(True, True, 0, 1e-5, 1e-7, 1e-40, 1e-40, None, None)
+    mesh, sub, surf = kmesh.neuron_2d_mesh(1)
+    S = Passive2D(params, ion_list, lib=lib)
+    S.setup_domain(mesh, sub, surf)
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    S.setup_membrane_model(stim, {1: mm_hh})
+    S.phi_M_prev_PDE.vector().set_local(g["phi_M0"])
+    t = Constant(0.0)
+    uh, c_elim = S.solve_system_passive(int(g["nsteps"]) * DT, t, sp, None)
+    ref = g["phi_M_trace"]
+    got = np.stack(trace)
+    assert np.abs(got - ref).max() / (np.abs(ref).max()) < rtol
+    n = ref.shape[1]
+    cfin = np.concatenate([uh[k].nodal().ravel() for k in range(2)])
+    assert rel_err(cfin, g["final_c"]) < 1e-8
+    assert rel_err(c_elim.nodal().ravel(), g["final_c_elim"]) < 1e-8
+    phi = uh[-1].nodal().ravel()
+    assert np.abs((phi - phi.mean()) - (g["final_phi"] - g["final_phi"].mean())).max() < 1e-7 * np.abs(g["final_phi"]).max()

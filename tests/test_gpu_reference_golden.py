@@ -52,3 +52,9 @@ def test_cuda_solver_emi_matches_the_reference(gpu_lib):
     """SolverEMI on the CUDA path against the reference's own solver_emi.py (executed on oracle/refexec)"""
     import solver_checks as sc
     sc.check_solver_emi_against_reference(gpu_lib)
+
+
+def test_cuda_passive_run_matches_the_reference(gpu_lib):
+    """solve_system_passive (PDE steps only, non-splitting Robin forms) on the CUDA path"""
+    import solver_checks as sc
+    sc.check_passive_run_against_reference(gpu_lib)

@@ -15,7 +15,7 @@ from oracle import refexec
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d,ref_run_2d_picard,ref_run_2d_emi"
+FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d,ref_run_2d_picard,ref_run_2d_emi,ref_run_2d_passive"
 
 
 @pytest.mark.skipif(not refexec.available(), reason="/root/reference is not present (GPU box)")
@@ -144,3 +144,9 @@ def test_emulation_solver_emi_matches_the_reference(emu_lib):
     """knpemidg.SolverEMI (run-script flow) against the reference's own solver_emi.py executed on oracle/refexec"""
     import solver_checks as sc
     sc.check_solver_emi_against_reference(emu_lib)
+
+
+def test_emulation_passive_run_matches_the_reference(emu_lib):
+    """Solver.solve_system_passive (non-splitting forms) against the reference's own passive loop"""
+    import solver_checks as sc
+    sc.check_passive_run_against_reference(emu_lib)
