@@ -226,6 +226,8 @@ static void build_mesh(knp_ctx* c, int64_t nc, int64_t nv, const double* coords,
   c->region.upload(region, nc, s);
   c->nbr.upload(c->h_nbr, s); c->finfo.upload(c->h_finfo, s); c->fmem.upload(c->h_fmem, s);
   c->mem_ci.upload(c->h_mem_ci, s); c->mem_fi.upload(c->h_mem_fi, s);
+  c->fgeo.alloc((size_t)FGeo<D>::N * ND * nc);
+  { FacetGeomKernel<D> gk{nc, c->grad.p, c->vol.p, c->h.p, c->nbr.p, c->finfo.p, c->fgeo.p}; parallel_for(s, nc, gk, 128); }
   {
     std::vector<int32_t> mc(c->h_mem_ci);
     mc.insert(mc.end(), c->h_mem_ce.begin(), c->h_mem_ce.end());
@@ -389,7 +391,7 @@ static void assemble_emi_t(knp_ctx* c) {
   parallel_for(s, c->nc, pre, 128);
   EmiArgs<D> k;
   k.P = c->P; k.nc = c->nc; k.nw = c->nc_own;
-  k.grad = c->grad.p; k.vol = c->vol.p; k.h = c->h.p;
+  k.grad = c->grad.p; k.vol = c->vol.p; k.h = c->h.p; k.fgeo = c->fgeo.p;
   k.nbr = c->nbr.p; k.finfo = c->finfo.p; k.fmem = c->fmem.p;
   k.kappa = c->kappa.p; k.q = c->q.p; k.phiM = c->phiM.p;
   for (int i = 0; i < MAX_IONS; ++i) k.Ich[i] = c->Ich[i].p;
@@ -420,7 +422,7 @@ static void assemble_knp_t(knp_ctx* c) {
   {
     KnpArgs<D> k;
     k.P = c->P; k.nc = c->nc; k.nw = c->nc_own; k.nion = c->P.N - 1;
-    k.grad = c->grad.p; k.vol = c->vol.p; k.h = c->h.p; k.region = c->region.p;
+    k.grad = c->grad.p; k.vol = c->vol.p; k.h = c->h.p; k.fgeo = c->fgeo.p; k.region = c->region.p;
     k.nbr = c->nbr.p; k.finfo = c->finfo.p; k.gphi = c->gphi.p;
     for (int i = 0; i < MAX_IONS; ++i) { k.cn[i] = nullptr; k.load[i] = nullptr; k.A[i] = nullptr; k.rhs[i] = nullptr; }
     for (int ion = 0; ion < k.nion; ++ion) {

@@ -94,6 +94,7 @@ struct knp_ctx {
   std::vector<int32_t> h_nbr, h_finfo, h_fmem;                 // [nd][nc]
   std::vector<int32_t> h_mem_facet, h_mem_ci, h_mem_ce, h_mem_tag, h_mem_fi;
   knp::DevBuf<double> grad, vol, h;
+  knp::DevBuf<double> fgeo;      // static facet geometry (knp_dg.h: FGeo), filled once by FacetGeomKernel
   knp::DevBuf<int32_t> region, nbr, finfo, fmem, mem_ci, mem_fi, memcell;
   int64_t nmc = 0;   // cells owning at least one membrane facet
   // parameters

@@ -109,6 +109,61 @@ KNP_HD double mult3(int a, int b, int c) {
 }
 
 // ---------------------------------------------------------------------------
+// Static facet geometry, computed once per mesh (knp_mesh_set) and read by both assembly kernels
+// at every time step instead of being re-derived from the two cells' gradients (a square root, two
+// divisions and 3 (D+1) gathered loads per cell side):
+//   fgeo[(k (D+1) + F) nc + cell],  k = 0           |F|
+//                                   k = 1           1 / avg(h) = 2 / (h_K + h_K')   (tag-0 facets; else 0)
+//                                   k = 2 .. 1+D    outward unit normal of `cell` on its facet F
+//                                   k = 2+D ..      grad(lambda^K'_{perm(j)}) . n, j = 0..D: the normal derivatives
+//                                                   of the NEIGHBOUR's basis functions in my vertex order
+// ---------------------------------------------------------------------------
+template <int D> struct FGeo {
+  static constexpr int ND = D + 1, N = 2 + D + ND;
+  KNP_HD static int64_t at(int k, int F, int64_t nc, int64_t cell) { return ((int64_t)k * ND + F) * nc + cell; }
+};
+
+template <int D>
+struct FacetGeomKernel {
+  static constexpr int ND = D + 1;
+  int64_t nc;
+  const double* grad; const double* vol; const double* h;
+  const int32_t* nbr; const int32_t* finfo;
+  double* fgeo;
+  KNP_HD void operator()(int64_t cell) const {
+    double g[ND][D];
+    for (int i = 0; i < ND; ++i)
+      for (int x = 0; x < D; ++x) g[i][x] = grad[(i * D + x) * nc + cell];
+    const double K = vol[cell], hK = h[cell];
+    for (int F = 0; F < ND; ++F) {
+      const int w = finfo[F * nc + cell];
+      double gn2 = 0.0;
+      for (int x = 0; x < D; ++x) gn2 += g[F][x] * g[F][x];
+      const double gnorm = sqrt(gn2);
+      const double inv_gnorm = 1.0 / gnorm;
+      double n[D];
+      for (int x = 0; x < D; ++x) n[x] = -g[F][x] * inv_gnorm;
+      fgeo[FGeo<D>::at(0, F, nc, cell)] = gnorm * D * K;
+      for (int x = 0; x < D; ++x) fgeo[FGeo<D>::at(2 + x, F, nc, cell)] = n[x];
+      double inv_havg = 0.0, gn_nb[ND];
+      for (int j = 0; j < ND; ++j) gn_nb[j] = 0.0;
+      const int64_t c2 = nbr[F * nc + cell];
+      if (fi_kind(w) == FK_SIP && c2 >= 0) {
+        inv_havg = 1.0 / (0.5 * (hK + h[c2]));
+        for (int j = 0; j < ND; ++j) {
+          const int64_t pj = fi_perm(w, j);
+          double a2 = 0.0;
+          for (int x = 0; x < D; ++x) a2 += grad[(pj * D + x) * nc + c2] * n[x];
+          gn_nb[j] = a2;
+        }
+      }
+      fgeo[FGeo<D>::at(1, F, nc, cell)] = inv_havg;
+      for (int j = 0; j < ND; ++j) fgeo[FGeo<D>::at(2 + D + j, F, nc, cell)] = gn_nb[j];
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
 // pre-pass over cells: nodal conductivity kappa and the diffusive flux vector
 //   kappa_m = F psi sum_k z_k^2 D_k c_k,m           (solver.py:306, ALL ions)
 //   q       = sum_k F z_k D_k grad c_k               (solver.py:309-310)
@@ -184,6 +239,7 @@ struct EmiArgs {
   int64_t nc;                    // local cells (owned + ghost): stride of every per-cell array
   int64_t nw;                    // cells whose rows are assembled (the owned ones, numbered first)
   const double* grad; const double* vol; const double* h;
+  const double* fgeo;            // static facet geometry (FGeo)
   const int32_t* nbr; const int32_t* finfo; const int32_t* fmem;
   const double* kappa; const double* q;
   const double* phiM;            // [nm]
@@ -268,31 +324,23 @@ KNP_HD int emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1]
   B.zeroO();
   if (kind == FK_NONE) return w;
   const int64_t c2 = a.nbr[F * nc + cell];
-  double gn2 = 0.0;
-#pragma unroll
-  for (int x = 0; x < D; ++x) gn2 += g[F][x] * g[F][x];
-  const double gnorm = sqrt(gn2);
-  const double area = gnorm * D * K;
-  const double inv_gnorm = 1.0 / gnorm;
+  const double area = a.fgeo[FGeo<D>::at(0, F, nc, cell)];
   double n[D];
 #pragma unroll
-  for (int x = 0; x < D; ++x) n[x] = -g[F][x] * inv_gnorm;
+  for (int x = 0; x < D; ++x) n[x] = a.fgeo[FGeo<D>::at(2 + x, F, nc, cell)];
   if (kind == FK_SIP) {
     // neighbour data gathered directly in my vertex order
     double gn_me[ND], gn_nb[ND], knb[ND];
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
       const int64_t pj = fi_perm(w, j);
-      double a1 = 0.0, a2 = 0.0;
+      double a1 = 0.0;
 #pragma unroll
-      for (int x = 0; x < D; ++x) {
-        a1 += g[j][x] * n[x];
-        a2 += a.grad[(pj * D + x) * nc + c2] * n[x];
-      }
-      gn_me[j] = a1; gn_nb[j] = a2;
+      for (int x = 0; x < D; ++x) a1 += g[j][x] * n[x];
+      gn_me[j] = a1; gn_nb[j] = a.fgeo[FGeo<D>::at(2 + D + j, F, nc, cell)];
       knb[j] = (j == F) ? 0.0 : a.kappa[pj * nc + c2];
     }
-    const double beta = a.P.tau_emi / (0.5 * (hK + a.h[c2]));
+    const double beta = a.P.tau_emi * a.fgeo[FGeo<D>::at(1, F, nc, cell)];
     double S_me[ND], S_nb[ND];
 #pragma unroll
     for (int i = 0; i < ND; ++i) {
@@ -567,6 +615,7 @@ struct KnpArgs {
   int64_t nw;                    // owned cells (rows assembled)
   int nion;                      // number of solved ions (N-1)
   const double* grad; const double* vol; const double* h;
+  const double* fgeo;            // static facet geometry (FGeo)
   const int32_t* region; const int32_t* nbr; const int32_t* finfo;
   const double* gphi;            // [D][nc]
   const double* cn[MAX_IONS];    // c_prev_n per solved ion
@@ -617,31 +666,22 @@ KNP_HD void knp_facet_geom(const KnpArgs<D>& a, int64_t cell, const double (&g)[
   G.kind = fi_kind(G.w);
   if (G.kind != FK_SIP) return;   // membrane / untagged facets: nothing in the KNP matrix
   const int64_t c2 = a.nbr[F * nc + cell];
-  double gn2 = 0.0;
-#pragma unroll
-  for (int x = 0; x < D; ++x) gn2 += g[F][x] * g[F][x];
-  const double gnorm = sqrt(gn2);
-  G.area = gnorm * D * K;
-  const double inv_gnorm = 1.0 / gnorm;
+  G.area = a.fgeo[FGeo<D>::at(0, F, nc, cell)];
   double n[D];
 #pragma unroll
-  for (int x = 0; x < D; ++x) n[x] = -g[F][x] * inv_gnorm;
+  for (int x = 0; x < D; ++x) n[x] = a.fgeo[FGeo<D>::at(2 + x, F, nc, cell)];
   G.regnb = a.region[c2];
-  G.beta = a.P.tau_knp / (0.5 * (hK + a.h[c2]));
+  G.beta = a.P.tau_knp * a.fgeo[FGeo<D>::at(1, F, nc, cell)];
   double d1 = 0.0, d2 = 0.0;
 #pragma unroll
   for (int x = 0; x < D; ++x) { d1 += gp[x] * n[x]; d2 -= a.gphi[x * nc + c2] * n[x]; }
   G.dphin_me = d1; G.dphin_nb = d2;
 #pragma unroll
   for (int j = 0; j < ND; ++j) {
-    const int64_t pj = fi_perm(G.w, j);
-    double a1 = 0.0, a2 = 0.0;
+    double a1 = 0.0;
 #pragma unroll
-    for (int x = 0; x < D; ++x) {
-      a1 += g[j][x] * n[x];
-      a2 += a.grad[(pj * D + x) * nc + c2] * n[x];
-    }
-    G.gn_me[j] = a1; G.gn_nb[j] = a2;
+    for (int x = 0; x < D; ++x) a1 += g[j][x] * n[x];
+    G.gn_me[j] = a1; G.gn_nb[j] = a.fgeo[FGeo<D>::at(2 + D + j, F, nc, cell)];
   }
 }
 
