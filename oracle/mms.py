@@ -12,8 +12,11 @@ and the MMS-only right-hand-side terms of the solver:
   EMI: src/knpemidg/solver.py:359, 365-366, 369, 372-374
   KNP: src/knpemidg/solver.py:645-646, 653-654, 657
 
-parity unpinned (the reference tests print rates and assert nothing); the pin
-is the expected rate itself (space ~2, time ~1).
+Pinned by tests/golden/ref_mms.npz: the reference's own setup_mms + Solver(mms=...) +
+solve_system_passive executed on oracle/refexec (the generator differentiates the UFL
+expressions symbolically as UFL's apply_derivatives does): step-0 tensors of the r = 2 case,
+the L2 errors the scripts print for r = 2..5 (space) and dt_0/4..dt_0/16 (time).  The reference's
+scripts themselves assert nothing; the expected rates (space ~2, time ~1) are the second pin.
 """
 import numpy as np
 import sympy as sy
@@ -27,8 +30,12 @@ MMS_NORMALS = {1: (-1.0, 0.0), 2: (0.0, -1.0), 3: (1.0, 0.0), 4: (0.0, 1.0)}
 
 
 class MMS:
-    def __init__(self, kind="space", dt=1e-10):
+    def __init__(self, kind="space", dt=1e-10, ufl_degree=None):
+        """ufl_degree: integrate the MMS loads with the rules of that degree - 13 is what UFL estimates for the
+        sin/cos data of mms_space.py (four trigonometric factors of estimated degree 3 each, times the test
+        function; oracle/refexec/ufl_numeric.py) - instead of the fixed rules below"""
         self.kind = kind
+        self.ufl_degree = ufl_degree
         self.t = 0.0
         # parameters (run_MMS_space.py:31-43 == run_MMS_time.py:47-56)
         self.D1 = [6.0, 3.0, 1.0]      # ICS  D_a1, D_b1, D_c1
@@ -115,7 +122,7 @@ class MMS:
 
     # -- right-hand sides ----------------------------------------------------
     def _volume(self, P, f_ics, f_ecs):
-        bq, wq = quad.duffy_rule(P.d, 5)
+        bq, wq = quad.duffy_rule(P.d, 5) if self.ufl_degree is None else quad.cell_rule(P.d, self.ufl_degree)
         xq = np.einsum("qa,cak->cqk", bq, P.X)
         ics = (P.cell_tag == 1)[:, None]
         fv = np.where(ics, self._ev(f_ics, xq), self._ev(f_ecs, xq))
@@ -125,7 +132,7 @@ class MMS:
 
     def _interface(self, P, b, g_by_tag, side, scale=1.0):
         """scale * int g[tag] * trace_side(v) dS(tag)."""
-        bf, wf = quad.interval_rule(9)
+        bf, wf = quad.interval_rule(9 if self.ufl_degree is None else self.ufl_degree)
         for tag, g in g_by_tag.items():
             sel = np.flatnonzero(P.mem_tag == tag)
             if len(sel) == 0:
@@ -141,7 +148,7 @@ class MMS:
         """scale * int dot(J, n) v ds over exterior facets."""
         mesh = P.mesh
         ext = mesh.exterior_facets()
-        bf, wf = quad.interval_rule(9)
+        bf, wf = quad.interval_rule(9 if self.ufl_degree is None else self.ufl_degree)
         cells = mesh.facet_cells[ext, 0]
         x = P.facet_points(ext, bf)
         L = P.basis_at(cells, x)
@@ -170,8 +177,9 @@ class MMS:
         return b
 
     # -- error norms (run_MMS_space.py:231-264) -------------------------------
-    def l2_error(self, P, uh, which, k=None, mean_free=False):
-        bq, wq = quad.duffy_rule(P.d, 6)
+    def l2_error(self, P, uh, which, k=None, mean_free=False, degree=None):
+        """degree=5: the rule the reference's scripts ask for (run_MMS_space.py:213-246, metadata quadrature_degree 5)"""
+        bq, wq = quad.duffy_rule(P.d, 6) if degree is None else quad.cell_rule(P.d, degree)
         xq = np.einsum("qa,cak->cqk", bq, P.X)
         uq = np.einsum("qa,ca->cq", bq, uh)
         f1 = self._sol[which + "1"] if k is None else self._sol[which + "1"][k]

@@ -81,6 +81,9 @@ class Mesh:
     def mpi_comm(self):
         return MPI.comm_world
 
+    def hmin(self):
+        return float(self._m.cell_diameter().min())
+
 
 class MeshFunction:
     def __init__(self, value_type, mesh, dim, value=0):
@@ -207,6 +210,8 @@ class Expression(U.Expr):
     every cell, which is the same thing for data that is polynomial (here: constant) per cell."""
 
     def __init__(self, fn, degree=1, **kw):
+        if isinstance(fn, str):
+            fn = _compile_cpp_expression(fn, kw)
         self.fn, self._degree = fn, degree
 
     def degree(self):
@@ -215,6 +220,28 @@ class Expression(U.Expr):
     def eval(self, ctx, side):
         x = ctx.x.reshape(-1, ctx.x.shape[-1])
         return np.asarray(self.fn(x), dtype=float).reshape(ctx.E, ctx.Q)[:, :, None, None, None]
+
+
+class _Coords:
+    def __init__(self, x):
+        self._x = x
+
+    def __getitem__(self, i):
+        return self._x[:, i]
+
+
+def _compile_cpp_expression(code, kw):
+    """the C++ strings of the reference's MMS initial data (tests/mms_space.py:41-51, mms_time.py:46-52):
+    arithmetic in x[0], x[1], pi, sin, cos, exp and the keyword parameters (numbers or Constants, read when
+    the expression is evaluated)"""
+    src = compile(" ".join(code.split()), "<Expression>", "eval")
+
+    def fn(x):
+        ns = {"x": _Coords(np.asarray(x)), "pi": np.pi, "sin": np.sin, "cos": np.cos, "exp": np.exp,
+              "pow": np.power, "sqrt": np.sqrt, "__builtins__": {}}
+        ns.update({k: float(v) for k, v in kw.items()})
+        return eval(src, ns) + np.zeros(len(x))
+    return fn
 
 
 def interpolate(f, V):
@@ -270,7 +297,33 @@ def FacetArea(mesh):
 
 
 def grad(f):
-    return U.Grad(f)
+    f = as_expr(f)
+    if isinstance(f, (U.Function, U.Argument)):
+        return U.Grad(f)
+    return U.sym_grad(f)                 # an expression of SpatialCoordinate (the MMS data)
+
+
+def div(v):
+    return U.sym_div(as_expr(v))
+
+
+def SpatialCoordinate(mesh):
+    return U.SpatialCoordinate(mesh)
+
+
+def sin(f):
+    return U.MathFunction("sin", as_expr(f))
+
+
+def cos(f):
+    return U.MathFunction("cos", as_expr(f))
+
+
+def exp(f):
+    return U.MathFunction("exp", as_expr(f))
+
+
+pi = np.pi
 
 
 def inner(a, b):

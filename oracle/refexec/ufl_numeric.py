@@ -203,6 +203,11 @@ class Expr:
     def __getitem__(self, i):
         return Component(self, i)
 
+    def __iter__(self):
+        if len(self.ufl_shape) != 1:
+            raise TypeError("iteration over a scalar expression")
+        return iter([Component(self, i) for i in range(self.ufl_shape[0])])
+
     # -- protocol --
     def const_value(self):
         raise TypeError(f"{type(self).__name__} is not a constant expression")
@@ -239,6 +244,11 @@ class Const(Expr):
 
 class Constant(Const):
     """dolfin.Constant (scalar); assign() mutates it, as `t.assign(...)` in solver.py:845"""
+
+    def __new__(cls, v, name=None):
+        if isinstance(v, (tuple, list, np.ndarray)):          # Constant((-1, 0)): the MMS normals (mms_space.py:77)
+            return ListVector([Const(float(x)) for x in v])
+        return super().__new__(cls)
 
     def __init__(self, v, name=None):
         super().__init__(float(v))
@@ -462,6 +472,165 @@ class Conditional(Expr):
         c = self.cond.eval(ctx, side)
         t, f = self.t.eval(ctx, side), self.f.eval(ctx, side)
         return np.where(c, t, f)
+
+
+class ListVector(Expr):
+    """as_vector([...]) / a vector Constant / the value of grad(scalar expression)"""
+
+    def __init__(self, comps):
+        self.comps = [as_expr(c) for c in comps]
+        assert all(c.ufl_shape == () for c in self.comps)
+        self.ufl_shape = (len(self.comps),)
+
+    def children(self):
+        return tuple(self.comps)
+
+    def degree(self):
+        return max(c.degree() for c in self.comps)
+
+    def eval(self, ctx, side):
+        vals = np.broadcast_arrays(*[c.eval(ctx, side) for c in self.comps])
+        return np.concatenate(vals, axis=2)
+
+
+class MathFunction(Expr):
+    """sin / cos / exp of a scalar; UFL estimates degree(argument) + 2"""
+    FN = {"sin": np.sin, "cos": np.cos, "exp": np.exp}
+
+    def __init__(self, name, a):
+        assert a.ufl_shape == ()
+        self.name, self.a = name, a
+
+    def children(self):
+        return (self.a,)
+
+    def const_value(self):
+        return float(self.FN[self.name](self.a.const_value()))
+
+    def degree(self):
+        d = self.a.degree()
+        return d + 2 if d else d                         # UFL: degree(sin(const)) == 0
+
+    def eval(self, ctx, side):
+        return self.FN[self.name](self.a.eval(ctx, side))
+
+
+class SpatialCoordinate(Expr):
+    def __init__(self, mesh):
+        self.mesh = mesh
+        self.ufl_shape = (mesh.gdim,)
+
+    def degree(self):
+        return 1                                        # affine cells
+
+    def eval(self, ctx, side):
+        return ctx.x[:, :, :, None, None]
+
+
+# -- derivatives of expressions of the spatial coordinate ------------------------------------
+# The reference's manufactured solutions (tests/mms_space.py:31-74, mms_time.py:28-74) are UFL
+# expressions of SpatialCoordinate; grad/div of them are expanded by UFL's apply_derivatives BEFORE
+# the quadrature degree is estimated, so the estimate sees products of sin/cos factors.  The same is
+# done here: differentiate the tree, drop exact zeros, then estimate on the result.
+def _is_zero(e):
+    return type(e) is Const and e.v == 0.0
+
+
+def _add(a, b):
+    if _is_zero(a):
+        return b
+    if _is_zero(b):
+        return a
+    return Sum(a, b)
+
+
+def _mul(a, b):
+    if _is_zero(a) or _is_zero(b):
+        return Const(0.0)
+    if type(a) is Const and a.v == 1.0:
+        return b
+    if type(b) is Const and b.v == 1.0:
+        return a
+    return Product(a, b)
+
+
+def _gdim(e):
+    if isinstance(e, (SpatialCoordinate, FacetNormal)):
+        return e.ufl_shape[0]
+    for c in e.children():
+        d = _gdim(c)
+        if d:
+            return d
+    return 0
+
+
+def component(v, k):
+    """scalar expression of component k of a vector-valued expression"""
+    if v.ufl_shape == ():
+        raise ValueError("component of a scalar")
+    if isinstance(v, ListVector):
+        return v.comps[k]
+    if isinstance(v, Sum):
+        return _add(component(v.a, k), component(v.b, k))
+    if isinstance(v, Neg):
+        return Neg(component(v.a, k))
+    if isinstance(v, Product):
+        return _mul(v.a, component(v.b, k)) if v.a.ufl_shape == () else _mul(component(v.a, k), v.b)
+    if isinstance(v, Division):
+        return Division(component(v.a, k), v.b)
+    return Component(v, k)
+
+
+def deriv(e, k):
+    """d e / d x_k of a scalar expression of SpatialCoordinate, Constants and numbers"""
+    assert e.ufl_shape == ()
+    if isinstance(e, Const):
+        return Const(0.0)
+    if isinstance(e, Component) and isinstance(e.a, SpatialCoordinate):
+        return Const(1.0 if e.i == k else 0.0)
+    if isinstance(e, Sum):
+        return _add(deriv(e.a, k), deriv(e.b, k))
+    if isinstance(e, Neg):
+        d = deriv(e.a, k)
+        return d if _is_zero(d) else Neg(d)
+    if isinstance(e, Product):
+        return _add(_mul(deriv(e.a, k), e.b), _mul(e.a, deriv(e.b, k)))
+    if isinstance(e, Division):
+        da, db = deriv(e.a, k), deriv(e.b, k)
+        out = Const(0.0) if _is_zero(da) else Division(da, e.b)
+        if not _is_zero(db):
+            out = _add(out, Neg(Division(_mul(e.a, db), Product(e.b, e.b))))
+        return out
+    if isinstance(e, Power):
+        da = deriv(e.a, k)
+        if _is_zero(da):
+            return da
+        p = e.p.const_value()
+        return _mul(_mul(Const(p), Power(e.a, Const(p - 1.0))), da)
+    if isinstance(e, MathFunction):
+        da = deriv(e.a, k)
+        if _is_zero(da):
+            return da
+        if e.name == "sin":
+            return _mul(MathFunction("cos", e.a), da)
+        if e.name == "cos":
+            return _mul(Neg(MathFunction("sin", e.a)), da)
+        return _mul(e, da)
+    raise NotImplementedError(f"derivative of {type(e).__name__}")
+
+
+def sym_grad(e):
+    d = _gdim(e)
+    if not d:
+        raise ValueError("grad of an expression without a spatial coordinate")
+    return ListVector([deriv(e, k) for k in range(d)])
+
+
+def sym_div(v):
+    out = Const(0.0)
+    for k in range(v.ufl_shape[0]):
+        out = _add(out, deriv(component(v, k), k))
+    return out
 
 
 # -- geometric quantities ----------------------------------------------------------------

@@ -21,6 +21,10 @@ with what the reference's own code produced from them:
                          (solver.py:850-927) in place of the split PDE step;
   ref_run_2d_emi.npz     the same problem, 25 steps, with the reference's EMI-only SolverEMI (solver_emi.py:52-822);
   ref_run_2d_passive.npz S.solve_system_passive() (solver.py:930-1011: PDE steps only, non-splitting forms), 10 steps;
+  ref_mms.npz            the reference's manufactured-solution study, BASELINE configs[0]: its own setup_mms
+                         (tests/mms_space.py, tests/mms_time.py), Solver(mms=...) and solve_system_passive as driven by
+                         tests/run_MMS_space.py / run_MMS_time.py - step-0 tensors and fields of the resolution-2 space case
+                         and of one time case, the L2 errors the scripts print for resolutions 2..5 and dt_0/4..dt_0/16;
   ref_run_astro.npz      S.solve_system_active() for 16 steps of the problem of
                          examples/local-astrocyte-depolarization/run_tortuosity.py (BASELINE configs[3]: three
                          membrane tags, neuronal + glial models, rho != 0, tortuosity, the time-windowed K+/Na+
@@ -333,6 +337,94 @@ def run_astro_case(nsteps=16, M=8):
                 final_E=np.stack([ion['E'].vector().get_local()[mem] for ion in ions]), t_end=np.array(float(t)))
 
 
+# ---- BASELINE configs[0]: tests/run_MMS_space.py, tests/run_MMS_time.py ------------------------------------
+class RefSolverMMS(Solver):
+    """the reference Solver as the MMS scripts construct it (run_MMS_space.py:194-195), recording the tensors the
+    first PDE step assembles (solve_emi / solve_knp re-assemble in place, solver.py:477-479, 730-731)"""
+
+    def __init__(self, params, ion_list, mms):
+        Solver.__init__(self, params=params, ion_list=ion_list, degree_emi=1, degree_knp=1, mms=mms)
+        self.step0 = None
+
+    def solve_for_time_step(self, k, t):
+        first = self.step0 is None
+        if first:       # the EMI forms as assembled (solve_emi removes the mean of its right-hand side in place, solver.py:489-490)
+            self.step0 = dict(zip(("A_emi_row", "A_emi_col", "A_emi_val"), coo(df.assemble(self.a_emi))))
+            self.step0["b_emi"] = df.assemble(self.L_emi).get_local().copy()
+        Solver.solve_for_time_step(self, k, t)
+        if first:
+            self.step0.update(zip(("A_knp_row", "A_knp_col", "A_knp_val"), coo(self.AA_knp)))
+            self.step0.update(b_knp=self.bb_knp.get_local().copy(), phi1=self.phi.vector().get_local().copy(),
+                              c1=self.c.vector().get_local().copy())
+
+
+def run_mms_case(kind="space", resolution=2, dt=1.0e-10, nsteps=2):
+    """one pass of the loop body of tests/run_MMS_space.py:24-246 (kind 'space': dt = 1e-10, Tstop = 2 dt) or of
+    tests/run_MMS_time.py (kind 'time': fixed mesh, dt = dt_0 / 2^i, Tstop = 2 dt_0): the reference's own
+    setup_mms (tests/mms_space.py / mms_time.py), its Solver(mms=...), solve_system_passive with direct solves, and
+    the script's L2 error integrals (quadrature degree 5, phi up to its mean), on the mesh of make_mesh_MMS.py"""
+    mms_mod = load_by_path("ref_mms_" + kind, os.path.join("/root/reference/tests", "mms_%s.py" % kind))
+    C = df.Constant
+    t = C(0.0)
+    D_a1, D_a2, D_b1, D_b2, D_c1, D_c2 = C(6), C(5), C(3), C(4), C(1), C(2)
+    C_a1, C_a2, C_b1, C_b2, C_c1, C_c2 = C(1), C(2), C(2), C(4), C(3), C(2)
+    z_a, z_b, z_c = C(1.0), C(-1.0), C(1.0)
+    F, C_M, R, temperature = C(1), C(1.0), C(1), C(1)
+    rho_sub = {0: C(0), 1: C(0), 2: C(0)}
+    fields = ('D_a1', 'D_a2', 'D_b1', 'D_b2', 'D_c1', 'D_c2', 'C_a1', 'C_a2', 'C_b1', 'C_b2', 'C_c1', 'C_c2',
+              'C_phi', 'z_a', 'z_b', 'z_c', 'dt', 'F', 'C_M', 'phi_M_init', 'R', 'temperature', 'phi_M_init_type', 'rho_sub')
+    params = namedtuple('params', fields)(D_a1, D_a2, D_b1, D_b2, D_c1, D_c2, C_a1, C_a2, C_b1, C_b2, C_c1, C_c2,
+                                          C_M / dt, z_a, z_b, z_c, dt, F, C_M, None, R, temperature, 'expression', rho_sub)
+    mesh, sub, surf = kmesh.mms_mesh(resolution)
+    sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
+    dmesh = df.Mesh(mesh)
+    subdomains = df.MeshFunction.from_array(dmesh, 2, sub)
+    surfaces = df.MeshFunction.from_array(dmesh, 1, surf)
+    mms = mms_mod.setup_mms(params, t, dmesh)
+    sol, rhs = mms.solution, mms.rhs
+    ions = []
+    for key, z, name, Ds, Cs in (("a", z_a, "Na", (D_a1, D_a2), (C_a1, C_a2)), ("b", z_b, "K", (D_b1, D_b2), (C_b1, C_b2)),
+                                 ("c", z_c, "Cl", (D_c1, D_c2), (C_c1, C_c2))):
+        ions.append({'D_sub': {1: C(Ds[0]), 0: C(Ds[1])}, 'z': z, 'name': name,
+                     'c_init_sub': {1: sol['c_%s1_init' % key], 0: sol['c_%s2_init' % key]}, 'c_init_sub_type': 'expression',
+                     'f1': rhs['volume_c_%s1' % key], 'f2': rhs['volume_c_%s2' % key],
+                     'g_robin_1': rhs['bdry']['u_%s1' % key], 'g_robin_2': rhs['bdry']['u_%s2' % key],
+                     'bdry': rhs['bdry']['neumann_' + key], 'C_sub': {1: C(Cs[0]), 0: C(Cs[1])}, 'f_source': C(0)})
+    S = RefSolverMMS(params, ions, mms)
+    S.setup_domain(dmesh, subdomains, surfaces)
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    sp = SolverParams(True, True, resolution, 1e-6, 1e-7, 1e-40, 1e-40, 0.9, 7.5)
+    uh, uh_cc = S.solve_system_passive(nsteps * dt, t, sp, None)
+    dX = df.Measure('dx', domain=dmesh, subdomain_data=subdomains)
+    md = {'quadrature_degree': 5}
+
+    def l2(e1, e2, u):
+        return np.sqrt(abs(df.assemble(df.inner(e2 - u, e2 - u) * dX(0, metadata=md) + df.inner(e1 - u, e1 - u) * dX(1, metadata=md))))
+
+    errors = [l2(sol['c_a1'], sol['c_a2'], uh[0]), l2(sol['c_b1'], sol['c_b2'], uh[1]), l2(sol['c_c1'], sol['c_c2'], uh_cc)]
+    mean_e = df.assemble(sol['phi_1'] * dX(1, metadata=md)) + df.assemble(sol['phi_2'] * dX(0, metadata=md))
+    mean_a = df.assemble(uh[2] * dX(1, metadata=md)) + df.assemble(uh[2] * dX(0, metadata=md))
+    pm = C(mean_e - mean_a)
+    errors.append(l2(sol['phi_1'] - pm, sol['phi_2'] - pm, uh[2]))
+    out = dict(S.step0)
+    out.update(resolution=np.array(resolution), dt=np.array(dt), nsteps=np.array(nsteps),
+               errors=np.array(errors), hmin=np.array(dmesh.hmin()), final_phi=S.phi.vector().get_local(),
+               final_c=S.c.vector().get_local(), final_c_elim=uh_cc.vector().get_local(), t_end=np.array(float(t)))
+    return out
+
+
+def run_mms_study():
+    """ref_mms.npz: the r = 2 space case with its step-0 tensors, the errors of r = 2..5 (run_MMS_space.py prints
+    these and the rates between them) and of the time study i = 2..4 on the r = 3 mesh (run_MMS_time.py, dt_0 = 1e-2)"""
+    out = {"space2_" + k: v for k, v in run_mms_case("space", 2).items()}
+    out.update({"time_" + k: v for k, v in run_mms_case("time", 3, dt=1.0e-2 / 4, nsteps=8).items()})
+    out["space_errors"] = np.stack([out["space2_errors"]] + [run_mms_case("space", r)["errors"] for r in (3, 4, 5)])
+    out["space_h"] = np.array([float(np.sqrt(2.0)) / 2 ** r for r in (2, 3, 4, 5)])
+    out["time_errors"] = np.stack([run_mms_case("time", 3, dt=1.0e-2 / 2 ** i, nsteps=2 * 2 ** i)["errors"] for i in (2, 3, 4)])
+    return out
+
+
 def main(outdir, only=None):
     os.makedirs(outdir, exist_ok=True)
 
@@ -355,6 +447,7 @@ def main(outdir, only=None):
     save("ref_run_2d_emi", run_emi_case)
     save("ref_run_2d_passive", run_passive_case)
     save("ref_run_astro", run_astro_case)          # ~2.5 min (4 224 LSODA calls through scipy)
+    save("ref_mms", run_mms_study)
     print("wrote", sorted(f for f in os.listdir(outdir) if f.endswith(".npz")))
 
 

@@ -310,3 +310,94 @@ def library_run_astro(lib, nsteps, M, rtol_emi=1e-5, rtol_knp=1e-7):
         eng.step()
         tr.append(eng.phi_M().copy())
     return np.stack(tr), eng
+
+
+# ---- the reference's manufactured-solution study (ref_mms.npz; tests/run_MMS_space.py, run_MMS_time.py) --------
+def mms_golden():
+    return np.load(os.path.join(GOLDEN, "ref_mms.npz"))
+
+
+def _coo(g, prefix, shape):
+    return sp.coo_matrix((g[prefix + "_val"], (g[prefix + "_row"], g[prefix + "_col"])), shape=shape).tocsr()
+
+
+def script_errors(S, L, t=0.0):
+    """the four L2 errors as the reference's scripts integrate them (quadrature degree 5, phi modulo its mean;
+    run_MMS_space.py:207-246): c_a, c_b, c_c (the eliminated ion), phi"""
+    mm, P = L.mm, L.P
+    mm.t = t
+    uh = S.c.split() + (S.phi,)
+    return np.array([mm.l2_error(P, uh[0].nodal(), "c", 0, degree=5), mm.l2_error(P, uh[1].nodal(), "c", 1, degree=5),
+                     mm.l2_error(P, S.ion_list[-1]["c"].nodal(), "c", 2, degree=5),
+                     mm.l2_error(P, uh[2].nodal(), "phi", mean_free=True, degree=5)])
+
+
+def _mms_rhs_close(what, P, b, ref):
+    """entries of cells at the interface carry C_phi g (1e9 at dt = 1e-10), the others the O(1) volume sources: the two
+    groups are compared separately, each to 1e-11 of its own largest entry"""
+    at = np.zeros(P.nc, dtype=bool)
+    at[P.mem_cell_i] = at[P.mem_cell_e] = True
+    d, r = np.abs(b - ref).reshape(P.nc, P.nd), np.abs(ref).reshape(P.nc, P.nd)
+    for name, sel in (("interface cells", at), ("other cells", ~at)):
+        assert d[sel].max() <= 1e-11 * r[sel].max(), (what, name, d[sel].max(), r[sel].max())
+
+
+def check_oracle_mms():
+    """oracle/mms.py + oracle/forms.py (MMS mode) against what the reference's own MMS code assembled at step 0 of
+    the r = 2 space case: matrices entrywise 1e-12 (A_knp on the reference's own phi), right-hand sides 1e-11 with
+    the sin/cos sources integrated by the rule of the degree UFL estimates (13), the fields after the two direct
+    solves (phi modulo constants: the interface coupling C_phi = 1e10 makes the EMI system ill-conditioned)."""
+    from oracle import mms as omms, stepper
+    g = mms_golden()
+    mesh, sub, surf = kmesh.mms_mesh(2)
+    mm = omms.MMS("space", dt=float(g["space2_dt"]), ufl_degree=13)
+    P = forms.Problem(mesh, sub.array(), surf.array(), **mm.problem_kwargs())
+    n = P.ndof
+    c0 = np.stack([mm.exact_field(P, "c", k, t=0.0) for k in range(3)])
+    O = stepper.OracleSolver(P, c0, mms=mm, splitting=False)
+    mm.t = 0.0
+    A, B, b = O.assemble_emi()
+    _assert_entrywise("A_emi (mms)", A, _coo(g, "space2_A_emi", (n, n)))
+    _mms_rhs_close("b_emi", P, b, g["space2_b_emi"])
+    O.solve_emi()
+    assert _rel_mod_const(O.phi.ravel(), g["space2_phi1"]) < 1e-6
+    O.phi = g["space2_phi1"].reshape(P.nc, P.nd).copy()          # the drift terms of A_knp on the reference's own phi
+    Ak, bk = O.assemble_knp()
+    full = _coo(g, "space2_A_knp", (2 * n, 2 * n))
+    assert abs(full[:n, n:]).sum() == 0.0 and abs(full[n:, :n]).sum() == 0.0
+    for k in range(2):
+        _assert_entrywise(f"A_knp[{k}] (mms)", Ak[k], full[k * n:(k + 1) * n, k * n:(k + 1) * n])
+        _mms_rhs_close(f"b_knp[{k}]", P, bk[k], g["space2_b_knp"][k * n:(k + 1) * n])
+    O.solve_knp()
+    assert rel_err(O.c[:2].ravel(), g["space2_c1"]) < 1e-12
+
+
+def check_library_mms(lib, resolutions=(2, 3, 4), time_levels=(2, 3)):
+    """the product path (Solver(mms=...) -> engine -> C ABI) against the reference-executed study: the step-0 matrices
+    of the r = 2 case entrywise, and the L2 errors the reference's scripts print, for the space study at
+    `resolutions` and the time study at dt_0 / 2^i, i in `time_levels` (r = 3 mesh)"""
+    import solver_checks as sc
+    g = mms_golden()
+    out = {}
+    errs, S, L = sc.run_mms(lib, 2, nsteps=1, ufl_degree=13)               # the matrices of the first step stay in the context
+    n = L.P.ndof
+    ctx = S.engine.ctx
+    _assert_entrywise("A_emi (mms)", ctx.matrix(0), _coo(g, "space2_A_emi", (n, n)))
+    full = _coo(g, "space2_A_knp", (2 * n, 2 * n))
+    for k in range(2):
+        _assert_entrywise(f"A_knp[{k}] (mms)", ctx.matrix(2 + k), full[k * n:(k + 1) * n, k * n:(k + 1) * n])
+    out["phi1"] = _rel_mod_const(S.phi.nodal().ravel(), g["space2_phi1"])
+    out["c1"] = rel_err(np.concatenate([f.nodal().ravel() for f in S.c.split()]), g["space2_c1"])
+    ref_r = {2: 0, 3: 1, 4: 2, 5: 3}
+    assert out["phi1"] < 1e-6 and out["c1"] < 1e-12, out
+    ref_r = {2: 0, 3: 1, 4: 2, 5: 3}
+    out["space"], out["time"] = [], []
+    for r in resolutions:
+        _, S, L = sc.run_mms(lib, r, ufl_degree=13)
+        out["space"].append(float(np.abs(script_errors(S, L) / g["space_errors"][ref_r[r]] - 1.0).max()))
+    for i in time_levels:
+        _, S, L = sc.run_mms_time(lib, i, r=3, script_initial_data=True)
+        out["time"].append(float(np.abs(script_errors(S, L, t=2.0e-2) / g["time_errors"][i - 2] - 1.0).max()))
+    # measured (emulation and B200): space 5e-8 .. 1.5e-7, time 8e-9 .. 2e-8
+    assert max(out["space"] + out["time"]) < 1e-6, out
+    return out

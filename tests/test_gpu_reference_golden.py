@@ -58,3 +58,8 @@ def test_cuda_passive_run_matches_the_reference(gpu_lib):
     """solve_system_passive (PDE steps only, non-splitting Robin forms) on the CUDA path"""
     import solver_checks as sc
     sc.check_passive_run_against_reference(gpu_lib)
+
+
+def test_cuda_mms_matches_the_reference(gpu_lib):
+    """BASELINE configs[0]: step-0 MMS-mode matrices entrywise, L2 errors of the space (r = 2..5) and time study 1e-6"""
+    gc.check_library_mms(gpu_lib, resolutions=(2, 3, 4, 5))

@@ -15,7 +15,7 @@ from oracle import refexec
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d,ref_run_2d_picard,ref_run_2d_emi,ref_run_2d_passive"
+FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d,ref_run_2d_picard,ref_run_2d_emi,ref_run_2d_passive,ref_mms"
 
 
 @pytest.mark.skipif(not refexec.available(), reason="/root/reference is not present (GPU box)")
@@ -150,3 +150,24 @@ def test_emulation_passive_run_matches_the_reference(emu_lib):
     """Solver.solve_system_passive (non-splitting forms) against the reference's own passive loop"""
     import solver_checks as sc
     sc.check_passive_run_against_reference(emu_lib)
+
+
+def test_oracle_mms_matches_the_reference():
+    """BASELINE configs[0]: the MMS-mode forms (solver.py:349-374, 632-657) and data (tests/mms_space.py)"""
+    gc.check_oracle_mms()
+
+
+def test_reference_mms_study_converges_at_the_expected_rates():
+    """what the reference's own scripts print when executed (they assert nothing): second order in space, first in time"""
+    g = gc.mms_golden()
+    e, h = g["space_errors"], g["space_h"]
+    rates = np.log(e[1:] / e[:-1]) / np.log(h[1:] / h[:-1])[:, None]
+    assert np.all(rates[-1] > 1.9) and np.all(rates[-1] < 2.05), rates
+    t = g["time_errors"]
+    assert np.all(np.log2(t[:-1] / t[1:])[-1] > 0.95), t
+
+
+def test_emulation_mms_matches_the_reference(emu_lib):
+    """the product path reproduces the L2 errors of the reference-executed MMS study (space r = 2, 3, 4; time dt_0/4, dt_0/8)
+    to 1e-6 and the step-0 matrices entrywise"""
+    gc.check_library_mms(emu_lib)

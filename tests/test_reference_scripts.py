@@ -124,6 +124,14 @@ def test_run_mms_space_script_unchanged(ref_env):
         assert 1.95 < rates[-1] < 2.05, (key, rates)
         assert np.all(np.diff(rates) > 0), (key, rates)        # approaching 2 from below
     assert abs(g["errors_ca"][3] - 7.846295e-4) < 1e-9          # r = 5, as through the oracle's data (solver_checks.run_mms)
+    # the same script through the reference's OWN solver (executed on oracle/refexec, tests/golden/ref_mms.npz): the
+    # four errors it prints at r = 2..5.  The product integrates the sin/cos loads with fixed rules (degree 8 cells,
+    # 11 facets), the reference with UFL's estimated degree 13: measured deviation 2.8e-7 at r = 2, 3e-8 .. 7e-8 above
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_mms.npz"))["space_errors"]
+    got = np.array([g["errors_ca"][:4], g["errors_cb"][:4], g["errors_cc"][:4], g["errors_phi"][:4]]).T
+    dev = np.abs(got / ref - 1.0).max(axis=1)
+    print("MMS space errors vs the reference-executed study:", dev)
+    assert np.all(dev < 2e-6), dev
 
 
 @pytest.mark.skipif(os.environ.get("KNP_SLOW_TESTS") != "1",
