@@ -6,12 +6,15 @@ code uses.  It exists so that the reference's own, unmodified `setup_varform_emi
 `minus`, `pcws_constant_project` (src/knpemidg/utils.py:61-124) and the step updates
 (solver.py:794-847) can be EXECUTED in this container, where FEniCS cannot be installed:
 the expression objects the reference builds with `grad/inner/dot/jump/avg/ln/abs/conditional`
-are kept as trees and evaluated at quadrature points when `assemble` is called.
+are kept as trees and evaluated at quadrature points when `assemble` is called.  The manufactured
+solutions of tests/mms_space.py / mms_time.py (sin/cos expressions of SpatialCoordinate and the time
+Constant under grad/div/dot) are differentiated symbolically first, as UFL's apply_derivatives does.
 
 What is restated here (and therefore not pinned by the reference itself) is only what the
 reference delegates to third-party code that is absent from /root/reference:
-  * UFL's degree estimation (sum of factor degrees, +2 for ln and non-integer powers, max over
-    sums and conditional branches, grad lowers the degree by one on affine cells);
+  * UFL's degree estimation (sum of factor degrees, +2 for ln, sin, cos and non-integer powers of
+    non-constant arguments, max over sums and conditional branches, SpatialCoordinate counts 1,
+    grad of a finite-element function lowers the degree by one on affine cells);
   * FFC/FIAT's default quadrature rule for that degree (oracle/quadrature.py);
   * dolfin's assembler: element tensors over cells / interior facets ('+' = first cell of
     the facet) / exterior facets added into a global tensor, integrals of one form that share
