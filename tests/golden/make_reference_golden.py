@@ -25,6 +25,9 @@ with what the reference's own code produced from them:
                          (tests/mms_space.py, tests/mms_time.py), Solver(mms=...) and solve_system_passive as driven by
                          tests/run_MMS_space.py / run_MMS_time.py - step-0 tensors and fields of the resolution-2 space case
                          and of one time case, the L2 errors the scripts print for resolutions 2..5 and dt_0/4..dt_0/16;
+  ref_run_emix.npz       S.solve_system_active() for 15 steps of the problem of examples/emix-simulations/run_EMIx_simulation.py
+                         (BASELINE configs[4], the workload of bench.py's headline number: glial + neuronal membrane models,
+                         ms / cm / mV units, synaptic stimulus) on the synthetic block knpemidg.mesh.emix_like_mesh(9);
   ref_run_astro.npz      S.solve_system_active() for 16 steps of the problem of
                          examples/local-astrocyte-depolarization/run_tortuosity.py (BASELINE configs[3]: three
                          membrane tags, neuronal + glial models, rho != 0, tortuosity, the time-windowed K+/Na+
@@ -337,6 +340,45 @@ def run_astro_case(nsteps=16, M=8):
                 final_E=np.stack([ion['E'].vector().get_local()[mem] for ion in ions]), t_end=np.array(float(t)))
 
 
+# ---- BASELINE configs[4] (bench.py's headline workload): examples/emix-simulations/run_EMIx_simulation.py ------
+def run_emix_case(nsteps=15, M=9):
+    """the problem definition of run_EMIx_simulation.py:56-259 (ms / cm / mV units, calibrated initial state, ions K, Cl
+    and eliminated Na, membrane models {1: mm_glial, 2: mm_hh} of examples/emix-simulations, synaptic stimulus 5 mS/cm^2
+    where x < 3e-4 cm, SolverEMIx.update_ode = the hook of RefSolver) on the synthetic block
+    knpemidg.mesh.emix_like_mesh(M, n_cells=100, length=1e-3) - the mesh family bench.py's headline number is quoted on"""
+    edir = os.path.join(REF_EX, "emix-simulations")
+    e_hh = load_by_path("emix_mm_hh", os.path.join(edir, "mm_hh.py"))
+    e_glial = load_by_path("emix_mm_glial", os.path.join(edir, "mm_glial.py"))
+    mesh, sub, surf = kmesh.emix_like_mesh(M, n_cells=100, length=1.0e-3)
+    sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
+    dt, C_M, temperature, F, R = 0.1, 2.0, 300e3, 96485e3, 8.314e3
+    K = (3.3236967382613933, 102.75563828644862, 124.15397583492471)               # ECS (0), glia (1), neuron (2)
+    Na = (100.71925900028181, 12.39731187972181, 12.838513108606818)
+    c = {"K": K, "Na": Na, "Cl": tuple(a + b for a, b in zip(K, Na))}
+    D = {"K": 1.96e-8, "Cl": 2.03e-8, "Na": 1.33e-8}
+    params = namedtuple('params', ('dt', 'n_steps_ODE', 'F', 'psi', 'C_phi', 'C_M', 'R', 'temperature',
+                                   'phi_M_init_type', 'rho_sub'))(
+        dt, 25, F, F / (R * temperature), C_M / dt, C_M, R, temperature, 'constant', {tg: df.Constant(0) for tg in range(3)})
+    ions = [{'c_init_sub': {tg: df.Constant(c[nm_][tg]) for tg in range(3)}, 'c_init_sub_type': 'constant',
+             'bdry': df.Constant((0, 0)), 'z': z, 'name': nm_, 'D_sub': {tg: df.Constant(D[nm_]) for tg in range(3)},
+             'f_source': df.Constant(0)} for nm_, z in (("K", 1.0), ("Cl", -1.0), ("Na", 1.0))]
+    S = RefSolver(params, ions)
+    dmesh = df.Mesh(mesh)
+    S.setup_domain(dmesh, df.MeshFunction.from_array(dmesh, 3, sub), df.MeshFunction.from_array(dmesh, 2, surf))
+    S.setup_parameters()
+    S.setup_FEM_spaces()
+    S.setup_membrane_model(StimParams(5, {'stim_amplitude': 5}, lambda x: x[0] < 3.0e-4), {1: e_glial, 2: e_hh})
+    t = df.Constant(0.0)
+    S.solve_system_active(nsteps * dt, t, SolverParams(True, True, 0, 1e-5, 1e-7, 1e-40, 2e-40, 0.9, 0.75))
+    mem = np.flatnonzero(np.isin(surf, (1, 2)))
+    return dict(nsteps=np.array(nsteps), M=np.array(M), mem_facets=mem.astype(np.int32), mem_tag=surf[mem].astype(np.int32),
+                phi_M_trace=np.stack(S.trace)[:, mem], final_phi=S.phi.vector().get_local(),
+                final_c=S.c.vector().get_local(), final_c_elim=ions[-1]['c'].vector().get_local(),
+                final_E=np.stack([ion['E'].vector().get_local()[mem] for ion in ions]),
+                final_states_glial=S.mem_models[0]['ode'].states.copy(), final_states_hh=S.mem_models[1]['ode'].states.copy(),
+                t_end=np.array(float(t)))
+
+
 # ---- BASELINE configs[0]: tests/run_MMS_space.py, tests/run_MMS_time.py ------------------------------------
 class RefSolverMMS(Solver):
     """the reference Solver as the MMS scripts construct it (run_MMS_space.py:194-195), recording the tensors the
@@ -448,6 +490,7 @@ def main(outdir, only=None):
     save("ref_run_2d_passive", run_passive_case)
     save("ref_run_astro", run_astro_case)          # ~2.5 min (4 224 LSODA calls through scipy)
     save("ref_mms", run_mms_study)
+    save("ref_run_emix", run_emix_case)            # ~2 min (3 600 LSODA calls through scipy)
     print("wrote", sorted(f for f in os.listdir(outdir) if f.endswith(".npz")))
 
 

@@ -312,6 +312,55 @@ def library_run_astro(lib, nsteps, M, rtol_emi=1e-5, rtol_knp=1e-7):
     return np.stack(tr), eng
 
 
+# ---- BASELINE configs[4], the workload of bench.py's headline number (ref_run_emix.npz) ---------------------------
+def emix_golden():
+    return np.load(os.path.join(GOLDEN, "ref_run_emix.npz"))
+
+
+def library_run_emix(lib, nsteps, M, rtol_emi=1e-10, rtol_knp=1e-11):
+    """bench.py's own engine builder (build_engine_emix) at a small M, stepped with tight Krylov tolerances"""
+    import bench
+    eng = bench.build_engine_emix(M, 0, lib=lib)
+    eng.rtol_emi, eng.rtol_knp = rtol_emi, rtol_knp
+    tr = []
+    for _ in range(nsteps):
+        eng.step()
+        tr.append(eng.phi_M().copy())
+    return np.stack(tr), eng
+
+
+def oracle_run_emix(nsteps, M):
+    """the oracle loop (oracle/stepper.py, direct solves, scipy LSODA) on the same problem"""
+    import bench
+    from knpemidg.models import mm_glial_emix, mm_hh_emix
+    from oracle import stepper
+    mesh, sub, surf = kmesh.emix_like_mesh(M, n_cells=100, length=1.0e-3)
+    P = forms.Problem(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), **bench.EMIX_PHYS)
+    c0 = np.stack([np.choose(sub.array(), [ci[0], ci[1], ci[2]])[:, None] * np.ones((P.nc, P.nd)) for ci in bench.EMIX_C_INIT])
+    O = stepper.OracleSolver(P, c0, models={1: mm_glial_emix, 2: mm_hh_emix}, stimulus={"stim_amplitude": 5.0},
+                             stimulus_locator=lambda x: x[0] < 3.0e-4, ion_names=["K", "Cl", "Na"], direct=True)
+    tr = []
+    for _ in range(nsteps):
+        O.step()
+        tr.append(O.phi_M.copy())
+    return np.stack(tr), O
+
+
+def check_library_emix(lib):
+    """the engine bench.py times, on the block emix_like_mesh(9), against the reference's own solve_system_active on the
+    problem of run_EMIx_simulation.py (15 steps: the stimulated neuron fires, -74 -> +48 mV; the glial membrane stays
+    within 1 uV of -83.085 mV)"""
+    g = emix_golden()
+    tr, eng = library_run_emix(lib, int(g["nsteps"]), int(g["M"]))
+    assert np.array_equal(eng.mem["facet"], g["mem_facets"])
+    dev = trace_deviation(tr, g["phi_M_trace"])
+    cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
+    out = dict(trace=dev, c=rel_err(cfin, g["final_c"]), c_elim=rel_err(eng.concentration(2).reshape(-1), g["final_c_elim"]),
+               phi=_rel_mod_const(eng.phi().reshape(-1), g["final_phi"]))
+    assert out["trace"] < 1e-6 and out["c"] < 1e-7 and out["c_elim"] < 1e-7 and out["phi"] < 1e-6, out
+    return out
+
+
 # ---- the reference's manufactured-solution study (ref_mms.npz; tests/run_MMS_space.py, run_MMS_time.py) --------
 def mms_golden():
     return np.load(os.path.join(GOLDEN, "ref_mms.npz"))

@@ -63,3 +63,9 @@ def test_cuda_passive_run_matches_the_reference(gpu_lib):
 def test_cuda_mms_matches_the_reference(gpu_lib):
     """BASELINE configs[0]: step-0 MMS-mode matrices entrywise, L2 errors of the space (r = 2..5) and time study 1e-6"""
     gc.check_library_mms(gpu_lib, resolutions=(2, 3, 4, 5))
+
+
+def test_cuda_emix_run_matches_the_reference(gpu_lib):
+    """BASELINE configs[4], the headline workload of bench.py (its own build_engine_emix, M = 9), through the CUDA path
+    against the reference's own time loop on the problem of run_EMIx_simulation.py: 15 steps, one action potential"""
+    gc.check_library_emix(gpu_lib)

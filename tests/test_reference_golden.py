@@ -19,8 +19,8 @@ FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d,ref_run_2d_pic
 
 
 @pytest.mark.skipif(not refexec.available(), reason="/root/reference is not present (GPU box)")
-@pytest.mark.parametrize("only", [FAST, pytest.param("ref_run_astro", marks=pytest.mark.skipif(
-    os.environ.get("KNP_SLOW_TESTS") != "1", reason="2.5 min; set KNP_SLOW_TESTS=1"))])
+@pytest.mark.parametrize("only", [FAST] + [pytest.param(name, marks=pytest.mark.skipif(
+    os.environ.get("KNP_SLOW_TESTS") != "1", reason="2.5 - 4 min; set KNP_SLOW_TESTS=1")) for name in ("ref_run_astro", "ref_run_emix")])
 def test_fixtures_regenerate_from_the_reference(tmp_path, only):
     """the committed fixtures are what the reference produces here, today"""
     subprocess.run([sys.executable, os.path.join(gc.GOLDEN, "make_reference_golden.py"), str(tmp_path), "--only=" + only],
@@ -171,3 +171,18 @@ def test_emulation_mms_matches_the_reference(emu_lib):
     """the product path reproduces the L2 errors of the reference-executed MMS study (space r = 2, 3, 4; time dt_0/4, dt_0/8)
     to 1e-6 and the step-0 matrices entrywise"""
     gc.check_library_mms(emu_lib)
+
+
+def test_emulation_emix_run_matches_the_reference(emu_lib):
+    """BASELINE configs[4] = the workload bench.py times: its own engine builder on emix_like_mesh(9) against the reference's
+    solve_system_active on the problem of run_EMIx_simulation.py (measured: trace 1.1e-8, concentrations 1e-9)"""
+    gc.check_library_emix(emu_lib)
+
+
+@pytest.mark.skipif(os.environ.get("KNP_SLOW_TESTS") != "1", reason="~2 min (scipy LSODA in Python); set KNP_SLOW_TESTS=1")
+def test_oracle_emix_run_matches_the_reference():
+    g = gc.emix_golden()
+    tr, O = gc.oracle_run_emix(int(g["nsteps"]), int(g["M"]))
+    assert gc.trace_deviation(tr, g["phi_M_trace"]) < 1e-6
+    assert gc.rel_err(O.c.reshape(-1), g["final_c"]) < 1e-7
+    assert gc.rel_err(O.c_elim.reshape(-1), g["final_c_elim"]) < 1e-7
