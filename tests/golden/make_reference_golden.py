@@ -25,6 +25,8 @@ with what the reference's own code produced from them:
                          (tests/mms_space.py, tests/mms_time.py), Solver(mms=...) and solve_system_passive as driven by
                          tests/run_MMS_space.py / run_MMS_time.py - step-0 tensors and fields of the resolution-2 space case
                          and of one time case, the L2 errors the scripts print for resolutions 2..5 and dt_0/4..dt_0/16;
+  ref_run_3d.npz         S.solve_system_active() for 8 steps of the four-axon bundle of examples/idealized-geometries/run_3D.py
+                         (BASELINE configs[2]) on its own resolution-0 mesh, mm_hh + mm_hh_no_stim;
   ref_run_emix.npz       S.solve_system_active() for 15 steps of the problem of examples/emix-simulations/run_EMIx_simulation.py
                          (BASELINE configs[4], the workload of bench.py's headline number: glial + neuronal membrane models,
                          ms / cm / mV units, synaptic stimulus) on the synthetic block knpemidg.mesh.emix_like_mesh(9);
@@ -278,6 +280,22 @@ def run_case(nsteps=40, picard=False):
                 final_states=S.mem_models[0]['ode'].states.copy(), t_end=np.array(float(t)))
 
 
+def run_3d_case(nsteps=8):
+    """BASELINE configs[2]: the problem of examples/idealized-geometries/run_3D.py (four axons; mm_hh on the membrane of
+    the first, mm_hh_no_stim on the other three, run_3D.py:196) on its own resolution-0 mesh (make_mesh_3D.py:81-111:
+    15 552 tetrahedra, 1 472 membrane facets)"""
+    mesh, sub, surf = kmesh.bundle_3d_mesh(0)
+    sub, surf = np.asarray(sub.array()), np.asarray(surf.array())
+    S, ions = build_solver(mesh, sub, surf, np.unique(sub), {1: mm_hh, 2: mm_hh_no_stim})
+    t = df.Constant(0.0)
+    S.solve_system_active(nsteps * PHYS["dt"], t, SolverParams(True, True, 0, 1e-5, 1e-7, 1e-40, 2e-40, 0.9, 0.75))
+    mem = np.flatnonzero(np.isin(surf, (1, 2)))
+    return dict(nsteps=np.array(nsteps), mem_facets=mem.astype(np.int32), mem_tag=surf[mem].astype(np.int32),
+                phi_M_trace=np.stack(S.trace)[:, mem], final_phi=S.phi.vector().get_local(),
+                final_c=S.c.vector().get_local(), final_c_elim=ions[-1]['c'].vector().get_local(),
+                final_E=np.stack([ion['E'].vector().get_local()[mem] for ion in ions]), t_end=np.array(float(t)))
+
+
 # ---- BASELINE configs[3]: examples/local-astrocyte-depolarization/run_tortuosity.py ------------------------
 ASTRO = dict(dt=0.1, C_M=1.0, T=307e3, F=96500e3, R=8.315e3, g_syn=26.0, t_syn=1.2, lambda_i=3.2 * 4, lambda_e=1.6 * 4,
              D={"K": 1.96e-8, "Na": 1.33e-8, "Cl": 2.03e-8},
@@ -490,7 +508,8 @@ def main(outdir, only=None):
     save("ref_run_2d_passive", run_passive_case)
     save("ref_run_astro", run_astro_case)          # ~2.5 min (4 224 LSODA calls through scipy)
     save("ref_mms", run_mms_study)
-    save("ref_run_emix", run_emix_case)            # ~2 min (3 600 LSODA calls through scipy)
+    save("ref_run_emix", run_emix_case)            # ~4 min (3 600 LSODA calls through scipy)
+    save("ref_run_3d", run_3d_case)                # the longest one: 11 776 LSODA calls, 3D direct solves with 124 k unknowns
     print("wrote", sorted(f for f in os.listdir(outdir) if f.endswith(".npz")))
 
 

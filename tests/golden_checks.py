@@ -241,6 +241,39 @@ def library_run(lib, nsteps, rtol_emi=1e-5, rtol_knp=1e-7):
     return np.stack(tr), eng
 
 
+# ---- BASELINE configs[2]: run_3D.py on its own resolution-0 mesh (ref_run_3d.npz) ----------------------------
+def library_run_3d(lib, nsteps, rtol_emi=1e-10, rtol_knp=1e-11):
+    from knpemidg.engine import Engine
+    from knpemidg.models import mm_hh, mm_hh_no_stim
+    mesh, sub, surf = kmesh.bundle_3d_mesh(0)
+    eng = Engine(mesh, sub.array(), surf.array(), membrane_tags=(1, 2), lib=lib, **RUN_PHYS)
+    eng.set_concentrations_by_tag(RUN_C_INIT)
+    for tag, mod in ((1, mm_hh), (2, mm_hh_no_stim)):                                 # run_3D.py:196
+        eng.add_membrane_model(tag, mod, ["K", "Cl", "Na"], stimulus={"stim_amplitude": 10.0},
+                               stimulus_locator=lambda x: x[0] < 20e-6)
+    eng.rtol_emi, eng.rtol_knp = rtol_emi, rtol_knp
+    eng.initialize(pc=1)
+    tr = []
+    for _ in range(nsteps):
+        eng.step()
+        tr.append(eng.phi_M().copy())
+    return np.stack(tr), eng
+
+
+def check_library_3d(lib):
+    """the four-axon bundle of run_3D.py (mm_hh on the first axon, mm_hh_no_stim on the other three) against the
+    reference's own solve_system_active on the same mesh"""
+    g = np.load(os.path.join(GOLDEN, "ref_run_3d.npz"))
+    tr, eng = library_run_3d(lib, int(g["nsteps"]))
+    assert np.array_equal(eng.mem["facet"], g["mem_facets"])
+    cfin = np.concatenate([eng.concentration(k).reshape(-1) for k in range(2)])
+    out = dict(trace=trace_deviation(tr, g["phi_M_trace"]), c=rel_err(cfin, g["final_c"]),
+               c_elim=rel_err(eng.concentration(2).reshape(-1), g["final_c_elim"]),
+               phi=_rel_mod_const(eng.phi().reshape(-1), g["final_phi"]))
+    assert out["trace"] < 1e-6 and out["c"] < 1e-7 and out["c_elim"] < 1e-7 and out["phi"] < 1e-6, out
+    return out
+
+
 # ---- BASELINE configs[3]: run_tortuosity.py on knpemidg.mesh.astro_like_mesh (ref_run_astro.npz) ---------
 ASTRO = dict(dt=0.1, C_M=1.0, T=307e3, F=96500e3, R=8.315e3, g_syn=26.0, t_syn=1.2, lambda_i=3.2 * 4, lambda_e=1.6 * 4)
 ASTRO_D = [1.96e-8, 1.33e-8, 2.03e-8]                                                # K, Na, Cl (cm^2/ms)

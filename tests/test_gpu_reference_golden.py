@@ -69,3 +69,9 @@ def test_cuda_emix_run_matches_the_reference(gpu_lib):
     """BASELINE configs[4], the headline workload of bench.py (its own build_engine_emix, M = 9), through the CUDA path
     against the reference's own time loop on the problem of run_EMIx_simulation.py: 15 steps, one action potential"""
     gc.check_library_emix(gpu_lib)
+
+
+def test_cuda_3d_bundle_run_matches_the_reference(gpu_lib):
+    """BASELINE configs[2]: run_3D.py's four-axon bundle (mm_hh + mm_hh_no_stim) through the CUDA path against the
+    reference's own time loop on the same mesh"""
+    gc.check_library_3d(gpu_lib)

@@ -20,7 +20,8 @@ FAST = "ref_forms_2d,ref_forms_2d_nosplit,ref_forms_3d,ref_run_2d,ref_run_2d_pic
 
 @pytest.mark.skipif(not refexec.available(), reason="/root/reference is not present (GPU box)")
 @pytest.mark.parametrize("only", [FAST] + [pytest.param(name, marks=pytest.mark.skipif(
-    os.environ.get("KNP_SLOW_TESTS") != "1", reason="2.5 - 4 min; set KNP_SLOW_TESTS=1")) for name in ("ref_run_astro", "ref_run_emix")])
+    os.environ.get("KNP_SLOW_TESTS") != "1", reason="2.5 - 4 min; set KNP_SLOW_TESTS=1")) for name in ("ref_run_astro", "ref_run_emix")] + [pytest.param("ref_run_3d", marks=pytest.mark.skipif(
+        os.environ.get("KNP_SLOW_TESTS") != "3d", reason="20 min (3D direct solves, 11 776 LSODA calls); set KNP_SLOW_TESTS=3d"))])
 def test_fixtures_regenerate_from_the_reference(tmp_path, only):
     """the committed fixtures are what the reference produces here, today"""
     subprocess.run([sys.executable, os.path.join(gc.GOLDEN, "make_reference_golden.py"), str(tmp_path), "--only=" + only],
@@ -186,3 +187,9 @@ def test_oracle_emix_run_matches_the_reference():
     assert gc.trace_deviation(tr, g["phi_M_trace"]) < 1e-6
     assert gc.rel_err(O.c.reshape(-1), g["final_c"]) < 1e-7
     assert gc.rel_err(O.c_elim.reshape(-1), g["final_c_elim"]) < 1e-7
+
+
+def test_emulation_3d_bundle_run_matches_the_reference(emu_lib):
+    """BASELINE configs[2]: the four-axon bundle of run_3D.py on its own resolution-0 mesh (15 552 tetrahedra), mm_hh +
+    mm_hh_no_stim, 8 steps, against the reference's own loop (measured: trace 3e-8, concentrations 3e-9 .. 8e-9)"""
+    gc.check_library_3d(emu_lib)
