@@ -47,7 +47,10 @@ int knp_sync(knp_ctx* ctx);
  *   facet_cells[nf*2] (second = -1 on the boundary), facet_tag[nf],
  *   mem_tags[n_mem_tags] = facet tags that carry a membrane (ODE model tags,
  *   or the MMS interface tags).  Membrane rows are the interior facets with
- *   such a tag in ascending facet index. */
+ *   such a tag in ascending facet index.
+ * Also computes, once, everything about the mesh that the per-step kernels would otherwise re-derive: P1 gradients,
+ * volumes, diameters and the per-cell-side table of facet area, 1/avg(h), unit normal and the neighbour's normal
+ * derivatives (what UFL's FacetNormal / CellDiameter / avg() deliver at every assemble() of solver.py:477-479, 730-731). */
 int knp_mesh_set(knp_ctx* ctx, int d, int64_t nc, int64_t nv, const double* coords,
                  const int32_t* cell_verts, const int32_t* cell_region,
                  int64_t nf, const int32_t* facet_cells, const int32_t* facet_tag,
