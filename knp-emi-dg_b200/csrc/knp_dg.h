@@ -312,9 +312,8 @@ struct SmemBlocks {   // O, D: rows of ND*ND (+pad) doubles; w: facet info word
 // indexed dynamically.  dg += share of the diagonal block, r += share of the rhs.
 // Returns the facet info word (column map).
 template <int D, int F, class Blocks>
-KNP_HD int emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1][D], double K,
-                     double hK, const double (&kap)[D + 1], const double (&qc)[D],
-                     const Blocks& B, double (&r)[D + 1]) {
+KNP_HD int emi_facet(const EmiArgs<D>& a, int64_t cell, const double (&g)[D + 1][D],
+                     const double (&kap)[D + 1], const double (&qc)[D], const Blocks& B, double (&r)[D + 1]) {
   constexpr int ND = D + 1;
   constexpr double c_m2 = 1.0 / (D * (D + 1));                  // facet mass
   constexpr double c_m3 = (D == 3) ? 1.0 / 60.0 : 1.0 / 24.0;   // facet cubic moment
@@ -423,7 +422,7 @@ struct EmiCellKernel {
     for (int i = 0; i < ND; ++i)
       #pragma unroll
       for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * a.nc + cell];
-    const double K = a.vol[cell], hK = a.h[cell];
+    const double K = a.vol[cell];
     double kap[ND], qc[D];
     double kbar = 0.0;
     #pragma unroll
@@ -440,10 +439,10 @@ struct EmiCellKernel {
     for (int f = 0; f < ND; ++f) {
       double O[ND][ND];
       int w;
-      if (f == 0) w = emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, RegBlocks<ND>{O, dg}, r);
-      else if (f == 1) w = emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, RegBlocks<ND>{O, dg}, r);
-      else if (f == 2) w = emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, RegBlocks<ND>{O, dg}, r);
-      else w = emi_facet<D, D>(a, cell, g, K, hK, kap, qc, RegBlocks<ND>{O, dg}, r);
+      if (f == 0) w = emi_facet<D, 0>(a, cell, g, kap, qc, RegBlocks<ND>{O, dg}, r);
+      else if (f == 1) w = emi_facet<D, 1>(a, cell, g, kap, qc, RegBlocks<ND>{O, dg}, r);
+      else if (f == 2) w = emi_facet<D, 2>(a, cell, g, kap, qc, RegBlocks<ND>{O, dg}, r);
+      else w = emi_facet<D, D>(a, cell, g, kap, qc, RegBlocks<ND>{O, dg}, r);
       double* Of = a.A + (int64_t)(1 + f) * a.nc * bs + cell * bs;
       #pragma unroll
       for (int i = 0; i < ND; ++i)
@@ -490,7 +489,7 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) emi_assemble_kernel(con
     for (int i = 0; i < ND; ++i)
       #pragma unroll
       for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * a.nc + cell];
-    const double K = a.vol[cell], hK = a.h[cell];
+    const double K = a.vol[cell];
     double kap[ND], qc[D];
     double kbar = 0.0;
     #pragma unroll
@@ -513,13 +512,13 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) emi_assemble_kernel(con
     const SmemBlocks<ND> blk{myO, myD, wf};
     double bdrow[ND], row[ND], ri;
     switch (f) {
-      case 0: emi_facet<D, 0>(a, cell, g, K, hK, kap, qc, blk, r);
+      case 0: emi_facet<D, 0>(a, cell, g, kap, qc, blk, r);
               emi_cell_row<D, 0>(a, g, K, kap, kbar, qc, row, bdrow, ri); break;
-      case 1: emi_facet<D, 1>(a, cell, g, K, hK, kap, qc, blk, r);
+      case 1: emi_facet<D, 1>(a, cell, g, kap, qc, blk, r);
               emi_cell_row<D, 1>(a, g, K, kap, kbar, qc, row, bdrow, ri); break;
-      case 2: emi_facet<D, 2>(a, cell, g, K, hK, kap, qc, blk, r);
+      case 2: emi_facet<D, 2>(a, cell, g, kap, qc, blk, r);
               emi_cell_row<D, 2>(a, g, K, kap, kbar, qc, row, bdrow, ri); break;
-      default: emi_facet<D, D>(a, cell, g, K, hK, kap, qc, blk, r);
+      default: emi_facet<D, D>(a, cell, g, kap, qc, blk, r);
               emi_cell_row<D, D>(a, g, K, kap, kbar, qc, row, bdrow, ri); break;
     }
     r[f] += ri;
@@ -658,8 +657,8 @@ KNP_HD void knp_cell_row(const Params& P, int ion, const double (&g)[D + 1][D], 
 
 // ion-independent part of facet F (neighbour data gathered in my vertex order, see emi_facet)
 template <int D, int F>
-KNP_HD void knp_facet_geom(const KnpArgs<D>& a, int64_t cell, const double (&g)[D + 1][D], double K,
-                           double hK, const double (&gp)[D], KnpFacetGeom<D>& G) {
+KNP_HD void knp_facet_geom(const KnpArgs<D>& a, int64_t cell, const double (&g)[D + 1][D],
+                           const double (&gp)[D], KnpFacetGeom<D>& G) {
   constexpr int ND = D + 1;
   const int64_t nc = a.nc;
   G.w = a.finfo[F * nc + cell];
@@ -811,14 +810,14 @@ struct KnpCellKernel {   // one index per cell, all solved ions (host emulation 
     double g[ND][D];
     for (int i = 0; i < ND; ++i)
       for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * a.nc + cell];
-    const double K = a.vol[cell], hK = a.h[cell];
+    const double K = a.vol[cell];
     double gp[D];
     for (int x = 0; x < D; ++x) gp[x] = a.gphi[x * a.nc + cell];
     KnpFacetGeom<D> G[ND];
-    knp_facet_geom<D, 0>(a, cell, g, K, hK, gp, G[0]);
-    knp_facet_geom<D, 1>(a, cell, g, K, hK, gp, G[1]);
-    knp_facet_geom<D, 2>(a, cell, g, K, hK, gp, G[2]);
-    if constexpr (D == 3) knp_facet_geom<D, D>(a, cell, g, K, hK, gp, G[D]);
+    knp_facet_geom<D, 0>(a, cell, g, gp, G[0]);
+    knp_facet_geom<D, 1>(a, cell, g, gp, G[1]);
+    knp_facet_geom<D, 2>(a, cell, g, gp, G[2]);
+    if constexpr (D == 3) knp_facet_geom<D, D>(a, cell, g, gp, G[D]);
     for (int ion = 0; ion < a.nion; ++ion) {
       const double Dme = a.P.D[ion][reg];
       double cnl[ND];
@@ -861,7 +860,7 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) knp_assemble_kernel(con
   const int64_t nc = a.nc;
   const bool active = cell < a.nw;
   double g[ND][D], gp[D];
-  double K = 0.0, hK = 0.0;
+  double K = 0.0;
   int reg = 0;
   KnpFacetGeom<D> G;
   G.w = 0; G.kind = FK_NONE;
@@ -871,14 +870,14 @@ __global__ void __launch_bounds__(ASM_CPB*(D + 1), MINB) knp_assemble_kernel(con
     for (int i = 0; i < ND; ++i)
 #pragma unroll
       for (int x = 0; x < D; ++x) g[i][x] = a.grad[(i * D + x) * nc + cell];
-    K = a.vol[cell]; hK = a.h[cell];
+    K = a.vol[cell];
 #pragma unroll
     for (int x = 0; x < D; ++x) gp[x] = a.gphi[x * nc + cell];
     switch (f) {   // warp uniform
-      case 0: knp_facet_geom<D, 0>(a, cell, g, K, hK, gp, G); break;
-      case 1: knp_facet_geom<D, 1>(a, cell, g, K, hK, gp, G); break;
-      case 2: knp_facet_geom<D, 2>(a, cell, g, K, hK, gp, G); break;
-      default: knp_facet_geom<D, D>(a, cell, g, K, hK, gp, G); break;
+      case 0: knp_facet_geom<D, 0>(a, cell, g, gp, G); break;
+      case 1: knp_facet_geom<D, 1>(a, cell, g, gp, G); break;
+      case 2: knp_facet_geom<D, 2>(a, cell, g, gp, G); break;
+      default: knp_facet_geom<D, D>(a, cell, g, gp, G); break;
     }
   }
   const int64_t ncell_blk = (a.nw - cell0 < ASM_CPB) ? (a.nw - cell0) : ASM_CPB;
