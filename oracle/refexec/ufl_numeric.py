@@ -150,9 +150,9 @@ class Expr:
         def eval(self, ctx, side, _raw=raw):
             key = (id(self), side)
             hit = ctx.memo.get(key)
-            if hit is None:
-                hit = ctx.memo[key] = _raw(self, ctx, side)
-            return hit
+            if hit is None:             # (the entry keeps the node alive: its id cannot be recycled while the context lives)
+                hit = ctx.memo[key] = (self, _raw(self, ctx, side))
+            return hit[1]
         cls.eval = eval
 
     # -- algebra --
